@@ -1,0 +1,155 @@
+"""Host-side packed-CSR container for batches of conflict graphs (the ingest format of the CUDA
+library, see include/distgcn_b200.h "Data layout").
+
+The reference handles one scipy matrix per call (``adj`` as loaded from the ``.mat`` files written by
+Data_Generation.py:214-219: float64 CSC, symmetric, zero diagonal).  Here thousands of such graphs
+are packed into one CSR so a single kernel launch covers all of them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def _pattern_csr(adj) -> Tuple[np.ndarray, np.ndarray]:
+    """(indptr, indices) of the non-zero pattern of one adjacency matrix - what
+    ``np.nonzero(adj[v])`` enumerates in the reference (heuristics.py:94)."""
+    if sp.issparse(adj):
+        a = adj.tocsr()
+        if a.nnz and (a.data == 0).any():
+            a = a.copy()
+            a.eliminate_zeros()
+    else:
+        a = sp.csr_matrix(np.asarray(adj))
+    if a.shape[0] != a.shape[1]:
+        raise ValueError("adjacency matrix must be square, got %s" % (a.shape,))
+    return a.indptr, a.indices
+
+
+@dataclass
+class PackedBatch:
+    """n_graphs graphs as one CSR; column indices are batch-global vertex ids."""
+    graph_ptr: np.ndarray  # int32 [n_graphs + 1]
+    row_ptr: np.ndarray    # int32 [n_nodes + 1]
+    col_idx: np.ndarray    # int32 [nnz]
+
+    @property
+    def n_graphs(self) -> int:
+        return int(self.graph_ptr.shape[0] - 1)
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.row_ptr.shape[0] - 1)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col_idx.shape[0])
+
+    def graph_sizes(self) -> np.ndarray:
+        return np.diff(self.graph_ptr)
+
+    def graph_nnz(self) -> np.ndarray:
+        return np.diff(self.row_ptr[self.graph_ptr])
+
+    def slice(self, g0: int, g1: int) -> "PackedBatch":
+        """Graphs g0 .. g1-1 as their own batch (vertex ids re-based)."""
+        v0, v1 = int(self.graph_ptr[g0]), int(self.graph_ptr[g1])
+        e0, e1 = int(self.row_ptr[v0]), int(self.row_ptr[v1])
+        return PackedBatch(
+            graph_ptr=(self.graph_ptr[g0:g1 + 1] - v0).astype(np.int32),
+            row_ptr=(self.row_ptr[v0:v1 + 1] - e0).astype(np.int32),
+            col_idx=(self.col_idx[e0:e1] - v0).astype(np.int32),
+        )
+
+    def graph_adj(self, g: int) -> sp.csr_matrix:
+        """Graph g back as a scipy CSR matrix (float64 ones), for interoperability."""
+        sub = self.slice(g, g + 1)
+        n = sub.n_nodes
+        return sp.csr_matrix((np.ones(sub.nnz), sub.col_idx, sub.row_ptr), shape=(n, n))
+
+    def validate(self) -> None:
+        """Structural checks the kernels rely on: in-range, same-graph, zero-diagonal, symmetric."""
+        n = self.n_nodes
+        if self.graph_ptr[0] != 0 or self.graph_ptr[-1] != n or (np.diff(self.graph_ptr) < 0).any():
+            raise ValueError("graph_ptr must be non-decreasing from 0 to n_nodes")
+        if self.row_ptr[0] != 0 or self.row_ptr[-1] != self.nnz or (np.diff(self.row_ptr) < 0).any():
+            raise ValueError("row_ptr must be non-decreasing from 0 to nnz")
+        if self.nnz == 0:
+            return
+        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(self.row_ptr))
+        cols = self.col_idx.astype(np.int64)
+        if cols.min() < 0 or cols.max() >= n:
+            raise ValueError("col_idx out of range")
+        gid = np.searchsorted(self.graph_ptr, rows, side="right") - 1
+        if (cols < self.graph_ptr[gid]).any() or (cols >= self.graph_ptr[gid + 1]).any():
+            raise ValueError("an edge crosses a graph boundary")
+        if (rows == cols).any():
+            raise ValueError("self-loops are not allowed (the reference's greedy search never terminates on them)")
+        a = sp.csr_matrix((np.ones(self.nnz, dtype=np.int8), cols, self.row_ptr.astype(np.int64)), shape=(n, n))
+        if (a != a.T).nnz:
+            raise ValueError("adjacency pattern is not symmetric")
+
+
+def pack_graphs(adjs: Iterable) -> PackedBatch:
+    """Pack scipy / dense adjacency matrices into one PackedBatch."""
+    gp: List[int] = [0]
+    rps: List[np.ndarray] = [np.zeros(1, dtype=np.int64)]
+    cis: List[np.ndarray] = []
+    nnz = 0
+    for adj in adjs:
+        indptr, indices = _pattern_csr(adj)
+        n = indptr.shape[0] - 1
+        rps.append(indptr[1:].astype(np.int64) + nnz)
+        cis.append(indices.astype(np.int64) + gp[-1])
+        nnz += int(indptr[-1])
+        gp.append(gp[-1] + n)
+    if gp[-1] >= 2 ** 31 or nnz >= 2 ** 31:
+        raise ValueError("batch too large for int32 indexing: %d nodes, %d nnz" % (gp[-1], nnz))
+    return PackedBatch(
+        graph_ptr=np.asarray(gp, dtype=np.int32),
+        row_ptr=np.concatenate(rps).astype(np.int32),
+        col_idx=(np.concatenate(cis) if cis else np.zeros(0)).astype(np.int32),
+    )
+
+
+def from_edge_lists(graph_ptr: Sequence[int], edge_ptr: Sequence[int], edge_u: np.ndarray,
+                    edge_v: np.ndarray) -> PackedBatch:
+    """Build a PackedBatch from per-graph undirected edge lists with graph-local endpoints (the
+    compact form of the tests/golden/*_full.npz fixtures)."""
+    graph_ptr = np.asarray(graph_ptr, dtype=np.int64)
+    edge_ptr = np.asarray(edge_ptr, dtype=np.int64)
+    n = int(graph_ptr[-1])
+    per_graph = np.diff(edge_ptr)
+    off = np.repeat(graph_ptr[:-1], per_graph)
+    u = edge_u.astype(np.int64) + off
+    v = edge_v.astype(np.int64) + off
+    rows = np.concatenate([u, v])
+    cols = np.concatenate([v, u])
+    a = sp.csr_matrix((np.ones(rows.shape[0], dtype=np.int8), (rows, cols)), shape=(n, n))
+    a.sort_indices()
+    return PackedBatch(graph_ptr=graph_ptr.astype(np.int32), row_ptr=a.indptr.astype(np.int32),
+                       col_idx=a.indices.astype(np.int32))
+
+
+def partition_by_work(batch: PackedBatch, n_parts: int, node_cost: float = 8.0) -> List[Tuple[int, int]]:
+    """Contiguous graph ranges [g0, g1) with balanced ``nnz + node_cost * n_nodes`` (SURVEY.md 8e:
+    independent graphs shard with no collective).  Always returns n_parts ranges (possibly empty)."""
+    if n_parts < 1:
+        raise ValueError("n_parts must be >= 1")
+    work = batch.graph_nnz().astype(np.float64) + node_cost * batch.graph_sizes().astype(np.float64)
+    csum = np.concatenate([[0.0], np.cumsum(work)])
+    total = csum[-1]
+    bounds = [0]
+    for p in range(1, n_parts):
+        target = total * p / n_parts
+        g = int(np.searchsorted(csum, target, side="left"))
+        # pick the boundary closest to the target
+        if g > 0 and abs(csum[g - 1] - target) <= abs(csum[min(g, batch.n_graphs)] - target):
+            g -= 1
+        g = min(max(g, bounds[-1]), batch.n_graphs)
+        bounds.append(g)
+    bounds.append(batch.n_graphs)
+    return [(bounds[i], bounds[i + 1]) for i in range(n_parts)]

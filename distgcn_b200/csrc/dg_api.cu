@@ -1,0 +1,719 @@
+// C-ABI of libdistgcn_b200.so (include/distgcn_b200.h): handles, staging of HOST-space arguments,
+// argument validation.  All arithmetic lives in dg_gcn.cu / dg_lgs.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "dg_common.cuh"
+
+namespace dg {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+void clear_error() { g_error[0] = '\0'; }
+
+int scratch(dg_context *ctx, int slot, size_t bytes, void **out) {
+    Buffer &b = ctx->slots[slot];
+    if (bytes < 256) bytes = 256;
+    if (b.cap < bytes) {
+        if (b.ptr) {
+            // the old buffer may still be in use by enqueued work
+            DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            DG_CUDA_CHECK(cudaFree(b.ptr));
+            b.ptr = nullptr;
+            b.cap = 0;
+        }
+        size_t cap = bytes + bytes / 4;
+        DG_CUDA_CHECK(cudaMalloc(&b.ptr, cap));
+        b.cap = cap;
+    }
+    *out = b.ptr;
+    return DG_OK;
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int stage_in(dg_context *ctx, int slot, const T *host, size_t count, T **dev) {
+    DG_TRY(scratch_as(ctx, slot, count, dev));
+    if (count)
+        DG_CUDA_CHECK(cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return DG_OK;
+}
+
+template <typename T>
+int copy_out(dg_context *ctx, T *host, const T *dev, size_t count) {
+    if (count && host)
+        DG_CUDA_CHECK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return DG_OK;
+}
+
+// synchronise and surface sticky kernel-side errors
+int finish(dg_context *ctx) {
+    DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flag[2] != 0) {
+        int code = ctx->h_flag[2];
+        ctx->h_flag[2] = 0;
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
+        set_error("local greedy search hit the round cap (NaN utilities or self-loops?)");
+        return code;
+    }
+    return DG_OK;
+}
+
+int check_ctx(const dg_context *ctx) {
+    DG_REQUIRE(ctx != nullptr, DG_ERR_INVALID, "null context");
+    return DG_OK;
+}
+
+int batch_alloc_aux(dg_batch *b, size_t n_nodes) {
+    if (b->cap_nodes >= n_nodes && b->dinv) return DG_OK;
+    if (b->dinv) cudaFree(b->dinv);
+    if (b->keep) cudaFree(b->keep);
+    if (b->x0) cudaFree(b->x0);
+    b->dinv = nullptr;
+    b->keep = nullptr;
+    b->x0 = nullptr;
+    DG_CUDA_CHECK(cudaMalloc(&b->dinv, sizeof(float) * std::max<size_t>(n_nodes, 1)));
+    b->cap_nodes = n_nodes;
+    return DG_OK;
+}
+
+int validate_graph_ptr(const std::vector<int32_t> &gp, int n_graphs, int n_nodes, int *max_nodes) {
+    DG_REQUIRE((int)gp.size() == n_graphs + 1, DG_ERR_INVALID, "graph_ptr length");
+    DG_REQUIRE(gp[0] == 0 && gp[n_graphs] == n_nodes, DG_ERR_INVALID,
+               "graph_ptr must start at 0 and end at n_nodes (got %d .. %d, n_nodes %d)", gp[0], gp[n_graphs],
+               n_nodes);
+    int mx = 0;
+    for (int g = 0; g < n_graphs; ++g) {
+        DG_REQUIRE(gp[g + 1] >= gp[g], DG_ERR_INVALID, "graph_ptr must be non-decreasing (graph %d)", g);
+        mx = std::max(mx, gp[g + 1] - gp[g]);
+    }
+    *max_nodes = mx;
+    return DG_OK;
+}
+
+}  // namespace
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" {
+
+int dg_version(void) { return DG_VERSION; }
+
+const char *dg_last_error(void) { return g_error; }
+
+int dg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// -------------------------------------------------------------------------------------------------
+int dg_context_create(int device, void *stream, dg_context **out) {
+    clear_error();
+    DG_REQUIRE(out != nullptr, DG_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int ndev = dg_device_count();
+    DG_REQUIRE(ndev > 0, DG_ERR_NO_DEVICE, "no CUDA device visible: distgcn_b200 has no CPU fallback");
+    DG_REQUIRE(device >= 0 && device < ndev, DG_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    DG_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DG_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    DG_REQUIRE(prop.major >= 10, DG_ERR_UNSUPPORTED,
+               "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+               prop.minor);
+    dg_context *ctx = new (std::nothrow) dg_context();
+    DG_REQUIRE(ctx != nullptr, DG_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    ctx->slots.resize(kSlotCount);
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->own_stream = false;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+            delete ctx;
+            return DG_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    if (cudaHostAlloc((void **)&ctx->h_flag, sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_status, sizeof(int) * 4) != cudaSuccess) {
+        set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        dg_context_destroy(ctx);
+        return DG_ERR_CUDA;
+    }
+    memset(ctx->h_flag, 0, sizeof(int) * 4);
+    cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 4, ctx->stream);
+    *out = ctx;
+    return DG_OK;
+}
+
+void dg_context_destroy(dg_context *ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->host_batch) {
+        dg_batch_destroy(ctx->host_batch);
+        ctx->host_batch = nullptr;
+    }
+    for (auto &b : ctx->slots)
+        if (b.ptr) cudaFree(b.ptr);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int dg_context_synchronize(dg_context *ctx) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    return finish(ctx);
+}
+
+void *dg_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void dg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t dg_context_launch_count(const dg_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// -------------------------------------------------------------------------------------------------
+int dg_model_create(dg_context *ctx, int n_layers, int n_supports, const int32_t *c_in, const int32_t *c_out,
+                    const float *const *weights, const float *const *bias, const int32_t *act,
+                    float leaky_alpha, int head, dg_model **out) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(out != nullptr, DG_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    DG_REQUIRE(n_layers >= 1 && n_layers <= kMaxLayers, DG_ERR_INVALID, "n_layers %d out of range", n_layers);
+    DG_REQUIRE(n_supports == 2, DG_ERR_UNSUPPORTED,
+               "n_supports %d: only the cheb1 supports [I, L] are implemented", n_supports);
+    DG_REQUIRE(c_in && c_out && weights && act, DG_ERR_INVALID, "null model argument");
+    DG_REQUIRE(head == DG_HEAD_LINEAR || head == DG_HEAD_PAIR_SOFTMAX, DG_ERR_INVALID, "unknown head %d", head);
+    for (int l = 0; l < n_layers; ++l) {
+        DG_REQUIRE(c_in[l] >= 1 && c_out[l] >= 1, DG_ERR_INVALID, "layer %d: empty shape", l);
+        DG_REQUIRE(c_out[l] <= kMaxWidth && (l == 0 || c_in[l] <= kMaxWidth), DG_ERR_UNSUPPORTED,
+                   "layer %d: width %d -> %d exceeds %d", l, c_in[l], c_out[l], kMaxWidth);
+        DG_REQUIRE(l == 0 || c_in[l] == c_out[l - 1], DG_ERR_INVALID, "layer %d: c_in %d != previous c_out %d", l,
+                   c_in[l], c_out[l - 1]);
+        DG_REQUIRE(act[l] >= DG_ACT_IDENTITY && act[l] <= DG_ACT_RELU, DG_ERR_INVALID, "layer %d: activation", l);
+        DG_REQUIRE(weights[2 * l] && weights[2 * l + 1], DG_ERR_INVALID, "layer %d: null weights", l);
+    }
+    if (head == DG_HEAD_PAIR_SOFTMAX)
+        DG_REQUIRE(c_out[n_layers - 1] % 2 == 0, DG_ERR_INVALID, "pair-softmax head needs an even output width");
+    DeviceGuard guard(ctx->device);
+    dg_model *m = new (std::nothrow) dg_model();
+    DG_REQUIRE(m != nullptr, DG_ERR_INVALID, "out of host memory");
+    m->ctx = ctx;
+    m->n_layers = n_layers;
+    m->n_supports = n_supports;
+    m->alpha = leaky_alpha;
+    m->head = head;
+    m->layers.resize(n_layers);
+    int status = DG_OK;
+    auto upload = [&](float **dst, const std::vector<float> &src) -> int {
+        DG_CUDA_CHECK(cudaMalloc((void **)dst, sizeof(float) * src.size()));
+        DG_CUDA_CHECK(cudaMemcpy(*dst, src.data(), sizeof(float) * src.size(), cudaMemcpyHostToDevice));
+        return DG_OK;
+    };
+    for (int l = 0; l < n_layers && status == DG_OK; ++l) {
+        dg_layer_dev &L = m->layers[l];
+        L.c_in = c_in[l];
+        L.c_out = c_out[l];
+        // layer 0 is applied in its rank-1 form (any input width); its padded matrix is only
+        // built when it fits the fused kernel
+        const bool fits = c_in[l] <= kMaxWidth;
+        L.cpi = fits ? pad_width(c_in[l]) : 0;
+        L.cpo = pad_width(c_out[l]);
+        L.act = act[l];
+        L.has_bias = bias && bias[l];
+        const float *w0 = weights[2 * l], *w1 = weights[2 * l + 1];
+        std::vector<float> hb(L.cpo, 0.f), cs0(L.cpo, 0.f), cs1(L.cpo, 0.f);
+        if (L.has_bias)
+            for (int c = 0; c < L.c_out; ++c) hb[c] = bias[l][c];
+        for (int c = 0; c < L.c_out; ++c) {
+            float s0 = 0.f, s1 = 0.f;  // sequential fp32 sums, the order TF's sparse x dense product uses
+            for (int k = 0; k < L.c_in; ++k) {
+                s0 += w0[(size_t)k * L.c_out + c];
+                s1 += w1[(size_t)k * L.c_out + c];
+            }
+            cs0[c] = s0;
+            cs1[c] = s1;
+        }
+        if (fits) {
+            std::vector<float> wc((size_t)2 * L.cpi * L.cpo, 0.f);
+            for (int k = 0; k < L.c_in; ++k)
+                for (int c = 0; c < L.c_out; ++c) {
+                    wc[(size_t)k * L.cpo + c] = w0[(size_t)k * L.c_out + c];
+                    wc[(size_t)(L.cpi + k) * L.cpo + c] = w1[(size_t)k * L.c_out + c];
+                }
+            status = upload(&L.wcat, wc);
+        }
+        if (status == DG_OK) status = upload(&L.bias, hb);
+        if (status == DG_OK) status = upload(&L.colsum0, cs0);
+        if (status == DG_OK) status = upload(&L.colsum1, cs1);
+    }
+    if (status == DG_OK && n_layers >= 2 && c_out[n_layers - 1] == 1) {
+        const int l = n_layers - 1;
+        const int cpi = pad_width(c_in[l]);
+        std::vector<float> t0(cpi, 0.f), t1(cpi, 0.f);
+        for (int k = 0; k < c_in[l]; ++k) {
+            t0[k] = weights[2 * l][k];
+            t1[k] = weights[2 * l + 1][k];
+        }
+        status = upload(&m->tail_w0, t0);
+        if (status == DG_OK) status = upload(&m->tail_w1, t1);
+        m->tail_bias = (bias && bias[l]) ? bias[l][0] : 0.f;
+    }
+    if (status != DG_OK) {
+        dg_model_destroy(m);
+        return status;
+    }
+    *out = m;
+    return DG_OK;
+}
+
+void dg_model_destroy(dg_model *m) {
+    if (!m) return;
+    DeviceGuard guard(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    for (auto &L : m->layers) {
+        if (L.wcat) cudaFree(L.wcat);
+        if (L.bias) cudaFree(L.bias);
+        if (L.colsum0) cudaFree(L.colsum0);
+        if (L.colsum1) cudaFree(L.colsum1);
+    }
+    if (m->tail_w0) cudaFree(m->tail_w0);
+    if (m->tail_w1) cudaFree(m->tail_w1);
+    delete m;
+}
+
+int dg_model_out_width(const dg_model *m) { return m ? m->layers.back().c_out : 0; }
+
+// -------------------------------------------------------------------------------------------------
+static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nnz, const int32_t *graph_ptr,
+                      const int32_t *row_ptr, const int32_t *col_idx, int mem, bool compute_dinv = true) {
+    dg_context *ctx = b->ctx;
+    DG_REQUIRE(n_graphs >= 0 && n_nodes >= 0 && nnz >= 0, DG_ERR_INVALID, "negative size");
+    DG_REQUIRE(graph_ptr && row_ptr && (col_idx || nnz == 0), DG_ERR_INVALID, "null CSR pointer");
+    b->n_graphs = n_graphs;
+    b->n_nodes = n_nodes;
+    b->nnz = nnz;
+    b->h_graph_ptr.resize((size_t)n_graphs + 1);
+    if (mem == DG_MEM_HOST) {
+        std::copy(graph_ptr, graph_ptr + n_graphs + 1, b->h_graph_ptr.begin());
+        DG_REQUIRE(row_ptr[0] == 0 && row_ptr[n_nodes] == nnz, DG_ERR_INVALID,
+                   "row_ptr must start at 0 and end at nnz (got %d .. %d, nnz %d)", row_ptr[0], row_ptr[n_nodes],
+                   nnz);
+    } else {
+        DG_CUDA_CHECK(cudaMemcpyAsync(b->h_graph_ptr.data(), graph_ptr, sizeof(int32_t) * ((size_t)n_graphs + 1),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    DG_TRY(validate_graph_ptr(b->h_graph_ptr, n_graphs, n_nodes, &b->max_graph_nodes));
+    if (mem == DG_MEM_HOST) {
+        if (b->cap_graphs < (size_t)n_graphs + 1 || !b->graph_ptr) {
+            if (b->graph_ptr) cudaFree(b->graph_ptr);
+            b->graph_ptr = nullptr;
+            b->cap_graphs = (size_t)n_graphs + 1 + (size_t)n_graphs / 4;
+            DG_CUDA_CHECK(cudaMalloc((void **)&b->graph_ptr, sizeof(int32_t) * b->cap_graphs));
+        }
+        const bool grow_nodes = b->cap_nodes < (size_t)n_nodes || !b->row_ptr;
+        if (grow_nodes) {
+            if (b->row_ptr) cudaFree(b->row_ptr);
+            b->row_ptr = nullptr;
+            size_t cap = (size_t)n_nodes + (size_t)n_nodes / 4;
+            DG_CUDA_CHECK(cudaMalloc((void **)&b->row_ptr, sizeof(int32_t) * (cap + 1)));
+            DG_TRY(batch_alloc_aux(b, cap));  // sets cap_nodes
+        }
+        if (b->cap_nnz < (size_t)nnz || !b->col_idx) {
+            if (b->col_idx) cudaFree(b->col_idx);
+            b->col_idx = nullptr;
+            b->cap_nnz = (size_t)nnz + (size_t)nnz / 4 + 1;
+            DG_CUDA_CHECK(cudaMalloc((void **)&b->col_idx, sizeof(int32_t) * b->cap_nnz));
+        }
+        b->owns_csr = true;
+        DG_CUDA_CHECK(cudaMemcpyAsync(b->graph_ptr, graph_ptr, sizeof(int32_t) * ((size_t)n_graphs + 1),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        DG_CUDA_CHECK(cudaMemcpyAsync(b->row_ptr, row_ptr, sizeof(int32_t) * ((size_t)n_nodes + 1),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz)
+            DG_CUDA_CHECK(cudaMemcpyAsync(b->col_idx, col_idx, sizeof(int32_t) * (size_t)nnz,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        b->owns_csr = false;
+        b->graph_ptr = const_cast<int32_t *>(graph_ptr);
+        b->row_ptr = const_cast<int32_t *>(row_ptr);
+        b->col_idx = const_cast<int32_t *>(col_idx);
+        DG_TRY(batch_alloc_aux(b, (size_t)n_nodes));
+    }
+    return compute_dinv ? batch_compute_dinv(b) : DG_OK;
+}
+
+int dg_batch_create(dg_context *ctx, int32_t n_graphs, int32_t n_nodes, int32_t nnz, const int32_t *graph_ptr,
+                    const int32_t *row_ptr, const int32_t *col_idx, int mem, dg_batch **out) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(out != nullptr, DG_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    DG_REQUIRE(mem == DG_MEM_HOST || mem == DG_MEM_DEVICE, DG_ERR_INVALID, "bad memory space %d", mem);
+    DeviceGuard guard(ctx->device);
+    dg_batch *b = new (std::nothrow) dg_batch();
+    DG_REQUIRE(b != nullptr, DG_ERR_INVALID, "out of host memory");
+    b->ctx = ctx;
+    int s = batch_fill(b, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, mem);
+    if (s == DG_OK && mem == DG_MEM_HOST) s = finish(ctx);  // the caller may free its arrays on return
+    if (s != DG_OK) {
+        dg_batch_destroy(b);
+        return s;
+    }
+    *out = b;
+    return DG_OK;
+}
+
+void dg_batch_destroy(dg_batch *b) {
+    if (!b) return;
+    DeviceGuard guard(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->owns_csr) {
+        if (b->graph_ptr) cudaFree(b->graph_ptr);
+        if (b->row_ptr) cudaFree(b->row_ptr);
+        if (b->col_idx) cudaFree(b->col_idx);
+    }
+    if (b->dinv) cudaFree(b->dinv);
+    if (b->keep) cudaFree(b->keep);
+    if (b->x0) cudaFree(b->x0);
+    delete b;
+}
+
+int dg_batch_set_keep(dg_batch *b, const uint8_t *keep, int mem) {
+    clear_error();
+    DG_REQUIRE(b != nullptr, DG_ERR_INVALID, "null batch");
+    dg_context *ctx = b->ctx;
+    DeviceGuard guard(ctx->device);
+    if (!keep) {
+        if (b->keep) {
+            DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(b->keep);
+            b->keep = nullptr;
+        }
+    } else {
+        if (!b->keep) DG_CUDA_CHECK(cudaMalloc((void **)&b->keep, std::max<size_t>(b->cap_nodes, 1)));
+        DG_CUDA_CHECK(cudaMemcpyAsync(b->keep, keep, (size_t)b->n_nodes,
+                                      mem == DG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+    }
+    DG_TRY(batch_compute_dinv(b));
+    return mem == DG_MEM_HOST ? finish(ctx) : DG_OK;
+}
+
+static int set_keep_from_weights_device(dg_batch *b, const double *d_wts) {
+    if (!b->keep) DG_CUDA_CHECK(cudaMalloc((void **)&b->keep, std::max<size_t>(b->cap_nodes, 1)));
+    DG_TRY(keep_from_weights_device(b->ctx, b->n_nodes, d_wts, b->keep));
+    return batch_compute_dinv(b);
+}
+
+int dg_batch_set_keep_from_weights(dg_batch *b, const double *wts, int mem) {
+    clear_error();
+    DG_REQUIRE(b != nullptr && wts != nullptr, DG_ERR_INVALID, "null argument");
+    dg_context *ctx = b->ctx;
+    DeviceGuard guard(ctx->device);
+    const double *d_wts = wts;
+    if (mem == DG_MEM_HOST) {
+        double *tmp = nullptr;
+        DG_TRY(stage_in(ctx, kSlotWts, wts, (size_t)b->n_nodes, &tmp));
+        d_wts = tmp;
+    }
+    DG_TRY(set_keep_from_weights_device(b, d_wts));
+    return mem == DG_MEM_HOST ? finish(ctx) : DG_OK;
+}
+
+int dg_batch_set_x0(dg_batch *b, const float *x0, int mem) {
+    clear_error();
+    DG_REQUIRE(b != nullptr, DG_ERR_INVALID, "null batch");
+    dg_context *ctx = b->ctx;
+    DeviceGuard guard(ctx->device);
+    if (!x0) {
+        if (b->x0) {
+            DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(b->x0);
+            b->x0 = nullptr;
+        }
+        return DG_OK;
+    }
+    if (!b->x0) DG_CUDA_CHECK(cudaMalloc((void **)&b->x0, sizeof(float) * std::max<size_t>(b->cap_nodes, 1)));
+    DG_CUDA_CHECK(cudaMemcpyAsync(b->x0, x0, sizeof(float) * (size_t)b->n_nodes,
+                                  mem == DG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    return mem == DG_MEM_HOST ? finish(ctx) : DG_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int dg_graph_convolution(dg_context *ctx, dg_batch *b, int32_t c_in, int32_t c_out, const float *w0,
+                         const float *w1, const float *bias, int act, float leaky_alpha, const float *x, float *y,
+                         int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(b && w0 && w1 && x && y, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(c_in >= 1 && c_out >= 1, DG_ERR_INVALID, "empty layer shape");
+    DG_REQUIRE(c_in <= kMaxWidth && c_out <= kMaxWidth, DG_ERR_UNSUPPORTED, "layer width %d -> %d exceeds %d", c_in,
+               c_out, kMaxWidth);
+    DG_REQUIRE(act >= DG_ACT_IDENTITY && act <= DG_ACT_RELU, DG_ERR_INVALID, "unknown activation %d", act);
+    DeviceGuard guard(ctx->device);
+    dg_layer_dev L;
+    L.c_in = c_in;
+    L.c_out = c_out;
+    L.cpi = pad_width(c_in);
+    L.cpo = pad_width(c_out);
+    L.act = act;
+    std::vector<float> wc((size_t)2 * L.cpi * L.cpo + L.cpo, 0.f);
+    for (int k = 0; k < c_in; ++k)
+        for (int c = 0; c < c_out; ++c) {
+            wc[(size_t)k * L.cpo + c] = w0[(size_t)k * c_out + c];
+            wc[(size_t)(L.cpi + k) * L.cpo + c] = w1[(size_t)k * c_out + c];
+        }
+    if (bias)
+        for (int c = 0; c < c_out; ++c) wc[(size_t)2 * L.cpi * L.cpo + c] = bias[c];
+    float *dw = nullptr;
+    DG_TRY(scratch_as(ctx, kSlotLayerW, wc.size(), &dw));
+    // synchronous copy: wc is a stack-lifetime staging vector
+    DG_CUDA_CHECK(cudaMemcpyAsync(dw, wc.data(), sizeof(float) * wc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    L.wcat = dw;
+    L.bias = dw + (size_t)2 * L.cpi * L.cpo;
+    const size_t n = (size_t)b->n_nodes;
+    const float *dx = x;
+    float *dy = y;
+    if (mem == DG_MEM_HOST) {
+        float *tx = nullptr;
+        DG_TRY(stage_in(ctx, kSlotStageIn0, x, n * c_in, &tx));
+        dx = tx;
+        DG_TRY(scratch_as(ctx, kSlotStageOut0, n * c_out, &dy));
+    }
+    DG_TRY(graph_convolution_device(ctx, b, L, leaky_alpha, dx, c_in, dy, c_out));
+    if (mem == DG_MEM_HOST) {
+        DG_TRY(copy_out(ctx, y, dy, n * c_out));
+        return finish(ctx);
+    }
+    return DG_OK;
+}
+
+int dg_gcn_forward(dg_context *ctx, const dg_model *m, dg_batch *b, float *out, int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(m && b && out, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(ctx->device);
+    const size_t count = (size_t)b->n_nodes * m->layers.back().c_out;
+    float *d_out = out;
+    if (mem == DG_MEM_HOST) DG_TRY(scratch_as(ctx, kSlotScore, count, &d_out));
+    DG_TRY(gcn_forward_device(ctx, m, b, d_out, nullptr, DG_PREDICT_MIS, nullptr));
+    if (mem == DG_MEM_HOST) {
+        DG_TRY(copy_out(ctx, out, d_out, count));
+        return finish(ctx);
+    }
+    return DG_OK;
+}
+
+int dg_utility(dg_context *ctx, const dg_batch *b, const float *score, int32_t score_stride, const double *wts,
+               int predict, double *util, int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(b && score && util, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(predict == DG_PREDICT_MIS || wts != nullptr, DG_ERR_INVALID, "weights required for predict=mwis");
+    DG_REQUIRE(score_stride >= 1, DG_ERR_INVALID, "score_stride must be >= 1");
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)b->n_nodes;
+    const float *d_score = score;
+    const double *d_wts = wts;
+    double *d_util = util;
+    if (mem == DG_MEM_HOST) {
+        float *ts = nullptr;
+        DG_TRY(stage_in(ctx, kSlotStageIn0, score, n * score_stride, &ts));
+        d_score = ts;
+        if (wts) {
+            double *tw = nullptr;
+            DG_TRY(stage_in(ctx, kSlotWts, wts, n, &tw));
+            d_wts = tw;
+        }
+        DG_TRY(scratch_as(ctx, kSlotUtil, n, &d_util));
+    }
+    DG_TRY(utility_device(ctx, (int)n, d_score, score_stride, d_wts, predict, d_util));
+    if (mem == DG_MEM_HOST) {
+        DG_TRY(copy_out(ctx, util, d_util, n));
+        return finish(ctx);
+    }
+    return DG_OK;
+}
+
+int dg_lgs(dg_context *ctx, const dg_batch *b, const double *util, int32_t nstep, uint8_t *member, uint8_t *nb_is,
+           int32_t *steps, int64_t *p2p, int64_t *bst, double *oh_vec, int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(b && util && member, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)b->n_nodes, G = (size_t)b->n_graphs;
+    if (mem == DG_MEM_DEVICE) return lgs_device(ctx, b, util, nstep, member, nb_is, steps, p2p, bst, oh_vec);
+    double *d_util = nullptr;
+    uint8_t *d_member = nullptr, *d_nbis = nullptr;
+    int32_t *d_steps = nullptr;
+    int64_t *d_p2p = nullptr, *d_bst = nullptr;
+    double *d_oh = nullptr;
+    DG_TRY(stage_in(ctx, kSlotUtil, util, n, &d_util));
+    DG_TRY(scratch_as(ctx, kSlotMember, n, &d_member));
+    if (nb_is) DG_TRY(scratch_as(ctx, kSlotNbis, n, &d_nbis));
+    if (steps) DG_TRY(scratch_as(ctx, kSlotSteps, G, &d_steps));
+    if (p2p) DG_TRY(scratch_as(ctx, kSlotP2p, G, &d_p2p));
+    if (bst) DG_TRY(scratch_as(ctx, kSlotBst, G, &d_bst));
+    if (oh_vec) DG_TRY(scratch_as(ctx, kSlotOh, n, &d_oh));
+    DG_TRY(lgs_device(ctx, b, d_util, nstep, d_member, d_nbis, d_steps, d_p2p, d_bst, d_oh));
+    DG_TRY(copy_out(ctx, member, d_member, n));
+    DG_TRY(copy_out(ctx, nb_is, d_nbis, n));
+    DG_TRY(copy_out(ctx, steps, d_steps, G));
+    DG_TRY(copy_out(ctx, p2p, d_p2p, G));
+    DG_TRY(copy_out(ctx, bst, d_bst, G));
+    DG_TRY(copy_out(ctx, oh_vec, d_oh, n));
+    return finish(ctx);
+}
+
+int dg_member_weight(dg_context *ctx, const dg_batch *b, const uint8_t *member, const double *wts, double *total,
+                     int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(b && member && wts && total, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(ctx->device);
+    if (mem == DG_MEM_DEVICE) return member_weight_device(ctx, b, member, wts, total);
+    uint8_t *d_member = nullptr;
+    double *d_wts = nullptr, *d_total = nullptr;
+    DG_TRY(stage_in(ctx, kSlotMember, member, (size_t)b->n_nodes, &d_member));
+    DG_TRY(stage_in(ctx, kSlotWts, wts, (size_t)b->n_nodes, &d_wts));
+    DG_TRY(scratch_as(ctx, kSlotTotal, (size_t)b->n_graphs, &d_total));
+    DG_TRY(member_weight_device(ctx, b, d_member, d_wts, d_total));
+    DG_TRY(copy_out(ctx, total, d_total, (size_t)b->n_graphs));
+    return finish(ctx);
+}
+
+// device-space body shared by dg_solve and dg_solve_host
+static int solve_device(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
+                        int remove_zero_weight, uint8_t *d_member, float *d_score, double *d_util, double *d_total,
+                        int32_t *d_steps) {
+    const size_t n = (size_t)b->n_nodes;
+    if (remove_zero_weight) DG_TRY(set_keep_from_weights_device(b, d_wts));
+    const int d_out = m->layers.back().c_out;
+    if (!d_score) DG_TRY(scratch_as(ctx, kSlotScore, n * d_out, &d_score));
+    if (!d_util) DG_TRY(scratch_as(ctx, kSlotUtil, n, &d_util));
+    // with several output columns the utility uses column 0, as act_vals.flatten() does for diver_num == 1
+    DG_TRY(gcn_forward_device(ctx, m, b, d_score, d_wts, predict, d_util));
+    DG_TRY(lgs_device(ctx, b, d_util, -1, d_member, nullptr, d_steps, nullptr, nullptr, nullptr));
+    if (d_total) DG_TRY(member_weight_device(ctx, b, d_member, d_wts, d_total));
+    return DG_OK;
+}
+
+int dg_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *wts, int predict,
+             int remove_zero_weight, uint8_t *member, float *score, double *util, double *total, int32_t *steps,
+             int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(m && b && wts && member, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(predict == DG_PREDICT_MWIS || predict == DG_PREDICT_MIS, DG_ERR_INVALID, "unknown predict mode");
+    DeviceGuard guard(ctx->device);
+    if (mem == DG_MEM_DEVICE)
+        return solve_device(ctx, m, b, wts, predict, remove_zero_weight, member, score, util, total, steps);
+    const size_t n = (size_t)b->n_nodes, G = (size_t)b->n_graphs;
+    const int d_out = m->layers.back().c_out;
+    double *d_wts = nullptr, *d_util = nullptr, *d_total = nullptr;
+    uint8_t *d_member = nullptr;
+    float *d_score = nullptr;
+    int32_t *d_steps = nullptr;
+    DG_TRY(stage_in(ctx, kSlotWts, wts, n, &d_wts));
+    DG_TRY(scratch_as(ctx, kSlotMember, n, &d_member));
+    DG_TRY(scratch_as(ctx, kSlotScore, n * d_out, &d_score));
+    DG_TRY(scratch_as(ctx, kSlotUtil, n, &d_util));
+    if (total) DG_TRY(scratch_as(ctx, kSlotTotal, G, &d_total));
+    if (steps) DG_TRY(scratch_as(ctx, kSlotSteps, G, &d_steps));
+    DG_TRY(solve_device(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, d_score, d_util, d_total, d_steps));
+    DG_TRY(copy_out(ctx, member, d_member, n));
+    DG_TRY(copy_out(ctx, score, d_score, n * d_out));
+    DG_TRY(copy_out(ctx, util, d_util, n));
+    DG_TRY(copy_out(ctx, total, d_total, G));
+    DG_TRY(copy_out(ctx, steps, d_steps, G));
+    return finish(ctx);
+}
+
+int dg_solve_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                  const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
+                  int predict, int remove_zero_weight, uint8_t *member, double *total) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(m && wts && member, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(ctx->device);
+    if (!ctx->host_batch) {
+        ctx->host_batch = new (std::nothrow) dg_batch();
+        DG_REQUIRE(ctx->host_batch != nullptr, DG_ERR_INVALID, "out of host memory");
+        ctx->host_batch->ctx = ctx;
+    }
+    dg_batch *b = ctx->host_batch;
+    if (b->keep && !remove_zero_weight) {
+        DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(b->keep);
+        b->keep = nullptr;
+    }
+    if (b->keep && b->cap_nodes < (size_t)n_nodes) {  // will be re-allocated at the new capacity
+        DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(b->keep);
+        b->keep = nullptr;
+    }
+    // with zero-weight removal the degrees are computed once the keep mask is known (solve_device)
+    DG_TRY(batch_fill(b, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, DG_MEM_HOST, !remove_zero_weight));
+    const size_t n = (size_t)n_nodes, G = (size_t)n_graphs;
+    double *d_wts = nullptr, *d_total = nullptr;
+    uint8_t *d_member = nullptr;
+    DG_TRY(stage_in(ctx, kSlotWts, wts, n, &d_wts));
+    DG_TRY(scratch_as(ctx, kSlotMember, n, &d_member));
+    if (total) DG_TRY(scratch_as(ctx, kSlotTotal, G, &d_total));
+    DG_TRY(solve_device(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, nullptr, nullptr, d_total, nullptr));
+    DG_TRY(copy_out(ctx, member, d_member, n));
+    DG_TRY(copy_out(ctx, total, d_total, G));
+    return finish(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// Internal declarations shared by the translation units of libdistgcn_b200.so.
+// The public surface is include/distgcn_b200.h; nothing here is exported.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/distgcn_b200.h"
+
+namespace dg {
+
+void set_error(const char *fmt, ...);
+void clear_error();
+
+#define DG_CUDA_CHECK(expr)                                                                    \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            dg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                          __LINE__);                                                           \
+            return DG_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define DG_REQUIRE(cond, code, ...)      \
+    do {                                 \
+        if (!(cond)) {                   \
+            dg::set_error(__VA_ARGS__);  \
+            return (code);               \
+        }                                \
+    } while (0)
+
+#define DG_TRY(expr)                 \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != DG_OK) return _s;  \
+    } while (0)
+
+constexpr int kMaxWidth = 64;      // widest layer the fused kernels cover
+constexpr int kMaxLayers = 256;
+constexpr int kLgsCtaMaxNodes = 8192;  // graphs up to this size run in the one-CTA-per-graph LGS kernel
+constexpr int kLgsRoundCap = 1 << 20;  // NaN utilities / self-loops never converge in the reference
+
+// grow-only device buffer
+struct Buffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace dg
+
+struct dg_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    uint64_t launches = 0;
+    std::vector<dg::Buffer> slots;  // named scratch, see dg::Slot
+    int *h_flag = nullptr;          // pinned, 4 ints: [0] LGS round read-back, [2] copy of *d_status
+    int *d_status = nullptr;        // device, sticky error status written by kernels
+    dg_batch *host_batch = nullptr; // reusable batch of dg_solve_host
+};
+
+namespace dg {
+
+enum Slot : int {
+    kSlotFeatA = 0,   // layer ping
+    kSlotFeatB,       // layer pong
+    kSlotPair,        // per-node float2 (x0, s) of the rank-1 first layer / (q, zs) of the scalar tail
+    kSlotPair2,
+    kSlotY,           // dinv * x0
+    kSlotScore,
+    kSlotUtil,
+    kSlotWts,
+    kSlotMember,
+    kSlotNbis,
+    kSlotSteps,
+    kSlotP2p,
+    kSlotBst,
+    kSlotOh,
+    kSlotTotal,
+    kSlotLgsWords,    // global-path bitmaps
+    kSlotLgsCount,
+    kSlotStageIn0,    // staging of HOST-space arguments
+    kSlotStageIn1,
+    kSlotStageIn2,
+    kSlotStageOut0,
+    kSlotStageOut1,
+    kSlotLayerW,      // dg_graph_convolution's transient weights
+    kSlotHostGraphPtr,
+    kSlotHostRowPtr,
+    kSlotHostColIdx,
+    kSlotCount
+};
+
+int scratch(dg_context *ctx, int slot, size_t bytes, void **out);
+
+template <typename T>
+inline int scratch_as(dg_context *ctx, int slot, size_t count, T **out) {
+    void *p = nullptr;
+    int s = scratch(ctx, slot, count * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return s;
+}
+
+}  // namespace dg
+
+struct dg_layer_dev {
+    int c_in = 0, c_out = 0;
+    int cpi = 0, cpo = 0;        // padded widths (32 or 64)
+    int act = 0;
+    bool has_bias = false;
+    float *wcat = nullptr;       // [2*cpi, cpo] row-major: rows 0..cpi-1 = W_0, rows cpi.. = W_1 (zero padded)
+    float *bias = nullptr;       // [cpo] (zeros when absent)
+    float *colsum0 = nullptr;    // [cpo]: sum over input rows of W_0 (rank-1 first layer)
+    float *colsum1 = nullptr;    // [cpo]
+};
+
+struct dg_model {
+    dg_context *ctx = nullptr;
+    int n_layers = 0;
+    int n_supports = 2;
+    float alpha = 0.2f;
+    int head = 0;
+    std::vector<dg_layer_dev> layers;
+    // host copies of the scalar-tail vectors (last layer when c_out == 1) live on the device too
+    float *tail_w0 = nullptr;    // [cpi_last] W_0[:,0] of the last layer
+    float *tail_w1 = nullptr;    // [cpi_last]
+    float tail_bias = 0.f;
+    std::vector<float> h_first_a0, h_first_a1, h_first_b;  // first-layer colsums on the host (L == 1 path)
+};
+
+struct dg_batch {
+    dg_context *ctx = nullptr;
+    int n_graphs = 0, n_nodes = 0, nnz = 0;
+    int max_graph_nodes = 0;
+    bool owns_csr = false;
+    int32_t *graph_ptr = nullptr, *row_ptr = nullptr, *col_idx = nullptr;  // device
+    std::vector<int32_t> h_graph_ptr;  // host copy (small) for launch planning
+    float *dinv = nullptr;     // [n_nodes] fp32(deg^-1/2) on the kept sub-graph, 0 for isolated/removed
+    uint8_t *keep = nullptr;   // [n_nodes] or nullptr = all kept
+    float *x0 = nullptr;       // [n_nodes] or nullptr = 1/F
+    size_t cap_nodes = 0, cap_nnz = 0, cap_graphs = 0;  // capacities when reused by dg_solve_host
+};
+
+namespace dg {
+
+// ---- kernels / drivers implemented in dg_gcn.cu ---------------------------------------------
+int batch_compute_dinv(dg_batch *b);
+int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *out /*device*/,
+                       const double *wts /*device or null*/, int predict, double *util /*device or null*/);
+int graph_convolution_device(dg_context *ctx, dg_batch *b, const dg_layer_dev &L, float alpha,
+                             const float *x, int ldx, float *y, int ldy);
+int utility_device(dg_context *ctx, int n, const float *score, int stride, const double *wts, int predict,
+                   double *util);
+int keep_from_weights_device(dg_context *ctx, int n, const double *wts, uint8_t *keep);
+
+// ---- implemented in dg_lgs.cu ------------------------------------------------------------------
+int lgs_device(dg_context *ctx, const dg_batch *b, const double *util, int nstep, uint8_t *member,
+               uint8_t *nb_is, int32_t *steps, int64_t *p2p, int64_t *bst, double *oh_vec);
+int member_weight_device(dg_context *ctx, const dg_batch *b, const uint8_t *member, const double *wts,
+                         double *total);
+
+inline int pad_width(int c) { return c <= 32 ? 32 : 64; }
+
+}  // namespace dg

@@ -1,0 +1,613 @@
+// GraphConvolution stack on a packed CSR batch - sm_100a kernels and their driver.
+//
+// What the reference computes per layer (gcn/layers.py:198-216, supports from gcn/utils.py:258-274):
+//     H' = act( H.W_0 + L.(H.W_1) + b ),      L = I - D^-1/2 A D^-1/2
+// L is never materialised here: with dinv = fp32(deg^-1/2) (0 for isolated / removed vertices)
+//     (L.Z)_i = Z_i - dinv_i * sum_{j in N(i)} dinv_j * Z_j .
+// The fused layer kernel aggregates first and projects second,
+//     H'_i = act( [H_i | (L.H)_i] . [W_0 ; W_1] + b ),
+// which is the same linear map as the reference's project-then-aggregate order (L.(H.W_1) ==
+// (L.H).W_1) but reads and writes each feature row once (B_layer of SURVEY.md 8d).
+//
+// Structure of a forward pass (n_supports == 2, "cheb1"):
+//   dinv (batch, once)                degree_kernel
+//   layer 0, rank-1: every feature column of the reference's input equals x0_i, so
+//       H1_i = act(x0_i * colsum(W_0) + s_i * colsum(W_1) + b),  s = L.x0
+//     needs only the scalar SpMV s                                  first_scalar_kernel
+//     and H1 is never written: consumers rebuild it from (x0_j, s_j) on the fly  (IMPLICIT_IN)
+//   layers 1 .. : gc_layer_kernel<CPI, CPO, IMPLICIT_IN, TAIL>
+//   last layer with one output column (diver_num == 1): projected BEFORE aggregation like the
+//     reference does - the preceding kernel's epilogue emits q_i = H_i.w_0 + z_i and
+//     zs_i = dinv_i * z_i (z = H.w_1) (TAIL), leaving the scalar SpMV     last_scalar_kernel
+//     fused with the fp64 utility product of mwis_dqn_call.py:232.
+#include <math.h>
+
+#include "dg_common.cuh"
+
+namespace dg {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kRowsPerWarp = 8;   // R: rows a warp aggregates, then projects together
+constexpr int kLanesPerScalarRow = 8;
+
+__device__ __forceinline__ float act_apply(float v, int act, float alpha) {
+    if (act == DG_ACT_LEAKY_RELU) return v >= 0.f ? v : alpha * v;
+    if (act == DG_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// degrees -> dinv.  Follows gcn/utils.py:122-125 (rowsum^-0.5 in fp64, inf -> 0), rounded to fp32.
+// With a keep mask the degree is taken on the kept sub-graph (mwis_dqn_call.py:202-207).
+// ---------------------------------------------------------------------------------------------
+__global__ void degree_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                              const uint8_t *__restrict__ keep, float *__restrict__ dinv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int beg = row_ptr[i], end = row_ptr[i + 1];
+    int deg = 0;
+    if (keep == nullptr) {
+        deg = end - beg;
+    } else if (keep[i]) {
+        for (int e = beg; e < end; ++e) deg += keep[col_idx[e]] != 0;
+    }
+    dinv[i] = deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f;
+}
+
+__global__ void keep_from_weights_kernel(int n, const double *__restrict__ wts, uint8_t *__restrict__ keep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = wts[i] != 0.0;  // rm_nodes = where(wts == 0), mwis_dqn_call.py:203
+}
+
+// y_j = dinv_j * x0_j : the quantity the first layer's scalar SpMV gathers
+__global__ void scaled_input_kernel(int n, const float *__restrict__ dinv, const uint8_t *__restrict__ keep,
+                                    const float *__restrict__ x0, float x0val, float *__restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float xi = (keep && !keep[i]) ? 0.f : (x0 ? x0[i] : x0val);
+    y[i] = dinv[i] * xi;
+}
+
+// s = L.x0 (scalar SpMV), one sub-warp of 8 lanes per row.  Writes (x0_i, s_i).
+__global__ void __launch_bounds__(256)
+first_scalar_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                    const float *__restrict__ dinv, const float *__restrict__ y,
+                    const uint8_t *__restrict__ keep, const float *__restrict__ x0, float x0val,
+                    float2 *__restrict__ pair_out) {
+    constexpr int LPR = kLanesPerScalarRow;
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = tid / LPR;
+    int sub = threadIdx.x % LPR;
+    float acc = 0.f;
+    if (row < n) {
+        int beg = row_ptr[row], end = row_ptr[row + 1];
+        for (int e = beg + sub; e < end; e += LPR) acc += __ldg(y + col_idx[e]);
+    }
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (row < n && sub == 0) {
+        float xi = (keep && !keep[row]) ? 0.f : (x0 ? x0[row] : x0val);
+        pair_out[row] = make_float2(xi, xi - dinv[row] * acc);
+    }
+}
+
+// Single-layer models (num_layer == 1, gcn/models.py:539-548): out = act(x0*a0 + s*a1 + b).
+__global__ void first_out_kernel(int n, int d_out, const float2 *__restrict__ pair,
+                                 const float *__restrict__ a0, const float *__restrict__ a1,
+                                 const float *__restrict__ bias, int act, float alpha,
+                                 const uint8_t *__restrict__ keep, float *__restrict__ out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d_out) return;
+    int i = idx / d_out, d = idx - i * d_out;
+    float2 p = pair[i];
+    float v = act_apply(fmaf(p.y, a1[d], fmaf(p.x, a0[d], bias[d])), act, alpha);
+    out[idx] = (keep && !keep[i]) ? 0.f : v;
+}
+
+// Two-layer models with one output (e.g. c64 l2): the hidden layer is the implicit rank-1 one, so the
+// last layer's projections are per-vertex work: q_i = H1_i.w_0 + z_i, zs_i = dinv_i * z_i, z = H1.w_1.
+__global__ void __launch_bounds__(256)
+node_project_kernel(int n, int c, const float2 *__restrict__ pair, const float *__restrict__ a0,
+                    const float *__restrict__ a1, const float *__restrict__ b0, int act, float alpha,
+                    const float *__restrict__ w0, const float *__restrict__ w1,
+                    const float *__restrict__ dinv, float2 *__restrict__ pair_out) {
+    __shared__ float sm[5 * kMaxWidth];
+    for (int k = threadIdx.x; k < c; k += blockDim.x) {
+        sm[k] = a0[k];
+        sm[kMaxWidth + k] = a1[k];
+        sm[2 * kMaxWidth + k] = b0[k];
+        sm[3 * kMaxWidth + k] = w0[k];
+        sm[4 * kMaxWidth + k] = w1[k];
+    }
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 p = pair[i];
+    float t0 = 0.f, t1 = 0.f;
+    for (int k = 0; k < c; ++k) {
+        float h = act_apply(fmaf(p.y, sm[kMaxWidth + k], fmaf(p.x, sm[k], sm[2 * kMaxWidth + k])), act, alpha);
+        t0 = fmaf(h, sm[3 * kMaxWidth + k], t0);
+        t1 = fmaf(h, sm[4 * kMaxWidth + k], t1);
+    }
+    pair_out[i] = make_float2(t0 + t1, dinv[i] * t1);
+}
+
+// Last layer with one output column: score_i = act(q_i - dinv_i * sum_j zs_j + b), then the utility
+// product of mwis_dqn_call.py:230-235 in fp64.  One sub-warp of 8 lanes per row.
+__global__ void __launch_bounds__(256)
+last_scalar_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                   const float *__restrict__ dinv, const float2 *__restrict__ pair, float bias, int act,
+                   float alpha, const uint8_t *__restrict__ keep, float *__restrict__ score,
+                   const double *__restrict__ wts, int predict, double *__restrict__ util) {
+    constexpr int LPR = kLanesPerScalarRow;
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = tid / LPR;
+    int sub = threadIdx.x % LPR;
+    float acc = 0.f;
+    if (row < n) {
+        int beg = row_ptr[row], end = row_ptr[row + 1];
+        for (int e = beg + sub; e < end; e += LPR) acc += __ldg(&pair[col_idx[e]].y);
+    }
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (row < n && sub == 0) {
+        float v = act_apply(pair[row].x - dinv[row] * acc + bias, act, alpha);
+        if (keep && !keep[row]) v = 0.f;
+        if (score) score[row] = v;
+        if (util) util[row] = (predict == DG_PREDICT_MWIS) ? (double)v * wts[row] : (double)v;
+    }
+}
+
+__global__ void utility_kernel(int n, const float *__restrict__ score, int stride,
+                               const double *__restrict__ wts, int predict, double *__restrict__ util) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = (double)score[(size_t)i * stride];
+    util[i] = (predict == DG_PREDICT_MWIS) ? a * wts[i] : a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fused hidden-layer kernel.
+//   CPI / CPO   padded input / output widths (32 or 64); padding columns carry zeros
+//   IMPLICIT_IN input rows are rebuilt from (x0_j, s_j) and the first layer's column sums
+//   TAIL        instead of writing H', emit (q, zs) for a following one-column last layer
+// A warp owns kRowsPerWarp consecutive rows.  Aggregation: CPI/4 lanes cover one neighbour row with
+// 128-bit loads, so 32/(CPI/4) neighbours are in flight per step; partial sums are combined with
+// warp shuffles.  Projection: the warp's rows sit in shared memory, lane c owns output column c
+// (and c+32), weights are read from shared memory once per 8 rows.
+// ---------------------------------------------------------------------------------------------
+struct LayerArgs {
+    int n;
+    const int *row_ptr;
+    const int *col_idx;
+    const float *dinv;
+    const float *hin;       // [n, CPI] (dense input)
+    const float2 *pair_in;  // (x0, s)   (implicit input)
+    const float *in_a0, *in_a1, *in_b;  // first layer's column sums / bias, [CPI]
+    int in_act;
+    const float *wcat;      // [2*CPI, CPO]
+    const float *bias;      // [CPO]
+    int act;
+    float alpha;
+    float *hout;            // [n, CPO]
+    const float *tail_w0, *tail_w1;  // [CPO]
+    float2 *pair_out;       // (q, zs)
+};
+
+template <int CPI, int CPO, bool IMPLICIT_IN, bool TAIL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+gc_layer_kernel(const LayerArgs a) {
+    constexpr int R = kRowsPerWarp;
+    constexpr int LPR = CPI / 4;    // lanes per feature row
+    constexpr int NG = 32 / LPR;    // neighbour rows in flight per step
+    constexpr int CO = CPO / 32;    // output columns per lane
+    constexpr int KU = 2 * CPI;     // length of [H_i | (L.H)_i]
+
+    extern __shared__ __align__(16) float smem[];
+    float *w_sm = smem;                       // [KU, CPO]
+    float *b_sm = w_sm + KU * CPO;            // [CPO]
+    float *u_all = b_sm + CPO;                // [warps][R][KU]
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float *u_sm = u_all + warp * (R * KU);
+
+    for (int k = threadIdx.x * 4; k < KU * CPO; k += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(w_sm + k) = __ldg(reinterpret_cast<const float4 *>(a.wcat + k));
+    for (int k = threadIdx.x; k < CPO; k += blockDim.x) b_sm[k] = a.bias[k];
+    __syncthreads();
+
+    const int g = lane / LPR;
+    const int q = lane % LPR;
+
+    float ia0[4], ia1[4], ib[4];
+    if (IMPLICIT_IN) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            ia0[e] = a.in_a0[4 * q + e];
+            ia1[e] = a.in_a1[4 * q + e];
+            ib[e] = a.in_b[4 * q + e];
+        }
+    }
+    auto implicit_row = [&](float px, float py) {
+        float4 v;
+        v.x = act_apply(fmaf(py, ia1[0], fmaf(px, ia0[0], ib[0])), a.in_act, a.alpha);
+        v.y = act_apply(fmaf(py, ia1[1], fmaf(px, ia0[1], ib[1])), a.in_act, a.alpha);
+        v.z = act_apply(fmaf(py, ia1[2], fmaf(px, ia0[2], ib[2])), a.in_act, a.alpha);
+        v.w = act_apply(fmaf(py, ia1[3], fmaf(px, ia0[3], ib[3])), a.in_act, a.alpha);
+        return v;
+    };
+
+    float tw0[CO], tw1[CO];
+    if (TAIL) {
+#pragma unroll
+        for (int cc = 0; cc < CO; ++cc) {
+            tw0[cc] = a.tail_w0[lane + 32 * cc];
+            tw1[cc] = a.tail_w1[lane + 32 * cc];
+        }
+    }
+
+    const int n_chunks = (a.n + R - 1) / R;
+    for (int chunk = blockIdx.x * kWarpsPerCta + warp; chunk < n_chunks; chunk += gridDim.x * kWarpsPerCta) {
+        const int row0 = chunk * R;
+        // ---- aggregation: u_r = [H_i | H_i - dinv_i * sum_j dinv_j H_j] --------------------------
+        for (int r = 0; r < R; ++r) {
+            const int i = row0 + r;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+            float di = 0.f;
+            if (i < a.n) {
+                const int beg = a.row_ptr[i], end = a.row_ptr[i + 1];
+                di = a.dinv[i];
+                if (IMPLICIT_IN) {
+                    float2 p = a.pair_in[i];
+                    hi = implicit_row(p.x, p.y);
+                } else {
+                    hi = __ldg(reinterpret_cast<const float4 *>(a.hin + (size_t)i * CPI) + q);
+                }
+                for (int base = beg; base < end; base += 32) {
+                    const int e = base + lane;
+                    int c = 0;
+                    float d = 0.f;
+                    float2 p = make_float2(0.f, 0.f);
+                    if (e < end) {
+                        c = __ldg(a.col_idx + e);
+                        d = __ldg(a.dinv + c);
+                        if (IMPLICIT_IN) p = __ldg(a.pair_in + c);
+                    }
+                    const int cnt = min(32, end - base);
+#pragma unroll 2
+                    for (int t = 0; t < cnt; t += NG) {
+                        const int src = t + g;
+                        const int jj = __shfl_sync(0xffffffffu, c, src);
+                        const float dj = __shfl_sync(0xffffffffu, d, src);
+                        float4 v;
+                        if (IMPLICIT_IN) {
+                            const float px = __shfl_sync(0xffffffffu, p.x, src);
+                            const float py = __shfl_sync(0xffffffffu, p.y, src);
+                            v = implicit_row(px, py);
+                        }
+                        if (dj != 0.f) {  // lanes past the row end and removed neighbours carry dinv == 0
+                            if (!IMPLICIT_IN)
+                                v = __ldg(reinterpret_cast<const float4 *>(a.hin + (size_t)jj * CPI) + q);
+                            acc.x = fmaf(dj, v.x, acc.x);
+                            acc.y = fmaf(dj, v.y, acc.y);
+                            acc.z = fmaf(dj, v.z, acc.z);
+                            acc.w = fmaf(dj, v.w, acc.w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int off = LPR; off < 32; off <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+                    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+                }
+            }
+            if (g == 0) {
+                float4 lh = make_float4(fmaf(-di, acc.x, hi.x), fmaf(-di, acc.y, hi.y),
+                                        fmaf(-di, acc.z, hi.z), fmaf(-di, acc.w, hi.w));
+                *reinterpret_cast<float4 *>(u_sm + r * KU + 4 * q) = hi;
+                *reinterpret_cast<float4 *>(u_sm + r * KU + CPI + 4 * q) = lh;
+            }
+        }
+        __syncwarp();
+        // ---- projection: out[r][c] = sum_k u[r][k] * Wcat[k][c] ----------------------------------
+        float out[R][CO];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int cc = 0; cc < CO; ++cc) out[r][cc] = b_sm[lane + 32 * cc];
+#pragma unroll 2
+        for (int k = 0; k < KU; k += 4) {
+            float w[4][CO];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int cc = 0; cc < CO; ++cc) w[e][cc] = w_sm[(k + e) * CPO + lane + 32 * cc];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 u = *reinterpret_cast<const float4 *>(u_sm + r * KU + k);
+#pragma unroll
+                for (int cc = 0; cc < CO; ++cc) {
+                    out[r][cc] = fmaf(u.x, w[0][cc], out[r][cc]);
+                    out[r][cc] = fmaf(u.y, w[1][cc], out[r][cc]);
+                    out[r][cc] = fmaf(u.z, w[2][cc], out[r][cc]);
+                    out[r][cc] = fmaf(u.w, w[3][cc], out[r][cc]);
+                }
+            }
+        }
+        __syncwarp();  // u_sm is rewritten by the next chunk
+        // ---- epilogue ----------------------------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = row0 + r;
+            if (!TAIL) {
+                if (i < a.n) {
+#pragma unroll
+                    for (int cc = 0; cc < CO; ++cc)
+                        a.hout[(size_t)i * CPO + lane + 32 * cc] = act_apply(out[r][cc], a.act, a.alpha);
+                }
+            } else {
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < CO; ++cc) {
+                    const float h = act_apply(out[r][cc], a.act, a.alpha);
+                    t0 = fmaf(h, tw0[cc], t0);
+                    t1 = fmaf(h, tw1[cc], t1);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+                }
+                if (lane == 0 && i < a.n) a.pair_out[i] = make_float2(t0 + t1, a.dinv[i] * t1);
+            }
+        }
+    }
+}
+
+template <int CPI, int CPO>
+constexpr size_t layer_smem_bytes() {
+    return sizeof(float) * (size_t)(2 * CPI * CPO + CPO + kWarpsPerCta * kRowsPerWarp * 2 * CPI);
+}
+
+template <int CPI, int CPO, bool IMPLICIT_IN, bool TAIL>
+int launch_layer_t(dg_context *ctx, const LayerArgs &args) {
+    auto kern = gc_layer_kernel<CPI, CPO, IMPLICIT_IN, TAIL>;
+    constexpr size_t smem = layer_smem_bytes<CPI, CPO>();
+    static int blocks_per_sm = 0;  // per instantiation; every context uses the same device kind
+    if (blocks_per_sm == 0) {
+        DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        DG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+        DG_REQUIRE(nb > 0, DG_ERR_CUDA, "gc_layer_kernel<%d,%d> does not fit on an SM", CPI, CPO);
+        blocks_per_sm = nb;
+    }
+    const int n_chunks = (args.n + kRowsPerWarp - 1) / kRowsPerWarp;
+    const int need = (n_chunks + kWarpsPerCta - 1) / kWarpsPerCta;
+    int grid = ctx->sm_count * blocks_per_sm;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<grid, kWarpsPerCta * 32, smem, ctx->stream>>>(args);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int launch_layer(dg_context *ctx, int cpi, int cpo, bool implicit_in, bool tail, const LayerArgs &args) {
+#define DG_DISPATCH(CI, CO_)                                                          \
+    if (cpi == CI && cpo == CO_) {                                                    \
+        if (implicit_in && tail) return launch_layer_t<CI, CO_, true, true>(ctx, args);   \
+        if (implicit_in) return launch_layer_t<CI, CO_, true, false>(ctx, args);          \
+        if (tail) return launch_layer_t<CI, CO_, false, true>(ctx, args);                 \
+        return launch_layer_t<CI, CO_, false, false>(ctx, args);                          \
+    }
+    DG_DISPATCH(32, 32)
+    DG_DISPATCH(32, 64)
+    DG_DISPATCH(64, 32)
+    DG_DISPATCH(64, 64)
+#undef DG_DISPATCH
+    set_error("unsupported padded layer shape %d -> %d", cpi, cpo);
+    return DG_ERR_UNSUPPORTED;
+}
+
+// copy [n, c] (leading dimension ld_src) into a zero-padded [n, cp] buffer and back
+__global__ void pad_rows_kernel(int n, int c, int cp, const float *__restrict__ src, int ld_src,
+                                float *__restrict__ dst) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * cp) return;
+    int i = (int)(idx / cp), k = (int)(idx - (size_t)i * cp);
+    dst[idx] = k < c ? src[(size_t)i * ld_src + k] : 0.f;
+}
+
+// out[i, 0..d) = head(hpad[i, 0..d)), zero for removed vertices
+__global__ void finalize_kernel(int n, int d_out, int cp, const float *__restrict__ hpad,
+                                const uint8_t *__restrict__ keep, int head, float *__restrict__ out,
+                                int ld_out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d_out) return;
+    int i = idx / d_out, d = idx - i * d_out;
+    float v = hpad[(size_t)i * cp + d];
+    if (head == DG_HEAD_PAIR_SOFTMAX) {
+        // softmax over the (2p, 2p+1) pair that column d belongs to (gcn/models.py:399-401)
+        int mate = d ^ 1;
+        float o = mate < d_out ? hpad[(size_t)i * cp + mate] : v;
+        float m = fmaxf(v, o);
+        float ev = expf(v - m), eo = expf(o - m);
+        v = ev / (ev + eo);
+    }
+    out[(size_t)i * ld_out + d] = (keep && !keep[i]) ? 0.f : v;
+}
+
+inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
+
+}  // namespace
+
+// =================================================================================================
+// drivers
+// =================================================================================================
+int batch_compute_dinv(dg_batch *b) {
+    dg_context *ctx = b->ctx;
+    if (b->n_nodes == 0) return DG_OK;
+    degree_kernel<<<grid_for(b->n_nodes, 256), 256, 0, ctx->stream>>>(b->n_nodes, b->row_ptr, b->col_idx,
+                                                                     b->keep, b->dinv);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int keep_from_weights_device(dg_context *ctx, int n, const double *wts, uint8_t *keep) {
+    if (n == 0) return DG_OK;
+    keep_from_weights_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, wts, keep);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int utility_device(dg_context *ctx, int n, const float *score, int stride, const double *wts, int predict,
+                   double *util) {
+    if (n == 0) return DG_OK;
+    utility_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, score, stride, wts, predict, util);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int graph_convolution_device(dg_context *ctx, dg_batch *b, const dg_layer_dev &L, float alpha, const float *x,
+                             int ldx, float *y, int ldy) {
+    const int n = b->n_nodes;
+    if (n == 0) return DG_OK;
+    float *fa = nullptr, *fb = nullptr;
+    DG_TRY(scratch_as(ctx, kSlotFeatA, (size_t)n * kMaxWidth, &fa));
+    DG_TRY(scratch_as(ctx, kSlotFeatB, (size_t)n * kMaxWidth, &fb));
+    pad_rows_kernel<<<grid_for((size_t)n * L.cpi, 256), 256, 0, ctx->stream>>>(n, L.c_in, L.cpi, x, ldx, fa);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    LayerArgs a{};
+    a.n = n;
+    a.row_ptr = b->row_ptr;
+    a.col_idx = b->col_idx;
+    a.dinv = b->dinv;
+    a.hin = fa;
+    a.wcat = L.wcat;
+    a.bias = L.bias;
+    a.act = L.act;
+    a.alpha = alpha;
+    a.hout = fb;
+    DG_TRY(launch_layer(ctx, L.cpi, L.cpo, false, false, a));
+    finalize_kernel<<<grid_for((size_t)n * L.c_out, 256), 256, 0, ctx->stream>>>(n, L.c_out, L.cpo, fb, nullptr,
+                                                                               DG_HEAD_LINEAR, y, ldy);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *out, const double *wts,
+                       int predict, double *util) {
+    const int n = b->n_nodes;
+    if (n == 0) return DG_OK;
+    const int L = m->n_layers;
+    const dg_layer_dev &first = m->layers[0];
+    const dg_layer_dev &last = m->layers[L - 1];
+    const int d_out = last.c_out;
+    cudaStream_t st = ctx->stream;
+
+    float *y = nullptr;
+    float2 *pair = nullptr, *pair2 = nullptr;
+    DG_TRY(scratch_as(ctx, kSlotY, (size_t)n, &y));
+    DG_TRY(scratch_as(ctx, kSlotPair, (size_t)n, &pair));
+    const float x0val = 1.0f / (float)first.c_in;  // gcn/utils.py:98-106 on constant rows
+    scaled_input_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, b->dinv, b->keep, b->x0, x0val, y);
+    ctx->launches++;
+    const int scalar_grid = grid_for((size_t)n * kLanesPerScalarRow, 256);
+    first_scalar_kernel<<<scalar_grid, 256, 0, st>>>(n, b->row_ptr, b->col_idx, b->dinv, y, b->keep, b->x0,
+                                                     x0val, pair);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+
+    if (L == 1) {
+        float *dst = out;
+        if (m->head == DG_HEAD_PAIR_SOFTMAX) DG_TRY(scratch_as(ctx, kSlotFeatA, (size_t)n * kMaxWidth, &dst));
+        first_out_kernel<<<grid_for((size_t)n * d_out, 256), 256, 0, st>>>(
+            n, d_out, pair, first.colsum0, first.colsum1, first.bias, first.act, m->alpha, b->keep, dst);
+        ctx->launches++;
+        if (m->head == DG_HEAD_PAIR_SOFTMAX) {
+            finalize_kernel<<<grid_for((size_t)n * d_out, 256), 256, 0, st>>>(n, d_out, d_out, dst, b->keep,
+                                                                             m->head, out, d_out);
+            ctx->launches++;
+        }
+        DG_CUDA_CHECK(cudaGetLastError());
+        if (util) DG_TRY(utility_device(ctx, n, out, d_out, wts, predict, util));
+        return DG_OK;
+    }
+
+    const bool scalar_tail = (d_out == 1 && m->head == DG_HEAD_LINEAR);
+    float *fa = nullptr, *fb = nullptr;
+    DG_TRY(scratch_as(ctx, kSlotFeatA, (size_t)n * kMaxWidth, &fa));
+    DG_TRY(scratch_as(ctx, kSlotFeatB, (size_t)n * kMaxWidth, &fb));
+    if (scalar_tail) DG_TRY(scratch_as(ctx, kSlotPair2, (size_t)n, &pair2));
+
+    const int last_fused = scalar_tail ? L - 2 : L - 1;  // last layer run through gc_layer_kernel
+    const float *cur = nullptr;
+    float *nxt = fa;
+    for (int l = 1; l <= last_fused; ++l) {
+        const dg_layer_dev &ly = m->layers[l];
+        LayerArgs a{};
+        a.n = n;
+        a.row_ptr = b->row_ptr;
+        a.col_idx = b->col_idx;
+        a.dinv = b->dinv;
+        const bool implicit_in = (l == 1);
+        if (implicit_in) {
+            a.pair_in = pair;
+            a.in_a0 = first.colsum0;
+            a.in_a1 = first.colsum1;
+            a.in_b = first.bias;
+            a.in_act = first.act;
+        } else {
+            a.hin = cur;
+        }
+        a.wcat = ly.wcat;
+        a.bias = ly.bias;
+        a.act = ly.act;
+        a.alpha = m->alpha;
+        const bool tail = scalar_tail && l == last_fused;
+        if (tail) {
+            a.tail_w0 = m->tail_w0;
+            a.tail_w1 = m->tail_w1;
+            a.pair_out = pair2;
+        } else {
+            a.hout = nxt;
+        }
+        DG_TRY(launch_layer(ctx, ly.cpi, ly.cpo, implicit_in, tail, a));
+        cur = nxt;
+        nxt = (nxt == fa) ? fb : fa;
+    }
+
+    if (scalar_tail) {
+        if (L == 2) {
+            node_project_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, first.c_out, pair, first.colsum0,
+                                                                  first.colsum1, first.bias, first.act, m->alpha,
+                                                                  m->tail_w0, m->tail_w1, b->dinv, pair2);
+            ctx->launches++;
+        }
+        last_scalar_kernel<<<scalar_grid, 256, 0, st>>>(n, b->row_ptr, b->col_idx, b->dinv, pair2, m->tail_bias,
+                                                        last.act, m->alpha, b->keep, out, wts, predict, util);
+        ctx->launches++;
+        DG_CUDA_CHECK(cudaGetLastError());
+        return DG_OK;
+    }
+
+    finalize_kernel<<<grid_for((size_t)n * d_out, 256), 256, 0, st>>>(n, d_out, last.cpo, cur, b->keep, m->head,
+                                                                     out, d_out);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    if (util) DG_TRY(utility_device(ctx, n, out, d_out, wts, predict, util));
+    return DG_OK;
+}
+
+}  // namespace dg

@@ -1,0 +1,394 @@
+// Local greedy MWIS (synchronous-round distributed greedy) on a packed CSR batch.
+//
+// Reference: heuristics.py:77-116 (local_greedy_search) and the instrumented variants at
+// heuristics.py:119-305.  Per round every vertex still in `remain` looks at its neighbours that are
+// still in `remain` (round-start state: `remain` is rebound only after the vertex loop,
+// heuristics.py:114) and joins the set iff it has none, or its weight is strictly larger than all of
+// theirs, or it ties with the heaviest and its index is smaller than the smallest-index neighbour
+// carrying that weight (heuristics.py:96-111).  That is exactly
+//     join(v)  <=>  for all u in N(v) & remain:  w_v > w_u  or  (w_v == w_u and v < u)
+// with IEEE-double comparisons (-0.0 == +0.0 is a tie).  Joined vertices and their remaining
+// neighbours (`nb_is`) leave `remain`.  The rule only reads round-start state, so evaluating all
+// vertices in parallel is the same computation as the reference's serial loop.
+//
+// `remain` and `joined` are bitmaps (frontier bitmaps); a warp owns one aligned 32-vertex word and
+// assembles it with __ballot_sync, so no atomics touch the bitmaps.
+//
+//   small graphs (<= kLgsCtaMaxNodes vertices): one CTA per graph runs ALL rounds inside one launch
+//       with the bitmaps in shared memory                                    lgs_cta_kernel
+//   large graphs: one launch pair per round over all vertices with global bitmaps; the host reads
+//       one int per round to detect convergence                              lgs_*_global kernels
+#include "dg_common.cuh"
+
+namespace dg {
+
+namespace {
+
+constexpr int kLgsCtaThreads = 128;
+
+__device__ __forceinline__ bool dominates(double wu, int u, double wv, int v) {
+    // true when neighbour u prevents v from joining
+    return (wu > wv) || (wu == wv && u < v);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kLgsCtaThreads)
+lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_ptr,
+               const int *__restrict__ col_idx, const double *__restrict__ util,
+               const uint8_t *__restrict__ keep, int nstep, int round_cap, int words_cap,
+               uint8_t *__restrict__ member, uint8_t *__restrict__ nb_is, int *__restrict__ steps,
+               long long *__restrict__ p2p, long long *__restrict__ bst, double *__restrict__ oh_vec,
+               int *__restrict__ status) {
+    extern __shared__ uint32_t lgs_words[];
+    uint32_t *remain = lgs_words;
+    uint32_t *joined = lgs_words + words_cap;
+    __shared__ unsigned long long p2p_sm;
+    __shared__ int member_sm;
+
+    const int g = blockIdx.x;
+    const int v0 = graph_ptr[g];
+    const int n = graph_ptr[g + 1] - v0;
+    const int lane = threadIdx.x & 31;
+    const int span = ((n + 31) / 32) * 32;  // vertices rounded up to whole words
+
+    if (threadIdx.x == 0) {
+        p2p_sm = 0ull;
+        member_sm = 0;
+    }
+    __syncthreads();
+    int n_remain = 0;
+    for (int base = 0; base < span; base += kLgsCtaThreads) {
+        const int v = base + threadIdx.x;
+        bool alive = false;
+        if (v < n) {
+            alive = keep ? keep[v0 + v] != 0 : true;
+            member[v0 + v] = 0;
+            if (nb_is) nb_is[v0 + v] = 0;
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0 && v < span) remain[v >> 5] = w;
+        n_remain += __syncthreads_count(alive);
+    }
+
+    int rounds = 0;
+    long long bst_acc = 0;
+    unsigned long long p2p_acc = 0;
+    int joined_mine = 0;
+    while (n_remain > 0 && (nstep < 0 || rounds < nstep)) {
+        if (rounds >= round_cap) {
+            if (threadIdx.x == 0) atomicExch(status, DG_ERR_NOT_CONVERGED);
+            break;
+        }
+        bst_acc += n_remain;  // heuristics.py:179
+        // ---- decide ------------------------------------------------------------------------------
+        for (int base = 0; base < span; base += kLgsCtaThreads) {
+            const int v = base + threadIdx.x;
+            const bool active = v < span ? (remain[v >> 5] >> lane) & 1u : false;
+            bool join = false;
+            if (active) {
+                const double wv = util[v0 + v];
+                const int beg = row_ptr[v0 + v], end = row_ptr[v0 + v + 1];
+                bool blocked = false;
+                int cnt = 0;
+                for (int e = beg; e < end; ++e) {
+                    const int u = col_idx[e] - v0;
+                    if ((remain[u >> 5] >> (u & 31)) & 1u) {
+                        ++cnt;
+                        if (dominates(util[v0 + u], u, wv, v)) {
+                            blocked = true;
+                            if (!STATS) break;
+                        }
+                    }
+                }
+                join = !blocked;
+                if (join) {
+                    member[v0 + v] = 1;
+                    ++joined_mine;
+                }
+                if (STATS) {
+                    p2p_acc += (unsigned)cnt;  // heuristics.py:185
+                    // heuristics.py:238,249: neighbours heard from, +1 "mute" broadcast when joining
+                    // with a non-empty neighbourhood
+                    if (oh_vec) oh_vec[v0 + v] += (double)(cnt + ((join && cnt > 0) ? 1 : 0));
+                }
+            }
+            const uint32_t jw = __ballot_sync(0xffffffffu, join);
+            if (lane == 0 && v < span) joined[v >> 5] = jw;
+        }
+        __syncthreads();
+        // ---- remove joined vertices and their remaining neighbours ---------------------------------
+        n_remain = 0;
+        for (int base = 0; base < span; base += kLgsCtaThreads) {
+            const int v = base + threadIdx.x;
+            bool still = false;
+            if (v < span) {
+                const bool active = (remain[v >> 5] >> lane) & 1u;
+                const bool join = (joined[v >> 5] >> lane) & 1u;
+                if (active && !join) {
+                    const int beg = row_ptr[v0 + v], end = row_ptr[v0 + v + 1];
+                    bool excluded = false;
+                    for (int e = beg; e < end; ++e) {
+                        const int u = col_idx[e] - v0;
+                        if ((joined[u >> 5] >> (u & 31)) & 1u) {
+                            excluded = true;
+                            break;
+                        }
+                    }
+                    if (excluded) {
+                        if (nb_is) nb_is[v0 + v] = 1;
+                    } else {
+                        still = true;
+                    }
+                }
+            }
+            const uint32_t rw = __ballot_sync(0xffffffffu, still);
+            if (lane == 0 && v < span) remain[v >> 5] = rw;
+            n_remain += __syncthreads_count(still);
+        }
+        ++rounds;
+    }
+    if (STATS) {
+        atomicAdd(&p2p_sm, p2p_acc);
+        atomicAdd(&member_sm, joined_mine);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (steps) steps[g] = rounds;
+        if (STATS) {
+            if (p2p) p2p[g] = (long long)p2p_sm;
+            if (bst) bst[g] = bst_acc + member_sm;  // heuristics.py:208
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// global path
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int graph_of(const int *__restrict__ graph_ptr, int n_graphs, int v) {
+    int lo = 0, hi = n_graphs;  // graph_ptr[lo] <= v < graph_ptr[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (graph_ptr[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void lgs_init_global(int n, int n_graphs, const int *__restrict__ graph_ptr,
+                                const uint8_t *__restrict__ keep, uint32_t *__restrict__ remain,
+                                uint8_t *__restrict__ member, uint8_t *__restrict__ nb_is,
+                                double *__restrict__ oh_vec, int *__restrict__ cnt) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool alive = false;
+    if (v < n) {
+        alive = keep ? keep[v] != 0 : true;
+        member[v] = 0;
+        if (nb_is) nb_is[v] = 0;
+        if (oh_vec) oh_vec[v] = 0.0;
+    }
+    const uint32_t w = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0 && (v >> 5) < (n + 31) / 32) remain[v >> 5] = w;
+    if (alive) {
+        if (n_graphs == 1) {
+            if (lane == (__ffs(w) - 1)) atomicAdd(&cnt[0], __popc(w));
+        } else {
+            atomicAdd(&cnt[graph_of(graph_ptr, n_graphs, v)], 1);
+        }
+    }
+}
+
+// per graph, at the start of a round: count the round if the graph still has remaining vertices
+__global__ void lgs_round_begin_global(int n_graphs, int *__restrict__ cnt, int *__restrict__ steps,
+                                       long long *__restrict__ bst, int *__restrict__ any_left) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_graphs) return;
+    const int c = cnt[g];
+    if (c > 0) {
+        if (steps) steps[g] += 1;
+        if (bst) bst[g] += c;
+        *any_left = 1;
+    }
+    cnt[g] = 0;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256)
+lgs_decide_global(int n, int n_graphs, const int *__restrict__ graph_ptr, const int *__restrict__ row_ptr,
+                  const int *__restrict__ col_idx, const double *__restrict__ util,
+                  const uint32_t *__restrict__ remain, uint32_t *__restrict__ joined,
+                  uint8_t *__restrict__ member, long long *__restrict__ p2p, long long *__restrict__ bst,
+                  double *__restrict__ oh_vec) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int n_words = (n + 31) / 32;
+    const bool active = (v >> 5) < n_words ? (remain[v >> 5] >> lane) & 1u : false;
+    bool join = false;
+    int cnt = 0;
+    if (active) {
+        const double wv = util[v];
+        const int beg = row_ptr[v], end = row_ptr[v + 1];
+        bool blocked = false;
+        for (int e = beg; e < end; ++e) {
+            const int u = col_idx[e];
+            if ((__ldg(remain + (u >> 5)) >> (u & 31)) & 1u) {
+                ++cnt;
+                if (dominates(util[u], u, wv, v)) {
+                    blocked = true;
+                    if (!STATS) break;
+                }
+            }
+        }
+        join = !blocked;
+        if (join) member[v] = 1;
+        if (STATS) {
+            if (oh_vec) oh_vec[v] += (double)(cnt + ((join && cnt > 0) ? 1 : 0));
+            const int g = n_graphs == 1 ? 0 : graph_of(graph_ptr, n_graphs, v);
+            if (p2p && cnt) atomicAdd((unsigned long long *)&p2p[g], (unsigned long long)cnt);
+            if (bst && join) atomicAdd((unsigned long long *)&bst[g], 1ull);  // the final + |mwis|
+        }
+    }
+    const uint32_t jw = __ballot_sync(0xffffffffu, join);
+    if (lane == 0 && (v >> 5) < n_words) joined[v >> 5] = jw;
+}
+
+__global__ void __launch_bounds__(256)
+lgs_remove_global(int n, int n_graphs, const int *__restrict__ graph_ptr, const int *__restrict__ row_ptr,
+                  const int *__restrict__ col_idx, const uint32_t *__restrict__ joined,
+                  uint32_t *__restrict__ remain, uint8_t *__restrict__ nb_is, int *__restrict__ cnt) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int n_words = (n + 31) / 32;
+    bool still = false;
+    if ((v >> 5) < n_words) {
+        const bool active = (remain[v >> 5] >> lane) & 1u;
+        const bool join = (joined[v >> 5] >> lane) & 1u;
+        if (active && !join) {
+            const int beg = row_ptr[v], end = row_ptr[v + 1];
+            bool excluded = false;
+            for (int e = beg; e < end; ++e) {
+                const int u = col_idx[e];
+                if ((__ldg(joined + (u >> 5)) >> (u & 31)) & 1u) {
+                    excluded = true;
+                    break;
+                }
+            }
+            if (excluded) {
+                if (nb_is) nb_is[v] = 1;
+            } else {
+                still = true;
+            }
+        }
+    }
+    const uint32_t rw = __ballot_sync(0xffffffffu, still);
+    if (lane == 0 && (v >> 5) < n_words) remain[v >> 5] = rw;
+    if (still) {
+        if (n_graphs == 1) {
+            if (lane == (__ffs(rw) - 1)) atomicAdd(&cnt[0], __popc(rw));
+        } else {
+            atomicAdd(&cnt[graph_of(graph_ptr, n_graphs, v)], 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+member_weight_kernel(const int *__restrict__ graph_ptr, const uint8_t *__restrict__ member,
+                     const double *__restrict__ wts, double *__restrict__ total) {
+    __shared__ double part[256];
+    const int g = blockIdx.x;
+    const int v0 = graph_ptr[g], v1 = graph_ptr[g + 1];
+    double acc = 0.0;
+    for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x)
+        if (member[v]) acc += wts[v];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[g] = part[0];
+}
+
+}  // namespace
+
+int lgs_device(dg_context *ctx, const dg_batch *b, const double *util, int nstep, uint8_t *member,
+               uint8_t *nb_is, int32_t *steps, int64_t *p2p, int64_t *bst, double *oh_vec) {
+    const int n = b->n_nodes;
+    const int G = b->n_graphs;
+    if (G == 0) return DG_OK;
+    cudaStream_t st = ctx->stream;
+    const bool stats = (p2p != nullptr) || (bst != nullptr) || (oh_vec != nullptr);
+    int *d_flag = nullptr;  // [1] any_left
+    DG_TRY(scratch_as(ctx, kSlotLgsCount, (size_t)G + 4, &d_flag));
+    int *d_cnt = d_flag + 4;
+
+    if (b->max_graph_nodes <= kLgsCtaMaxNodes) {
+        if (oh_vec && n) DG_CUDA_CHECK(cudaMemsetAsync(oh_vec, 0, sizeof(double) * (size_t)n, st));
+        const int words_cap = (b->max_graph_nodes + 31) / 32 + 1;
+        const size_t smem = sizeof(uint32_t) * 2 * (size_t)words_cap;
+        if (stats) {
+            lgs_cta_kernel<true><<<G, kLgsCtaThreads, smem, st>>>(
+                b->graph_ptr, b->row_ptr, b->col_idx, util, b->keep, nstep, kLgsRoundCap, words_cap, member,
+                nb_is, steps, (long long *)p2p, (long long *)bst, oh_vec, ctx->d_status);
+        } else {
+            lgs_cta_kernel<false><<<G, kLgsCtaThreads, smem, st>>>(
+                b->graph_ptr, b->row_ptr, b->col_idx, util, b->keep, nstep, kLgsRoundCap, words_cap, member,
+                nb_is, steps, nullptr, nullptr, nullptr, ctx->d_status);
+        }
+        ctx->launches++;
+        DG_CUDA_CHECK(cudaGetLastError());
+        // The status word is read back asynchronously and examined by the next synchronising call
+        // (dg_context_synchronize or any HOST-space call): a non-converged graph can only come from
+        // NaN utilities or self-loops, which the reference does not survive either.
+        DG_CUDA_CHECK(cudaMemcpyAsync(ctx->h_flag + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        return DG_OK;
+    }
+
+    // ---- global path --------------------------------------------------------------------------
+    const int n_words = (n + 31) / 32;
+    uint32_t *words = nullptr;
+    DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)2 * n_words + 2, &words));
+    uint32_t *remain = words, *joined = words + n_words;
+    DG_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (size_t)G, st));
+    if (steps) DG_CUDA_CHECK(cudaMemsetAsync(steps, 0, sizeof(int32_t) * (size_t)G, st));
+    if (p2p) DG_CUDA_CHECK(cudaMemsetAsync(p2p, 0, sizeof(int64_t) * (size_t)G, st));
+    if (bst) DG_CUDA_CHECK(cudaMemsetAsync(bst, 0, sizeof(int64_t) * (size_t)G, st));
+    const int vgrid = (n_words * 32 + 255) / 256;
+    lgs_init_global<<<vgrid, 256, 0, st>>>(n, G, b->graph_ptr, b->keep, remain, member, nb_is, oh_vec, d_cnt);
+    ctx->launches++;
+    int rounds = 0;
+    while (nstep < 0 || rounds < nstep) {
+        DG_REQUIRE(rounds < kLgsRoundCap, DG_ERR_NOT_CONVERGED,
+                   "local greedy search hit the round cap (NaN utilities or self-loops?)");
+        DG_CUDA_CHECK(cudaMemsetAsync(d_flag + 1, 0, sizeof(int), st));
+        lgs_round_begin_global<<<(G + 255) / 256, 256, 0, st>>>(G, d_cnt, steps, (long long *)bst, d_flag + 1);
+        ctx->launches++;
+        DG_CUDA_CHECK(cudaMemcpyAsync(ctx->h_flag, d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DG_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (ctx->h_flag[0] == 0) break;
+        if (stats) {
+            lgs_decide_global<true><<<vgrid, 256, 0, st>>>(n, G, b->graph_ptr, b->row_ptr, b->col_idx, util,
+                                                           remain, joined, member, (long long *)p2p,
+                                                           (long long *)bst, oh_vec);
+        } else {
+            lgs_decide_global<false><<<vgrid, 256, 0, st>>>(n, G, b->graph_ptr, b->row_ptr, b->col_idx, util,
+                                                            remain, joined, member, nullptr, nullptr, nullptr);
+        }
+        lgs_remove_global<<<vgrid, 256, 0, st>>>(n, G, b->graph_ptr, b->row_ptr, b->col_idx, joined, remain,
+                                                 nb_is, d_cnt);
+        ctx->launches += 2;
+        DG_CUDA_CHECK(cudaGetLastError());
+        ++rounds;
+    }
+    return DG_OK;
+}
+
+int member_weight_device(dg_context *ctx, const dg_batch *b, const uint8_t *member, const double *wts,
+                         double *total) {
+    if (b->n_graphs == 0) return DG_OK;
+    member_weight_kernel<<<b->n_graphs, 256, 0, ctx->stream>>>(b->graph_ptr, member, wts, total);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+}  // namespace dg

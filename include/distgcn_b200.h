@@ -1,0 +1,174 @@
+/*
+ * distgcn_b200 - C-ABI of the B200-native GCN-scored local-greedy MWIS path.
+ *
+ * This is the drop-in boundary.  The reference (zhongyuanzhao/distgcn) is pure Python on TensorFlow,
+ * so it has no FFI of its own; each entry point below names the reference Python interface it
+ * replaces (paths relative to the reference root) and INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.  No torch / C++ types cross this boundary: plain pointers,
+ * sizes and opaque handles only.
+ *
+ * Memory spaces.  Every call that moves data takes `int mem`:
+ *   DG_MEM_HOST   - all data pointers of the call are host pointers; the library stages them through
+ *                   its own device buffers and the call returns after the stream has drained.
+ *   DG_MEM_DEVICE - all data pointers are device pointers valid on the context's device; the call
+ *                   only enqueues work on the context's stream (no synchronisation, zero copy).
+ *
+ * Data layout ("packed batch"): n_graphs independent graphs stored as one CSR over n_nodes rows.
+ *   graph_ptr[g] .. graph_ptr[g+1]-1   are the vertices of graph g            (int32, n_graphs+1)
+ *   row_ptr[v]   .. row_ptr[v+1]-1     index the neighbours of vertex v       (int32, n_nodes+1)
+ *   col_idx[e]                         batch-global vertex id of a neighbour  (int32, nnz)
+ * The pattern must be symmetric with a zero diagonal (the reference's conflict graphs,
+ * Data_Generation.py:214-219); edge weights are implicit 1.  A vertex's index inside its graph is
+ * v - graph_ptr[g]; ascending batch-global id == ascending local id, which is what the index
+ * tie-break of the greedy heuristic needs.
+ *
+ * Threading: a dg_context is bound to one device and one stream; use one context per host thread.
+ * Handles created from a context must be destroyed before the context.
+ */
+#ifndef DISTGCN_B200_H
+#define DISTGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DG_VERSION 100
+
+#if defined(__GNUC__)
+#define DG_API __attribute__((visibility("default")))
+#else
+#define DG_API
+#endif
+
+/* status codes */
+#define DG_OK 0
+#define DG_ERR_INVALID 1        /* bad argument (message in dg_last_error) */
+#define DG_ERR_CUDA 2           /* a CUDA runtime call failed */
+#define DG_ERR_UNSUPPORTED 3    /* shape outside what the kernels cover (e.g. width > 64) */
+#define DG_ERR_NOT_CONVERGED 4  /* greedy rounds hit the round cap (NaN utilities / self-loops) */
+#define DG_ERR_NO_DEVICE 5      /* no CUDA device: there is no CPU fallback */
+
+#define DG_MEM_HOST 0
+#define DG_MEM_DEVICE 1
+
+/* activations (gcn/layers.py:216 applies self.act; gcn/models.py:541-573 picks it per layer) */
+#define DG_ACT_IDENTITY 0
+#define DG_ACT_LEAKY_RELU 1     /* tf.nn.leaky_relu, alpha passed to dg_model_create (0.2 in TF) */
+#define DG_ACT_RELU 2
+
+/* utility modes (FLAGS.predict, runtime_config.py:29; used at mwis_dqn_call.py:230-235) */
+#define DG_PREDICT_MWIS 0       /* utility = fp64(score) * weight */
+#define DG_PREDICT_MIS 1        /* utility = fp64(score) */
+
+/* output heads */
+#define DG_HEAD_LINEAR 0        /* GCN_DQN / GCN2_DQN: outputs_softmax = outputs (gcn/models.py:524) */
+#define DG_HEAD_PAIR_SOFTMAX 1  /* GCN_DEEP_DIVER: softmax over each (2d, 2d+1) pair (gcn/models.py:399-401) */
+
+typedef struct dg_context dg_context;
+typedef struct dg_model dg_model;
+typedef struct dg_batch dg_batch;
+
+/* ---- library ------------------------------------------------------------------------------- */
+DG_API int dg_version(void);
+/* Message of the last failing call on this thread ("" if none).  Replaces the reference's
+ * exceptions / asserts (gcn/layers.py:72-74,182). */
+DG_API const char *dg_last_error(void);
+/* Number of visible CUDA devices (0 = none; every other call then fails with DG_ERR_NO_DEVICE). */
+DG_API int dg_device_count(void);
+
+/* ---- context: replaces the module-level tf.compat.v1.Session (mwis_dqn_call.py:336-344) ------ */
+/* `stream` is a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL for a private
+ * non-blocking stream. */
+DG_API int dg_context_create(int device, void *stream, dg_context **out);
+DG_API void dg_context_destroy(dg_context *ctx);
+DG_API int dg_context_synchronize(dg_context *ctx);
+/* Pinned host memory for staging HOST-space calls at full PCIe speed. */
+DG_API void *dg_host_alloc(uint64_t bytes);
+DG_API void dg_host_free(void *p);
+/* Number of kernel launches this context has enqueued so far (bench.py's gpu_launches). */
+DG_API uint64_t dg_context_launch_count(const dg_context *ctx);
+
+/* ---- model: replaces GCN_DQN / GCN_DEEP_DIVER / GCN2_DQN._build (gcn/models.py:536-573, --------
+ * 411-434, 670-708) + Saver.restore (mwis_dqn_call.py:188-192).  `weights` holds
+ * n_layers*n_supports host pointers, weights[l*n_supports + k] = "weights_k" of layer l, row-major
+ * [c_in[l], c_out[l]] (gcn/layers.py:175-183); `bias` is NULL or n_layers host pointers with NULL
+ * for bias-free layers.  Widths up to 64 and n_supports == 2 ("cheb1": T_0 = I, T_1 = L) are
+ * supported. */
+DG_API int dg_model_create(dg_context *ctx, int n_layers, int n_supports, const int32_t *c_in,
+                    const int32_t *c_out, const float *const *weights, const float *const *bias,
+                    const int32_t *act, float leaky_alpha, int head, dg_model **out);
+DG_API void dg_model_destroy(dg_model *model);
+DG_API int dg_model_out_width(const dg_model *model);
+
+/* ---- batch: replaces makestate's support construction (mwis_dqn_call.py:129-138, --------------
+ * gcn/utils.py:120-128,258-274): only the pattern is stored; L = I - D^-1/2 A D^-1/2 is applied
+ * from the degree vector and never materialised. */
+DG_API int dg_batch_create(dg_context *ctx, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                    const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, int mem,
+                    dg_batch **out);
+DG_API void dg_batch_destroy(dg_batch *batch);
+/* Vertex mask: keep[v] == 0 removes v (and its edges) from its graph, as the zero-weight removal of
+ * mwis_dqn_call.py:202-207 does; degrees are recomputed on the kept sub-graph.  NULL keeps all. */
+DG_API int dg_batch_set_keep(dg_batch *batch, const uint8_t *keep, int mem);
+/* keep[v] = (wts[v] != 0), computed on the device (mwis_dqn_call.py:203-204). */
+DG_API int dg_batch_set_keep_from_weights(dg_batch *batch, const double *wts, int mem);
+/* Per-vertex input feature value x0[v] shared by all feature columns (what makestate produces:
+ * mwis_dqn_call.py:131-135, mwis_gdpg_call.py:84-91).  NULL = 1/feature_size on kept vertices. */
+DG_API int dg_batch_set_x0(dg_batch *batch, const float *x0, int mem);
+
+/* ---- operators ------------------------------------------------------------------------------ */
+/* One GraphConvolution layer on dense inputs: y = act(x.W_0 + L.(x.W_1) + b).
+ * Replaces GraphConvolution.__call__ (gcn/layers.py:189-216).  x is [n_nodes, c_in] row-major,
+ * y is [n_nodes, c_out]; W_k are host pointers ([c_in, c_out]); bias may be NULL. */
+DG_API int dg_graph_convolution(dg_context *ctx, dg_batch *batch, int32_t c_in, int32_t c_out,
+                         const float *w0, const float *w1, const float *bias, int act,
+                         float leaky_alpha, const float *x, float *y, int mem);
+
+/* The whole stack.  Replaces DQNAgent.predict's sess.run of model.outputs_softmax
+ * (mwis_dqn_call.py:140-143).  out is [n_nodes, dg_model_out_width] row-major fp32; rows of removed
+ * vertices are 0. */
+DG_API int dg_gcn_forward(dg_context *ctx, const dg_model *model, dg_batch *batch, float *out, int mem);
+
+/* util[v] = fp64(score[v*score_stride]) * wts[v]  (DG_PREDICT_MWIS) or fp64(score) (DG_PREDICT_MIS).
+ * Replaces mwis_dqn_call.py:230-235. */
+DG_API int dg_utility(dg_context *ctx, const dg_batch *batch, const float *score, int32_t score_stride,
+               const double *wts, int predict, double *util, int mem);
+
+/* Local greedy MWIS on every graph of the batch.  Replaces heuristics.local_greedy_search and its
+ * _count/_stats/_overhead/_nstep variants (heuristics.py:77-305).
+ *   util     fp64 utilities (n_nodes), compared exactly as IEEE doubles
+ *   nstep    < 0: run to completion; otherwise stop after nstep rounds (heuristics.py:279)
+ *   member   out, n_nodes bytes, 1 = in the set
+ *   nb_is    out or NULL, n_nodes bytes, the reference's nb_is set (heuristics.py:305)
+ *   steps    out or NULL, n_graphs int32, rounds executed per graph (heuristics.py:160)
+ *   p2p,bst  out or NULL, n_graphs int64, message counts (heuristics.py:185,179,208)
+ *   oh_vec   out or NULL, n_nodes fp64, per-vertex overhead (heuristics.py:238,249)
+ * Vertices removed by dg_batch_set_keep start outside `remain`. */
+DG_API int dg_lgs(dg_context *ctx, const dg_batch *batch, const double *util, int32_t nstep, uint8_t *member,
+           uint8_t *nb_is, int32_t *steps, int64_t *p2p, int64_t *bst, double *oh_vec, int mem);
+
+/* total[g] = sum of wts over the members of graph g (mwis_dqn_call.py:241). */
+DG_API int dg_member_weight(dg_context *ctx, const dg_batch *batch, const uint8_t *member, const double *wts,
+                     double *total, int mem);
+
+/* Fused path: (optional) zero-weight removal -> GCN -> utility -> LGS -> totals.  Replaces
+ * DQNAgent.solve_mwis(adj_0, wts_0, train=False) (mwis_dqn_call.py:198-261) for a whole batch.
+ * score/util/total/steps may be NULL. */
+DG_API int dg_solve(dg_context *ctx, const dg_model *model, dg_batch *batch, const double *wts, int predict,
+             int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
+             int32_t *steps, int mem);
+
+/* One-shot host form of dg_solve: host CSR in, host membership out; the batch lives in the
+ * context's reusable device buffers.  This is what bench.py's e2e number calls. */
+DG_API int dg_solve_host(dg_context *ctx, const dg_model *model, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                  const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
+                  const double *wts, int predict, int remove_zero_weight, uint8_t *member,
+                  double *total);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DISTGCN_B200_H */

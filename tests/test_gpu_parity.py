@@ -1,0 +1,372 @@
+"""GPU parity tests: the CUDA library (through its C-ABI, via ctypes) against the CPU oracle and the
+golden vectors made by the reference's own code.  Run on the B200 box with ``pytest -m gpu``.
+
+Bars (BASELINE.json north_star): LGS membership / counters bit-exact; GCN scores within 1e-5
+relative to the batch's score scale (fp32, different summation order than TensorFlow's)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-5  # north_star: "GCN outputs within 1e-5 relative (fp32)"
+
+
+def _engine():
+    from distgcn_b200 import engine
+    return engine
+
+
+def _rel_err(a, ref):
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    return float(np.abs(a.astype(np.float64) - ref.astype(np.float64)).max()) / scale
+
+
+# ------------------------------------------------------------------------------------------------
+# local greedy search
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fixture", ["lgs_ref_small.npz", "lgs_ref_ties.npz"])
+def test_lgs_matches_reference_vectors(gpu_ctx, fixture):
+    E = _engine()
+    ref = util.load_npz(fixture)
+    if fixture == "lgs_ref_small.npz":
+        pb, w = util.small_graphs()
+    else:
+        pb, w = util.packed_from_npz(ref), ref["weights"]
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    r = E.lgs(gpu_ctx, batch, w, want_nb_is=True, want_overhead=True)
+    assert np.array_equal(r.member, ref["member"])
+    assert np.array_equal(r.steps, ref["steps"])
+    assert np.array_equal(r.p2p, ref["p2p"])
+    assert np.array_equal(r.bst, ref["bst"])
+    assert np.array_equal(r.oh_vec, ref["oh_vec"])
+    # plain variant (no statistics: early-exit neighbour scan) must give the same set
+    r0 = E.lgs(gpu_ctx, batch, w)
+    assert np.array_equal(r0.member, ref["member"])
+    assert np.array_equal(r0.steps, ref["steps"])
+    for k in (1, 2):
+        rk = E.lgs(gpu_ctx, batch, w, nstep=k, want_nb_is=True)
+        assert np.array_equal(rk.member, ref["member_n%d" % k])
+        assert np.array_equal(rk.nb_is, ref["nbis_n%d" % k])
+    # totals: the reference sums in set order, so compare with a tolerance
+    tot = E.member_weight(gpu_ctx, batch, r.member, w)
+    assert np.allclose(tot, ref["total"], rtol=1e-12, atol=1e-12)
+    batch.close()
+
+
+def test_lgs_keep_mask_equals_removal(gpu_ctx):
+    E = _engine()
+    from oracle import lgs as L
+    pb, w = util.small_graphs()
+    rng = np.random.default_rng(11)
+    keep = (rng.random(pb.n_nodes) < 0.75).astype(np.uint8)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    batch.set_keep(keep)
+    r = E.lgs(gpu_ctx, batch, w, want_nb_is=True, want_overhead=True)
+    o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, w, init_remain=keep)
+    assert np.array_equal(r.member, o.member)
+    assert np.array_equal(r.nb_is, o.nb_is)
+    assert np.array_equal(r.steps, o.steps)
+    assert np.array_equal(r.p2p, o.p2p)
+    assert np.array_equal(r.bst, o.bst)
+    assert np.array_equal(r.oh_vec, o.oh_vec)
+    batch.close()
+
+
+def test_lgs_edge_cases(gpu_ctx):
+    E = _engine()
+    from distgcn_b200.batch import PackedBatch, pack_graphs
+    # empty batch
+    pb = PackedBatch(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    r = E.lgs(gpu_ctx, batch, np.zeros(0))
+    assert r.member.shape == (0,)
+    batch.close()
+    # batch containing an empty graph, a single vertex and an edgeless graph
+    adjs = [sp.csr_matrix((0, 0)), sp.csr_matrix((1, 1)), sp.csr_matrix((5, 5)),
+            sp.csr_matrix(np.array([[0, 1], [1, 0]], dtype=float))]
+    pb = pack_graphs(adjs)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    w = np.array([1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 2.0, 2.0])
+    r = E.lgs(gpu_ctx, batch, w, want_overhead=True)
+    assert r.member.tolist() == [1, 1, 1, 1, 1, 1, 1, 0]  # the tie on the edge goes to the lower index
+    assert r.steps.tolist() == [0, 1, 1, 1]
+    assert r.p2p.tolist() == [0, 0, 0, 2]
+    assert r.bst.tolist() == [0, 2, 10, 3]
+    # nstep == 0 runs no round
+    r0 = E.lgs(gpu_ctx, batch, w, nstep=0)
+    assert r0.member.sum() == 0 and r0.steps.tolist() == [0, 0, 0, 0]
+    batch.close()
+
+
+def test_lgs_nan_reports_not_converged(gpu_ctx, monkeypatch):
+    """NaN utilities never converge in the reference (it loops forever); the library reports it."""
+    E = _engine()
+    from distgcn_b200 import _lib
+    from distgcn_b200.batch import pack_graphs
+    pb = pack_graphs([sp.csr_matrix(np.array([[0, 1], [1, 0]], dtype=float))])
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    # two NaNs block each other for ever
+    with pytest.raises(_lib.DistGCNError) as ei:
+        E.lgs(gpu_ctx, batch, np.array([np.nan, np.nan]))
+    assert ei.value.code == _lib.ERR_NOT_CONVERGED
+    # the context stays usable afterwards
+    r = E.lgs(gpu_ctx, batch, np.array([1.0, 2.0]))
+    assert r.member.tolist() == [0, 1]
+    batch.close()
+
+
+def test_lgs_global_path_large_graph(gpu_ctx):
+    """Graphs above the one-CTA limit take the per-round global-bitmap kernels."""
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    rng = np.random.default_rng(3)
+    adjs = []
+    for n, deg in ((20000, 8), (9000, 3), (50, 4)):
+        m = n * deg // 2
+        u = rng.integers(0, n, m)
+        v = rng.integers(0, n, m)
+        ok = u != v
+        a = sp.coo_matrix((np.ones(ok.sum()), (u[ok], v[ok])), shape=(n, n))
+        a = ((a + a.T) > 0).astype(np.float64).tocsr()
+        adjs.append(a)
+    pb = pack_graphs(adjs)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    for w in (rng.random(pb.n_nodes), rng.integers(0, 4, pb.n_nodes).astype(np.float64)):
+        r = E.lgs(gpu_ctx, batch, w, want_nb_is=True, want_overhead=True)
+        o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, w)
+        assert np.array_equal(r.member, o.member)
+        assert np.array_equal(r.nb_is, o.nb_is)
+        assert np.array_equal(r.steps, o.steps)
+        assert np.array_equal(r.p2p, o.p2p)
+        assert np.array_equal(r.bst, o.bst)
+        assert np.array_equal(r.oh_vec, o.oh_vec)
+        r2 = E.lgs(gpu_ctx, batch, w, nstep=2, want_nb_is=True)
+        o2 = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, w, nstep=2)
+        assert np.array_equal(r2.member, o2.member) and np.array_equal(r2.nb_is, o2.nb_is)
+    keep = (rng.random(pb.n_nodes) < 0.6).astype(np.uint8)
+    batch.set_keep(keep)
+    w = rng.random(pb.n_nodes)
+    r = E.lgs(gpu_ctx, batch, w)
+    o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, w, init_remain=keep)
+    assert np.array_equal(r.member, o.member) and np.array_equal(r.steps, o.steps)
+    batch.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# GCN forward
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("short", list(util.CKPTS))
+def test_gcn_forward_matches_oracle(gpu_ctx, short):
+    E = _engine()
+    gold = util.load_npz("gcn_oracle_small.npz")
+    pb, w = util.small_graphs()
+    layers = util.load_layers(short)
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    out = E.gcn_forward(gpu_ctx, model, batch)
+    assert out.shape == (pb.n_nodes, 1)
+    ref = gold[short + "_act"]
+    err = _rel_err(out[:, 0], ref)
+    print("%s: max|err|/max|ref| = %.3g (scale %.3g)" % (short, err, np.abs(ref).max()))
+    assert err <= SCORE_RTOL
+    # per-graph bound as well: no graph may hide behind another graph's scale
+    for g in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        assert _rel_err(out[v0:v1, 0], ref[v0:v1]) <= 2 * SCORE_RTOL, "graph %d" % g
+    batch.close()
+    model.close()
+
+
+@pytest.mark.parametrize("short", ["is4sat_l1", "is4sat_l20_c32", "is4sat_l2_c64", "dqnba_l20_c32"])
+def test_solve_membership_matches_reference_lgs(gpu_ctx, short):
+    """End to end (GCN -> utility -> LGS) against memberships the reference's LGS produced from the
+    oracle's utilities."""
+    E = _engine()
+    gold = util.load_npz("gcn_oracle_small.npz")
+    pb, w = util.small_graphs()
+    layers = util.load_layers(short)
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True, want_steps=True)
+    assert _rel_err(r.score[:, 0], gold[short + "_act"]) <= SCORE_RTOL
+    assert _rel_err(r.util, gold[short + "_util"]) <= SCORE_RTOL
+    _assert_membership(pb, r, w, gold[short + "_member"], gold[short + "_util"])
+    tot = np.array([w[pb.graph_ptr[g]:pb.graph_ptr[g + 1]][r.member[pb.graph_ptr[g]:pb.graph_ptr[g + 1]] == 1].sum()
+                    for g in range(pb.n_graphs)])
+    assert np.allclose(r.total, tot, rtol=1e-12)
+    # one-shot host form gives the same answer
+    m2, t2 = E.solve_host(gpu_ctx, model, pb, w)
+    assert np.array_equal(m2, r.member) and np.allclose(t2, r.total, rtol=1e-12)
+    batch.close()
+    model.close()
+
+
+def _assert_membership(pb, r, w, ref_member, ref_util):
+    """Membership must equal the reference's.  A graph may differ only if the oracle's own utilities
+    contain a near-tie between neighbours that fp32 rounding can flip; then the GPU set must still be
+    exactly what the reference's rule gives on the GPU's utilities."""
+    from oracle import lgs as L
+    bad = []
+    for g in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        if not np.array_equal(r.member[v0:v1], ref_member[v0:v1]):
+            bad.append(g)
+    for g in bad:
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        sub = pb.slice(g, g + 1)
+        o = L.run(sub.row_ptr, sub.col_idx, r.util[v0:v1])
+        assert np.array_equal(o.member, r.member[v0:v1]), "graph %d: LGS not exact on the GPU's own utilities" % g
+    assert len(bad) == 0, "graphs with membership different from the reference: %s" % bad
+
+
+@pytest.mark.parametrize("short", ["is4sat_l1", "is4sat_l20_c32", "is4sat_l2_c64"])
+def test_zero_weight_removal(gpu_ctx, short):
+    E = _engine()
+    gold = util.load_npz("gcn_oracle_small.npz")
+    pb, _ = util.small_graphs()
+    wz = gold["wz"]
+    layers = util.load_layers(short)
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    r = E.solve(gpu_ctx, model, batch, wz, remove_zero_weight=True, want_score=True, want_util=True)
+    assert _rel_err(r.score[:, 0], gold[short + "_wz_act"]) <= SCORE_RTOL
+    assert np.all(r.score[wz == 0, 0] == 0)
+    assert r.member[wz == 0].sum() == 0
+    _assert_membership(pb, r, wz, gold[short + "_wz_member"], gold[short + "_wz_util"])
+    batch.close()
+    model.close()
+
+
+@pytest.mark.parametrize("fam,short", [("er", "is4sat_l1"), ("ba", "is4sat_l20_c32")])
+def test_full_config_sets(gpu_ctx, fam, short):
+    """BASELINE configs 1 and 2 at full size: all 500 shipped graphs in one batch."""
+    E = _engine()
+    pb, w, z = util.full_set(fam)
+    assert pb.n_graphs == 500
+    layers = util.load_layers(short)
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True)
+    err = _rel_err(r.score[:, 0], z["oracle_act"])
+    print("%s full: score err %.3g" % (fam, err))
+    assert err <= SCORE_RTOL
+    ref_member = np.unpackbits(z["member_gcn_lgs"])[:pb.n_nodes]
+    ref_util = z["oracle_act"].astype(np.float64) * w
+    _assert_membership(pb, r, w, ref_member, ref_util)
+    # plain LGS on the raw weights (the "LGS" baseline of wireless_dqn_test_mc.py:242-248)
+    raw = E.lgs(gpu_ctx, batch, w)
+    assert np.array_equal(raw.member, np.unpackbits(z["member_raw_lgs"])[:pb.n_nodes])
+    # size-independent properties: independence and maximality of every returned set
+    a = sp.csr_matrix((np.ones(pb.nnz), pb.col_idx, pb.row_ptr), shape=(pb.n_nodes, pb.n_nodes))
+    for mem in (r.member, raw.member):
+        m = mem.astype(np.float64)
+        assert (a @ m)[mem == 1].sum() == 0          # no two members adjacent
+        assert np.all(((a @ m) > 0) | (mem == 1))    # every non-member has a member neighbour
+    batch.close()
+    model.close()
+
+
+def test_graph_convolution_operator(gpu_ctx):
+    """Single layer on dense inputs (GraphConvolution.__call__, gcn/layers.py:189-216)."""
+    E = _engine()
+    from oracle import gcn_oracle as G
+    pb, _ = util.small_graphs()
+    sub = pb.slice(10, 14)
+    batch = E.DeviceBatch(gpu_ctx, sub)
+    rng = np.random.default_rng(0)
+    a = sp.csr_matrix((np.ones(sub.nnz), sub.col_idx, sub.row_ptr), shape=(sub.n_nodes, sub.n_nodes))
+    sup = [G.to_fp32_csr(t) for t in G.laplacian_supports(a, 1)]
+    for c_in, c_out, act, use_bias in ((32, 32, 1, False), (7, 19, 2, True), (64, 64, 1, True), (48, 1, 0, False),
+                                      (1, 64, 1, False), (33, 5, 0, True)):
+        x = rng.standard_normal((sub.n_nodes, c_in)).astype(np.float32)
+        w0 = (rng.standard_normal((c_in, c_out)) / np.sqrt(c_in)).astype(np.float32)
+        w1 = (rng.standard_normal((c_in, c_out)) / np.sqrt(c_in)).astype(np.float32)
+        b = rng.standard_normal(c_out).astype(np.float32) if use_bias else None
+        y = E.graph_convolution(gpu_ctx, batch, x, w0, w1, b, act=act)
+        ref = G.graph_convolution(x, sup, [w0, w1], b, act)
+        assert y.shape == ref.shape
+        assert _rel_err(y, ref) <= SCORE_RTOL, (c_in, c_out)
+    batch.close()
+
+
+def test_other_heads_and_gen2(gpu_ctx):
+    """GCN2_DQN (bias, activation on every layer) and the GCN_DEEP_DIVER pair-softmax head, with
+    synthetic weights (no shipped checkpoint uses them)."""
+    E = _engine()
+    from oracle import gcn_oracle as G
+    from distgcn_b200.ckpt import LayerWeights
+    pb, w = util.small_graphs()
+    sub = pb.slice(20, 30)
+    a = sp.csr_matrix((np.ones(sub.nnz), sub.col_idx, sub.row_ptr), shape=(sub.n_nodes, sub.n_nodes))
+    sup = G.laplacian_supports(a, 1)
+    rng = np.random.default_rng(1)
+
+    def rand_layers(dims, bias):
+        out = []
+        for ci, co in zip(dims[:-1], dims[1:]):
+            lw = LayerWeights(weights=[(rng.standard_normal((ci, co)) / np.sqrt(ci + co)).astype(np.float32)
+                                       for _ in range(2)])
+            if bias:
+                lw.bias = (0.1 * rng.standard_normal(co)).astype(np.float32)
+            out.append(lw)
+        return out
+
+    batch = E.DeviceBatch(gpu_ctx, sub)
+    n = sub.n_nodes
+    # gen-2: bias + leaky-ReLU everywhere, features = ones row-normalised (mwis_gdpg_call.py:84-91)
+    for dims in ((4, 32, 32, 1), (1, 64, 1), (2, 16, 16, 16, 1), (8, 1)):
+        layers = rand_layers(dims, bias=True)
+        model = E.Model(gpu_ctx, layers, E.gcn2_dqn_acts(len(layers)))
+        out = E.gcn_forward(gpu_ctx, model, batch)
+        feats = G.features_gen2(np.ones(n), dims[0], "mwis")
+        ref = G.gcn_forward(feats, sup, layers, "gcn2_dqn")
+        assert _rel_err(out, ref) <= SCORE_RTOL, dims
+        model.close()
+    # diversity head: 2*diver_num outputs, softmax per pair
+    for diver in (1, 3):
+        dims = (1, 32, 32, 2 * diver)
+        layers = rand_layers(dims, bias=False)
+        model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)), head=E.HEAD_PAIR_SOFTMAX)
+        out = E.gcn_forward(gpu_ctx, model, batch)
+        feats = G.features_gen1(np.ones(n), 1)
+        ref = G.pair_softmax(G.gcn_forward(feats, sup, layers, "gcn_deep_diver"), diver)
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() <= 1e-5
+        assert np.allclose(out.reshape(n, diver, 2).sum(axis=2), 1.0, atol=1e-6)
+        model.close()
+    # per-vertex x0 (gen-2 'mis' features: w / (max w + 1e-9), un-normalised)
+    layers = rand_layers((1, 32, 1), bias=True)
+    model = E.Model(gpu_ctx, layers, E.gcn2_dqn_acts(2))
+    wv = rng.random(n)
+    feats = G.features_gen2(wv, 1, "mis")
+    batch.set_x0(np.asarray(feats.todense()).reshape(-1).astype(np.float32))
+    out = E.gcn_forward(gpu_ctx, model, batch)
+    ref = G.gcn_forward(feats, sup, layers, "gcn2_dqn")
+    assert _rel_err(out, ref) <= SCORE_RTOL
+    batch.set_x0(None)
+    model.close()
+    batch.close()
+
+
+def test_error_reporting(gpu_ctx):
+    E = _engine()
+    from distgcn_b200 import _lib
+    from distgcn_b200.ckpt import LayerWeights
+    too_wide = [LayerWeights(weights=[np.zeros((1, 128), np.float32)] * 2),
+                LayerWeights(weights=[np.zeros((128, 1), np.float32)] * 2)]
+    with pytest.raises(_lib.DistGCNError) as ei:
+        E.Model(gpu_ctx, too_wide, [1, 0])
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    cheb2 = [LayerWeights(weights=[np.zeros((1, 1), np.float32)] * 3)]
+    with pytest.raises(_lib.DistGCNError) as ei:
+        E.Model(gpu_ctx, cheb2, [0])
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    from distgcn_b200.batch import PackedBatch
+    bad = PackedBatch(np.array([0, 5], np.int32), np.array([0, 1, 2], np.int32), np.array([1, 0], np.int32))
+    with pytest.raises(_lib.DistGCNError) as ei:
+        E.DeviceBatch(gpu_ctx, bad)
+    assert ei.value.code == _lib.ERR_INVALID

@@ -1,0 +1,95 @@
+"""Shared helpers for the test-suite: golden fixture loading and oracle glue."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+from distgcn_b200 import ckpt
+from distgcn_b200.batch import PackedBatch, from_edge_lists
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CKPTS = {
+    "is4sat_l1": "result_IS4SAT_deep_ld1_c32_l1_cheb1_diver1_mwis_dqn",
+    "is4sat_l20_c32": "result_IS4SAT_deep_ld1_c32_l20_cheb1_diver1_mwis_dqn",
+    "is4sat_l2_c64": "result_IS4SAT_deep_ld1_c64_l2_cheb1_diver1_mwis_dqn",
+    "dqnba_l20_c32": "result_DQNBA_deep_ld1_c32_l20_cheb1_diver1_mwis_dqn",
+    "dqnmed_l1_bias": "result_DQNMED_deep_ld1_c16_l1_cheb1_diver1_mwis_dqn",
+    "is4sat_ld32_l3_c32": "result_IS4SAT_deep_ld32_c32_l3_cheb1_diver1_mwis_dqn",
+    "is4sat_l3_c16": "result_IS4SAT_deep_ld1_c16_l3_cheb1_diver1_mwis_dqn",
+    "is4sat_l2_c8": "result_IS4SAT_deep_ld1_c8_l2_cheb1_diver1_mwis_dqn",
+}
+
+
+def ckpt_dir(short: str) -> str:
+    return os.path.join(GOLDEN, "ckpt", CKPTS[short])
+
+
+def load_layers(short: str):
+    return ckpt.load_gcn_weights(ckpt_dir(short))
+
+
+def load_npz(name: str):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def packed_from_npz(z) -> PackedBatch:
+    return PackedBatch(graph_ptr=z["graph_ptr"].astype(np.int32), row_ptr=z["row_ptr"].astype(np.int32),
+                       col_idx=z["col_idx"].astype(np.int32))
+
+
+def small_graphs():
+    z = load_npz("graphs_small.npz")
+    return packed_from_npz(z), z["weights"].astype(np.float64)
+
+
+def full_set(fam: str):
+    """('er'|'ba') -> (PackedBatch, weights, fixture dict)."""
+    z = load_npz("%s_test2_full.npz" % fam)
+    pb = from_edge_lists(z["graph_ptr"], z["edge_ptr"], z["edge_u"], z["edge_v"])
+    return pb, z["weights"].astype(np.float64), z
+
+
+def graph_csr(pb: PackedBatch, g: int) -> sp.csr_matrix:
+    return pb.graph_adj(g)
+
+
+def oracle_solve_graph(adj: sp.csr_matrix, w: np.ndarray, layers, predict: str = "mwis", kind: str = "gcn_dqn"):
+    """Oracle restatement of DQNAgent.solve_mwis (mwis_dqn_call.py:198-261) for one graph:
+    returns (score[N] fp32 with zeros on removed vertices, util[N] fp64, member[N] uint8)."""
+    from oracle import gcn_oracle as G
+    from oracle import lgs as L
+    keep = np.where(w > 0)[0]
+    a = sp.csr_matrix(adj)[keep][:, keep].tocsr()
+    wk = w[keep]
+    n = w.shape[0]
+    score = np.zeros(n, dtype=np.float32)
+    util = np.zeros(n, dtype=np.float64)
+    member = np.zeros(n, dtype=np.uint8)
+    if keep.shape[0] == 0:
+        return score, util, member
+    feats = G.features_gen1(wk, layers[0].c_in)
+    sup = G.laplacian_supports(a, len(layers[0].weights) - 1)
+    act = G.gcn_forward(feats, sup, layers, kind)
+    u = G.utility(act[:, 0], wk, predict)
+    r = L.run(a.indptr, a.indices, u)
+    score[keep] = act[:, 0]
+    util[keep] = u
+    member[keep] = r.member
+    return score, util, member
+
+
+def random_graph_batch(rng, n_graphs, n_lo, n_hi, p_lo=0.02, p_hi=0.15):
+    """Synthetic ER batch (numpy only)."""
+    from distgcn_b200.batch import pack_graphs
+    adjs = []
+    for _ in range(n_graphs):
+        n = int(rng.integers(n_lo, n_hi + 1))
+        p = float(rng.uniform(p_lo, p_hi))
+        upper = np.triu(rng.random((n, n)) < p, k=1)
+        a = sp.csr_matrix((upper | upper.T).astype(np.float64))
+        adjs.append(a)
+    return pack_graphs(adjs), adjs

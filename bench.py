@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the GCN-scored local-greedy MWIS path (BASELINE.json metric: graphs/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path (zero-weight removal -> 20-layer GCN -> utility -> local greedy
+MWIS) over one batch of conflict graphs.  Default workload = BASELINE.json configs[1]: the 500 graphs
+of BA_Graph_Uniform_GEN21_test2 (committed fixture tests/golden/ba_test2_full.npz) with the shipped
+checkpoint result_IS4SAT_deep_ld1_c32_l20_cheb1_diver1_mwis_dqn.  With N GPUs every rank owns its own
+batch (graph batches shard with no collective): weak scaling.
+
+Printed JSON line (rank 0): see the keys below; `value` = graphs/s with inputs resident in HBM,
+`e2e` = graphs/s through the public host API (pinned host CSR in, membership out, copies timed),
+`roofline` = the fused GraphConvolution layer kernel against the measured HBM peak, `cpu_baseline` =
+the oracle port on this box's host cores.  `--impl reference` times that CPU port alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "graphs_per_sec_gcn_lgs"
+UNIT = "graphs/s"
+ROTATING_COPIES = 16  # distinct resident input sets cycled through the timed steps (> L2 in total)
+
+
+# --------------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------------
+def synth_er_batch(rng, n_graphs, n_lo=100, n_hi=300, p=0.1):
+    """Config-4 style synthetic G(N, p) graphs, N ~ U{n_lo..n_hi}, numpy only."""
+    from distgcn_b200.batch import PackedBatch
+    sizes = rng.integers(n_lo, n_hi + 1, n_graphs)
+    gp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    rows, cols = [], []
+    for g in range(n_graphs):
+        n = int(sizes[g])
+        m = rng.binomial(n * (n - 1) // 2, p)
+        # sample m distinct unordered pairs by rejection on a slightly larger draw
+        u = rng.integers(0, n, int(m * 1.3) + 8)
+        v = rng.integers(0, n, int(m * 1.3) + 8)
+        ok = u < v
+        key = np.unique(u[ok].astype(np.int64) * n + v[ok])[:m]
+        uu, vv = key // n + gp[g], key % n + gp[g]
+        rows.append(np.concatenate([uu, vv]))
+        cols.append(np.concatenate([vv, uu]))
+    rows = np.concatenate(rows)
+    cols = np.concatenate(cols)
+    order = np.lexsort((cols, rows))
+    rows, cols = rows[order], cols[order]
+    n_total = int(gp[-1])
+    rp = np.zeros(n_total + 1, dtype=np.int64)
+    np.add.at(rp, rows + 1, 1)
+    rp = np.cumsum(rp)
+    return PackedBatch(gp.astype(np.int32), rp.astype(np.int32), cols.astype(np.int32)), rng.random(n_total)
+
+
+def shuffled_copy(pb, w, rng):
+    """Same graphs in a different order (a distinct input set at distinct addresses)."""
+    from distgcn_b200.batch import PackedBatch
+    perm = rng.permutation(pb.n_graphs)
+    sizes = pb.graph_sizes()[perm]
+    gp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    rps = [np.zeros(1, np.int64)]
+    cis, ws = [], []
+    nnz = 0
+    for k, g in enumerate(perm):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        e0, e1 = int(pb.row_ptr[v0]), int(pb.row_ptr[v1])
+        rps.append(pb.row_ptr[v0 + 1:v1 + 1].astype(np.int64) - e0 + nnz)
+        cis.append(pb.col_idx[e0:e1].astype(np.int64) - v0 + gp[k])
+        ws.append(w[v0:v1])
+        nnz += e1 - e0
+    return (PackedBatch(gp.astype(np.int32), np.concatenate(rps).astype(np.int32),
+                        np.concatenate(cis).astype(np.int32)), np.concatenate(ws), perm)
+
+
+def load_workload(name, seed):
+    """-> (PackedBatch, weights, layers, description)"""
+    from tests import util
+    rng = np.random.default_rng(seed)
+    if name == "ba500":
+        pb, w, _ = util.full_set("ba")
+        return pb, w, util.load_layers("is4sat_l20_c32"), \
+            "BA_Graph_Uniform_GEN21_test2 (500 graphs, N=100-300) x IS4SAT c32 l20 checkpoint, local greedy MWIS"
+    if name == "er500":
+        pb, w, _ = util.full_set("er")
+        return pb, w, util.load_layers("is4sat_l1"), \
+            "ER_Graph_Uniform_GEN21_test2 (500 graphs) x IS4SAT c32 l1 checkpoint, local greedy MWIS"
+    if name.startswith("synth-er-"):
+        n_graphs = int(name.split("-")[-1])
+        pb, w = synth_er_batch(rng, n_graphs)
+        return pb, w, util.load_layers("is4sat_l20_c32"), \
+            "synthetic G(N,0.1), N~U{100..300}, %d graphs x IS4SAT c32 l20 checkpoint (config-4 batch)" % n_graphs
+    raise SystemExit("unknown workload %r" % name)
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="dg_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            sm, mx = [], []
+            reasons = set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                           samples=len(sm))
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_rate(pb, w, layers, n_graphs_sample, repeats, n_procs=0):
+    """graphs/s of the CPU port on `n_graphs_sample` graphs, best of `repeats` passes."""
+    from oracle import pipeline
+    solver = pipeline.BatchSolver(pb.graph_ptr, pb.row_ptr, pb.col_idx, w, layers, "mwis", n_procs)
+    try:
+        solver.solve(0, min(pb.n_graphs, max(solver.n_procs, 8)))  # warm the workers
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            solver.solve(0, n_graphs_sample)
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+        return n_graphs_sample / best, solver.n_procs
+    finally:
+        solver.close()
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    from oracle import pipeline
+    pb, w, layers, desc = load_workload(args.workload, args.seed)
+    n_procs = os.cpu_count() or 1
+    solver = pipeline.BatchSolver(pb.graph_ptr, pb.row_ptr, pb.col_idx, w, layers, "mwis", n_procs)
+    try:
+        # size the per-step sample so that the whole run stays within ~2 minutes
+        probe = min(pb.n_graphs, 4 * n_procs)
+        solver.solve(0, probe)
+        t0 = time.perf_counter()
+        solver.solve(0, probe)
+        per_graph = (time.perf_counter() - t0) / probe
+        budget = 120.0 / max(args.steps + args.warmup, 1)
+        sample = int(max(n_procs, min(pb.n_graphs, budget / max(per_graph, 1e-9))))
+        for _ in range(args.warmup):
+            solver.solve(0, sample)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            solver.solve(0, sample)
+        dt = time.perf_counter() - t0
+    finally:
+        solver.close()
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "reference dataset fixture (CPU port of the reference path; the reference itself is Python+TensorFlow and cannot run on this box)",
+        "config": {"workload": desc, "sample_graphs_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_procs, "kind": "port",
+                         "sample": "%d graphs per step, %d steps, %d worker processes (numpy/scipy GCN restatement + C local greedy search)"
+                                   % (sample, args.steps, n_procs)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    import torch
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from distgcn_b200 import engine as E
+    import ctypes as C
+
+    pb0, w0, layers, desc = load_workload(args.workload, args.seed)
+    rng = np.random.default_rng(args.seed + 1000 * rank)
+    ctx = E.Context(local_rank)
+    lib = ctx._lib
+    model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
+
+    # ---- R rotating input sets, resident on the device (value) and in pinned host memory (e2e) ----
+    copies = []
+    input_bytes = 0
+    R = ROTATING_COPIES if pb0.nnz * 4 * ROTATING_COPIES < (8 << 30) else 2
+    for r in range(R):
+        pb, w, _ = shuffled_copy(pb0, w0, rng) if r else (pb0, w0, None)
+        dev_batch = E.DeviceBatch(ctx, pb)
+        d_w = torch.from_numpy(w).to("cuda:%d" % local_rank)
+        d_member = torch.empty(pb.n_nodes, dtype=torch.uint8, device=d_w.device)
+        d_total = torch.empty(pb.n_graphs, dtype=torch.float64, device=d_w.device)
+        h = {k: E.pinned_empty(a.shape, a.dtype) for k, a in
+             (("gp", pb.graph_ptr), ("rp", pb.row_ptr), ("ci", pb.col_idx), ("w", w))}
+        h["gp"][:], h["rp"][:], h["ci"][:], h["w"][:] = pb.graph_ptr, pb.row_ptr, pb.col_idx, w
+        h_member = E.pinned_empty(pb.n_nodes, np.uint8)
+        h_total = E.pinned_empty(pb.n_graphs, np.float64)
+        from distgcn_b200.batch import PackedBatch
+        copies.append(dict(pb=pb, w=w, dev=dev_batch, d_w=d_w, d_member=d_member, d_total=d_total,
+                           h_pb=PackedBatch(h["gp"], h["rp"], h["ci"]), h_w=h["w"], h_member=h_member,
+                           h_total=h_total))
+        input_bytes += 4 * (pb.n_graphs + 1) + 4 * (pb.n_nodes + 1) + 4 * pb.nnz + 8 * pb.n_nodes
+    n_graphs = pb0.n_graphs
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+
+    def device_step(i):
+        c = copies[i % R]
+        E.solve_device(ctx, model, c["dev"], c["d_w"], c["d_member"], predict="mwis", remove_zero_weight=True,
+                       total=c["d_total"])
+
+    def host_step(i):
+        c = copies[i % R]
+        E.solve_host(ctx, model, c["h_pb"], c["h_w"], predict="mwis", remove_zero_weight=True,
+                     member=c["h_member"], total=c["h_total"])
+
+    # ---- value: inputs resident in HBM, CUDA events on the library's stream ----------------------
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    lib.dg_profile_enable(ctx.handle, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    t0 = time.perf_counter()
+    ev = DeviceTimer(ctx)
+    ev.start()
+    for i in range(args.steps):
+        device_step(args.warmup + i)
+    dev_ms = ev.stop()  # synchronises the library's stream
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    tot_ms, n_launch, alg_bytes = C.c_double(), C.c_uint64(), C.c_double()
+    E.check(lib.dg_profile_collect(ctx.handle, C.byref(tot_ms), C.byref(n_launch), C.byref(alg_bytes)))
+    lib.dg_profile_enable(ctx.handle, 0)
+    barrier()
+
+    # ---- e2e: public host API, pinned host buffers, copies inside the timed region ---------------
+    for i in range(max(3, args.warmup // 2)):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        host_step(i)
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+
+    # sanity: both paths produce the same membership for copy 0 (not timed)
+    device_step(0)
+    host_step(0)
+    ctx.synchronize()
+    same = bool(np.array_equal(copies[0]["d_member"].cpu().numpy(), np.asarray(copies[0]["h_member"])))
+
+    if use_dist:
+        t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        value = world * n_graphs * args.steps / (dev_ms / 1e3)
+        e2e_value = world * n_graphs * args.steps / (e2e_ms / 1e3)
+        c0 = copies[0]["pb"]
+        h2d = 4 * (c0.n_graphs + 1) + 4 * (c0.n_nodes + 1) + 4 * c0.nnz + 8 * c0.n_nodes
+        d2h = c0.n_nodes + 8 * c0.n_graphs
+        kern_launches = int(n_launch.value)
+        achieved = (alg_bytes.value / 1e9) / (tot_ms.value / 1e3) if tot_ms.value > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 scores, f64 utilities",
+            "data": "reference dataset fixture (real BA/ER test2 graphs + shipped checkpoint)" if not
+                    args.workload.startswith("synth") else "synthetic",
+            "config": {"workload": desc, "graphs_per_step_per_gpu": n_graphs, "nodes_per_step": int(c0.n_nodes),
+                       "nnz_per_step": int(c0.nnz), "parallelism": "graph-batch sharding, no collectives",
+                       "l2_policy": "inputs larger than L2: %d rotating resident input sets, %.0f MB in total"
+                                    % (R, input_bytes / 1e6),
+                       "paths_agree": same},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "gc_layer_kernel (fused GraphConvolution layer)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "launches_timed": kern_launches,
+                         "avg_launch_us": 1e3 * tot_ms.value / max(kern_launches, 1),
+                         "algorithmic_bytes_per_launch": alg_bytes.value / max(kern_launches, 1),
+                         "share_of_step": tot_ms.value / dev_ms if dev_ms > 0 else None,
+                         "peak_source": peak_src},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            sample = min(n_graphs, 500)
+            rate, cores = cpu_rate(pb0, w0, layers, sample, repeats=3)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d graphs of the same workload, best of 3 passes, %d worker processes "
+                                              "(numpy/scipy GCN restatement + C local greedy search; the reference's own "
+                                              "Python/TensorFlow code cannot run on this box)" % (sample, cores)}
+        print(json.dumps(line))
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+class DeviceTimer:
+    """CUDA events recorded on the library's own stream (dg_timer_start / dg_timer_stop): the kernels
+    are launched on that private stream, which torch.cuda.Event would not see."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def start(self):
+        from distgcn_b200 import engine as E
+        E.check(self.ctx._lib.dg_timer_start(self.ctx.handle))
+
+    def stop(self):
+        import ctypes as C
+        from distgcn_b200 import engine as E
+        ms = C.c_double()
+        E.check(self.ctx._lib.dg_timer_stop(self.ctx.handle, C.byref(ms)))
+        return float(ms.value)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ba500")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -44,6 +44,10 @@ SIGNATURES = {
     "dg_host_alloc": (_p, [C.c_uint64]),
     "dg_host_free": (None, [_p]),
     "dg_context_launch_count": (C.c_uint64, [_p]),
+    "dg_timer_start": (C.c_int, [_p]),
+    "dg_timer_stop": (C.c_int, [_p, _p]),
+    "dg_profile_enable": (C.c_int, [_p, C.c_int]),
+    "dg_profile_collect": (C.c_int, [_p, _p, _p, _p]),
     "dg_model_create": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, C.c_float, C.c_int, C.POINTER(_p)]),
     "dg_model_destroy": (None, [_p]),
     "dg_model_out_width": (C.c_int, [_p]),

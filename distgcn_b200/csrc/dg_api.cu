@@ -41,6 +41,26 @@ int scratch(dg_context *ctx, int slot, size_t bytes, void **out) {
     return DG_OK;
 }
 
+constexpr size_t kProfMaxPairs = 8192;
+
+void prof_begin(dg_context *ctx) {
+    if (!ctx->prof_on || ctx->prof_used / 2 >= kProfMaxPairs) return;
+    if (ctx->prof_events.size() < ctx->prof_used + 2) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        ctx->prof_events.push_back(a);
+        ctx->prof_events.push_back(b);
+    }
+    cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream);
+}
+
+void prof_end(dg_context *ctx, double algorithmic_bytes) {
+    if (!ctx->prof_on || ctx->prof_used / 2 >= kProfMaxPairs || ctx->prof_events.size() < ctx->prof_used + 2) return;
+    cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream);
+    ctx->prof_used += 2;
+    ctx->prof_bytes += algorithmic_bytes;
+}
+
 namespace {
 
 struct DeviceGuard {
@@ -191,6 +211,9 @@ void dg_context_destroy(dg_context *ctx) {
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->d_status) cudaFree(ctx->d_status);
+    for (auto e : ctx->prof_events) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->timer_ev[k]) cudaEventDestroy(ctx->timer_ev[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -216,6 +239,55 @@ void dg_host_free(void *p) {
 }
 
 uint64_t dg_context_launch_count(const dg_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int dg_timer_start(dg_context *ctx) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->timer_ev[k]) DG_CUDA_CHECK(cudaEventCreate(&ctx->timer_ev[k]));
+    DG_CUDA_CHECK(cudaEventRecord(ctx->timer_ev[0], ctx->stream));
+    return DG_OK;
+}
+
+int dg_timer_stop(dg_context *ctx, double *elapsed_ms) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(ctx->timer_ev[0] && ctx->timer_ev[1], DG_ERR_INVALID, "dg_timer_stop without dg_timer_start");
+    DeviceGuard guard(ctx->device);
+    DG_CUDA_CHECK(cudaEventRecord(ctx->timer_ev[1], ctx->stream));
+    DG_CUDA_CHECK(cudaEventSynchronize(ctx->timer_ev[1]));
+    float ms = 0.f;
+    DG_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->timer_ev[0], ctx->timer_ev[1]));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return DG_OK;
+}
+
+int dg_profile_enable(dg_context *ctx, int on) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    ctx->prof_on = on != 0;
+    return DG_OK;
+}
+
+int dg_profile_collect(dg_context *ctx, double *total_ms, uint64_t *launches, double *algorithmic_bytes) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    for (size_t k = 0; k + 1 < ctx->prof_used; k += 2) {
+        float ms = 0.f;
+        DG_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->prof_events[k], ctx->prof_events[k + 1]));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = ctx->prof_used / 2;
+    if (algorithmic_bytes) *algorithmic_bytes = ctx->prof_bytes;
+    ctx->prof_used = 0;
+    ctx->prof_bytes = 0.0;
+    return DG_OK;
+}
 
 // -------------------------------------------------------------------------------------------------
 int dg_model_create(dg_context *ctx, int n_layers, int n_supports, const int32_t *c_in, const int32_t *c_out,

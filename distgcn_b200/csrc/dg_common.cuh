@@ -63,6 +63,12 @@ struct dg_context {
     int *h_flag = nullptr;          // pinned, 4 ints: [0] LGS round read-back, [2] copy of *d_status
     int *d_status = nullptr;        // device, sticky error status written by kernels
     dg_batch *host_batch = nullptr; // reusable batch of dg_solve_host
+    // optional device timing of the dominant kernel (gc_layer_kernel), see dg_profile_*
+    cudaEvent_t timer_ev[2] = {nullptr, nullptr};
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs: [2k] start, [2k+1] stop
+    size_t prof_used = 0;                  // events recorded since the last collect
+    double prof_bytes = 0.0;               // algorithmic bytes of the recorded launches
 };
 
 namespace dg {
@@ -166,5 +172,9 @@ int member_weight_device(dg_context *ctx, const dg_batch *b, const uint8_t *memb
                          double *total);
 
 inline int pad_width(int c) { return c <= 32 ? 32 : 64; }
+
+// profiling helpers (dg_api.cu)
+void prof_begin(dg_context *ctx);
+void prof_end(dg_context *ctx, double algorithmic_bytes);
 
 }  // namespace dg

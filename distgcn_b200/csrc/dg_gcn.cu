@@ -180,6 +180,7 @@ __global__ void utility_kernel(int n, const float *__restrict__ score, int strid
 // ---------------------------------------------------------------------------------------------
 struct LayerArgs {
     int n;
+    int nnz;
     const int *row_ptr;
     const int *col_idx;
     const float *dinv;
@@ -392,7 +393,15 @@ int launch_layer_t(dg_context *ctx, const LayerArgs &args) {
     int grid = ctx->sm_count * blocks_per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    // B_layer: CSR pattern + dinv + one read of the input rows + one write of the output
+    // rows (two floats per vertex for the implicit / tail forms) + the weight matrix
+    const double n = (double)args.n;
+    const double nnz = (double)args.nnz;
+    const double bytes = 4.0 * (n + 1) + 4.0 * nnz + 4.0 * n + 4.0 * n * (IMPLICIT_IN ? 2 : CPI) +
+                         4.0 * n * (TAIL ? 2 : CPO) + 4.0 * (2 * CPI * CPO + CPO);
+    prof_begin(ctx);
     kern<<<grid, kWarpsPerCta * 32, smem, ctx->stream>>>(args);
+    prof_end(ctx, bytes);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -489,6 +498,7 @@ int graph_convolution_device(dg_context *ctx, dg_batch *b, const dg_layer_dev &L
     DG_CUDA_CHECK(cudaGetLastError());
     LayerArgs a{};
     a.n = n;
+    a.nnz = b->nnz;
     a.row_ptr = b->row_ptr;
     a.col_idx = b->col_idx;
     a.dinv = b->dinv;
@@ -558,6 +568,7 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
         const dg_layer_dev &ly = m->layers[l];
         LayerArgs a{};
         a.n = n;
+        a.nnz = b->nnz;
         a.row_ptr = b->row_ptr;
         a.col_idx = b->col_idx;
         a.dinv = b->dinv;

@@ -27,8 +27,10 @@ namespace {
 constexpr int kLgsCtaThreads = 128;
 
 __device__ __forceinline__ bool dominates(double wu, int u, double wv, int v) {
-    // true when neighbour u prevents v from joining
-    return (wu > wv) || (wu == wv && u < v);
+    // true when remaining neighbour u prevents v from joining: v needs w_v > w_u, or a tie that its
+    // smaller index wins.  Written as a negation so that a NaN on either side blocks v, as
+    // np.max / the float comparisons of heuristics.py:102-106 do.
+    return !((wv > wu) || (wv == wu && v < u));
 }
 
 template <bool STATS>

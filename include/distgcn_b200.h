@@ -90,6 +90,18 @@ DG_API void dg_host_free(void *p);
 /* Number of kernel launches this context has enqueued so far (bench.py's gpu_launches). */
 DG_API uint64_t dg_context_launch_count(const dg_context *ctx);
 
+/* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,
+ * waits for it and returns the elapsed device time between the two in milliseconds. */
+DG_API int dg_timer_start(dg_context *ctx);
+DG_API int dg_timer_stop(dg_context *ctx, double *elapsed_ms);
+
+/* Device timing of the dominant kernel (the fused GraphConvolution layer kernel): when enabled, every
+ * launch is bracketed by CUDA events on the context's stream.  dg_profile_collect synchronises and
+ * returns the summed duration, the number of launches and their algorithmic bytes (DESIGN.md
+ * "B_layer") since the previous collect.  At most 8192 launches are kept between collects. */
+DG_API int dg_profile_enable(dg_context *ctx, int on);
+DG_API int dg_profile_collect(dg_context *ctx, double *total_ms, uint64_t *launches, double *algorithmic_bytes);
+
 /* ---- model: replaces GCN_DQN / GCN_DEEP_DIVER / GCN2_DQN._build (gcn/models.py:536-573, --------
  * 411-434, 670-708) + Saver.restore (mwis_dqn_call.py:188-192).  `weights` holds
  * n_layers*n_supports host pointers, weights[l*n_supports + k] = "weights_k" of layer l, row-major

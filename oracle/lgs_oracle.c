@@ -70,7 +70,8 @@ long long lgs_oracle_run(int n, const long long *row_ptr, const int *col_idx, co
                 int u = col_idx[e];
                 if (!remain[u]) continue;                    /* nb_set ∩ remain, heuristics.py:95 */
                 ++cnt;
-                if (!have || wts[u] > wbar) { wbar = wts[u]; have = 1; }
+                /* np.max propagates NaN (heuristics.py:102) */
+                if (!have || wts[u] > wbar || wts[u] != wts[u]) { if (!(wbar != wbar)) wbar = wts[u]; have = 1; }
             }
             c_p2p += cnt;                                    /* heuristics.py:185 */
             if (oh_vec) oh_vec[v] += (double)cnt;            /* heuristics.py:238 */

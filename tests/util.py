@@ -57,29 +57,10 @@ def graph_csr(pb: PackedBatch, g: int) -> sp.csr_matrix:
     return pb.graph_adj(g)
 
 
-def oracle_solve_graph(adj: sp.csr_matrix, w: np.ndarray, layers, predict: str = "mwis", kind: str = "gcn_dqn"):
-    """Oracle restatement of DQNAgent.solve_mwis (mwis_dqn_call.py:198-261) for one graph:
-    returns (score[N] fp32 with zeros on removed vertices, util[N] fp64, member[N] uint8)."""
-    from oracle import gcn_oracle as G
-    from oracle import lgs as L
-    keep = np.where(w > 0)[0]
-    a = sp.csr_matrix(adj)[keep][:, keep].tocsr()
-    wk = w[keep]
-    n = w.shape[0]
-    score = np.zeros(n, dtype=np.float32)
-    util = np.zeros(n, dtype=np.float64)
-    member = np.zeros(n, dtype=np.uint8)
-    if keep.shape[0] == 0:
-        return score, util, member
-    feats = G.features_gen1(wk, layers[0].c_in)
-    sup = G.laplacian_supports(a, len(layers[0].weights) - 1)
-    act = G.gcn_forward(feats, sup, layers, kind)
-    u = G.utility(act[:, 0], wk, predict)
-    r = L.run(a.indptr, a.indices, u)
-    score[keep] = act[:, 0]
-    util[keep] = u
-    member[keep] = r.member
-    return score, util, member
+def oracle_solve_graph(adj, w, layers, predict: str = "mwis", kind: str = "gcn_dqn"):
+    """Oracle restatement of DQNAgent.solve_mwis for one graph (oracle/pipeline.py)."""
+    from oracle import pipeline
+    return pipeline.solve_graph(adj, w, layers, predict, kind)
 
 
 def random_graph_batch(rng, n_graphs, n_lo, n_hi, p_lo=0.02, p_hi=0.15):

@@ -377,6 +377,97 @@ int dg_model_create(dg_context *ctx, int n_layers, int n_supports, const int32_t
         if (status == DG_OK) status = upload(&m->tail_w1, t1);
         m->tail_bias = (bias && bias[l]) ? bias[l][0] : 0.f;
     }
+    // operands of the graph-resident fused kernel
+    if (status == DG_OK) {
+        std::vector<int> hacts(act, act + n_layers);
+        status = [&]() -> int {
+            DG_CUDA_CHECK(cudaMalloc((void **)&m->d_acts, sizeof(int) * n_layers));
+            DG_CUDA_CHECK(cudaMemcpy(m->d_acts, hacts.data(), sizeof(int) * n_layers, cudaMemcpyHostToDevice));
+            return DG_OK;
+        }();
+    }
+    if (status == DG_OK && head == DG_HEAD_LINEAR && c_out[n_layers - 1] == 1) {
+        int widest = 1;
+        for (int l = 0; l + 1 < n_layers; ++l) widest = std::max(widest, (int)c_out[l]);
+        const int cp = pad_width(widest);
+        const bool has_hidden = n_layers >= 3;
+        if (cp == 32 || !has_hidden) {
+            const dg_layer_dev &L0 = m->layers[0];
+            std::vector<float> first(3 * cp, 0.f), tail(2 * cp, 0.f);
+            // layer 0 as the rank-1 map x0 * colsum(W_0) + s * colsum(W_1) + b (padded to cp columns)
+            std::vector<float> cs0(L0.cpo), cs1(L0.cpo), b0(L0.cpo);
+            status = [&]() -> int {
+                DG_CUDA_CHECK(cudaMemcpy(cs0.data(), L0.colsum0, sizeof(float) * L0.cpo, cudaMemcpyDeviceToHost));
+                DG_CUDA_CHECK(cudaMemcpy(cs1.data(), L0.colsum1, sizeof(float) * L0.cpo, cudaMemcpyDeviceToHost));
+                DG_CUDA_CHECK(cudaMemcpy(b0.data(), L0.bias, sizeof(float) * L0.cpo, cudaMemcpyDeviceToHost));
+                return DG_OK;
+            }();
+            const int ncopy = n_layers == 1 ? 1 : std::min(cp, L0.cpo);
+            for (int c = 0; c < ncopy && c < L0.c_out; ++c) {
+                first[c] = cs0[c];
+                first[cp + c] = cs1[c];
+                first[2 * cp + c] = b0[c];
+            }
+            if (n_layers >= 2) {
+                const int l = n_layers - 1;
+                for (int k = 0; k < c_in[l]; ++k) {
+                    tail[k] = weights[2 * l][k];
+                    tail[cp + k] = weights[2 * l + 1][k];
+                }
+            }
+            if (status == DG_OK) status = upload(&m->fused_first, first);
+            if (status == DG_OK) status = upload(&m->fused_tail, tail);
+            if (status == DG_OK && has_hidden) {
+                const size_t blob = (size_t)2 * cp * cp + cp;
+                std::vector<float> wall(blob * (n_layers - 2), 0.f);
+                for (int l = 1; l + 1 < n_layers; ++l) {
+                    float *dst = &wall[blob * (l - 1)];
+                    for (int k = 0; k < c_in[l]; ++k)
+                        for (int c = 0; c < c_out[l]; ++c) {
+                            dst[(size_t)k * cp + c] = weights[2 * l][(size_t)k * c_out[l] + c];
+                            dst[(size_t)(cp + k) * cp + c] = weights[2 * l + 1][(size_t)k * c_out[l] + c];
+                        }
+                    if (bias && bias[l])
+                        for (int c = 0; c < c_out[l]; ++c) dst[(size_t)2 * cp * cp + c] = bias[l][c];
+                }
+                status = upload(&m->fused_wall, wall);
+                if (status == DG_OK && cp == 32) {
+                    // tensor-core layout: every weight split into TF32 hi + lo (round to nearest, ties
+                    // away, as cvt.rna does), rows padded to 40 words (conflict-free fragment loads)
+                    auto tf32_rna = [](float x) -> float {
+                        uint32_t b;
+                        memcpy(&b, &x, 4);
+                        if ((b & 0x7f800000u) == 0x7f800000u) return x;  // inf / nan unchanged
+                        b += 0x00001000u;
+                        b &= 0xffffe000u;
+                        float y;
+                        memcpy(&y, &b, 4);
+                        return y;
+                    };
+                    const int ws = 40;
+                    const size_t mblob = (size_t)2 * 64 * ws + 32;
+                    std::vector<float> wm(mblob * (n_layers - 2), 0.f);
+                    for (int l = 1; l + 1 < n_layers; ++l) {
+                        const float *src = &wall[blob * (l - 1)];  // [64][32] rows: W_0 then W_1, then bias
+                        float *dst = &wm[mblob * (l - 1)];
+                        for (int k = 0; k < 64; ++k)
+                            for (int c = 0; c < 32; ++c) {
+                                const float v = src[(size_t)k * 32 + c];
+                                const float hi = tf32_rna(v);
+                                dst[(size_t)k * ws + c] = hi;
+                                dst[(size_t)64 * ws + (size_t)k * ws + c] = tf32_rna(v - hi);
+                            }
+                        for (int c = 0; c < 32; ++c) dst[(size_t)2 * 64 * ws + c] = src[(size_t)2 * 32 * 32 + c];
+                    }
+                    status = upload(&m->fused_wall_mma, wm);
+                }
+            }
+            if (status == DG_OK) {
+                m->fused_cp = cp;
+                if (n_layers == 1) m->tail_bias = 0.f;
+            }
+        }
+    }
     if (status != DG_OK) {
         dg_model_destroy(m);
         return status;
@@ -397,6 +488,11 @@ void dg_model_destroy(dg_model *m) {
     }
     if (m->tail_w0) cudaFree(m->tail_w0);
     if (m->tail_w1) cudaFree(m->tail_w1);
+    if (m->fused_first) cudaFree(m->fused_first);
+    if (m->fused_wall) cudaFree(m->fused_wall);
+    if (m->fused_wall_mma) cudaFree(m->fused_wall_mma);
+    if (m->fused_tail) cudaFree(m->fused_tail);
+    if (m->d_acts) cudaFree(m->d_acts);
     delete m;
 }
 
@@ -423,6 +519,22 @@ static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nn
         DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
     DG_TRY(validate_graph_ptr(b->h_graph_ptr, n_graphs, n_nodes, &b->max_graph_nodes));
+    // row_ptr at the graph boundaries (host copy): per-graph nnz for the fused kernel's tile table
+    b->tiles_valid = false;
+    b->h_graph_e.resize((size_t)n_graphs + 1);
+    if (mem == DG_MEM_HOST) {
+        for (int g = 0; g <= n_graphs; ++g) b->h_graph_e[g] = row_ptr[b->h_graph_ptr[g]];
+    } else {
+        for (int g = 0; g <= n_graphs; ++g)
+            DG_CUDA_CHECK(cudaMemcpyAsync(&b->h_graph_e[g], row_ptr + b->h_graph_ptr[g], sizeof(int32_t),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+        DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    b->max_graph_nnz = 0;
+    for (int g = 0; g < n_graphs; ++g) {
+        DG_REQUIRE(b->h_graph_e[g + 1] >= b->h_graph_e[g], DG_ERR_INVALID, "row_ptr decreases at graph %d", g);
+        b->max_graph_nnz = std::max(b->max_graph_nnz, b->h_graph_e[g + 1] - b->h_graph_e[g]);
+    }
     if (mem == DG_MEM_HOST) {
         if (b->cap_graphs < (size_t)n_graphs + 1 || !b->graph_ptr) {
             if (b->graph_ptr) cudaFree(b->graph_ptr);
@@ -495,6 +607,7 @@ void dg_batch_destroy(dg_batch *b) {
     if (b->dinv) cudaFree(b->dinv);
     if (b->keep) cudaFree(b->keep);
     if (b->x0) cudaFree(b->x0);
+    if (b->tiles_dev) cudaFree(b->tiles_dev);
     delete b;
 }
 
@@ -709,6 +822,11 @@ static int solve_device(dg_context *ctx, const dg_model *m, dg_batch *b, const d
                         int remove_zero_weight, uint8_t *d_member, float *d_score, double *d_util, double *d_total,
                         int32_t *d_steps) {
     const size_t n = (size_t)b->n_nodes;
+    // small graphs: everything in one graph-resident kernel (dg_fused.cu)
+    bool handled = false;
+    DG_TRY(fused_try_solve(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, d_score, d_util, d_total, d_steps,
+                           &handled));
+    if (handled) return DG_OK;
     if (remove_zero_weight) DG_TRY(set_keep_from_weights_device(b, d_wts));
     const int d_out = m->layers.back().c_out;
     if (!d_score) DG_TRY(scratch_as(ctx, kSlotScore, n * d_out, &d_score));

@@ -137,7 +137,14 @@ struct dg_model {
     float *tail_w0 = nullptr;    // [cpi_last] W_0[:,0] of the last layer
     float *tail_w1 = nullptr;    // [cpi_last]
     float tail_bias = 0.f;
-    std::vector<float> h_first_a0, h_first_a1, h_first_b;  // first-layer colsums on the host (L == 1 path)
+    // operands of the graph-resident fused kernel (dg_fused.cu); fused_cp == 0 when the model is not
+    // eligible (several output columns, pair-softmax head, hidden layers wider than 32)
+    int fused_cp = 0;
+    float *fused_first = nullptr;  // [3*cp]: colsum(W_0), colsum(W_1), bias of layer 0
+    float *fused_wall = nullptr;   // hidden layers 1..L-2, each [2*cp*cp + cp]: W_0 rows, W_1 rows, bias
+    float *fused_wall_mma = nullptr;  // same layers for the tensor-core path: TF32 hi [64x40], lo [64x40], bias [32]
+    float *fused_tail = nullptr;   // [2*cp]: W_0[:,0], W_1[:,0] of the last layer
+    int *d_acts = nullptr;         // [n_layers]
 };
 
 struct dg_batch {
@@ -151,9 +158,65 @@ struct dg_batch {
     uint8_t *keep = nullptr;   // [n_nodes] or nullptr = all kept
     float *x0 = nullptr;       // [n_nodes] or nullptr = 1/F
     size_t cap_nodes = 0, cap_nnz = 0, cap_graphs = 0;  // capacities when reused by dg_solve_host
+    std::vector<int32_t> h_graph_e;  // row_ptr at the graph boundaries (host), n_graphs + 1
+    int max_graph_nnz = 0;
+    // tile table of the fused kernel, cached per (cap_n, cap_nnz)
+    int *tiles_dev = nullptr;
+    size_t tiles_cap = 0;
+    int n_tiles = 0, tiles_cap_n = 0, tiles_cap_nnz = 0, tiles_cp = 0;
+    bool tiles_hidden = false;
+    size_t tiles_wblob = 0;
+    bool tiles_valid = false;
 };
 
 namespace dg {
+
+// ---- graph-resident fused kernel (dg_fused.cu) -------------------------------------------------
+constexpr int kFusedMaxTileGraphs = 64;
+
+struct FusedSmemPlan {  // byte offsets into dynamic shared memory
+    size_t feat_a, feat_b, wbuf, wblob_bytes, util, mbar, dinv, sa, sb, x0s, rp, words, gstart, gcnt, gsteps, col16,
+        gid, vid, slotof, total;
+    int n_words;
+};
+
+struct FusedParams {
+    const int *tiles;  // 8 ints per tile: v0, n, e0, nnz, g0, ng, -, -
+    int n_tiles;
+    int *tile_counter;
+    const int *graph_ptr, *row_ptr, *col_idx;
+    const double *wts;
+    const uint8_t *keep_in;
+    const float *x0;
+    float x0val;
+    int remove_zero;
+    int n_layers;
+    const float *first;
+    int first_act;
+    const float *wall;
+    int use_mma;       // hidden-layer projection on the tensor cores (split TF32), else FFMA
+    int wblob_bytes;   // bytes of one hidden layer's weight blob in `wall`
+    const int *acts;
+    const float *tail;
+    float tail_bias;
+    int last_act;
+    float alpha;
+    int predict;
+    int cap_n, cap_nnz;
+    uint8_t *member;
+    float *score;
+    double *util;
+    double *total;
+    int *steps;
+    int *status;
+    int round_cap;
+    long long *dbg;  // optional per-CTA phase timers (16 slots per CTA), see DG_FUSED_TIMING in bench tools
+};
+
+// Runs the whole solve in the fused kernel when model and batch are eligible; *handled tells.
+int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
+                    int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
+                    int32_t *steps, bool *handled);
 
 // ---- kernels / drivers implemented in dg_gcn.cu ---------------------------------------------
 int batch_compute_dinv(dg_batch *b);

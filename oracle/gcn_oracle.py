@@ -162,6 +162,34 @@ def gcn_forward(features, supports, layers, kind: str = "gcn_dqn", acts: Optiona
     return h
 
 
+def gcn_forward_fp64(features, supports, layers, kind: str = "gcn_dqn", acts: Optional[Sequence[int]] = None) -> np.ndarray:
+    """The same network evaluated in float64 on the fp32-rounded inputs TensorFlow is fed (supports,
+    features and weights rounded to fp32, arithmetic exact to ~1e-16).  Not a restatement of the
+    reference (which computes in fp32) but the yardstick for fp32 implementations: numpy's fp32
+    forward above is itself ~1e-5 (relative to the score scale) away from it on the 20-layer
+    checkpoints, which is why two correct fp32 implementations can differ by up to ~2e-5."""
+    sup64 = [to_fp32_csr(t).astype(np.float64) for t in supports]
+    if acts is None:
+        acts = layer_activations(len(layers), kind)
+    h = to_fp32_csr(features).astype(np.float64)
+    alpha = np.float64(LEAKY_ALPHA)
+    for lw, act in zip(layers, acts):
+        total = None
+        for t, w in zip(sup64, lw.weights):
+            pre = h @ np.asarray(w, dtype=np.float32).astype(np.float64)
+            pre = np.asarray(pre.todense()) if sp.issparse(pre) else np.asarray(pre)
+            part = np.asarray(t @ pre)
+            total = part if total is None else total + part
+        if lw.bias is not None:
+            total = total + np.asarray(lw.bias, dtype=np.float32).astype(np.float64)
+        if act == ACT_LEAKY_RELU:
+            total = np.where(total >= 0, total, alpha * total)
+        elif act == ACT_RELU:
+            total = np.maximum(total, 0.0)
+        h = total
+    return h
+
+
 def pair_softmax(outputs: np.ndarray, diver_num: int) -> np.ndarray:
     """GCN_DEEP_DIVER head: softmax over each consecutive (neg, pos) column pair.   Follows
     gcn/models.py:399-401 with output_dim == 2."""

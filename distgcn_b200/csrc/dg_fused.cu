@@ -1042,10 +1042,20 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     }
     const size_t smem = fused_smem_bytes(m->fused_cp, p.cap_n, p.cap_nnz, has_hidden, wblob);
     DG_CUDA_CHECK(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), ctx->stream));
-    if (m->fused_cp == 32) {
-        DG_TRY(launch_t<32>(ctx, p, smem, p.n_tiles));
-    } else {
-        DG_TRY(launch_t<64>(ctx, p, smem, p.n_tiles));
+    // Work-equivalent algorithmic bytes (SURVEY.md 8d / DESIGN.md): what the same layers would move if each
+    // were a streaming pass - B_layer per hidden layer, a scalar SpMV pass for the first and the last layer,
+    // one pass of the greedy search.  The fused kernel itself only reads CSR + weights and writes the
+    // membership (see `traffic` in bench.py's roofline), so this figure measures work, not HBM pressure.
+    {
+        const double n = (double)b->n_nodes, nnz = (double)b->nnz, cp = (double)m->fused_cp;
+        const double csr = 4.0 * (n + 1) + 4.0 * nnz;
+        const double hidden = (double)std::max(0, m->n_layers - 2) * (csr + 4.0 * n + 8.0 * n * cp + 8.0 * cp * cp);
+        const double scalar_passes = 2.0 * (csr + 12.0 * n);
+        const double lgs = csr + 9.0 * n;
+        prof_begin(ctx);
+        int st = m->fused_cp == 32 ? launch_t<32>(ctx, p, smem, p.n_tiles) : launch_t<64>(ctx, p, smem, p.n_tiles);
+        prof_end(ctx, hidden + scalar_passes + lgs);
+        if (st != DG_OK) return st;
     }
     DG_CUDA_CHECK(cudaMemcpyAsync(ctx->h_flag + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (p.dbg) {  // debugging aid: print the phase timers of this launch

@@ -1,0 +1,133 @@
+"""GPU tests of the drop-in Python API (the reference's call sites): they read like the
+reference's own usage - DQNAgent.load / solve_mwis, heuristics.local_greedy_search*, GraphConvolution."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _flags(**kw):
+    from distgcn_b200.runtime_config import make_flags
+    base = dict(feature_size=1, hidden1=32, num_layer=20, diver_num=1, max_degree=1, predict="mwis")
+    base.update(kw)
+    return make_flags(**base)
+
+
+def test_dqn_agent_solve_mwis_like_the_reference_scripts():
+    from distgcn_b200.mwis_dqn_call import DQNAgent
+    gold = util.load_npz("gcn_oracle_small.npz")
+    pb, w = util.small_graphs()
+    agent = DQNAgent(1, 5000, flags=_flags())
+    agent.load(util.ckpt_dir("is4sat_l20_c32"))      # dqn_agent.load(find_model_folder(FLAGS, 'dqn'))
+    for g in (0, 9, 30, 49):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        adj = sp.csc_matrix(pb.graph_adj(g))          # the .mat files hold CSC matrices
+        mwis, total_wt, one = agent.solve_mwis(adj, w[v0:v1])
+        ref = set(np.flatnonzero(gold["is4sat_l20_c32_member"][v0:v1]).tolist())
+        assert mwis == ref and one == 1.0
+        assert abs(total_wt - w[v0:v1][sorted(ref)].sum()) < 1e-9
+        # zero-weight vertices are removed and results come back in ORIGINAL vertex ids
+        wz = gold["wz"][v0:v1]
+        mwis_z, total_z, _ = agent.solve_mwis(adj, wz)
+        ref_z = set(np.flatnonzero(gold["is4sat_l20_c32_wz_member"][v0:v1]).tolist())
+        assert mwis_z == ref_z and all(wz[i] > 0 for i in mwis_z)
+    member, total = agent.solve_mwis_batch(pb, w)
+    assert np.array_equal(member, gold["is4sat_l20_c32_member"])
+    with pytest.raises(NotImplementedError):
+        agent.solve_mwis(sp.csr_matrix((2, 2)), np.ones(2), train=True)
+    with pytest.raises(ValueError):
+        agent.solve_mwis(sp.csr_matrix((2, 2)), np.array([1.0, -1.0]))
+
+
+def test_dqn_agent_predict_and_makestate():
+    from distgcn_b200.mwis_dqn_call import DQNAgent
+    gold = util.load_npz("gcn_oracle_small.npz")
+    pb, w = util.small_graphs()
+    agent = DQNAgent(1, 5000, flags=_flags(num_layer=1))
+    agent.load(util.ckpt_dir("is4sat_l1"))
+    g = 12
+    v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+    state = agent.makestate(pb.graph_adj(g), w[v0:v1].reshape(-1, 1))
+    act_values, action = agent.predict(state)
+    assert act_values.shape == (v1 - v0, 1) and act_values.dtype == np.float32
+    ref = gold["is4sat_l1_act"][v0:v1]
+    assert np.abs(act_values[:, 0] - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert action.shape == (1,) and int(action[0]) == int(np.argmax(act_values[:, 0]))
+    # a silent no-op when the directory has no `checkpoint` file, like the reference
+    agent.load("/nonexistent/dir")
+
+
+def test_heuristics_entry_points_match_reference_vectors():
+    from distgcn_b200 import heuristics as H
+    ref = util.load_npz("lgs_ref_small.npz")
+    pb, w = util.small_graphs()
+    for g in (1, 26, 44):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        adj, wg = pb.graph_adj(g), w[v0:v1]
+        want = set(np.flatnonzero(ref["member"][v0:v1]).tolist())
+        mwis, total = H.local_greedy_search(adj, wg)
+        assert mwis == want and abs(total - ref["total"][g]) < 1e-9
+        mwis, total, step = H.local_greedy_search_count(adj, wg)
+        assert mwis == want and step == ref["steps"][g]
+        mwis, total, step, p2p, bst = H.local_greedy_search_stats(adj, wg)
+        assert (step, p2p, bst) == (ref["steps"][g], ref["p2p"][g], ref["bst"][g])
+        mwis, total, step, p2p, bst, oh = H.local_greedy_search_overhead(adj, wg)
+        assert np.array_equal(oh, ref["oh_vec"][v0:v1])
+        mwis1, _, nb1 = H.local_greedy_search_nstep(adj, wg, nstep=1)
+        assert mwis1 == set(np.flatnonzero(ref["member_n1"][v0:v1]).tolist())
+        assert nb1 == set(np.flatnonzero(ref["nbis_n1"][v0:v1]).tolist())
+        # weights of any shape are flattened (heuristics.py:84)
+        mwis2, _ = H.local_greedy_search(sp.csc_matrix(adj), wg.reshape(1, -1))
+        assert mwis2 == want
+    res = H.local_greedy_search_batch(pb, w, stats=True)
+    assert np.array_equal(res.member, ref["member"]) and np.array_equal(res.p2p, ref["p2p"])
+
+
+def test_graph_convolution_layer_call():
+    from distgcn_b200 import engine as E
+    from distgcn_b200 import layers as L
+    from distgcn_b200.runtime import default_context
+    from oracle import gcn_oracle as G
+    pb, _ = util.small_graphs()
+    sub = pb.slice(5, 8)
+    ph = L.make_placeholders(2, 16)
+    ph["batch"] = E.DeviceBatch(default_context(), sub)
+    layer = L.GraphConvolution(input_dim=16, output_dim=24, placeholders=ph, act=lambda x: np.maximum(x, 0), bias=True,
+                               flags=_flags(), rng=np.random.default_rng(3))
+    layer.vars["bias"] = np.linspace(-0.1, 0.1, 24).astype(np.float32)
+    x = np.random.default_rng(4).standard_normal((sub.n_nodes, 16)).astype(np.float32)
+    y = layer(x)
+    a = sp.csr_matrix((np.ones(sub.nnz), sub.col_idx, sub.row_ptr), shape=(sub.n_nodes, sub.n_nodes))
+    sup = [G.to_fp32_csr(t) for t in G.laplacian_supports(a, 1)]
+    ref = G.graph_convolution(x, sup, layer.weights, layer.vars["bias"], G.ACT_RELU)
+    assert np.abs(y - ref).max() <= 1e-5 * np.abs(ref).max()
+    ys = layer(sp.csr_matrix(x))  # sparse inputs are accepted like the first layer's
+    assert np.array_equal(ys, y)
+
+
+def test_gen2_solver_entry_points():
+    from distgcn_b200.mwis_gdpg_call import MWISSolver
+    from oracle import gcn_oracle as G
+    from oracle import lgs as Lg
+    pb, w = util.small_graphs()
+    g = 33
+    v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+    adj, wg = pb.graph_adj(g), w[v0:v1]
+    for predict in ("mwis", "mis"):
+        solver = MWISSolver(_flags(feature_size=1, hidden1=16, num_layer=3, predict=predict), 5000, bias=True)
+        rng = np.random.default_rng(7)
+        for layer in solver.model.layers:
+            layer.vars["bias"] = (0.05 * rng.standard_normal(layer.output_dim)).astype(np.float32)
+        mwis, total = solver.solve_mwis(adj, wg, grd=1.0)
+        feats = G.features_gen2(wg, 1, predict)
+        sup = G.laplacian_supports(adj, 1)
+        act = G.gcn_forward(feats, sup, solver.model.layers_as_weights(), "gcn2_dqn")
+        util_ref = G.utility(act[:, 0], wg, predict)
+        want = set(np.flatnonzero(Lg.run(adj.indptr, adj.indices, util_ref).member).tolist())
+        assert mwis == want
+        assert abs(total - wg[sorted(want)].sum()) < 1e-9
+        act_vals, state = solver.utility(adj, wg)
+        assert np.abs(act_vals - act).max() <= 1e-5 * max(np.abs(act).max(), 1e-30)

@@ -36,6 +36,7 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
+static_assert(kWarps == 16, "the row ownership pattern of the layer loop assumes 16 warps");
 
 __device__ __forceinline__ float act_apply(float v, int act, float alpha) {
     if (act == DG_ACT_LEAKY_RELU) return v >= 0.f ? v : alpha * v;
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         if (t >= P.n_tiles) break;
         const int *td = P.tiles + (size_t)t * 8;
         const int v0 = td[0], n = td[1], e0 = td[2], g0 = td[4], ng = td[5];
+        const long long t_tile = timing ? clock64() : 0;
         const int span = ((n + 31) / 32) * 32;
 
         // weights of the first hidden layer start streaming in right away
@@ -397,16 +399,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                 const int act = P.acts[h + 1];
                 bool w_ready = false;
                 for (int pbase = 0; pbase < G8; pbase += 4 * kWarps) {
-                    // groups owned in this pass: slot group e*16 + (w or 15 - w), snake order over the
-                    // degree-sorted groups
-                    int grp_of[4];
+                    // Rows owned in this pass: from each block e of 128 consecutive slots the warp owns
+                    // the 8 rows  own_row(e, k) = 128 (pbase/16 + e) + 16 k + ((warp + k) & 15),  k = 0..7.
+                    // Slots are sorted by degree, so the heaviest rows go to 16 different warps (row-level
+                    // round robin) and every warp's load is the same up to one row per stripe; the 8 rows
+                    // have distinct residues mod 8, which keeps the projection's row loads conflict-free.
+                    const int blk0 = pbase / kWarps;
                     int emask = 0;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        grp_of[e] = pbase + e * kWarps + ((e & 1) ? (kWarps - 1 - warp) : warp);
-                        if (grp_of[e] < G8) emask |= 1 << e;
-                    }
+                    for (int e = 0; e < 4; ++e)
+                        if (128 * (blk0 + e) < n) emask |= 1 << e;
                     if (emask == 0) continue;
+#define DG_OWN_ROW(e, k) (128 * (blk0 + (e)) + 16 * (k) + ((warp + (k)) & 15))
                     // -- aggregation: one lane group (CP/4 lanes) per row, NG rows in flight per warp,
                     //    4 neighbours per step, no predicates (padded lists), no cross-lane reduction
                     {
@@ -415,7 +419,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             if (!((emask >> e) & 1)) continue;
-                            const int row_base = grp_of[e] * 8;
                             // the 8 rows of the group are handled as 8 / NG interleaved streams per lane
                             // group (rows g, g + NG, ...): independent dependency chains in flight
                             constexpr int NS = 8 / NG;
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                             int trips = 0;
 #pragma unroll
                             for (int sidx = 0; sidx < NS; ++sidx) {
-                                const int row = row_base + sidx * NG + g;
+                                const int row = DG_OWN_ROW(e, sidx * NG + g);
                                 const bool valid = row < n;
                                 pb[sidx] = valid ? rp[row] : 0;
                                 cnt[sidx] = valid ? ((rp[row + 1] - pb[sidx]) >> 2) : 0;
@@ -432,6 +435,70 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                                 acc[sidx] = make_float4(0.f, 0.f, 0.f, 0.f);
                                 acc2[sidx] = make_float4(0.f, 0.f, 0.f, 0.f);
                             }
+                            // Heavy rows (hubs) first, one at a time, by the WHOLE warp: the neighbour list is
+                            // dealt to the NG x NS (lane group, stream) segments, partial sums are combined
+                            // with shuffles.  This cuts the dependent-load chain of a degree-150 row from 38
+                            // steps to 5; without it the hub rows are the critical path of every layer.
+                            {
+                                constexpr int kCoopTrips = 8;
+                                unsigned hmask = 0;
+#pragma unroll
+                                for (int sidx = 0; sidx < NS; ++sidx) {
+                                    const unsigned bal = __ballot_sync(0xffffffffu, cnt[sidx] > kCoopTrips);
+#pragma unroll
+                                    for (int gg = 0; gg < NG; ++gg)
+                                        if ((bal >> (gg * LPR)) & 1u) hmask |= 1u << (sidx * NG + gg);
+                                }
+                                while (hmask) {
+                                    const int k = __ffs(hmask) - 1;
+                                    hmask &= hmask - 1;
+                                    const int own_s = k / NG, own_g = k % NG;
+                                    int sel_pb = 0, sel_cnt = 0;
+#pragma unroll
+                                    for (int sidx = 0; sidx < NS; ++sidx)
+                                        if (sidx == own_s) sel_pb = pb[sidx], sel_cnt = cnt[sidx];
+                                    const int pbk = __shfl_sync(0xffffffffu, sel_pb, own_g * LPR);
+                                    const int cntk = __shfl_sync(0xffffffffu, sel_cnt, own_g * LPR);
+                                    float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    for (int base_t = 0; base_t < cntk; base_t += NG * NS) {
+#pragma unroll
+                                        for (int ss = 0; ss < NS; ++ss) {
+                                            const int tt = base_t + ss * NG + g;
+                                            if (tt < cntk) {
+                                                const uint2 cw = *reinterpret_cast<const uint2 *>(col16 + pbk + 4 * tt);
+                                                const int j0 = cw.x & 0xffffu, j1 = cw.x >> 16;
+                                                const int j2 = cw.y & 0xffffu, j3 = cw.y >> 16;
+                                                const float d0 = dinv[j0], d1 = dinv[j1], d2 = dinv[j2], d3 = dinv[j3];
+                                                const float4 x0v = *reinterpret_cast<const float4 *>(curq + j0 * (CP + 4));
+                                                const float4 x1v = *reinterpret_cast<const float4 *>(curq + j1 * (CP + 4));
+                                                const float4 x2v = *reinterpret_cast<const float4 *>(curq + j2 * (CP + 4));
+                                                const float4 x3v = *reinterpret_cast<const float4 *>(curq + j3 * (CP + 4));
+                                                part.x += fmaf(d0, x0v.x, d1 * x1v.x) + fmaf(d2, x2v.x, d3 * x3v.x);
+                                                part.y += fmaf(d0, x0v.y, d1 * x1v.y) + fmaf(d2, x2v.y, d3 * x3v.y);
+                                                part.z += fmaf(d0, x0v.z, d1 * x1v.z) + fmaf(d2, x2v.z, d3 * x3v.z);
+                                                part.w += fmaf(d0, x0v.w, d1 * x1v.w) + fmaf(d2, x2v.w, d3 * x3v.w);
+                                            }
+                                        }
+                                    }
+#pragma unroll
+                                    for (int off = LPR; off < 32; off <<= 1) {
+                                        part.x += __shfl_xor_sync(0xffffffffu, part.x, off);
+                                        part.y += __shfl_xor_sync(0xffffffffu, part.y, off);
+                                        part.z += __shfl_xor_sync(0xffffffffu, part.z, off);
+                                        part.w += __shfl_xor_sync(0xffffffffu, part.w, off);
+                                    }
+#pragma unroll
+                                    for (int sidx = 0; sidx < NS; ++sidx) {
+                                        if (sidx == own_s && g == own_g) {
+                                            acc[sidx] = part;
+                                            cnt[sidx] = 0;  // done: the streamed loop below skips it
+                                        }
+                                    }
+                                }
+                            }
+                            trips = 0;
+#pragma unroll
+                            for (int sidx = 0; sidx < NS; ++sidx) trips = max(trips, cnt[sidx]);
                             trips = __reduce_max_sync(0xffffffffu, trips);
                             for (int tt = 0; tt < trips; ++tt) {
 #pragma unroll
@@ -466,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                             }
 #pragma unroll
                             for (int sidx = 0; sidx < NS; ++sidx) {
-                                const int row = row_base + sidx * NG + g;
+                                const int row = DG_OWN_ROW(e, sidx * NG + g);
                                 if (row < n) {
                                     const float di = dinv[row];
                                     const float4 hi = *reinterpret_cast<const float4 *>(curq + row * (CP + 4));
@@ -504,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                         }
                         int rows[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) rows[e] = min(grp_of[e] * 8 + rg, n - 1);
+                        for (int e = 0; e < 4; ++e) rows[e] = min(DG_OWN_ROW(e, rg), n - 1);
 #pragma unroll 1
                         for (int src = 0; src < 2; ++src) {
                             const float *feat = src == 0 ? cur : nxt;
@@ -540,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                         __syncwarp();  // every lane has finished reading the warp's rows
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int row = grp_of[e] * 8 + rg;
+                            const int row = DG_OWN_ROW(e, rg);
                             if (((emask >> e) & 1) && row < n) {
                                 float4 o0, o1;
                                 o0.x = act_apply(acc[e][0], act, P.alpha);
@@ -571,8 +638,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                         int ra[2], rb[2];
 #pragma unroll
                         for (int mt = 0; mt < 2; ++mt) {
-                            ra[mt] = min(grp_of[2 * mt] * 8 + g, n - 1) * (CP + 4);
-                            rb[mt] = min(grp_of[2 * mt + 1] * 8 + g, n - 1) * (CP + 4);
+                            ra[mt] = min(DG_OWN_ROW(2 * mt, g), n - 1) * (CP + 4);
+                            rb[mt] = min(DG_OWN_ROW(2 * mt + 1, g), n - 1) * (CP + 4);
                         }
                         const int mmask = ((emask & 3) ? 1 : 0) | ((emask & 12) ? 2 : 0);
                         float accm[2][4][4], accc[2][4][4];
@@ -649,7 +716,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                         __syncwarp();  // every lane has finished reading the warp's rows
 #pragma unroll
                         for (int mt = 0; mt < 2; ++mt) {
-                            const int rowa = grp_of[2 * mt] * 8 + g, rowb = grp_of[2 * mt + 1] * 8 + g;
+                            const int rowa = DG_OWN_ROW(2 * mt, g), rowb = DG_OWN_ROW(2 * mt + 1, g);
                             const bool oka = ((emask >> (2 * mt)) & 1) && rowa < n;
                             const bool okb = ((emask >> (2 * mt + 1)) & 1) && rowb < n;
 #pragma unroll
@@ -672,6 +739,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                         }
                     }
                     DG_TICK(4)
+#undef DG_OWN_ROW
                 }
                 // every thread consumes this layer's weight-barrier phase exactly once
                 if (!w_ready) mbar_wait(&mbar[0], wuse & 1u);
@@ -798,6 +866,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                     }
                 }
                 const uint32_t rw = __ballot_sync(0xffffffffu, still);
+                __syncwarp();  // every lane has read this word (WAR within the warp)
                 if (lane == 0 && v < span) remain[v >> 5] = rw;
                 if (still) atomicAdd(&gcnt[gid[v]], 1);
             }
@@ -822,7 +891,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         }
         __syncthreads();  // shared memory is recycled by the next tile
         DG_TICK(7)
-        if (timing) tm[8] += 1;
+        if (timing) {
+            tm[8] += 1;
+            P.dbg[(size_t)gridDim.x * 16 + (size_t)t * 4 + 0] = clock64() - t_tile;
+            P.dbg[(size_t)gridDim.x * 16 + (size_t)t * 4 + 1] = n;
+            P.dbg[(size_t)gridDim.x * 16 + (size_t)t * 4 + 2] = rp[n];
+            P.dbg[(size_t)gridDim.x * 16 + (size_t)t * 4 + 3] = ng;
+        }
     }
     if (timing) {
         tm[9] = clock64() - t_begin;
@@ -860,9 +935,14 @@ struct Tile {
     int v0, n, e0, nnz, g0, ng;
 };
 
-// cost model of a tile for scheduling decisions: shared-memory wavefronts of the layer loop
-// (one per gathered neighbour row, ~20 per projected row) - see profiles/r01_notes.md
-inline long long tile_cost(const Tile &t) { return (long long)t.nnz + 3LL * t.n + 20LL * t.n + 64; }
+// Cost model of a tile for scheduling decisions, in SM cycles for an 18-hidden-layer model, fitted to
+// per-tile clock64() measurements on B200 (profiles/r01_notes.md, "tile cost fit", rms error 3 %):
+// ~41 cycles per padded neighbour entry, ~300 per row, and a large constant - every warp streams the
+// whole weight matrix through shared memory once per layer whatever the tile size, plus staging and the
+// greedy rounds - which is why few large tiles beat many small ones.
+inline long long tile_cost(const Tile &t) {
+    return 41LL * ((long long)t.nnz + 3LL * t.n / 2) + 300LL * t.n + 200000LL;
+}
 
 void pack_tiles(const dg_batch *b, int cap_n, int cap_nnz, std::vector<Tile> *out) {
     out->clear();
@@ -1036,8 +1116,9 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     p.dbg = nullptr;
     if (getenv("DG_FUSED_TIMING")) {
         long long *dbg = nullptr;
-        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * 4 * 16, &dbg));
-        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ctx->sm_count * 4 * 16, ctx->stream));
+        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * 4 * 16 + (size_t)p.n_tiles * 4, &dbg));
+        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * 4 * 16 + (size_t)p.n_tiles * 4),
+                                      ctx->stream));
         p.dbg = dbg;
     }
     const size_t smem = fused_smem_bytes(m->fused_cp, p.cap_n, p.cap_nnz, has_hidden, wblob);
@@ -1059,7 +1140,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     }
     DG_CUDA_CHECK(cudaMemcpyAsync(ctx->h_flag + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (p.dbg) {  // debugging aid: print the phase timers of this launch
-        std::vector<long long> h((size_t)ctx->sm_count * 4 * 16);
+        std::vector<long long> h((size_t)ctx->sm_count * 4 * 16 + (size_t)p.n_tiles * 4);
         DG_CUDA_CHECK(cudaMemcpyAsync(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
         DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         const char *names[10] = {"stage", "gather", "wait_g", "wait_w", "project", "wait_p", "tail", "lgs", "tiles", "total"};
@@ -1078,6 +1159,17 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
             }
             fprintf(stderr, "[fused timing] %-8s min %10lld avg %12.0f max %10lld (%d CTAs)\n", names[k], mn,
                     cnt ? sum / cnt : 0.0, mx, cnt);
+        }
+        if (const char *path = getenv("DG_FUSED_TILE_DUMP")) {  // per-tile (cycles, rows, padded nnz, graphs)
+            if (FILE *f = fopen(path, "w")) {
+                const int grid = std::min(p.n_tiles, ctx->sm_count * 4);
+                (void)grid;
+                const size_t base = (size_t)std::min(p.n_tiles, ctx->sm_count) * 16;
+                for (int t = 0; t < p.n_tiles; ++t)
+                    fprintf(f, "%lld %lld %lld %lld\n", h[base + (size_t)t * 4], h[base + (size_t)t * 4 + 1],
+                            h[base + (size_t)t * 4 + 2], h[base + (size_t)t * 4 + 3]);
+                fclose(f);
+            }
         }
     }
     *handled = true;

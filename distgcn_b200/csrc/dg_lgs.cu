@@ -144,6 +144,7 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
                 }
             }
             const uint32_t rw = __ballot_sync(0xffffffffu, still);
+            __syncwarp();  // every lane has read this word (WAR within the warp)
             if (lane == 0 && v < span) remain[v >> 5] = rw;
             n_remain += __syncthreads_count(still);
         }

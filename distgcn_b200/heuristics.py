@@ -85,6 +85,16 @@ def local_greedy_search_nstep(adj, wts, nstep=1):
     return mwis, np.sum(w[list(mwis)]), _member_set(res.nb_is)
 
 
+def greedy_search(adj, wts):
+    """Centralised greedy (heuristics.py:13-35): visit vertices by descending weight, take a vertex unless
+    a taken vertex is adjacent.  For DISTINCT weights this lexicographically-first independent set is
+    exactly what the synchronous local greedy rounds converge to (a vertex that dominates its remaining
+    neighbourhood is the next one the sorted scan would take), so it runs on the same kernel.  With equal
+    weights the reference's own result depends on numpy's unstable argsort; here ties go to the smaller
+    index, which is one of the orders the reference can produce."""
+    return local_greedy_search(adj, wts)
+
+
 # ---- batched forms --------------------------------------------------------------------------------
 def local_greedy_search_batch(graphs, wts, nstep=-1, stats=False, overhead=False, nb_is=False):
     """Many graphs at once.  `graphs`: PackedBatch, DeviceBatch or a list of adjacency matrices.

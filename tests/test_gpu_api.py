@@ -131,3 +131,19 @@ def test_gen2_solver_entry_points():
         assert abs(total - wg[sorted(want)].sum()) < 1e-9
         act_vals, state = solver.utility(adj, wg)
         assert np.abs(act_vals - act).max() <= 1e-5 * max(np.abs(act).max(), 1e-30)
+
+
+@pytest.mark.parametrize("fam", ["er", "ba"])
+def test_greedy_search_reproduces_stored_greedy_utility(fam):
+    """Every shipped .mat stores greedy_utility = greedy_search on the raw weights
+    (Data_Generation.py:149-153,204); the weights are distinct U(0,1) draws."""
+    from distgcn_b200 import heuristics as H
+    pb, w, z = util.full_set(fam)
+    res = H.local_greedy_search_batch(pb, w)
+    tot = np.array([w[pb.graph_ptr[g]:pb.graph_ptr[g + 1]][res.member[pb.graph_ptr[g]:pb.graph_ptr[g + 1]] == 1].sum()
+                    for g in range(pb.n_graphs)])
+    assert np.allclose(tot, z["greedy_utility"], rtol=1e-12, atol=1e-12)
+    g = 17
+    v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+    mwis, total = H.greedy_search(pb.graph_adj(g), w[v0:v1])
+    assert abs(total - z["greedy_utility"][g]) < 1e-12

@@ -210,6 +210,7 @@ struct FusedParams {
     int *steps;
     int *status;
     int round_cap;
+    int do_lgs;        // 0: stop after the scores (dg_gcn_forward)
     long long *dbg;  // optional per-CTA phase timers (16 slots per CTA), see DG_FUSED_TIMING in bench tools
 };
 

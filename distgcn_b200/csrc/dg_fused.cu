@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                 const int vtx = v0 + vid[sl];
                 k = P.keep_in ? P.keep_in[vtx] != 0 : true;
                 if (P.remove_zero) k = k && (P.wts[vtx] != 0.0);  // mwis_dqn_call.py:203
-                P.member[vtx] = 0;
+                if (P.member) P.member[vtx] = 0;
             }
             const uint32_t w = __ballot_sync(0xffffffffu, k);
             if (lane == 0 && sl < span) {
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         // ---- 7. local greedy search rounds (heuristics.py:77-116), all graphs of the tile together ----
         int n_remain = 1;
         int rounds = 0;
-        while (true) {
+        while (P.do_lgs) {
             // per-graph round accounting (heuristics.py:119-160): a graph's step count grows while it
             // still has remaining vertices
             int any = 0;
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                             }
                         }
                     }
-                    if (join) P.member[v0 + myid] = 1;
+                    if (join && P.member) P.member[v0 + myid] = 1;
                 }
                 const uint32_t jw = __ballot_sync(0xffffffffu, join);
                 if (lane == 0 && v < span) {
@@ -1067,6 +1067,8 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
                     int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
                     int32_t *steps, bool *handled) {
     *handled = false;
+    // member == nullptr: scores only (dg_gcn_forward); the greedy rounds are skipped
+    if (member == nullptr && (d_wts == nullptr) && predict == DG_PREDICT_MWIS) return DG_OK;
     if (getenv("DG_DISABLE_FUSED")) return DG_OK;
     if (m->fused_cp == 0 || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
     if ((int)b->h_graph_e.size() != b->n_graphs + 1) return DG_OK;
@@ -1113,6 +1115,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     p.steps = steps;
     p.status = ctx->d_status;
     p.round_cap = kLgsRoundCap;
+    p.do_lgs = member != nullptr ? 1 : 0;
     p.dbg = nullptr;
     if (getenv("DG_FUSED_TIMING")) {
         long long *dbg = nullptr;

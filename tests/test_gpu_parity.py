@@ -176,9 +176,14 @@ def test_lgs_global_path_large_graph(gpu_ctx):
 # ------------------------------------------------------------------------------------------------
 # GCN forward
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["fused", "layer_kernels"])
 @pytest.mark.parametrize("short", list(util.CKPTS))
-def test_gcn_forward_matches_oracle(gpu_ctx, short):
+def test_gcn_forward_matches_oracle(gpu_ctx, short, path, monkeypatch):
     E = _engine()
+    if path == "layer_kernels":
+        monkeypatch.setenv("DG_DISABLE_FUSED", "1")  # force the streaming per-layer kernels
+    else:
+        monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
     gold = util.load_npz("gcn_oracle_small.npz")
     pb, w = util.small_graphs()
     layers = util.load_layers(short)
@@ -188,7 +193,7 @@ def test_gcn_forward_matches_oracle(gpu_ctx, short):
     assert out.shape == (pb.n_nodes, 1)
     ref = gold[short + "_act"]
     exact = util.exact_scores(pb, w, layers)
-    _check_scores(short + " (layer kernels)", out[:, 0], ref, exact, len(layers))
+    _check_scores(short + " (forward, %s)" % path, out[:, 0], ref, exact, len(layers))
     # per-graph bound as well: no graph may hide behind another graph's scale
     for g in range(pb.n_graphs):
         v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
@@ -197,11 +202,19 @@ def test_gcn_forward_matches_oracle(gpu_ctx, short):
     model.close()
 
 
+@pytest.mark.parametrize("path", ["fused", "layer_kernels", "fused_mma"])
 @pytest.mark.parametrize("short", ["is4sat_l1", "is4sat_l20_c32", "is4sat_l2_c64", "dqnba_l20_c32"])
-def test_solve_membership_matches_reference_lgs(gpu_ctx, short):
+def test_solve_membership_matches_reference_lgs(gpu_ctx, short, path, monkeypatch):
     """End to end (GCN -> utility -> LGS) against memberships the reference's LGS produced from the
-    oracle's utilities."""
+    oracle's utilities; through the graph-resident kernel, the per-layer kernels, and the optional
+    tensor-core projection."""
     E = _engine()
+    monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    monkeypatch.delenv("DG_FUSED_MMA", raising=False)
+    if path == "layer_kernels":
+        monkeypatch.setenv("DG_DISABLE_FUSED", "1")
+    elif path == "fused_mma":
+        monkeypatch.setenv("DG_FUSED_MMA", "1")
     gold = util.load_npz("gcn_oracle_small.npz")
     pb, w = util.small_graphs()
     layers = util.load_layers(short)
@@ -209,7 +222,7 @@ def test_solve_membership_matches_reference_lgs(gpu_ctx, short):
     batch = E.DeviceBatch(gpu_ctx, pb)
     r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True, want_steps=True)
     exact = util.exact_scores(pb, w, layers)
-    _check_scores(short + " (solve)", r.score[:, 0], gold[short + "_act"], exact, len(layers))
+    _check_scores(short + " (solve, %s)" % path, r.score[:, 0], gold[short + "_act"], exact, len(layers))
     assert np.array_equal(r.util, r.score[:, 0].astype(np.float64) * w)  # the fp64 product is exact
     _assert_membership(pb, r, w, gold[short + "_member"], gold[short + "_util"])
     tot = np.array([w[pb.graph_ptr[g]:pb.graph_ptr[g + 1]][r.member[pb.graph_ptr[g]:pb.graph_ptr[g + 1]] == 1].sum()

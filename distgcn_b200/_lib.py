@@ -62,6 +62,18 @@ SIGNATURES = {
     "dg_lgs": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, C.c_int]),
     "dg_member_weight": (C.c_int, [_p, _p, _p, _p, _p, C.c_int]),
     "dg_solve": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, _p, _p, C.c_int]),
+    "dg_part_create": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, C.c_int, C.POINTER(_p)]),
+    "dg_part_destroy": (None, [_p]),
+    "dg_part_prepare": (C.c_int, [_p, _i32, _p, _p, _p, _p]),
+    "dg_part_first": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p]),
+    "dg_part_project": (C.c_int, [_p, _p, _p, _p, _p]),
+    "dg_part_layer": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
+    "dg_part_tail": (C.c_int, [_p, _p, _p, _p, _p]),
+    "dg_part_last": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int, _p, _p]),
+    "dg_model_padded_width": (C.c_int, [_p, _i32]),
+    "dg_part_lgs_init": (C.c_int, [_p, _p, _p, _p, _p]),
+    "dg_part_lgs_decide": (C.c_int, [_p, _p, _p, _p, _p]),
+    "dg_part_lgs_remove": (C.c_int, [_p, _p, _p, _p]),
     "dg_solve_host": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
 }
 

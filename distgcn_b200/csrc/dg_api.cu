@@ -906,4 +906,155 @@ int dg_solve_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t 
     return finish(ctx);
 }
 
+// -------------------------------------------------------------------------------------------------
+// row-partitioned giant graph
+int dg_part_create(dg_context *ctx, int32_t n_global, int32_t row0, int32_t n_local, int32_t nnz_local,
+                   const int32_t *row_ptr_local, const int32_t *col_idx_global, int mem, dg_part **out) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(out != nullptr, DG_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    DG_REQUIRE(n_global >= 0 && row0 >= 0 && n_local >= 0 && nnz_local >= 0, DG_ERR_INVALID, "negative size");
+    DG_REQUIRE(row0 % 32 == 0 && n_local % 32 == 0, DG_ERR_INVALID,
+               "row0 (%d) and n_local (%d) must be multiples of 32 (bitmap words)", row0, n_local);
+    DG_REQUIRE(row_ptr_local && (col_idx_global || nnz_local == 0), DG_ERR_INVALID, "null CSR pointer");
+    DeviceGuard guard(ctx->device);
+    dg_part *p = new (std::nothrow) dg_part();
+    DG_REQUIRE(p != nullptr, DG_ERR_INVALID, "out of host memory");
+    p->ctx = ctx;
+    p->n_global = n_global;
+    p->row0 = row0;
+    p->n_local = n_local;
+    p->nnz = nnz_local;
+    int st = [&]() -> int {
+        if (mem == DG_MEM_DEVICE) {
+            p->row_ptr = const_cast<int32_t *>(row_ptr_local);
+            p->col_idx = const_cast<int32_t *>(col_idx_global);
+            return DG_OK;
+        }
+        DG_REQUIRE(row_ptr_local[0] == 0 && row_ptr_local[n_local] == nnz_local, DG_ERR_INVALID,
+                   "row_ptr_local must run from 0 to nnz_local");
+        p->owns = true;
+        DG_CUDA_CHECK(cudaMalloc((void **)&p->row_ptr, sizeof(int32_t) * ((size_t)n_local + 1)));
+        DG_CUDA_CHECK(cudaMalloc((void **)&p->col_idx, sizeof(int32_t) * std::max<size_t>((size_t)nnz_local, 1)));
+        DG_CUDA_CHECK(cudaMemcpyAsync(p->row_ptr, row_ptr_local, sizeof(int32_t) * ((size_t)n_local + 1),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz_local)
+            DG_CUDA_CHECK(cudaMemcpyAsync(p->col_idx, col_idx_global, sizeof(int32_t) * (size_t)nnz_local,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        return finish(ctx);
+    }();
+    if (st != DG_OK) {
+        dg_part_destroy(p);
+        return st;
+    }
+    *out = p;
+    return DG_OK;
+}
+
+void dg_part_destroy(dg_part *p) {
+    if (!p) return;
+    DeviceGuard guard(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->owns) {
+        if (p->row_ptr) cudaFree(p->row_ptr);
+        if (p->col_idx) cudaFree(p->col_idx);
+    }
+    delete p;
+}
+
+static inline PartView part_view(const dg_part *p) {
+    return PartView{p->n_global, p->row0, p->n_local, p->nnz, p->row_ptr, p->col_idx};
+}
+
+int dg_part_prepare(dg_part *p, int32_t feature_size, const uint8_t *keep, const float *x0, float *dinv, float *y) {
+    clear_error();
+    DG_REQUIRE(p && dinv && y && feature_size >= 1, DG_ERR_INVALID, "bad argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_prepare(p->ctx, part_view(p), keep, x0, 1.0f / (float)feature_size, dinv, y);
+}
+
+int dg_part_first(dg_part *p, int32_t feature_size, const float *dinv, const float *y, const uint8_t *keep,
+                  const float *x0, float *pair) {
+    clear_error();
+    DG_REQUIRE(p && dinv && y && pair && feature_size >= 1, DG_ERR_INVALID, "bad argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_first(p->ctx, part_view(p), dinv, y, keep, x0, 1.0f / (float)feature_size,
+                      reinterpret_cast<float2 *>(pair));
+}
+
+static int check_part_model(const dg_part *p, const dg_model *m) {
+    DG_REQUIRE(p && m, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(m->n_layers >= 2 && m->layers.back().c_out == 1 && m->head == DG_HEAD_LINEAR && m->tail_w0,
+               DG_ERR_UNSUPPORTED, "the row-partitioned path needs >= 2 layers and a one-column linear head");
+    return DG_OK;
+}
+
+int dg_part_project(dg_part *p, const dg_model *m, const float *dinv, const float *pair, float *pair2) {
+    clear_error();
+    DG_TRY(check_part_model(p, m));
+    DG_REQUIRE(m->n_layers == 2, DG_ERR_INVALID, "dg_part_project is for two-layer models");
+    DG_REQUIRE(dinv && pair && pair2, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_project(p->ctx, part_view(p), m, dinv, reinterpret_cast<const float2 *>(pair),
+                        reinterpret_cast<float2 *>(pair2));
+}
+
+int dg_part_layer(dg_part *p, const dg_model *m, int32_t layer, const float *dinv, const float *pair, const float *hin,
+                  float *hout) {
+    clear_error();
+    DG_TRY(check_part_model(p, m));
+    DG_REQUIRE(layer >= 1 && layer <= m->n_layers - 2, DG_ERR_INVALID, "layer %d is not a hidden layer", layer);
+    DG_REQUIRE(dinv && hout && (layer == 1 ? pair != nullptr : hin != nullptr), DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(m->layers[layer].wcat != nullptr, DG_ERR_UNSUPPORTED, "layer %d is too wide", layer);
+    DeviceGuard guard(p->ctx->device);
+    return part_layer(p->ctx, part_view(p), m, layer, dinv, reinterpret_cast<const float2 *>(pair), hin, hout);
+}
+
+int dg_part_tail(dg_part *p, const dg_model *m, const float *dinv, const float *hin, float *pair2) {
+    clear_error();
+    DG_TRY(check_part_model(p, m));
+    DG_REQUIRE(m->n_layers >= 3 && dinv && hin && pair2, DG_ERR_INVALID, "bad argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_tail(p->ctx, part_view(p), m, dinv, hin, reinterpret_cast<float2 *>(pair2));
+}
+
+int dg_part_last(dg_part *p, const dg_model *m, const float *dinv, const float *pair2, const uint8_t *keep,
+                 const double *wts, int predict, float *score, double *util) {
+    clear_error();
+    DG_TRY(check_part_model(p, m));
+    DG_REQUIRE(dinv && pair2 && (score || util), DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(predict == DG_PREDICT_MIS || wts != nullptr || util == nullptr, DG_ERR_INVALID,
+               "weights required for predict=mwis");
+    DeviceGuard guard(p->ctx->device);
+    return part_last(p->ctx, part_view(p), m, dinv, reinterpret_cast<const float2 *>(pair2), keep, wts, predict, score,
+                     util);
+}
+
+int dg_model_padded_width(const dg_model *m, int32_t layer) {
+    if (!m || layer < 0 || layer >= m->n_layers) return 0;
+    return m->layers[layer].cpo;
+}
+
+int dg_part_lgs_init(dg_part *p, const uint8_t *keep, uint32_t *remain, uint8_t *member, int64_t *count) {
+    clear_error();
+    DG_REQUIRE(p && remain && member && count, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_lgs_init(p->ctx, part_view(p), keep, remain, member, reinterpret_cast<long long *>(count));
+}
+
+int dg_part_lgs_decide(dg_part *p, const double *util, const uint32_t *remain, uint32_t *joined, uint8_t *member) {
+    clear_error();
+    DG_REQUIRE(p && util && remain && joined && member, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_lgs_decide(p->ctx, part_view(p), util, remain, joined, member);
+}
+
+int dg_part_lgs_remove(dg_part *p, const uint32_t *joined, uint32_t *remain, int64_t *count) {
+    clear_error();
+    DG_REQUIRE(p && joined && remain && count, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_lgs_remove(p->ctx, part_view(p), joined, remain, reinterpret_cast<long long *>(count));
+}
+
 }  // extern "C"

@@ -169,7 +169,41 @@ struct dg_batch {
     bool tiles_valid = false;
 };
 
+struct dg_part {  // one rank's row slice of a single large graph (device CSR, global column ids)
+    dg_context *ctx = nullptr;
+    int n_global = 0, row0 = 0, n_local = 0, nnz = 0;
+    bool owns = false;
+    int32_t *row_ptr = nullptr, *col_idx = nullptr;
+};
+
 namespace dg {
+
+struct PartView {
+    int n_global, row0, n_local, nnz;
+    const int *row_ptr, *col_idx;
+};
+
+// row-slice drivers (dg_gcn.cu / dg_lgs.cu): every per-vertex array is GLOBAL sized, a call reads any
+// vertex and writes only rows row0 .. row0+n_local-1
+int part_prepare(dg_context *ctx, const PartView &pv, const uint8_t *keep, const float *x0, float x0val, float *dinv,
+                 float *y);
+int part_scale(dg_context *ctx, const PartView &pv, const uint8_t *keep, const float *x0, float x0val,
+               const float *dinv, float *y);
+int part_first(dg_context *ctx, const PartView &pv, const float *dinv, const float *y, const uint8_t *keep,
+               const float *x0, float x0val, float2 *pair);
+int part_project(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair,
+                 float2 *pair2);
+int part_layer(dg_context *ctx, const PartView &pv, const dg_model *m, int layer, const float *dinv,
+               const float2 *pair, const float *hin, float *hout);
+int part_tail(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float *hin,
+              float2 *pair2);
+int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair2,
+              const uint8_t *keep, const double *wts, int predict, float *score, double *util);
+int part_lgs_init(dg_context *ctx, const PartView &pv, const uint8_t *keep, uint32_t *remain, uint8_t *member,
+                  long long *cnt);
+int part_lgs_decide(dg_context *ctx, const PartView &pv, const double *util, const uint32_t *remain, uint32_t *joined,
+                    uint8_t *member);
+int part_lgs_remove(dg_context *ctx, const PartView &pv, const uint32_t *joined, uint32_t *remain, long long *cnt);
 
 // ---- graph-resident fused kernel (dg_fused.cu) -------------------------------------------------
 constexpr int kFusedMaxTileGraphs = 64;

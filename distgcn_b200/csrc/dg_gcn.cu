@@ -42,7 +42,9 @@ __device__ __forceinline__ float act_apply(float v, int act, float alpha) {
 // degrees -> dinv.  Follows gcn/utils.py:122-125 (rowsum^-0.5 in fp64, inf -> 0), rounded to fp32.
 // With a keep mask the degree is taken on the kept sub-graph (mwis_dqn_call.py:202-207).
 // ---------------------------------------------------------------------------------------------
-__global__ void degree_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+// Row-slice form (row0 != 0): the launch covers rows row0 .. row0+n-1 of a larger graph; row_ptr is the
+// slice's own (local) array, every per-vertex array is indexed by GLOBAL vertex id.
+__global__ void degree_kernel(int n, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
                               const uint8_t *__restrict__ keep, float *__restrict__ dinv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -50,10 +52,10 @@ __global__ void degree_kernel(int n, const int *__restrict__ row_ptr, const int 
     int deg = 0;
     if (keep == nullptr) {
         deg = end - beg;
-    } else if (keep[i]) {
+    } else if (keep[row0 + i]) {
         for (int e = beg; e < end; ++e) deg += keep[col_idx[e]] != 0;
     }
-    dinv[i] = deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f;
+    dinv[row0 + i] = deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f;
 }
 
 __global__ void keep_from_weights_kernel(int n, const double *__restrict__ wts, uint8_t *__restrict__ keep) {
@@ -137,7 +139,7 @@ node_project_kernel(int n, int c, const float2 *__restrict__ pair, const float *
 // Last layer with one output column: score_i = act(q_i - dinv_i * sum_j zs_j + b), then the utility
 // product of mwis_dqn_call.py:230-235 in fp64.  One sub-warp of 8 lanes per row.
 __global__ void __launch_bounds__(256)
-last_scalar_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+last_scalar_kernel(int n, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
                    const float *__restrict__ dinv, const float2 *__restrict__ pair, float bias, int act,
                    float alpha, const uint8_t *__restrict__ keep, float *__restrict__ score,
                    const double *__restrict__ wts, int predict, double *__restrict__ util) {
@@ -153,10 +155,11 @@ last_scalar_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict
 #pragma unroll
     for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (row < n && sub == 0) {
-        float v = act_apply(pair[row].x - dinv[row] * acc + bias, act, alpha);
-        if (keep && !keep[row]) v = 0.f;
-        if (score) score[row] = v;
-        if (util) util[row] = (predict == DG_PREDICT_MWIS) ? (double)v * wts[row] : (double)v;
+        const int gr = row0 + row;
+        float v = act_apply(pair[gr].x - dinv[gr] * acc + bias, act, alpha);
+        if (keep && !keep[gr]) v = 0.f;
+        if (score) score[gr] = v;
+        if (util) util[gr] = (predict == DG_PREDICT_MWIS) ? (double)v * wts[gr] : (double)v;
     }
 }
 
@@ -181,6 +184,7 @@ __global__ void utility_kernel(int n, const float *__restrict__ score, int strid
 struct LayerArgs {
     int n;
     int nnz;
+    int row0;  // row-slice form: rows row0 .. row0+n-1 of a larger graph, per-vertex arrays global
     const int *row_ptr;
     const int *col_idx;
     const float *dinv;
@@ -261,12 +265,12 @@ gc_layer_kernel(const LayerArgs a) {
             float di = 0.f;
             if (i < a.n) {
                 const int beg = a.row_ptr[i], end = a.row_ptr[i + 1];
-                di = a.dinv[i];
+                di = a.dinv[a.row0 + i];
                 if (IMPLICIT_IN) {
-                    float2 p = a.pair_in[i];
+                    float2 p = a.pair_in[a.row0 + i];
                     hi = implicit_row(p.x, p.y);
                 } else {
-                    hi = __ldg(reinterpret_cast<const float4 *>(a.hin + (size_t)i * CPI) + q);
+                    hi = __ldg(reinterpret_cast<const float4 *>(a.hin + (size_t)(a.row0 + i) * CPI) + q);
                 }
                 for (int base = beg; base < end; base += 32) {
                     const int e = base + lane;
@@ -350,7 +354,7 @@ gc_layer_kernel(const LayerArgs a) {
                 if (i < a.n) {
 #pragma unroll
                     for (int cc = 0; cc < CO; ++cc)
-                        a.hout[(size_t)i * CPO + lane + 32 * cc] = act_apply(out[r][cc], a.act, a.alpha);
+                        a.hout[(size_t)(a.row0 + i) * CPO + lane + 32 * cc] = act_apply(out[r][cc], a.act, a.alpha);
                 }
             } else {
                 float t0 = 0.f, t1 = 0.f;
@@ -365,7 +369,7 @@ gc_layer_kernel(const LayerArgs a) {
                     t0 += __shfl_xor_sync(0xffffffffu, t0, off);
                     t1 += __shfl_xor_sync(0xffffffffu, t1, off);
                 }
-                if (lane == 0 && i < a.n) a.pair_out[i] = make_float2(t0 + t1, a.dinv[i] * t1);
+                if (lane == 0 && i < a.n) a.pair_out[a.row0 + i] = make_float2(t0 + t1, a.dinv[a.row0 + i] * t1);
             }
         }
     }
@@ -454,7 +458,126 @@ __global__ void finalize_kernel(int n, int d_out, int cp, const float *__restric
 
 inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
 
+// (q, zs) of a one-column last layer from dense rows: q_i = H_i.w_0 + z_i, zs_i = dinv_i z_i, z = H.w_1
+__global__ void __launch_bounds__(256)
+tail_project_kernel(int n, int row0, int cp, const float *__restrict__ hin, const float *__restrict__ w0,
+                    const float *__restrict__ w1, const float *__restrict__ dinv, float2 *__restrict__ pair_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *row = reinterpret_cast<const float4 *>(hin + (size_t)(row0 + i) * cp);
+    float t0 = 0.f, t1 = 0.f;
+    for (int c = 0; c < cp / 4; ++c) {
+        const float4 h = __ldg(row + c);
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(w0) + c);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(w1) + c);
+        t0 = fmaf(h.x, a.x, t0), t0 = fmaf(h.y, a.y, t0), t0 = fmaf(h.z, a.z, t0), t0 = fmaf(h.w, a.w, t0);
+        t1 = fmaf(h.x, b.x, t1), t1 = fmaf(h.y, b.y, t1), t1 = fmaf(h.z, b.z, t1), t1 = fmaf(h.w, b.w, t1);
+    }
+    pair_out[row0 + i] = make_float2(t0 + t1, dinv[row0 + i] * t1);
+}
+
 }  // namespace
+
+// =================================================================================================
+// row-slice drivers: one giant graph partitioned by rows over several GPUs.  Arrays are
+// global sized and indexed by global vertex id; each call writes rows row0 .. row0+n_local-1 only and
+// the caller all-gathers what the next call reads from other ranks' rows.
+// =================================================================================================
+int part_prepare(dg_context *ctx, const PartView &pv, const uint8_t *keep, const float *x0, float x0val, float *dinv,
+                 float *y) {
+    if (pv.n_local == 0) return DG_OK;
+    degree_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.row_ptr, pv.col_idx, keep,
+                                                                     dinv);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return part_scale(ctx, pv, keep, x0, x0val, dinv, y);
+}
+
+int part_scale(dg_context *ctx, const PartView &pv, const uint8_t *keep, const float *x0, float x0val,
+               const float *dinv, float *y) {
+    if (pv.n_local == 0) return DG_OK;
+    scaled_input_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(
+        pv.n_local, dinv + pv.row0, keep ? keep + pv.row0 : nullptr, x0 ? x0 + pv.row0 : nullptr, x0val, y + pv.row0);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int part_first(dg_context *ctx, const PartView &pv, const float *dinv, const float *y, const uint8_t *keep,
+               const float *x0, float x0val, float2 *pair) {
+    if (pv.n_local == 0) return DG_OK;
+    first_scalar_kernel<<<grid_for((size_t)pv.n_local * kLanesPerScalarRow, 256), 256, 0, ctx->stream>>>(
+        pv.n_local, pv.row_ptr, pv.col_idx, dinv + pv.row0, y, keep ? keep + pv.row0 : nullptr,
+        x0 ? x0 + pv.row0 : nullptr, x0val, pair + pv.row0);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int part_project(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair,
+                 float2 *pair2) {
+    if (pv.n_local == 0) return DG_OK;
+    const dg_layer_dev &first = m->layers[0];
+    node_project_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(
+        pv.n_local, first.c_out, pair + pv.row0, first.colsum0, first.colsum1, first.bias, first.act, m->alpha,
+        m->tail_w0, m->tail_w1, dinv + pv.row0, pair2 + pv.row0);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int part_layer(dg_context *ctx, const PartView &pv, const dg_model *m, int layer, const float *dinv,
+               const float2 *pair, const float *hin, float *hout) {
+    if (pv.n_local == 0) return DG_OK;
+    const dg_layer_dev &first = m->layers[0];
+    const dg_layer_dev &ly = m->layers[layer];
+    LayerArgs a{};
+    a.n = pv.n_local;
+    a.nnz = pv.nnz;
+    a.row0 = pv.row0;
+    a.row_ptr = pv.row_ptr;
+    a.col_idx = pv.col_idx;
+    a.dinv = dinv;
+    const bool implicit_in = layer == 1;
+    if (implicit_in) {
+        a.pair_in = pair;
+        a.in_a0 = first.colsum0;
+        a.in_a1 = first.colsum1;
+        a.in_b = first.bias;
+        a.in_act = first.act;
+    } else {
+        a.hin = hin;
+    }
+    a.wcat = ly.wcat;
+    a.bias = ly.bias;
+    a.act = ly.act;
+    a.alpha = m->alpha;
+    a.hout = hout;
+    return launch_layer(ctx, ly.cpi, ly.cpo, implicit_in, false, a);
+}
+
+int part_tail(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float *hin,
+              float2 *pair2) {
+    if (pv.n_local == 0) return DG_OK;
+    const int cp = m->layers[m->n_layers - 1].cpi;
+    tail_project_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(pv.n_local, pv.row0, cp, hin, m->tail_w0,
+                                                                           m->tail_w1, dinv, pair2);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair2,
+              const uint8_t *keep, const double *wts, int predict, float *score, double *util) {
+    if (pv.n_local == 0) return DG_OK;
+    const dg_layer_dev &last = m->layers[m->n_layers - 1];
+    last_scalar_kernel<<<grid_for((size_t)pv.n_local * kLanesPerScalarRow, 256), 256, 0, ctx->stream>>>(
+        pv.n_local, pv.row0, pv.row_ptr, pv.col_idx, dinv, pair2, m->tail_bias, last.act, m->alpha, keep, score, wts,
+        predict, util);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
 
 // =================================================================================================
 // drivers
@@ -462,7 +585,7 @@ inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block)
 int batch_compute_dinv(dg_batch *b) {
     dg_context *ctx = b->ctx;
     if (b->n_nodes == 0) return DG_OK;
-    degree_kernel<<<grid_for(b->n_nodes, 256), 256, 0, ctx->stream>>>(b->n_nodes, b->row_ptr, b->col_idx,
+    degree_kernel<<<grid_for(b->n_nodes, 256), 256, 0, ctx->stream>>>(b->n_nodes, 0, b->row_ptr, b->col_idx,
                                                                      b->keep, b->dinv);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
@@ -612,7 +735,7 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
                                                                   m->tail_w0, m->tail_w1, b->dinv, pair2);
             ctx->launches++;
         }
-        last_scalar_kernel<<<scalar_grid, 256, 0, st>>>(n, b->row_ptr, b->col_idx, b->dinv, pair2, m->tail_bias,
+        last_scalar_kernel<<<scalar_grid, 256, 0, st>>>(n, 0, b->row_ptr, b->col_idx, b->dinv, pair2, m->tail_bias,
                                                         last.act, m->alpha, b->keep, out, wts, predict, util);
         ctx->launches++;
         DG_CUDA_CHECK(cudaGetLastError());

@@ -293,6 +293,82 @@ lgs_remove_global(int n, int n_graphs, const int *__restrict__ graph_ptr, const 
     }
 }
 
+// ---- row-slice form (one giant graph partitioned by rows over several GPUs) ----------------------
+// The launch covers rows row0 .. row0+n_local-1 (row0 and n_local multiples of 32, so a warp still owns
+// one aligned bitmap word); row_ptr is the slice's local array, col_idx / util / bitmaps / member are
+// indexed by GLOBAL vertex id.  Between the kernels the caller all-gathers the bitmap words it wrote.
+__global__ void __launch_bounds__(256)
+lgs_part_init(int n_local, int row0, int n_global, const uint8_t *__restrict__ keep, uint32_t *__restrict__ remain,
+              uint8_t *__restrict__ member, long long *__restrict__ cnt) {
+    const int vl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = row0 + vl;
+    const int lane = threadIdx.x & 31;
+    bool alive = false;
+    if (vl < n_local && v < n_global) {
+        alive = keep ? keep[v] != 0 : true;
+        member[v] = 0;
+    }
+    const uint32_t w = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0 && vl < n_local) remain[v >> 5] = w;
+    if (alive && lane == (__ffs(w) - 1)) atomicAdd((unsigned long long *)cnt, (unsigned long long)__popc(w));
+}
+
+__global__ void __launch_bounds__(256)
+lgs_part_decide(int n_local, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                const double *__restrict__ util, const uint32_t *__restrict__ remain,
+                uint32_t *__restrict__ joined, uint8_t *__restrict__ member) {
+    const int vl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = row0 + vl;
+    const int lane = threadIdx.x & 31;
+    const bool active = vl < n_local ? (remain[v >> 5] >> lane) & 1u : false;
+    bool join = false;
+    if (active) {
+        const double wv = util[v];
+        const int beg = row_ptr[vl], end = row_ptr[vl + 1];
+        join = true;
+        for (int e = beg; e < end; ++e) {
+            const int u = col_idx[e];
+            if ((__ldg(remain + (u >> 5)) >> (u & 31)) & 1u) {
+                if (dominates(util[u], u, wv, v)) {
+                    join = false;
+                    break;
+                }
+            }
+        }
+        if (join) member[v] = 1;
+    }
+    const uint32_t jw = __ballot_sync(0xffffffffu, join);
+    if (lane == 0 && vl < n_local) joined[v >> 5] = jw;
+}
+
+__global__ void __launch_bounds__(256)
+lgs_part_remove(int n_local, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                const uint32_t *__restrict__ joined, uint32_t *__restrict__ remain, long long *__restrict__ cnt) {
+    const int vl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = row0 + vl;
+    const int lane = threadIdx.x & 31;
+    bool still = false;
+    if (vl < n_local) {
+        const bool active = (remain[v >> 5] >> lane) & 1u;
+        const bool join = (joined[v >> 5] >> lane) & 1u;
+        if (active && !join) {
+            const int beg = row_ptr[vl], end = row_ptr[vl + 1];
+            still = true;
+            for (int e = beg; e < end; ++e) {
+                const int u = col_idx[e];
+                if ((__ldg(joined + (u >> 5)) >> (u & 31)) & 1u) {
+                    still = false;
+                    break;
+                }
+            }
+        }
+    }
+    const uint32_t rw = __ballot_sync(0xffffffffu, still);
+    __syncwarp();
+    if (lane == 0 && vl < n_local) remain[v >> 5] = rw;
+    if (still && lane == (__ffs(rw) - 1)) atomicAdd((unsigned long long *)cnt, (unsigned long long)__popc(rw));
+}
+
 __global__ void __launch_bounds__(256)
 member_weight_kernel(const int *__restrict__ graph_ptr, const uint8_t *__restrict__ member,
                      const double *__restrict__ wts, double *__restrict__ total) {
@@ -382,6 +458,35 @@ int lgs_device(dg_context *ctx, const dg_batch *b, const double *util, int nstep
         DG_CUDA_CHECK(cudaGetLastError());
         ++rounds;
     }
+    return DG_OK;
+}
+
+int part_lgs_init(dg_context *ctx, const PartView &pv, const uint8_t *keep, uint32_t *remain, uint8_t *member,
+                  long long *cnt) {
+    if (pv.n_local == 0) return DG_OK;
+    lgs_part_init<<<(pv.n_local + 255) / 256, 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.n_global, keep, remain,
+                                                                    member, cnt);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int part_lgs_decide(dg_context *ctx, const PartView &pv, const double *util, const uint32_t *remain, uint32_t *joined,
+                    uint8_t *member) {
+    if (pv.n_local == 0) return DG_OK;
+    lgs_part_decide<<<(pv.n_local + 255) / 256, 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.row_ptr, pv.col_idx,
+                                                                      util, remain, joined, member);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int part_lgs_remove(dg_context *ctx, const PartView &pv, const uint32_t *joined, uint32_t *remain, long long *cnt) {
+    if (pv.n_local == 0) return DG_OK;
+    lgs_part_remove<<<(pv.n_local + 255) / 256, 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.row_ptr, pv.col_idx,
+                                                                      joined, remain, cnt);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
 }
 

@@ -75,3 +75,186 @@ class ShardedSolver:
             full_member[v0:v1] = m
             full_total[g0:g1] = t
         return full_member, full_total
+
+
+# ======================================================================================================
+# One giant graph, row-partitioned (BASELINE config 5)
+# ======================================================================================================
+def row_slices(n_global: int, world_size: int) -> Tuple[int, int]:
+    """(slice rows, padded global size): equal slices, multiples of 32 so bitmap words never straddle ranks."""
+    per = -(-n_global // world_size)
+    per = (per + 31) // 32 * 32
+    return per, per * world_size
+
+
+def slice_csr(indptr: np.ndarray, indices: np.ndarray, n_global: int, rank: int, world_size: int):
+    """Local CSR (row_ptr starting at 0, GLOBAL column ids) of `rank`'s slice of a global CSR; rows past
+    n_global are empty."""
+    per, _ = row_slices(n_global, world_size)
+    r0 = rank * per
+    r1 = min(n_global, r0 + per)
+    rp = np.zeros(per + 1, dtype=np.int64)
+    if r1 > r0:
+        seg = indptr[r0:r1 + 1].astype(np.int64)
+        rp[: r1 - r0 + 1] = seg - seg[0]
+        rp[r1 - r0 + 1:] = rp[r1 - r0]
+        ci = indices[int(seg[0]):int(seg[-1])]
+    else:
+        ci = indices[:0]
+    return rp.astype(np.int32), np.ascontiguousarray(ci, dtype=np.int32)
+
+
+class RowPartitionedSolver:
+    """GCN-scored local greedy MWIS of ONE graph whose rows are spread over `world_size` GPUs.
+
+    Every rank holds rows [rank*per, (rank+1)*per) as a local CSR with global column ids and global-sized
+    per-vertex arrays; each kernel writes the rank's rows and the rows are all-gathered (NCCL over NVLink)
+    before the next kernel reads neighbours.  What crosses the links per solve: keep bytes, y (fp32), for each
+    hidden layer the feature rows it reads, (q, zs) pairs, utilities (fp64), and per greedy round two bitmaps
+    of n/8 bytes plus one 8-byte count.  A model without hidden layers (c64 l2, config 5) exchanges scalars
+    only - the rank-1 first layer and project-first last layer of DESIGN.md section 2.
+    """
+
+    def __init__(self, model, n_global: int, row_ptr_local: np.ndarray, col_idx_global: np.ndarray, rank: int = 0,
+                 world_size: int = 1, group=None, device: Optional[int] = None):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib, engine
+        self.torch, self.C, self.check = torch, C, _lib.check
+        self.rank, self.world, self.group = int(rank), int(world_size), group
+        self.n_global = int(n_global)
+        self.per, self.n_pad = row_slices(self.n_global, self.world)
+        self.row0 = self.rank * self.per
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        # One dedicated (non-default) stream for everything: the library enqueues its kernels on it and the
+        # torch ops / NCCL collectives of solve() run under torch.cuda.stream(self.stream), so kernels and
+        # all-gathers are ordered without host synchronisation.  (torch's default stream has handle 0,
+        # which dg_context_create would take as "make a private stream".)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.ctx = engine.Context(self.device.index, stream=self.stream.cuda_stream)
+        self.lib = self.ctx._lib
+        self.model = engine.Model(self.ctx, model.layers_as_weights() if hasattr(model, "layers_as_weights") else model[0],
+                                  [l.act_code for l in model.layers] if hasattr(model, "layers") else model[1])
+        if self.model.n_layers < 2 or self.model.out_width != 1:
+            raise NotImplementedError("row-partitioned path: >= 2 layers and one output column")
+        rp = np.ascontiguousarray(row_ptr_local, dtype=np.int32)
+        ci = np.ascontiguousarray(col_idx_global, dtype=np.int32)
+        if rp.shape[0] != self.per + 1:
+            raise ValueError("row_ptr_local must have %d entries" % (self.per + 1))
+        with torch.cuda.stream(self.stream):
+            self.d_rp = torch.from_numpy(rp).to(self.device)
+            self.d_ci = torch.from_numpy(ci).to(self.device)
+        self.stream.synchronize()
+        h = C.c_void_p()
+        self.check(self.lib.dg_part_create(self.ctx.handle, self.n_pad, self.row0, self.per, int(ci.shape[0]),
+                                           C.c_void_p(self.d_rp.data_ptr()), C.c_void_p(self.d_ci.data_ptr()),
+                                           _lib.MEM_DEVICE, C.byref(h)))
+        self.part = h
+        self.exchanged_bytes = 0
+
+    def _p(self, t):
+        return None if t is None else self.C.c_void_p(t.data_ptr())
+
+    def _gather(self, full, elems_per_row=1):
+        """Make this rank's rows of `full` (viewed as [n_pad * elems_per_row]) visible everywhere."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        flat = full.view(-1)
+        chunk = self.per * elems_per_row
+        mine = flat[self.rank * chunk:(self.rank + 1) * chunk].clone()
+        dist.all_gather_into_tensor(flat, mine, group=self.group)
+        self.exchanged_bytes += (self.world - 1) * chunk * full.element_size()
+
+    def solve(self, wts_local: np.ndarray, predict="mwis", remove_zero_weight=True):
+        """wts_local: this rank's `per` weights (rows past n_global ignored).  Returns (member_local uint8
+        [per], score_local float32 [per], rounds)."""
+        with self.torch.cuda.stream(self.stream):
+            return self._solve(wts_local, predict, remove_zero_weight)
+
+    def _solve(self, wts_local, predict, remove_zero_weight):
+        torch, lib, part, m = self.torch, self.lib, self.part, self.model
+        from . import engine
+        dev, n_pad, per, r0 = self.device, self.n_pad, self.per, self.row0
+        w_local = np.zeros(per, dtype=np.float64)
+        w_in = np.asarray(wts_local, dtype=np.float64).reshape(-1)
+        w_local[: w_in.shape[0]] = w_in
+        valid = np.arange(r0, r0 + per) < self.n_global
+        keep_local = valid & ((w_local != 0) if remove_zero_weight else True)
+        wts = torch.zeros(n_pad, dtype=torch.float64, device=dev)
+        wts[r0:r0 + per] = torch.from_numpy(w_local).to(dev)
+        keep = torch.zeros(n_pad, dtype=torch.uint8, device=dev)
+        keep[r0:r0 + per] = torch.from_numpy(keep_local.astype(np.uint8)).to(dev)
+        self._gather(keep)
+        F = m.feature_size
+        dinv = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        y = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        pair = torch.zeros(n_pad, 2, dtype=torch.float32, device=dev)
+        pair2 = torch.zeros(n_pad, 2, dtype=torch.float32, device=dev)
+        self.check(lib.dg_part_prepare(part, F, self._p(keep), None, self._p(dinv), self._p(y)))
+        self._gather(y)
+        self.check(lib.dg_part_first(part, F, self._p(dinv), self._p(y), self._p(keep), None, self._p(pair)))
+        L = m.n_layers
+        if L == 2:
+            self.check(lib.dg_part_project(part, m.handle, self._p(dinv), self._p(pair), self._p(pair2)))
+        else:
+            self._gather(dinv)
+            self._gather(pair, 2)
+            hin = None
+            for layer in range(1, L - 1):
+                cp = int(lib.dg_model_padded_width(m.handle, layer))
+                hout = torch.zeros(n_pad, cp, dtype=torch.float32, device=dev)
+                self.check(lib.dg_part_layer(part, m.handle, layer, self._p(dinv), self._p(pair), self._p(hin),
+                                             self._p(hout)))
+                if layer < L - 2:
+                    self._gather(hout, cp)  # the next hidden layer reads neighbours' rows
+                hin = hout
+            self.check(lib.dg_part_tail(part, m.handle, self._p(dinv), self._p(hin), self._p(pair2)))
+        self._gather(pair2, 2)
+        score = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        util = torch.zeros(n_pad, dtype=torch.float64, device=dev)
+        self.check(lib.dg_part_last(part, m.handle, self._p(dinv), self._p(pair2), self._p(keep), self._p(wts),
+                                    engine.predict_code(predict), self._p(score), self._p(util)))
+        self._gather(util)
+        # greedy rounds
+        words = n_pad // 32
+        remain = torch.zeros(words, dtype=torch.int32, device=dev)
+        joined = torch.zeros(words, dtype=torch.int32, device=dev)
+        member = torch.zeros(n_pad, dtype=torch.uint8, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.check(lib.dg_part_lgs_init(part, self._p(keep), self._p(remain), self._p(member), self._p(count)))
+        rounds = 0
+        while True:
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(count, group=self.group)
+            if int(count.item()) == 0:
+                break
+            if rounds >= (1 << 20):
+                raise RuntimeError("local greedy search did not converge (NaN utilities or self-loops?)")
+            self._gather_words(remain)
+            self.check(lib.dg_part_lgs_decide(part, self._p(util), self._p(remain), self._p(joined), self._p(member)))
+            self._gather_words(joined)
+            count.zero_()
+            self.check(lib.dg_part_lgs_remove(part, self._p(joined), self._p(remain), self._p(count)))
+            rounds += 1
+        self.stream.synchronize()
+        return (member[r0:r0 + per].cpu().numpy(), score[r0:r0 + per].cpu().numpy(), rounds)
+
+    def _gather_words(self, words):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        chunk = self.per // 32
+        mine = words[self.rank * chunk:(self.rank + 1) * chunk].clone()
+        dist.all_gather_into_tensor(words, mine, group=self.group)
+        self.exchanged_bytes += (self.world - 1) * chunk * 4
+
+    def close(self):
+        if self.part is not None:
+            self.lib.dg_part_destroy(self.part)
+            self.part = None
+        self.model.close()
+        self.ctx.close()

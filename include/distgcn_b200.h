@@ -69,6 +69,7 @@ extern "C" {
 typedef struct dg_context dg_context;
 typedef struct dg_model dg_model;
 typedef struct dg_batch dg_batch;
+typedef struct dg_part dg_part;
 
 /* ---- library ------------------------------------------------------------------------------- */
 DG_API int dg_version(void);
@@ -178,6 +179,45 @@ DG_API int dg_solve_host(dg_context *ctx, const dg_model *model, int32_t n_graph
                   const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
                   const double *wts, int predict, int remove_zero_weight, uint8_t *member,
                   double *total);
+
+/* ---- one giant graph, row-partitioned over several GPUs (no reference counterpart: the
+ * reference handles one 100-300 vertex graph per call) ------------------------------------------------
+ * A dg_part is one rank's slice: rows row0 .. row0+n_local-1 of a graph with n_global vertices (row0 and
+ * n_local multiples of 32), as a local CSR (row_ptr starts at 0) whose column ids are GLOBAL.  Every array
+ * argument below is a DEVICE pointer to a GLOBAL-sized array indexed by global vertex id (float2 arrays as
+ * 2*n_global floats, bitmaps as n_global/32 words).  A call may read any vertex's entry and writes only
+ * this part's rows; between calls the caller makes the written rows visible to the other ranks
+ * (all-gather over NVLink, e.g. torch.distributed / NCCL - see distgcn_b200/shard.py).  The sequence for a
+ * model without hidden layers (e.g. c64 l2) exchanges only scalars: y, (q,zs), utilities, bitmap words. */
+DG_API int dg_part_create(dg_context *ctx, int32_t n_global, int32_t row0, int32_t n_local, int32_t nnz_local,
+                          const int32_t *row_ptr_local, const int32_t *col_idx_global, int mem, dg_part **out);
+DG_API void dg_part_destroy(dg_part *part);
+/* dinv rows (degrees over kept neighbours; keep must be complete) and y = dinv * x0 rows */
+DG_API int dg_part_prepare(dg_part *part, int32_t feature_size, const uint8_t *keep, const float *x0, float *dinv,
+                           float *y);
+/* first layer, rank-1: pair rows = (x0, s = (L x0)); reads y of the neighbours */
+DG_API int dg_part_first(dg_part *part, int32_t feature_size, const float *dinv, const float *y, const uint8_t *keep,
+                         const float *x0, float *pair);
+/* two-layer models: pair2 rows = (q, zs) of the one-column last layer, from this part's pair rows */
+DG_API int dg_part_project(dg_part *part, const dg_model *model, const float *dinv, const float *pair, float *pair2);
+/* hidden layer `layer` (1 .. n_layers-2): hout rows [n_global, padded width]; reads neighbours' pair (layer 1)
+ * or hin rows (later layers) and dinv */
+DG_API int dg_part_layer(dg_part *part, const dg_model *model, int32_t layer, const float *dinv, const float *pair,
+                         const float *hin, float *hout);
+/* models with hidden layers: pair2 rows = (q, zs) from this part's rows of the last hidden layer's output */
+DG_API int dg_part_tail(dg_part *part, const dg_model *model, const float *dinv, const float *hin, float *pair2);
+/* last layer + utility: score / util rows; reads neighbours' pair2 */
+DG_API int dg_part_last(dg_part *part, const dg_model *model, const float *dinv, const float *pair2,
+                        const uint8_t *keep, const double *wts, int predict, float *score, double *util);
+/* padded width of the features hidden layer `layer` writes (32 or 64) */
+DG_API int dg_model_padded_width(const dg_model *model, int32_t layer);
+/* greedy rounds: init writes this part's remain words and member rows and adds its remaining count to
+ * *count; decide reads all remain words / utilities and writes this part's joined words and member rows;
+ * remove reads all joined words, rewrites this part's remain words and adds its remaining count */
+DG_API int dg_part_lgs_init(dg_part *part, const uint8_t *keep, uint32_t *remain, uint8_t *member, int64_t *count);
+DG_API int dg_part_lgs_decide(dg_part *part, const double *util, const uint32_t *remain, uint32_t *joined,
+                              uint8_t *member);
+DG_API int dg_part_lgs_remove(dg_part *part, const uint32_t *joined, uint32_t *remain, int64_t *count);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,69 @@
+"""torchrun --nproc-per-node 2 tests/run_partition_2gpu.py : row-partitioned solve on 2 GPUs (NCCL) against
+the CPU oracle for a 2-layer model and against the single-GPU result for a deep one."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import util  # noqa: E402
+from tests.test_gpu_partition import _big_graph, _ModelSpec  # noqa: E402
+from distgcn_b200 import engine as E  # noqa: E402
+from distgcn_b200.batch import pack_graphs  # noqa: E402
+from distgcn_b200.shard import RowPartitionedSolver, row_slices, slice_csr  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    rng = np.random.default_rng(11)
+    n = int(os.environ.get("DG_PART_N", "200003"))
+    a = _big_graph(rng, n, 16)
+    w = rng.random(n)
+    w[rng.random(n) < 0.05] = 0.0
+    ok = True
+    for short in ("is4sat_l2_c64", "is4sat_l3_c16"):
+        layers = util.load_layers(short)
+        acts = E.gcn_dqn_acts(len(layers))
+        per, n_pad = row_slices(n, world)
+        rp, ci = slice_csr(a.indptr, a.indices, n, rank, world)
+        solver = RowPartitionedSolver(_ModelSpec(layers, acts), n, rp, ci, rank=rank, world_size=world)
+        w_local = w[rank * per:min(n, (rank + 1) * per)]
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        member, score, rounds = solver.solve(w_local)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (member, score))
+        if rank == 0:
+            full_m = np.concatenate([g[0] for g in gathered])[:n]
+            full_s = np.concatenate([g[1] for g in gathered])[:n]
+            ctx = E.Context(torch.cuda.current_device())
+            model = E.Model(ctx, layers, acts)
+            batch = E.DeviceBatch(ctx, pack_graphs([a]))
+            ref = E.solve(ctx, model, batch, w, want_score=True)
+            same = bool(np.array_equal(full_m, ref.member))
+            err = float(np.abs(full_s - ref.score[:, 0]).max() / max(np.abs(ref.score).max(), 1e-30))
+            print("PART %s n=%d world=%d rounds=%d ms=%.2f exchanged_MB=%.1f membership_equal=%s score_err=%.2e"
+                  % (short, n, world, rounds, ms, solver.exchanged_bytes / 1e6, same, err))
+            ok = ok and same and err < 2e-6
+            batch.close(); model.close(); ctx.close()
+        solver.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("PARTITION_2GPU_OK" if ok else "PARTITION_2GPU_FAILED")
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

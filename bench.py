@@ -330,15 +330,45 @@ def run_ours(args):
     barrier()
 
     # ---- e2e: public host API, pinned host buffers, copies inside the timed region ---------------
+    # (a) one call at a time (dg_solve_host): copy in, solve, copy out, return
     for i in range(max(3, args.warmup // 2)):
         host_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         host_step(i)
+    e2e_sync_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    # (b) the streaming form of the same API (engine.HostPipeline over dg_solve_host_async): every step still
+    # copies its own CSR + weights from pinned host memory and its membership + totals back, but two contexts
+    # take turns so that one batch's copies overlap the other's kernels.  This is the headline e2e number.
+    pipe = E.HostPipeline(local_rank, layers, E.gcn_dqn_acts(len(layers)), depth=2)
+
+    def pipe_step(i):
+        c = copies[i % R]
+        pipe.submit(c["h_pb"], c["h_w"], c["h_member"], c["h_total"], predict="mwis", remove_zero_weight=True)
+
+    for i in range(max(4, args.warmup // 2)):
+        pipe_step(i)
+    pipe.wait()
+    barrier()
+    pipe_launches0 = pipe.launch_count
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        pipe_step(i)
+    pipe.wait()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    pipe_launches = pipe.launch_count - pipe_launches0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    # the pipelined results equal the resident-path results for the last R steps (not timed)
+    pipe_same = True
+    for r in range(min(R, args.steps)):
+        device_step(r)
+        ctx.synchronize()
+        pipe_same = pipe_same and bool(np.array_equal(copies[r]["d_member"].cpu().numpy(),
+                                                      np.asarray(copies[r]["h_member"])))
+    pipe.close()
 
     # sanity: both paths produce the same membership for copy 0 (not timed)
     device_step(0)
@@ -347,9 +377,9 @@ def run_ours(args):
     same = bool(np.array_equal(copies[0]["d_member"].cpu().numpy(), np.asarray(copies[0]["h_member"])))
 
     if use_dist:
-        t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda:%d" % local_rank)
+        t = torch.tensor([dev_ms, e2e_ms, wall_ms, e2e_sync_ms], dtype=torch.float64, device="cuda:%d" % local_rank)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
+        dev_ms, e2e_ms, wall_ms, e2e_sync_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -370,9 +400,14 @@ def run_ours(args):
                        "nnz_per_step": int(c0.nnz), "parallelism": "graph-batch sharding, no collectives",
                        "l2_policy": "inputs larger than L2: %d rotating resident input sets, %.0f MB in total"
                                     % (R, input_bytes / 1e6),
-                       "paths_agree": same},
+                       "paths_agree": bool(same and pipe_same)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "engine.HostPipeline.submit (dg_solve_host_async, 2 contexts in turn): pinned host CSR + "
+                           "weights in, membership + totals out, every step; wall clock over the K steps",
+                    "gpu_launches": int(pipe_launches),
+                    "one_call_at_a_time": {"value": world * n_graphs * args.steps / (e2e_sync_ms / 1e3),
+                                           "ms_per_step": e2e_sync_ms / args.steps, "api": "dg_solve_host"}},
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm",

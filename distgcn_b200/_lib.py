@@ -75,6 +75,7 @@ SIGNATURES = {
     "dg_part_lgs_decide": (C.c_int, [_p, _p, _p, _p, _p]),
     "dg_part_lgs_remove": (C.c_int, [_p, _p, _p, _p]),
     "dg_solve_host": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
+    "dg_solve_host_async": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
 }
 
 _lib = None

@@ -869,9 +869,10 @@ int dg_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *wts,
     return finish(ctx);
 }
 
-int dg_solve_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
-                  const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
-                  int predict, int remove_zero_weight, uint8_t *member, double *total) {
+static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                           const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
+                           const double *wts, int predict, int remove_zero_weight, uint8_t *member, double *total,
+                           bool wait) {
     clear_error();
     DG_TRY(check_ctx(ctx));
     DG_REQUIRE(m && wts && member, DG_ERR_INVALID, "null argument");
@@ -903,7 +904,21 @@ int dg_solve_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t 
     DG_TRY(solve_device(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, nullptr, nullptr, d_total, nullptr));
     DG_TRY(copy_out(ctx, member, d_member, n));
     DG_TRY(copy_out(ctx, total, d_total, G));
-    return finish(ctx);
+    return wait ? finish(ctx) : DG_OK;
+}
+
+int dg_solve_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                  const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
+                  int predict, int remove_zero_weight, uint8_t *member, double *total) {
+    return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, wts, predict,
+                           remove_zero_weight, member, total, true);
+}
+
+int dg_solve_host_async(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                        const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
+                        int predict, int remove_zero_weight, uint8_t *member, double *total) {
+    return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, wts, predict,
+                           remove_zero_weight, member, total, false);
 }
 
 // -------------------------------------------------------------------------------------------------

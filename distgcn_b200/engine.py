@@ -358,8 +358,10 @@ def solve_device(ctx: Context, model: Model, batch: DeviceBatch, wts, member, pr
 
 
 def solve_host(ctx: Context, model: Model, packed: PackedBatch, wts, predict="mwis", remove_zero_weight: bool = True,
-               member: Optional[np.ndarray] = None, total: Optional[np.ndarray] = None):
-    """One-shot host CSR in / host membership out (dg_solve_host): H2D, kernels and D2H in one call."""
+               member: Optional[np.ndarray] = None, total: Optional[np.ndarray] = None, wait: bool = True):
+    """One-shot host CSR in / host membership out (dg_solve_host): H2D, kernels and D2H in one call.
+    ``wait=False`` only enqueues (dg_solve_host_async): the arrays must stay alive (and should be pinned,
+    see ``pinned_empty``) until ``ctx.synchronize()``."""
     gp, rp, ci = packed.graph_ptr, packed.row_ptr, packed.col_idx
     for a in (gp, rp, ci):
         if a.dtype != np.int32 or not a.flags.c_contiguous:
@@ -370,9 +372,57 @@ def solve_host(ctx: Context, model: Model, packed: PackedBatch, wts, predict="mw
         member = np.empty(n, dtype=np.uint8)
     if total is None:
         total = np.empty(g, dtype=np.float64)
-    check(ctx._lib.dg_solve_host(ctx.handle, model.handle, g, n, packed.nnz, _ptr(gp), _ptr(rp), _ptr(ci), _ptr(w),
-                                 predict_code(predict), 1 if remove_zero_weight else 0, _ptr(member), _ptr(total)))
+    fn = ctx._lib.dg_solve_host if wait else ctx._lib.dg_solve_host_async
+    check(fn(ctx.handle, model.handle, g, n, packed.nnz, _ptr(gp), _ptr(rp), _ptr(ci), _ptr(w),
+             predict_code(predict), 1 if remove_zero_weight else 0, _ptr(member), _ptr(total)))
     return member, total
+
+
+class HostPipeline:
+    """Streams of host batches through ``depth`` contexts used in turn (the ingest side
+    becomes the bottleneck once the kernels are fast): while one context's kernels run, the next batch's CSR
+    is already crossing PCIe on the other context's stream and the finished membership is on its way back.
+    ``submit`` returns the slot it used; results of a slot are valid after ``wait(slot)`` (``submit`` waits for
+    the slot's previous batch itself).  Every array passed to ``submit`` must stay alive until then and should
+    come from ``pinned_empty``."""
+
+    def __init__(self, device: int, layers: Sequence, acts: Sequence[int], depth: int = 2, alpha: float = LEAKY_ALPHA,
+                 head: int = HEAD_LINEAR):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.ctxs = [Context(device) for _ in range(depth)]
+        self.models = [Model(c, layers, acts, alpha, head) for c in self.ctxs]
+        self._busy = [None] * depth
+        self._next = 0
+
+    @property
+    def launch_count(self) -> int:
+        return sum(c.launch_count for c in self.ctxs)
+
+    def submit(self, packed: PackedBatch, wts, member: np.ndarray, total: Optional[np.ndarray] = None,
+               predict="mwis", remove_zero_weight: bool = True) -> int:
+        slot = self._next
+        self._next = (slot + 1) % len(self.ctxs)
+        self.wait(slot)
+        solve_host(self.ctxs[slot], self.models[slot], packed, wts, predict, remove_zero_weight, member, total,
+                   wait=False)
+        self._busy[slot] = (packed, wts, member, total)  # keep the arrays alive
+        return slot
+
+    def wait(self, slot: Optional[int] = None) -> None:
+        for s in (range(len(self.ctxs)) if slot is None else (slot,)):
+            if self._busy[s] is not None:
+                self._busy[s] = None
+                self.ctxs[s].synchronize()
+
+    def close(self) -> None:
+        try:
+            self.wait()
+        finally:
+            for m in self.models:
+                m.close()
+            for c in self.ctxs:
+                c.close()
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:

@@ -179,6 +179,15 @@ DG_API int dg_solve_host(dg_context *ctx, const dg_model *model, int32_t n_graph
                   const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
                   const double *wts, int predict, int remove_zero_weight, uint8_t *member,
                   double *total);
+/* Enqueue-only form of dg_solve_host for streams of batches: the H2D copies, the kernels and the D2H copies are
+ * queued on the context's stream and the call returns without waiting; dg_context_synchronize (which also reports a
+ * DG_ERR_NOT_CONVERGED raised by the kernels) completes it.  The caller's arrays must stay valid until then and
+ * should be pinned (dg_host_alloc) - pageable memory makes the copies synchronous.  Two contexts used alternately
+ * overlap one batch's copies with the other's kernels (distgcn_b200.engine.HostPipeline; bench.py's e2e number). */
+DG_API int dg_solve_host_async(dg_context *ctx, const dg_model *model, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                        const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
+                        const double *wts, int predict, int remove_zero_weight, uint8_t *member,
+                        double *total);
 
 /* ---- one giant graph, row-partitioned over several GPUs (no reference counterpart: the
  * reference handles one 100-300 vertex graph per call) ------------------------------------------------

@@ -147,3 +147,33 @@ def test_greedy_search_reproduces_stored_greedy_utility(fam):
     v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
     mwis, total = H.greedy_search(pb.graph_adj(g), w[v0:v1])
     assert abs(total - z["greedy_utility"][g]) < 1e-12
+
+
+def test_host_pipeline_matches_one_call_at_a_time():
+    """engine.HostPipeline (dg_solve_host_async on two contexts in turn) returns what dg_solve_host returns."""
+    from distgcn_b200 import engine as E
+    gold = util.load_npz("gcn_oracle_small.npz")
+    pb, w = util.small_graphs()
+    layers = util.load_layers("is4sat_l20_c32")
+    pipe = E.HostPipeline(0, layers, E.gcn_dqn_acts(len(layers)), depth=2)
+    subs = []
+    for k, (g0, g1) in enumerate([(0, 50), (0, 17), (17, 50), (5, 6), (30, 50)]):
+        sub = pb.slice(g0, g1)
+        v0, v1 = int(pb.graph_ptr[g0]), int(pb.graph_ptr[g1])
+        h = {n: E.pinned_empty(a.shape, a.dtype) for n, a in
+             (("gp", sub.graph_ptr), ("rp", sub.row_ptr), ("ci", sub.col_idx), ("w", w[v0:v1]))}
+        h["gp"][:], h["rp"][:], h["ci"][:], h["w"][:] = sub.graph_ptr, sub.row_ptr, sub.col_idx, w[v0:v1]
+        member = E.pinned_empty(sub.n_nodes, np.uint8)
+        total = E.pinned_empty(sub.n_graphs, np.float64)
+        from distgcn_b200.batch import PackedBatch
+        pipe.submit(PackedBatch(h["gp"], h["rp"], h["ci"]), h["w"], member, total)
+        subs.append((v0, v1, g0, g1, member, total))
+    pipe.wait()
+    ref_member = gold["is4sat_l20_c32_member"]
+    for v0, v1, g0, g1, member, total in subs:
+        assert np.array_equal(np.asarray(member), ref_member[v0:v1])
+        for g in range(g0, g1):
+            a, b = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+            assert abs(total[g - g0] - w[a:b][ref_member[a:b] != 0].sum()) < 1e-9
+    assert pipe.launch_count >= len(subs)
+    pipe.close()

@@ -1,0 +1,84 @@
+"""Multi-channel wireless scheduling (BASELINE configs[2]): graph construction on the CPU, the batched slot
+loop on the GPU against the per-instance CPU restatement of wireless_dqn_test_mc.py:225-366."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import util
+
+
+def test_multichannel_conflict_graph_structure():
+    from distgcn_b200 import wireless as W
+    rng = np.random.default_rng(3)
+    links, adj_i, xys = W.poisson_link_conflict_graph(rng)
+    nf = adj_i.shape[0]
+    assert nf > 10 and links.shape == (nf, 2)
+    assert (adj_i != adj_i.T).nnz == 0 and adj_i.diagonal().sum() == 0
+    # links are node pairs within r_c; links sharing a node conflict
+    d = np.linalg.norm(xys[links[:, 0]] - xys[links[:, 1]], axis=1)
+    assert (d <= W.SIM_RC).all()
+    a = adj_i.toarray()
+    for i in range(nf):
+        for j in range(i + 1, nf):
+            if set(links[i]) & set(links[j]):
+                assert a[i, j] == 1
+    K = 3
+    adj_list = W.multichannel_conflict_simulate(adj_i, K, 0.8, rng)
+    kept = [m.nnz / max(adj_i.nnz, 1) for m in adj_list]
+    assert all(0.6 < k < 0.95 for k in kept)
+    for m in adj_list:
+        assert (m != m.T).nnz == 0 and (m.multiply(adj_i) != m).nnz == 0   # a sub-graph of the base conflict graph
+    gK = W.multichannel_conflict_graph(adj_list).toarray()
+    assert gK.shape == (K * nf, K * nf) and (gK == gK.T).all() and np.trace(gK) == 0
+    for k1 in range(K):
+        for k2 in range(K):
+            blk = gK[k1 * nf:(k1 + 1) * nf, k2 * nf:(k2 + 1) * nf]
+            if k1 == k2:
+                assert (blk == adj_list[k1].toarray()).all()       # wireless_rollout_test_flood.py:124-130
+            else:
+                assert (blk == np.eye(nf)).all()                    # single-radio clique, :114-122
+
+
+def test_traffic_follows_the_reference_draw_order():
+    from distgcn_b200 import wireless as W
+    arr, rates = W.traffic(treeseed=4, load=0.3, nflows=7, n_ch=3, timeslots=50)
+    assert arr.shape == (50, 7) and rates.shape == (50, 7, 3)
+    assert rates.min() >= 0 and rates.max() <= 100 and rates.dtype.kind == "i"
+    assert (arr >= 0).all() and (arr == np.round(arr)).all()
+    # same numbers as drawing from the legacy global generator, as the reference does (:178-204)
+    np.random.seed(4)
+    ia = np.random.exponential(1.0 / 15.0, (7, int(2 * 50 * 15.0)))
+    at = np.cumsum(ia, axis=1)
+    acc = np.stack([np.count_nonzero(at < t, axis=1) for t in range(50)], axis=1)
+    assert np.array_equal(arr, np.diff(acc, prepend=0).T)
+    lr = np.random.normal(50.0, 25.0, size=[50, 7, 3]).astype(int)
+    assert np.array_equal(rates, np.clip(lr, 0, 100))
+    assert abs(arr[1:].mean() - 15.0) < 2.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", ["Greedy", "DGCN-LGS", "LGS-Seq", "DGCN-LGS-Seq"])
+@pytest.mark.parametrize("ck", ["is4sat_l1", "is4sat_l20_c32"])
+def test_batched_slot_loop_matches_per_instance_restatement(algo, ck):
+    from distgcn_b200 import engine as E
+    from distgcn_b200 import wireless as W
+    from oracle import wireless_oracle as WO
+    if algo in ("Greedy", "LGS-Seq") and ck != "is4sat_l1":
+        pytest.skip("no model involved")
+    n_slots = 14
+    insts = W.make_instances(n_networks=3, loads=[0.2, 0.9], n_ch=3, timeslots=n_slots + 1, seed=11, n_nodes=60,
+                             area=150.0)
+    layers = util.load_layers(ck)
+    ctx = E.Context(0)
+    model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
+    sim = W.BatchedScheduler(ctx, insts, algo, model)
+    qs = sim.run()
+    assert qs.shape == (n_slots, sim.n_links) and sim.solver_calls == n_slots * (3 if sim.seq else 1)
+    for k, inst in enumerate(insts):
+        q_ref, _ = WO.run_instance(inst.adj_list, inst.adj_gK, inst.arrivals, inst.rates, algo, layers, n_slots=n_slots)
+        l0, l1 = int(sim.lp[k]), int(sim.lp[k + 1])
+        assert np.array_equal(qs[:, l0:l1], q_ref[1:]), "instance %d: queue trajectories differ" % k
+    assert qs.sum() > 0
+    sim.close()
+    model.close()
+    ctx.close()

@@ -74,6 +74,13 @@ SIGNATURES = {
     "dg_part_lgs_init": (C.c_int, [_p, _p, _p, _p, _p]),
     "dg_part_lgs_decide": (C.c_int, [_p, _p, _p, _p, _p]),
     "dg_part_lgs_remove": (C.c_int, [_p, _p, _p, _p]),
+    "dg_peer_alloc": (C.c_int, [_p, C.c_uint64, _p, _p]),
+    "dg_peer_open": (C.c_int, [_p, _p, _p]),
+    "dg_peer_close": (C.c_int, [_p, _p]),
+    "dg_peer_free": (C.c_int, [_p, _p]),
+    "dg_part_set_peers": (C.c_int, [_p, _i32, _i32, _p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "dg_part_keep": (C.c_int, [_p, _p, C.c_int, _i32, _p]),
+    "dg_part_barrier": (C.c_int, [_p, _p]),
     "dg_solve_host": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
     "dg_solve_host_async": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
 }

@@ -979,7 +979,7 @@ void dg_part_destroy(dg_part *p) {
 }
 
 static inline PartView part_view(const dg_part *p) {
-    return PartView{p->n_global, p->row0, p->n_local, p->nnz, p->row_ptr, p->col_idx};
+    return PartView{p->n_global, p->row0, p->n_local, p->nnz, p->row_ptr, p->col_idx, p->peers};
 }
 
 int dg_part_prepare(dg_part *p, int32_t feature_size, const uint8_t *keep, const float *x0, float *dinv, float *y) {
@@ -1012,7 +1012,7 @@ int dg_part_project(dg_part *p, const dg_model *m, const float *dinv, const floa
     DG_REQUIRE(dinv && pair && pair2, DG_ERR_INVALID, "null argument");
     DeviceGuard guard(p->ctx->device);
     return part_project(p->ctx, part_view(p), m, dinv, reinterpret_cast<const float2 *>(pair),
-                        reinterpret_cast<float2 *>(pair2));
+                        pair2);
 }
 
 int dg_part_layer(dg_part *p, const dg_model *m, int32_t layer, const float *dinv, const float *pair, const float *hin,
@@ -1031,7 +1031,7 @@ int dg_part_tail(dg_part *p, const dg_model *m, const float *dinv, const float *
     DG_TRY(check_part_model(p, m));
     DG_REQUIRE(m->n_layers >= 3 && dinv && hin && pair2, DG_ERR_INVALID, "bad argument");
     DeviceGuard guard(p->ctx->device);
-    return part_tail(p->ctx, part_view(p), m, dinv, hin, reinterpret_cast<float2 *>(pair2));
+    return part_tail(p->ctx, part_view(p), m, dinv, hin, pair2);
 }
 
 int dg_part_last(dg_part *p, const dg_model *m, const float *dinv, const float *pair2, const uint8_t *keep,
@@ -1042,7 +1042,7 @@ int dg_part_last(dg_part *p, const dg_model *m, const float *dinv, const float *
     DG_REQUIRE(predict == DG_PREDICT_MIS || wts != nullptr || util == nullptr, DG_ERR_INVALID,
                "weights required for predict=mwis");
     DeviceGuard guard(p->ctx->device);
-    return part_last(p->ctx, part_view(p), m, dinv, reinterpret_cast<const float2 *>(pair2), keep, wts, predict, score,
+    return part_last(p->ctx, part_view(p), m, dinv, pair2, keep, wts, predict, score,
                      util);
 }
 
@@ -1063,6 +1063,104 @@ int dg_part_lgs_decide(dg_part *p, const double *util, const uint32_t *remain, u
     DG_REQUIRE(p && util && remain && joined && member, DG_ERR_INVALID, "null argument");
     DeviceGuard guard(p->ctx->device);
     return part_lgs_decide(p->ctx, part_view(p), util, remain, joined, member);
+}
+
+// ---- peer arenas (CUDA IPC) and the fused exchange -------------------------------------------------------
+int dg_peer_alloc(dg_context *ctx, uint64_t bytes, void **dev_ptr, uint8_t *handle_out) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(dev_ptr && handle_out && bytes > 0, DG_ERR_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == DG_PEER_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(ctx->device);
+    void *p = nullptr;
+    DG_CUDA_CHECK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return DG_ERR_CUDA;
+    }
+    DG_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return DG_OK;
+}
+
+int dg_peer_open(dg_context *ctx, const uint8_t *handle, void **peer_ptr) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(handle && peer_ptr, DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    DG_CUDA_CHECK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DG_OK;
+}
+
+int dg_peer_close(dg_context *ctx, void *peer_ptr) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    if (peer_ptr) DG_CUDA_CHECK(cudaIpcCloseMemHandle(peer_ptr));
+    return DG_OK;
+}
+
+int dg_peer_free(dg_context *ctx, void *dev_ptr) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    if (dev_ptr) {
+        DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        DG_CUDA_CHECK(cudaFree(dev_ptr));
+    }
+    return DG_OK;
+}
+
+int dg_part_set_peers(dg_part *p, int32_t world, int32_t rank, void *const *arena_bases, uint64_t arena_bytes,
+                      uint64_t flags_offset, uint64_t counts_offset) {
+    clear_error();
+    DG_REQUIRE(p != nullptr, DG_ERR_INVALID, "null part");
+    DG_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, DG_ERR_INVALID,
+               "world %d / rank %d out of range (at most %d ranks)", world, rank, kMaxPeers);
+    DG_REQUIRE(world == 1 || arena_bases != nullptr, DG_ERR_INVALID, "null arena table");
+    DG_REQUIRE(flags_offset % 4 == 0 && counts_offset % 8 == 0 &&
+                   flags_offset + 4ull * world <= arena_bytes && counts_offset + 8ull * world <= arena_bytes,
+               DG_ERR_INVALID, "flag / count blocks outside the arena");
+    PeerMap pm;
+    pm.world = world;
+    pm.rank = rank;
+    pm.bytes = arena_bytes;
+    for (int r = 0; r < world && world > 1; ++r) {
+        DG_REQUIRE(arena_bases[r] != nullptr, DG_ERR_INVALID, "arena of rank %d is null", r);
+        pm.base[r] = static_cast<char *>(arena_bases[r]);
+    }
+    p->peers = pm;
+    p->flags_off = flags_offset;
+    p->counts_off = counts_offset;
+    p->epoch = 0;
+    return DG_OK;
+}
+
+int dg_part_keep(dg_part *p, const double *wts, int remove_zero_weight, int32_t n_real, uint8_t *keep) {
+    clear_error();
+    DG_REQUIRE(p && keep && (wts || !remove_zero_weight), DG_ERR_INVALID, "null argument");
+    DeviceGuard guard(p->ctx->device);
+    return part_keep(p->ctx, part_view(p), wts, remove_zero_weight, n_real, keep);
+}
+
+int dg_part_barrier(dg_part *p, const int64_t *count) {
+    clear_error();
+    DG_REQUIRE(p != nullptr, DG_ERR_INVALID, "null part");
+    DeviceGuard guard(p->ctx->device);
+    if (p->peers.world <= 1) return DG_OK;
+    p->epoch += 1;
+    DG_TRY(part_barrier(p->ctx, p->peers, p->flags_off, p->epoch, reinterpret_cast<const long long *>(count),
+                        p->counts_off));
+    DG_CUDA_CHECK(cudaMemcpyAsync(p->ctx->h_flag + 2, p->ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost,
+                                  p->ctx->stream));
+    return DG_OK;
 }
 
 int dg_part_lgs_remove(dg_part *p, const uint32_t *joined, uint32_t *remain, int64_t *count) {

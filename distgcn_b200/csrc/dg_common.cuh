@@ -44,6 +44,35 @@ constexpr int kMaxLayers = 256;
 constexpr int kLgsCtaMaxNodes = 8192;  // graphs up to this size run in the one-CTA-per-graph LGS kernel
 constexpr int kLgsRoundCap = 1 << 20;  // NaN utilities / self-loops never converge in the reference
 
+// Symmetric peer arenas of a row-partitioned solve (one process per GPU, NVLink / NVSwitch peer memory).
+// Every rank allocates one arena of the same size and layout and maps the other ranks' arenas through CUDA
+// IPC; base[r] is rank r's arena as seen from THIS process.  A kernel that produces a quantity other ranks
+// read next stores it with peer_store(): to its own arena and, at the same offset, to every peer's - the
+// exchange is fused into the producing kernel's epilogue instead of a separate all-gather.  world == 1 (or
+// a pointer outside the arena) degenerates to a plain store.
+constexpr int kMaxPeers = 8;
+struct PeerMap {
+    int world = 1;
+    int rank = 0;
+    unsigned long long bytes = 0;
+    char *base[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+#ifdef __CUDACC__
+template <typename T>
+__device__ __forceinline__ void peer_store(const PeerMap &pm, T *own, T v) {
+    *own = v;
+    if (pm.world > 1) {
+        const unsigned long long off = (unsigned long long)(reinterpret_cast<char *>(own) - pm.base[pm.rank]);
+        if (off < pm.bytes) {
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+                if (r < pm.world && r != pm.rank) *reinterpret_cast<T *>(pm.base[r] + off) = v;
+        }
+    }
+}
+#endif
+
 // grow-only device buffer
 struct Buffer {
     void *ptr = nullptr;
@@ -100,6 +129,7 @@ enum Slot : int {
     kSlotHostGraphPtr,
     kSlotHostRowPtr,
     kSlotHostColIdx,
+    kSlotPartial,     // per-slice partial sums of member_weight
     kSlotCount
 };
 
@@ -174,6 +204,9 @@ struct dg_part {  // one rank's row slice of a single large graph (device CSR, g
     int n_global = 0, row0 = 0, n_local = 0, nnz = 0;
     bool owns = false;
     int32_t *row_ptr = nullptr, *col_idx = nullptr;
+    dg::PeerMap peers;          // world == 1 until dg_part_set_peers
+    unsigned long long flags_off = 0, counts_off = 0;  // arena offsets of the barrier flags / per-rank counts
+    unsigned epoch = 0;         // barrier generation
 };
 
 namespace dg {
@@ -181,6 +214,7 @@ namespace dg {
 struct PartView {
     int n_global, row0, n_local, nnz;
     const int *row_ptr, *col_idx;
+    PeerMap pm;
 };
 
 // row-slice drivers (dg_gcn.cu / dg_lgs.cu): every per-vertex array is GLOBAL sized, a call reads any
@@ -192,13 +226,17 @@ int part_scale(dg_context *ctx, const PartView &pv, const uint8_t *keep, const f
 int part_first(dg_context *ctx, const PartView &pv, const float *dinv, const float *y, const uint8_t *keep,
                const float *x0, float x0val, float2 *pair);
 int part_project(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair,
-                 float2 *pair2);
+                 float *pair2);
 int part_layer(dg_context *ctx, const PartView &pv, const dg_model *m, int layer, const float *dinv,
                const float2 *pair, const float *hin, float *hout);
 int part_tail(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float *hin,
-              float2 *pair2);
-int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair2,
+              float *pair2);
+int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float *pair2,
               const uint8_t *keep, const double *wts, int predict, float *score, double *util);
+int part_keep(dg_context *ctx, const PartView &pv, const double *wts, int remove_zero_weight, int n_real,
+              uint8_t *keep);
+int part_barrier(dg_context *ctx, const PeerMap &pm, unsigned long long flags_off, unsigned epoch,
+                 const long long *count_src, unsigned long long counts_off);
 int part_lgs_init(dg_context *ctx, const PartView &pv, const uint8_t *keep, uint32_t *remain, uint8_t *member,
                   long long *cnt);
 int part_lgs_decide(dg_context *ctx, const PartView &pv, const double *util, const uint32_t *remain, uint32_t *joined,

@@ -30,7 +30,6 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kRowsPerWarp = 8;   // R: rows a warp aggregates, then projects together
-constexpr int kLanesPerScalarRow = 8;
 
 __device__ __forceinline__ float act_apply(float v, int act, float alpha) {
     if (act == DG_ACT_LEAKY_RELU) return v >= 0.f ? v : alpha * v;
@@ -42,20 +41,77 @@ __device__ __forceinline__ float act_apply(float v, int act, float alpha) {
 // degrees -> dinv.  Follows gcn/utils.py:122-125 (rowsum^-0.5 in fp64, inf -> 0), rounded to fp32.
 // With a keep mask the degree is taken on the kept sub-graph (mwis_dqn_call.py:202-207).
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// CSR-stream scalar gather-sum: the shape of every scalar pass over the graph (degrees on a kept
+// sub-graph, s = L.x0, the one-column last layer).  A CTA owns kStreamRows consecutive rows; their
+// edges are one contiguous run of col_idx, which the CTA streams in tiles: every thread loads
+// kStreamPer column ids with coalesced 4-byte loads and issues the kStreamPer gathers of the source
+// value back to back (independent chains: the loads in flight per SM are what a random gather needs
+// to approach the L2 / HBM sector rate), parks the values in shared memory, and after a barrier thread t
+// sums the part of row t that lies inside the tile, in ascending edge order (the order in which the
+// reference's COO SpMM accumulates, gcn/layers.py:206).  The shared array is skewed by one word per 32
+// so that rows of equal length (stride = degree) do not collide on a bank.
 // Row-slice form (row0 != 0): the launch covers rows row0 .. row0+n-1 of a larger graph; row_ptr is the
 // slice's own (local) array, every per-vertex array is indexed by GLOBAL vertex id.
-__global__ void degree_kernel(int n, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                              const uint8_t *__restrict__ keep, float *__restrict__ dinv) {
+// ---------------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 256;
+constexpr int kStreamRows = 256;
+constexpr int kStreamPer = 8;
+constexpr int kStreamTile = kStreamThreads * kStreamPer;
+
+__device__ __forceinline__ int stream_skew(int i) { return i + (i >> 5); }
+
+// acc = sum over the edges e of row (r0 + threadIdx.x) of fetch(col_idx[e]); T = float or int
+template <typename T, typename Fetch>
+__device__ __forceinline__ T csr_stream_sum(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                            T *vals, Fetch fetch) {
+    const int t = threadIdx.x;
+    const int r0 = blockIdx.x * kStreamRows;
+    const int nr = min(kStreamRows, n - r0);
+    const int e0 = row_ptr[r0], e1 = row_ptr[r0 + nr];
+    int rb = 0, re = 0;
+    if (t < nr) {
+        rb = row_ptr[r0 + t];
+        re = row_ptr[r0 + t + 1];
+    }
+    T acc = T(0);
+    for (int c0 = e0 & ~31; c0 < e1; c0 += kStreamTile) {
+        int c[kStreamPer];
+        T v[kStreamPer];
+#pragma unroll
+        for (int k = 0; k < kStreamPer; ++k) {
+            const int e = c0 + k * kStreamThreads + t;
+            c[k] = (e >= e0 && e < e1) ? __ldg(col_idx + e) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kStreamPer; ++k) v[k] = c[k] >= 0 ? fetch(c[k]) : T(0);
+#pragma unroll
+        for (int k = 0; k < kStreamPer; ++k) vals[stream_skew(k * kStreamThreads + t)] = v[k];
+        __syncthreads();
+        const int lo = max(rb, c0) - c0, hi = min(re, c0 + kStreamTile) - c0;
+        for (int i = lo; i < hi; ++i) acc += vals[stream_skew(i)];
+        __syncthreads();
+    }
+    return acc;
+}
+
+// degrees -> dinv.  Follows gcn/utils.py:122-125 (rowsum^-0.5 in fp64, inf -> 0), rounded to fp32.
+// With a keep mask the degree is taken on the kept sub-graph (mwis_dqn_call.py:202-207).
+__global__ void degree_kernel(int n, int row0, const int *__restrict__ row_ptr, float *__restrict__ dinv,
+                              const PeerMap pm) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int beg = row_ptr[i], end = row_ptr[i + 1];
-    int deg = 0;
-    if (keep == nullptr) {
-        deg = end - beg;
-    } else if (keep[row0 + i]) {
-        for (int e = beg; e < end; ++e) deg += keep[col_idx[e]] != 0;
-    }
-    dinv[row0 + i] = deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f;
+    const int deg = row_ptr[i + 1] - row_ptr[i];
+    peer_store(pm, dinv + row0 + i, deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f);
+}
+
+__global__ void __launch_bounds__(kStreamThreads)
+degree_keep_kernel(int n, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                   const uint8_t *__restrict__ keep, float *__restrict__ dinv, const PeerMap pm) {
+    __shared__ int vals[kStreamTile + kStreamTile / 32 + 1];
+    const int deg = csr_stream_sum<int>(n, row_ptr, col_idx, vals, [&](int c) { return (int)(__ldg(keep + c) != 0); });
+    const int i = blockIdx.x * kStreamRows + threadIdx.x;
+    if (i < n) peer_store(pm, dinv + row0 + i, (deg > 0 && keep[row0 + i]) ? (float)(1.0 / sqrt((double)deg)) : 0.f);
 }
 
 __global__ void keep_from_weights_kernel(int n, const double *__restrict__ wts, uint8_t *__restrict__ keep) {
@@ -63,35 +119,40 @@ __global__ void keep_from_weights_kernel(int n, const double *__restrict__ wts, 
     if (i < n) keep[i] = wts[i] != 0.0;  // rm_nodes = where(wts == 0), mwis_dqn_call.py:203
 }
 
+// row-partitioned runs: keep[v] = v is a real vertex (padding rows past n_real are not) and, with zero-weight
+// removal, wts[v] != 0 (mwis_dqn_call.py:203); stored to every rank's arena
+__global__ void part_keep_kernel(int n_local, int row0, int n_real, const double *__restrict__ wts, int remove_zero,
+                                 uint8_t *__restrict__ keep, const PeerMap pm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    const int v = row0 + i;
+    const bool k = v < n_real && (!remove_zero || wts[v] != 0.0);
+    peer_store(pm, keep + v, (uint8_t)(k ? 1 : 0));
+}
+
 // y_j = dinv_j * x0_j : the quantity the first layer's scalar SpMV gathers
 __global__ void scaled_input_kernel(int n, const float *__restrict__ dinv, const uint8_t *__restrict__ keep,
-                                    const float *__restrict__ x0, float x0val, float *__restrict__ y) {
+                                    const float *__restrict__ x0, float x0val, float *__restrict__ y,
+                                    const PeerMap pm) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float xi = (keep && !keep[i]) ? 0.f : (x0 ? x0[i] : x0val);
-    y[i] = dinv[i] * xi;
+    peer_store(pm, y + i, dinv[i] * xi);
 }
 
-// s = L.x0 (scalar SpMV), one sub-warp of 8 lanes per row.  Writes (x0_i, s_i).
-__global__ void __launch_bounds__(256)
+// s = L.x0 (scalar SpMV, CSR-stream).  Writes (x0_i, s_i).  Row-slice form: dinv / keep / x0 / pair_out are
+// already offset to the slice's first row, y is the global array.
+__global__ void __launch_bounds__(kStreamThreads)
 first_scalar_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
                     const float *__restrict__ dinv, const float *__restrict__ y,
                     const uint8_t *__restrict__ keep, const float *__restrict__ x0, float x0val,
-                    float2 *__restrict__ pair_out) {
-    constexpr int LPR = kLanesPerScalarRow;
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = tid / LPR;
-    int sub = threadIdx.x % LPR;
-    float acc = 0.f;
+                    float2 *__restrict__ pair_out, const PeerMap pm) {
+    __shared__ float vals[kStreamTile + kStreamTile / 32 + 1];
+    const float acc = csr_stream_sum<float>(n, row_ptr, col_idx, vals, [&](int c) { return __ldg(y + c); });
+    const int row = blockIdx.x * kStreamRows + threadIdx.x;
     if (row < n) {
-        int beg = row_ptr[row], end = row_ptr[row + 1];
-        for (int e = beg + sub; e < end; e += LPR) acc += __ldg(y + col_idx[e]);
-    }
-#pragma unroll
-    for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (row < n && sub == 0) {
         float xi = (keep && !keep[row]) ? 0.f : (x0 ? x0[row] : x0val);
-        pair_out[row] = make_float2(xi, xi - dinv[row] * acc);
+        peer_store(pm, pair_out + row, make_float2(xi, xi - dinv[row] * acc));
     }
 }
 
@@ -114,52 +175,58 @@ __global__ void __launch_bounds__(256)
 node_project_kernel(int n, int c, const float2 *__restrict__ pair, const float *__restrict__ a0,
                     const float *__restrict__ a1, const float *__restrict__ b0, int act, float alpha,
                     const float *__restrict__ w0, const float *__restrict__ w1,
-                    const float *__restrict__ dinv, float2 *__restrict__ pair_out) {
-    __shared__ float sm[5 * kMaxWidth];
-    for (int k = threadIdx.x; k < c; k += blockDim.x) {
-        sm[k] = a0[k];
-        sm[kMaxWidth + k] = a1[k];
-        sm[2 * kMaxWidth + k] = b0[k];
-        sm[3 * kMaxWidth + k] = w0[k];
-        sm[4 * kMaxWidth + k] = w1[k];
+                    const float *__restrict__ dinv, float *__restrict__ q_out, float *__restrict__ zs_out,
+                    const PeerMap pm) {
+    __shared__ __align__(16) float sm[5 * kMaxWidth];
+    for (int k = threadIdx.x; k < kMaxWidth; k += blockDim.x) {  // columns past c carry zeros: no contribution
+        const bool in = k < c;
+        sm[k] = in ? a0[k] : 0.f;
+        sm[kMaxWidth + k] = in ? a1[k] : 0.f;
+        sm[2 * kMaxWidth + k] = in ? b0[k] : 0.f;
+        sm[3 * kMaxWidth + k] = in ? w0[k] : 0.f;
+        sm[4 * kMaxWidth + k] = in ? w1[k] : 0.f;
     }
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float2 p = pair[i];
     float t0 = 0.f, t1 = 0.f;
-    for (int k = 0; k < c; ++k) {
-        float h = act_apply(fmaf(p.y, sm[kMaxWidth + k], fmaf(p.x, sm[k], sm[2 * kMaxWidth + k])), act, alpha);
-        t0 = fmaf(h, sm[3 * kMaxWidth + k], t0);
-        t1 = fmaf(h, sm[4 * kMaxWidth + k], t1);
+    const float4 *s4 = reinterpret_cast<const float4 *>(sm);
+    const int c4 = (c + 3) / 4;
+    for (int k = 0; k < c4; ++k) {  // 128-bit broadcast loads: the loop is LSU-bound with scalar ones
+        const float4 va0 = s4[k], va1 = s4[kMaxWidth / 4 + k], vb = s4[2 * (kMaxWidth / 4) + k];
+        const float4 vw0 = s4[3 * (kMaxWidth / 4) + k], vw1 = s4[4 * (kMaxWidth / 4) + k];
+        float h;
+        h = act_apply(fmaf(p.y, va1.x, fmaf(p.x, va0.x, vb.x)), act, alpha);
+        t0 = fmaf(h, vw0.x, t0), t1 = fmaf(h, vw1.x, t1);
+        h = act_apply(fmaf(p.y, va1.y, fmaf(p.x, va0.y, vb.y)), act, alpha);
+        t0 = fmaf(h, vw0.y, t0), t1 = fmaf(h, vw1.y, t1);
+        h = act_apply(fmaf(p.y, va1.z, fmaf(p.x, va0.z, vb.z)), act, alpha);
+        t0 = fmaf(h, vw0.z, t0), t1 = fmaf(h, vw1.z, t1);
+        h = act_apply(fmaf(p.y, va1.w, fmaf(p.x, va0.w, vb.w)), act, alpha);
+        t0 = fmaf(h, vw0.w, t0), t1 = fmaf(h, vw1.w, t1);
     }
-    pair_out[i] = make_float2(t0 + t1, dinv[i] * t1);
+    q_out[i] = t0 + t1;
+    peer_store(pm, zs_out + i, dinv[i] * t1);
 }
 
 // Last layer with one output column: score_i = act(q_i - dinv_i * sum_j zs_j + b), then the utility
-// product of mwis_dqn_call.py:230-235 in fp64.  One sub-warp of 8 lanes per row.
-__global__ void __launch_bounds__(256)
+// product of mwis_dqn_call.py:230-235 in fp64 (CSR-stream).  q and zs are separate planes: only zs is
+// gathered (and, row-partitioned, exchanged between ranks).
+__global__ void __launch_bounds__(kStreamThreads)
 last_scalar_kernel(int n, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                   const float *__restrict__ dinv, const float2 *__restrict__ pair, float bias, int act,
-                   float alpha, const uint8_t *__restrict__ keep, float *__restrict__ score,
-                   const double *__restrict__ wts, int predict, double *__restrict__ util) {
-    constexpr int LPR = kLanesPerScalarRow;
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = tid / LPR;
-    int sub = threadIdx.x % LPR;
-    float acc = 0.f;
+                   const float *__restrict__ dinv, const float *__restrict__ q, const float *__restrict__ zs,
+                   float bias, int act, float alpha, const uint8_t *__restrict__ keep, float *__restrict__ score,
+                   const double *__restrict__ wts, int predict, double *__restrict__ util, const PeerMap pm) {
+    __shared__ float vals[kStreamTile + kStreamTile / 32 + 1];
+    const float acc = csr_stream_sum<float>(n, row_ptr, col_idx, vals, [&](int c) { return __ldg(zs + c); });
+    const int row = blockIdx.x * kStreamRows + threadIdx.x;
     if (row < n) {
-        int beg = row_ptr[row], end = row_ptr[row + 1];
-        for (int e = beg + sub; e < end; e += LPR) acc += __ldg(&pair[col_idx[e]].y);
-    }
-#pragma unroll
-    for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (row < n && sub == 0) {
         const int gr = row0 + row;
-        float v = act_apply(pair[gr].x - dinv[gr] * acc + bias, act, alpha);
+        float v = act_apply(q[gr] - dinv[gr] * acc + bias, act, alpha);
         if (keep && !keep[gr]) v = 0.f;
         if (score) score[gr] = v;
-        if (util) util[gr] = (predict == DG_PREDICT_MWIS) ? (double)v * wts[gr] : (double)v;
+        if (util) peer_store(pm, util + gr, (predict == DG_PREDICT_MWIS) ? (double)v * wts[gr] : (double)v);
     }
 }
 
@@ -198,7 +265,8 @@ struct LayerArgs {
     float alpha;
     float *hout;            // [n, CPO]
     const float *tail_w0, *tail_w1;  // [CPO]
-    float2 *pair_out;       // (q, zs)
+    float *tail_q, *tail_zs;  // (q, zs) planes
+    PeerMap pm;             // row-partitioned runs: output rows / zs are also stored to the peers' arenas
 };
 
 template <int CPI, int CPO, bool IMPLICIT_IN, bool TAIL>
@@ -354,7 +422,8 @@ gc_layer_kernel(const LayerArgs a) {
                 if (i < a.n) {
 #pragma unroll
                     for (int cc = 0; cc < CO; ++cc)
-                        a.hout[(size_t)(a.row0 + i) * CPO + lane + 32 * cc] = act_apply(out[r][cc], a.act, a.alpha);
+                        peer_store(a.pm, a.hout + (size_t)(a.row0 + i) * CPO + lane + 32 * cc,
+                                   act_apply(out[r][cc], a.act, a.alpha));
                 }
             } else {
                 float t0 = 0.f, t1 = 0.f;
@@ -369,7 +438,10 @@ gc_layer_kernel(const LayerArgs a) {
                     t0 += __shfl_xor_sync(0xffffffffu, t0, off);
                     t1 += __shfl_xor_sync(0xffffffffu, t1, off);
                 }
-                if (lane == 0 && i < a.n) a.pair_out[a.row0 + i] = make_float2(t0 + t1, a.dinv[a.row0 + i] * t1);
+                if (lane == 0 && i < a.n) {
+                    a.tail_q[a.row0 + i] = t0 + t1;
+                    peer_store(a.pm, a.tail_zs + a.row0 + i, a.dinv[a.row0 + i] * t1);
+                }
             }
         }
     }
@@ -461,7 +533,8 @@ inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block)
 // (q, zs) of a one-column last layer from dense rows: q_i = H_i.w_0 + z_i, zs_i = dinv_i z_i, z = H.w_1
 __global__ void __launch_bounds__(256)
 tail_project_kernel(int n, int row0, int cp, const float *__restrict__ hin, const float *__restrict__ w0,
-                    const float *__restrict__ w1, const float *__restrict__ dinv, float2 *__restrict__ pair_out) {
+                    const float *__restrict__ w1, const float *__restrict__ dinv, float *__restrict__ q_out,
+                    float *__restrict__ zs_out, const PeerMap pm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 *row = reinterpret_cast<const float4 *>(hin + (size_t)(row0 + i) * cp);
@@ -473,7 +546,8 @@ tail_project_kernel(int n, int row0, int cp, const float *__restrict__ hin, cons
         t0 = fmaf(h.x, a.x, t0), t0 = fmaf(h.y, a.y, t0), t0 = fmaf(h.z, a.z, t0), t0 = fmaf(h.w, a.w, t0);
         t1 = fmaf(h.x, b.x, t1), t1 = fmaf(h.y, b.y, t1), t1 = fmaf(h.z, b.z, t1), t1 = fmaf(h.w, b.w, t1);
     }
-    pair_out[row0 + i] = make_float2(t0 + t1, dinv[row0 + i] * t1);
+    q_out[row0 + i] = t0 + t1;
+    peer_store(pm, zs_out + row0 + i, dinv[row0 + i] * t1);
 }
 
 }  // namespace
@@ -483,11 +557,24 @@ tail_project_kernel(int n, int row0, int cp, const float *__restrict__ hin, cons
 // global sized and indexed by global vertex id; each call writes rows row0 .. row0+n_local-1 only and
 // the caller all-gathers what the next call reads from other ranks' rows.
 // =================================================================================================
+int part_keep(dg_context *ctx, const PartView &pv, const double *wts, int remove_zero_weight, int n_real,
+              uint8_t *keep) {
+    if (pv.n_local == 0) return DG_OK;
+    part_keep_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(pv.n_local, pv.row0, n_real, wts,
+                                                                        remove_zero_weight, keep, pv.pm);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
 int part_prepare(dg_context *ctx, const PartView &pv, const uint8_t *keep, const float *x0, float x0val, float *dinv,
                  float *y) {
     if (pv.n_local == 0) return DG_OK;
-    degree_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.row_ptr, pv.col_idx, keep,
-                                                                     dinv);
+    if (keep)
+        degree_keep_kernel<<<grid_for(pv.n_local, kStreamRows), kStreamThreads, 0, ctx->stream>>>(
+            pv.n_local, pv.row0, pv.row_ptr, pv.col_idx, keep, dinv, pv.pm);
+    else
+        degree_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.row_ptr, dinv, pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return part_scale(ctx, pv, keep, x0, x0val, dinv, y);
@@ -497,7 +584,8 @@ int part_scale(dg_context *ctx, const PartView &pv, const uint8_t *keep, const f
                const float *dinv, float *y) {
     if (pv.n_local == 0) return DG_OK;
     scaled_input_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(
-        pv.n_local, dinv + pv.row0, keep ? keep + pv.row0 : nullptr, x0 ? x0 + pv.row0 : nullptr, x0val, y + pv.row0);
+        pv.n_local, dinv + pv.row0, keep ? keep + pv.row0 : nullptr, x0 ? x0 + pv.row0 : nullptr, x0val, y + pv.row0,
+        pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -506,21 +594,21 @@ int part_scale(dg_context *ctx, const PartView &pv, const uint8_t *keep, const f
 int part_first(dg_context *ctx, const PartView &pv, const float *dinv, const float *y, const uint8_t *keep,
                const float *x0, float x0val, float2 *pair) {
     if (pv.n_local == 0) return DG_OK;
-    first_scalar_kernel<<<grid_for((size_t)pv.n_local * kLanesPerScalarRow, 256), 256, 0, ctx->stream>>>(
+    first_scalar_kernel<<<grid_for(pv.n_local, kStreamRows), kStreamThreads, 0, ctx->stream>>>(
         pv.n_local, pv.row_ptr, pv.col_idx, dinv + pv.row0, y, keep ? keep + pv.row0 : nullptr,
-        x0 ? x0 + pv.row0 : nullptr, x0val, pair + pv.row0);
+        x0 ? x0 + pv.row0 : nullptr, x0val, pair + pv.row0, pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
 }
 
 int part_project(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair,
-                 float2 *pair2) {
+                 float *pair2) {
     if (pv.n_local == 0) return DG_OK;
     const dg_layer_dev &first = m->layers[0];
     node_project_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(
         pv.n_local, first.c_out, pair + pv.row0, first.colsum0, first.colsum1, first.bias, first.act, m->alpha,
-        m->tail_w0, m->tail_w1, dinv + pv.row0, pair2 + pv.row0);
+        m->tail_w0, m->tail_w1, dinv + pv.row0, pair2 + pv.row0, pair2 + pv.n_global + pv.row0, pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -553,27 +641,28 @@ int part_layer(dg_context *ctx, const PartView &pv, const dg_model *m, int layer
     a.act = ly.act;
     a.alpha = m->alpha;
     a.hout = hout;
+    a.pm = pv.pm;
     return launch_layer(ctx, ly.cpi, ly.cpo, implicit_in, false, a);
 }
 
 int part_tail(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float *hin,
-              float2 *pair2) {
+              float *pair2) {
     if (pv.n_local == 0) return DG_OK;
     const int cp = m->layers[m->n_layers - 1].cpi;
     tail_project_kernel<<<grid_for(pv.n_local, 256), 256, 0, ctx->stream>>>(pv.n_local, pv.row0, cp, hin, m->tail_w0,
-                                                                           m->tail_w1, dinv, pair2);
+                                                                           m->tail_w1, dinv, pair2, pair2 + pv.n_global, pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
 }
 
-int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float2 *pair2,
+int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float *pair2,
               const uint8_t *keep, const double *wts, int predict, float *score, double *util) {
     if (pv.n_local == 0) return DG_OK;
     const dg_layer_dev &last = m->layers[m->n_layers - 1];
-    last_scalar_kernel<<<grid_for((size_t)pv.n_local * kLanesPerScalarRow, 256), 256, 0, ctx->stream>>>(
-        pv.n_local, pv.row0, pv.row_ptr, pv.col_idx, dinv, pair2, m->tail_bias, last.act, m->alpha, keep, score, wts,
-        predict, util);
+    last_scalar_kernel<<<grid_for(pv.n_local, kStreamRows), kStreamThreads, 0, ctx->stream>>>(
+        pv.n_local, pv.row0, pv.row_ptr, pv.col_idx, dinv, pair2, pair2 + pv.n_global, m->tail_bias, last.act, m->alpha, keep, score, wts,
+        predict, util, pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -585,8 +674,11 @@ int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const floa
 int batch_compute_dinv(dg_batch *b) {
     dg_context *ctx = b->ctx;
     if (b->n_nodes == 0) return DG_OK;
-    degree_kernel<<<grid_for(b->n_nodes, 256), 256, 0, ctx->stream>>>(b->n_nodes, 0, b->row_ptr, b->col_idx,
-                                                                     b->keep, b->dinv);
+    if (b->keep)
+        degree_keep_kernel<<<grid_for(b->n_nodes, kStreamRows), kStreamThreads, 0, ctx->stream>>>(
+            b->n_nodes, 0, b->row_ptr, b->col_idx, b->keep, b->dinv, PeerMap{});
+    else
+        degree_kernel<<<grid_for(b->n_nodes, 256), 256, 0, ctx->stream>>>(b->n_nodes, 0, b->row_ptr, b->dinv, PeerMap{});
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -656,15 +748,16 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
     cudaStream_t st = ctx->stream;
 
     float *y = nullptr;
-    float2 *pair = nullptr, *pair2 = nullptr;
+    float2 *pair = nullptr;
+    float *tail_q = nullptr, *tail_zs = nullptr;  // (q, zs) planes of the one-column last layer
     DG_TRY(scratch_as(ctx, kSlotY, (size_t)n, &y));
     DG_TRY(scratch_as(ctx, kSlotPair, (size_t)n, &pair));
     const float x0val = 1.0f / (float)first.c_in;  // gcn/utils.py:98-106 on constant rows
-    scaled_input_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, b->dinv, b->keep, b->x0, x0val, y);
+    scaled_input_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, b->dinv, b->keep, b->x0, x0val, y, PeerMap{});
     ctx->launches++;
-    const int scalar_grid = grid_for((size_t)n * kLanesPerScalarRow, 256);
-    first_scalar_kernel<<<scalar_grid, 256, 0, st>>>(n, b->row_ptr, b->col_idx, b->dinv, y, b->keep, b->x0,
-                                                     x0val, pair);
+    const int scalar_grid = grid_for(n, kStreamRows);
+    first_scalar_kernel<<<scalar_grid, kStreamThreads, 0, st>>>(n, b->row_ptr, b->col_idx, b->dinv, y, b->keep, b->x0,
+                                                                x0val, pair, PeerMap{});
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
 
@@ -688,7 +781,10 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
     float *fa = nullptr, *fb = nullptr;
     DG_TRY(scratch_as(ctx, kSlotFeatA, (size_t)n * kMaxWidth, &fa));
     DG_TRY(scratch_as(ctx, kSlotFeatB, (size_t)n * kMaxWidth, &fb));
-    if (scalar_tail) DG_TRY(scratch_as(ctx, kSlotPair2, (size_t)n, &pair2));
+    if (scalar_tail) {
+        DG_TRY(scratch_as(ctx, kSlotPair2, (size_t)2 * n, &tail_q));
+        tail_zs = tail_q + n;
+    }
 
     const int last_fused = scalar_tail ? L - 2 : L - 1;  // last layer run through gc_layer_kernel
     const float *cur = nullptr;
@@ -719,7 +815,8 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
         if (tail) {
             a.tail_w0 = m->tail_w0;
             a.tail_w1 = m->tail_w1;
-            a.pair_out = pair2;
+            a.tail_q = tail_q;
+            a.tail_zs = tail_zs;
         } else {
             a.hout = nxt;
         }
@@ -732,11 +829,13 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
         if (L == 2) {
             node_project_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, first.c_out, pair, first.colsum0,
                                                                   first.colsum1, first.bias, first.act, m->alpha,
-                                                                  m->tail_w0, m->tail_w1, b->dinv, pair2);
+                                                                  m->tail_w0, m->tail_w1, b->dinv, tail_q, tail_zs,
+                                                                  PeerMap{});
             ctx->launches++;
         }
-        last_scalar_kernel<<<scalar_grid, 256, 0, st>>>(n, 0, b->row_ptr, b->col_idx, b->dinv, pair2, m->tail_bias,
-                                                        last.act, m->alpha, b->keep, out, wts, predict, util);
+        last_scalar_kernel<<<scalar_grid, kStreamThreads, 0, st>>>(n, 0, b->row_ptr, b->col_idx, b->dinv, tail_q, tail_zs,
+                                                                   m->tail_bias, last.act, m->alpha, b->keep, out, wts,
+                                                                   predict, util, PeerMap{});
         ctx->launches++;
         DG_CUDA_CHECK(cudaGetLastError());
         return DG_OK;

@@ -18,6 +18,8 @@
 //       with the bitmaps in shared memory                                    lgs_cta_kernel
 //   large graphs: one launch pair per round over all vertices with global bitmaps; the host reads
 //       one int per round to detect convergence                              lgs_*_global kernels
+#include <algorithm>
+
 #include "dg_common.cuh"
 
 namespace dg {
@@ -191,12 +193,11 @@ __global__ void lgs_init_global(int n, int n_graphs, const int *__restrict__ gra
     }
     const uint32_t w = __ballot_sync(0xffffffffu, alive);
     if (lane == 0 && (v >> 5) < (n + 31) / 32) remain[v >> 5] = w;
-    if (alive) {
-        if (n_graphs == 1) {
-            if (lane == (__ffs(w) - 1)) atomicAdd(&cnt[0], __popc(w));
-        } else {
-            atomicAdd(&cnt[graph_of(graph_ptr, n_graphs, v)], 1);
-        }
+    if (n_graphs == 1) {  // one atomic per CTA: a giant graph would otherwise serialise on one address
+        const int c = __syncthreads_count(alive);
+        if (threadIdx.x == 0 && c) atomicAdd(&cnt[0], c);
+    } else if (alive) {
+        atomicAdd(&cnt[graph_of(graph_ptr, n_graphs, v)], 1);
     }
 }
 
@@ -284,12 +285,11 @@ lgs_remove_global(int n, int n_graphs, const int *__restrict__ graph_ptr, const 
     }
     const uint32_t rw = __ballot_sync(0xffffffffu, still);
     if (lane == 0 && (v >> 5) < n_words) remain[v >> 5] = rw;
-    if (still) {
-        if (n_graphs == 1) {
-            if (lane == (__ffs(rw) - 1)) atomicAdd(&cnt[0], __popc(rw));
-        } else {
-            atomicAdd(&cnt[graph_of(graph_ptr, n_graphs, v)], 1);
-        }
+    if (n_graphs == 1) {
+        const int c = __syncthreads_count(still);
+        if (threadIdx.x == 0 && c) atomicAdd(&cnt[0], c);
+    } else if (still) {
+        atomicAdd(&cnt[graph_of(graph_ptr, n_graphs, v)], 1);
     }
 }
 
@@ -299,7 +299,7 @@ lgs_remove_global(int n, int n_graphs, const int *__restrict__ graph_ptr, const 
 // indexed by GLOBAL vertex id.  Between the kernels the caller all-gathers the bitmap words it wrote.
 __global__ void __launch_bounds__(256)
 lgs_part_init(int n_local, int row0, int n_global, const uint8_t *__restrict__ keep, uint32_t *__restrict__ remain,
-              uint8_t *__restrict__ member, long long *__restrict__ cnt) {
+              uint8_t *__restrict__ member, long long *__restrict__ cnt, const PeerMap pm) {
     const int vl = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = row0 + vl;
     const int lane = threadIdx.x & 31;
@@ -309,14 +309,15 @@ lgs_part_init(int n_local, int row0, int n_global, const uint8_t *__restrict__ k
         member[v] = 0;
     }
     const uint32_t w = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0 && vl < n_local) remain[v >> 5] = w;
-    if (alive && lane == (__ffs(w) - 1)) atomicAdd((unsigned long long *)cnt, (unsigned long long)__popc(w));
+    if (lane == 0 && vl < n_local) peer_store(pm, remain + (v >> 5), w);
+    const int c = __syncthreads_count(alive);
+    if (threadIdx.x == 0 && c) atomicAdd((unsigned long long *)cnt, (unsigned long long)c);
 }
 
 __global__ void __launch_bounds__(256)
 lgs_part_decide(int n_local, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
                 const double *__restrict__ util, const uint32_t *__restrict__ remain,
-                uint32_t *__restrict__ joined, uint8_t *__restrict__ member) {
+                uint32_t *__restrict__ joined, uint8_t *__restrict__ member, const PeerMap pm) {
     const int vl = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = row0 + vl;
     const int lane = threadIdx.x & 31;
@@ -338,12 +339,13 @@ lgs_part_decide(int n_local, int row0, const int *__restrict__ row_ptr, const in
         if (join) member[v] = 1;
     }
     const uint32_t jw = __ballot_sync(0xffffffffu, join);
-    if (lane == 0 && vl < n_local) joined[v >> 5] = jw;
+    if (lane == 0 && vl < n_local) peer_store(pm, joined + (v >> 5), jw);
 }
 
 __global__ void __launch_bounds__(256)
 lgs_part_remove(int n_local, int row0, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                const uint32_t *__restrict__ joined, uint32_t *__restrict__ remain, long long *__restrict__ cnt) {
+                const uint32_t *__restrict__ joined, uint32_t *__restrict__ remain, long long *__restrict__ cnt,
+                const PeerMap pm) {
     const int vl = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = row0 + vl;
     const int lane = threadIdx.x & 31;
@@ -365,18 +367,54 @@ lgs_part_remove(int n_local, int row0, const int *__restrict__ row_ptr, const in
     }
     const uint32_t rw = __ballot_sync(0xffffffffu, still);
     __syncwarp();
-    if (lane == 0 && vl < n_local) remain[v >> 5] = rw;
-    if (still && lane == (__ffs(rw) - 1)) atomicAdd((unsigned long long *)cnt, (unsigned long long)__popc(rw));
+    if (lane == 0 && vl < n_local) peer_store(pm, remain + (v >> 5), rw);
+    const int c = __syncthreads_count(still);
+    if (threadIdx.x == 0 && c) atomicAdd((unsigned long long *)cnt, (unsigned long long)c);
 }
 
+// Cross-rank barrier on the stream (one CTA): thread r publishes this rank's count into rank r's arena, raises
+// this rank's flag there (release, system scope), then waits until rank r has raised its flag here (acquire).
+// Everything the ranks stored to each other's arenas in earlier kernels of their streams is visible after
+// it.  A rank that never arrives would spin forever, so the wait gives up after ~4 s and reports through *status.
+__global__ void peer_barrier_kernel(const PeerMap pm, unsigned long long flags_off, unsigned epoch,
+                                    const long long *__restrict__ count_src, unsigned long long counts_off,
+                                    int *__restrict__ status) {
+    const int r = threadIdx.x;
+    if (r >= pm.world) return;
+    if (count_src) {
+        long long *slot = reinterpret_cast<long long *>(pm.base[r] + counts_off) + pm.rank;
+        *slot = *count_src;
+    }
+    __threadfence_system();
+    unsigned *remote = reinterpret_cast<unsigned *>(pm.base[r] + flags_off) + pm.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const unsigned *local = reinterpret_cast<const unsigned *>(pm.base[pm.rank] + flags_off) + r;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local) : "memory");
+        if ((int)(seen - epoch) >= 0) break;
+        if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+            atomicExch(status, DG_ERR_CUDA);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+// total[g] = sum of wts over the members of graph g.  Graphs are cut into `splits` equal slices, CTA (g, s) sums
+// slice s with a fixed tree and a second pass adds the slices in order: deterministic, and a giant graph is
+// spread over the whole GPU instead of one CTA.
 __global__ void __launch_bounds__(256)
 member_weight_kernel(const int *__restrict__ graph_ptr, const uint8_t *__restrict__ member,
-                     const double *__restrict__ wts, double *__restrict__ total) {
+                     const double *__restrict__ wts, int splits, double *__restrict__ out) {
     __shared__ double part[256];
-    const int g = blockIdx.x;
+    const int g = blockIdx.x / splits, sidx = blockIdx.x - g * splits;
     const int v0 = graph_ptr[g], v1 = graph_ptr[g + 1];
+    const int per = (v1 - v0 + splits - 1) / splits;
+    const int a = v0 + sidx * per, b = min(v1, a + per);
     double acc = 0.0;
-    for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x)
+    for (int v = a + threadIdx.x; v < b; v += blockDim.x)
         if (member[v]) acc += wts[v];
     part[threadIdx.x] = acc;
     __syncthreads();
@@ -384,7 +422,16 @@ member_weight_kernel(const int *__restrict__ graph_ptr, const uint8_t *__restric
         if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) total[g] = part[0];
+    if (threadIdx.x == 0) out[blockIdx.x] = part[0];
+}
+
+__global__ void member_weight_combine_kernel(int n_graphs, int splits, const double *__restrict__ partial,
+                                             double *__restrict__ total) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_graphs) return;
+    double acc = 0.0;
+    for (int s = 0; s < splits; ++s) acc += partial[(size_t)g * splits + s];
+    total[g] = acc;
 }
 
 }  // namespace
@@ -465,7 +512,7 @@ int part_lgs_init(dg_context *ctx, const PartView &pv, const uint8_t *keep, uint
                   long long *cnt) {
     if (pv.n_local == 0) return DG_OK;
     lgs_part_init<<<(pv.n_local + 255) / 256, 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.n_global, keep, remain,
-                                                                    member, cnt);
+                                                                    member, cnt, pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -475,7 +522,7 @@ int part_lgs_decide(dg_context *ctx, const PartView &pv, const double *util, con
                     uint8_t *member) {
     if (pv.n_local == 0) return DG_OK;
     lgs_part_decide<<<(pv.n_local + 255) / 256, 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.row_ptr, pv.col_idx,
-                                                                      util, remain, joined, member);
+                                                                      util, remain, joined, member, pv.pm);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -484,7 +531,16 @@ int part_lgs_decide(dg_context *ctx, const PartView &pv, const double *util, con
 int part_lgs_remove(dg_context *ctx, const PartView &pv, const uint32_t *joined, uint32_t *remain, long long *cnt) {
     if (pv.n_local == 0) return DG_OK;
     lgs_part_remove<<<(pv.n_local + 255) / 256, 256, 0, ctx->stream>>>(pv.n_local, pv.row0, pv.row_ptr, pv.col_idx,
-                                                                      joined, remain, cnt);
+                                                                      joined, remain, cnt, pv.pm);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int part_barrier(dg_context *ctx, const PeerMap &pm, unsigned long long flags_off, unsigned epoch,
+                 const long long *count_src, unsigned long long counts_off) {
+    if (pm.world <= 1) return DG_OK;
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(pm, flags_off, epoch, count_src, counts_off, ctx->d_status);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
@@ -493,8 +549,22 @@ int part_lgs_remove(dg_context *ctx, const PartView &pv, const uint32_t *joined,
 int member_weight_device(dg_context *ctx, const dg_batch *b, const uint8_t *member, const double *wts,
                          double *total) {
     if (b->n_graphs == 0) return DG_OK;
-    member_weight_kernel<<<b->n_graphs, 256, 0, ctx->stream>>>(b->graph_ptr, member, wts, total);
-    ctx->launches++;
+    // one slice per 16 Ki vertices of the largest graph, bounded so that the grid stays small for large batches
+    long long splits = (b->max_graph_nodes + 16383) / 16384;
+    splits = std::max<long long>(1, std::min<long long>(splits, 4096));
+    while (splits > 1 && splits * b->n_graphs > (1LL << 22)) splits /= 2;
+    if (splits == 1) {
+        member_weight_kernel<<<b->n_graphs, 256, 0, ctx->stream>>>(b->graph_ptr, member, wts, 1, total);
+        ctx->launches++;
+    } else {
+        double *partial = nullptr;
+        DG_TRY(scratch_as(ctx, kSlotPartial, (size_t)splits * b->n_graphs, &partial));
+        member_weight_kernel<<<(unsigned)(splits * b->n_graphs), 256, 0, ctx->stream>>>(b->graph_ptr, member, wts,
+                                                                                       (int)splits, partial);
+        member_weight_combine_kernel<<<(b->n_graphs + 255) / 256, 256, 0, ctx->stream>>>(b->n_graphs, (int)splits,
+                                                                                        partial, total);
+        ctx->launches += 2;
+    }
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
 }

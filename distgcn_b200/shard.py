@@ -6,8 +6,8 @@ conflict graphs shard trivially: every rank takes a contiguous range of graphs b
 ``torch.distributed`` is used only for the rendezvous and for collecting results (gloo on CPU in the
 tests, nccl's process group with CPU tensors via gather_object on the GPU box).
 
-A single graph too large for one GPU would need a row partition with a per-layer halo exchange
-(SURVEY.md 8e, config 5); that path is not built yet - see DESIGN.md "Multi-GPU".
+A single graph too large for one GPU is row-partitioned with a per-layer halo exchange (SURVEY.md 8e,
+config 5): ``RowPartitionedSolver`` below.
 """
 from __future__ import annotations
 
@@ -110,13 +110,13 @@ class RowPartitionedSolver:
     Every rank holds rows [rank*per, (rank+1)*per) as a local CSR with global column ids and global-sized
     per-vertex arrays; each kernel writes the rank's rows and the rows are all-gathered (NCCL over NVLink)
     before the next kernel reads neighbours.  What crosses the links per solve: keep bytes, y (fp32), for each
-    hidden layer the feature rows it reads, (q, zs) pairs, utilities (fp64), and per greedy round two bitmaps
+    hidden layer the feature rows it reads, zs (fp32), utilities (fp64), and per greedy round two bitmaps
     of n/8 bytes plus one 8-byte count.  A model without hidden layers (c64 l2, config 5) exchanges scalars
     only - the rank-1 first layer and project-first last layer of DESIGN.md section 2.
     """
 
     def __init__(self, model, n_global: int, row_ptr_local: np.ndarray, col_idx_global: np.ndarray, rank: int = 0,
-                 world_size: int = 1, group=None, device: Optional[int] = None):
+                 world_size: int = 1, group=None, device: Optional[int] = None, exchange: str = "nccl"):
         import ctypes as C
 
         import torch
@@ -153,6 +153,143 @@ class RowPartitionedSolver:
                                            _lib.MEM_DEVICE, C.byref(h)))
         self.part = h
         self.exchanged_bytes = 0
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.exchange = exchange if self.world > 1 else "nccl"
+        self.arena = None
+        if self.exchange == "p2p":
+            self._setup_arena()
+
+    # ---- peer arenas: the exchange fused into the kernels (include/distgcn_b200.h, "peer arenas") ----------
+    def _setup_arena(self):
+        import torch.distributed as dist
+        C, lib = self.C, self.lib
+        L = self.model.n_layers
+        cp = max([int(lib.dg_model_padded_width(self.model.handle, l)) for l in range(1, L - 1)] or [0])
+        n_pad = self.n_pad
+        off, lay = 0, {}
+
+        def take(name, nbytes):
+            nonlocal off
+            lay[name] = off
+            off += (nbytes + 255) // 256 * 256
+
+        take("keep", n_pad)
+        take("y", 4 * n_pad)
+        take("pair2", 8 * n_pad)
+        take("util", 8 * n_pad)
+        take("remain", n_pad // 8)
+        take("joined", n_pad // 8)
+        if L > 2:
+            take("dinv", 4 * n_pad)
+            take("pair", 8 * n_pad)
+        if L > 3:   # rows of hidden layers that a following hidden layer gathers
+            take("hid0", 4 * n_pad * cp)
+            take("hid1", 4 * n_pad * cp)
+        take("flags", 4 * 8)
+        take("counts", 8 * 8)
+        self.arena_bytes, self.lay = off, lay
+        base = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        self.check(lib.dg_peer_alloc(self.ctx.handle, C.c_uint64(off), C.byref(base), handle))
+        self.arena = int(base.value)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        bases = (C.c_void_p * self.world)()
+        self._opened = []
+        for r in range(self.world):
+            if r == self.rank:
+                bases[r] = self.arena
+            else:
+                q = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                self.check(lib.dg_peer_open(self.ctx.handle, hb, C.byref(q)))
+                bases[r] = q.value
+                self._opened.append(int(q.value))
+        self.check(lib.dg_part_set_peers(self.part, self.world, self.rank, bases, C.c_uint64(off),
+                                         C.c_uint64(lay["flags"]), C.c_uint64(lay["counts"])))
+        dist.barrier(group=self.group)   # every rank has mapped every arena before anyone stores into one
+
+    def _a(self, name):
+        return self.C.c_void_p(self.arena + self.lay[name])
+
+    def _solve_p2p(self, wts_local, predict, remove_zero_weight):
+        torch, lib, part, m, C = self.torch, self.lib, self.part, self.model, self.C
+        from . import engine
+        dev, n_pad, per, r0 = self.device, self.n_pad, self.per, self.row0
+        w_local = np.zeros(per, dtype=np.float64)
+        w_in = np.asarray(wts_local, dtype=np.float64).reshape(-1)
+        w_local[: w_in.shape[0]] = w_in
+        wts = torch.zeros(n_pad, dtype=torch.float64, device=dev)
+        wts[r0:r0 + per] = torch.from_numpy(w_local).to(dev)
+        F, L = m.feature_size, m.n_layers
+        barrier = lambda cnt=None: self.check(lib.dg_part_barrier(part, cnt))  # noqa: E731
+        barrier()   # the previous solve has drained on every rank
+        self.check(lib.dg_part_keep(part, self._p(wts), 1 if remove_zero_weight else 0, self.n_global, self._a("keep")))
+        barrier()
+        dinv_t = None
+        if L > 2:
+            dinv = self._a("dinv")
+        else:
+            dinv_t = torch.empty(n_pad, dtype=torch.float32, device=dev)
+            dinv = self._p(dinv_t)
+        self.check(lib.dg_part_prepare(part, F, self._a("keep"), None, dinv, self._a("y")))
+        barrier()
+        if L > 2:
+            pair = self._a("pair")
+        else:
+            pair_t = torch.empty(n_pad, 2, dtype=torch.float32, device=dev)
+            pair = self._p(pair_t)
+        self.check(lib.dg_part_first(part, F, dinv, self._a("y"), self._a("keep"), None, pair))
+        if L == 2:
+            self.check(lib.dg_part_project(part, m.handle, dinv, pair, self._a("pair2")))
+        else:
+            barrier()   # (x0, s) pairs and dinv of the neighbours
+            hin, keepalive = None, []
+            for layer in range(1, L - 1):
+                cp = int(lib.dg_model_padded_width(m.handle, layer))
+                if layer < L - 2:
+                    hout = self._a("hid%d" % (layer % 2))   # gathered by the next hidden layer: pushed to the peers
+                else:
+                    t = torch.empty(n_pad, cp, dtype=torch.float32, device=dev)   # only this rank's rows are read
+                    keepalive.append(t)
+                    hout = self._p(t)
+                self.check(lib.dg_part_layer(part, m.handle, layer, dinv, pair, hin, hout))
+                if layer < L - 2:
+                    barrier()
+                hin = hout
+            self.check(lib.dg_part_tail(part, m.handle, dinv, hin, self._a("pair2")))
+        barrier()   # zs
+        score = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.check(lib.dg_part_last(part, m.handle, dinv, self._a("pair2"), self._a("keep"), self._p(wts),
+                                    engine.predict_code(predict), self._p(score), self._a("util")))
+        barrier()   # utilities
+        member = torch.zeros(n_pad, dtype=torch.uint8, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        counts_view = _device_view(self.arena + self.lay["counts"], (self.world,), "<i8", dev)
+        self.check(lib.dg_part_lgs_init(part, self._a("keep"), self._a("remain"), self._p(member), self._p(count)))
+        barrier(self._p(count))
+        rounds = 0
+        while True:
+            if int(counts_view.sum().item()) == 0:
+                break
+            if rounds >= (1 << 20):
+                raise RuntimeError("local greedy search did not converge (NaN utilities or self-loops?)")
+            self.check(lib.dg_part_lgs_decide(part, self._a("util"), self._a("remain"), self._a("joined"),
+                                              self._p(member)))
+            barrier()
+            count.zero_()
+            self.check(lib.dg_part_lgs_remove(part, self._a("joined"), self._a("remain"), self._p(count)))
+            barrier(self._p(count))
+            rounds += 1
+        self.ctx.synchronize()   # also surfaces a barrier time-out
+        # bytes this rank stored into its peers' arenas (what an all-gather would have moved)
+        per_solve = per * (1 + 4 + 4 + 8) + (rounds * 2 + 1) * (per // 8)
+        if L > 2:
+            per_solve += per * (4 + 8) + sum(per * 4 * int(lib.dg_model_padded_width(m.handle, l))
+                                            for l in range(1, L - 2))
+        self.exchanged_bytes += (self.world - 1) * per_solve
+        return (member[r0:r0 + per].cpu().numpy(), score[r0:r0 + per].cpu().numpy(), rounds)
 
     def _p(self, t):
         return None if t is None else self.C.c_void_p(t.data_ptr())
@@ -172,6 +309,8 @@ class RowPartitionedSolver:
         """wts_local: this rank's `per` weights (rows past n_global ignored).  Returns (member_local uint8
         [per], score_local float32 [per], rounds)."""
         with self.torch.cuda.stream(self.stream):
+            if self.exchange == "p2p":
+                return self._solve_p2p(wts_local, predict, remove_zero_weight)
             return self._solve(wts_local, predict, remove_zero_weight)
 
     def _solve(self, wts_local, predict, remove_zero_weight):
@@ -192,7 +331,7 @@ class RowPartitionedSolver:
         dinv = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         y = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         pair = torch.zeros(n_pad, 2, dtype=torch.float32, device=dev)
-        pair2 = torch.zeros(n_pad, 2, dtype=torch.float32, device=dev)
+        pair2 = torch.zeros(2, n_pad, dtype=torch.float32, device=dev)   # planar: q plane, zs plane
         self.check(lib.dg_part_prepare(part, F, self._p(keep), None, self._p(dinv), self._p(y)))
         self._gather(y)
         self.check(lib.dg_part_first(part, F, self._p(dinv), self._p(y), self._p(keep), None, self._p(pair)))
@@ -212,7 +351,7 @@ class RowPartitionedSolver:
                     self._gather(hout, cp)  # the next hidden layer reads neighbours' rows
                 hin = hout
             self.check(lib.dg_part_tail(part, m.handle, self._p(dinv), self._p(hin), self._p(pair2)))
-        self._gather(pair2, 2)
+        self._gather(pair2[1])   # only zs is read from other ranks' rows
         score = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         util = torch.zeros(n_pad, dtype=torch.float64, device=dev)
         self.check(lib.dg_part_last(part, m.handle, self._p(dinv), self._p(pair2), self._p(keep), self._p(wts),
@@ -256,5 +395,26 @@ class RowPartitionedSolver:
         if self.part is not None:
             self.lib.dg_part_destroy(self.part)
             self.part = None
+        if self.arena is not None:
+            import torch.distributed as dist
+            self.ctx.synchronize()
+            dist.barrier(group=self.group)   # nobody stores into an arena that is about to go away
+            for q in self._opened:
+                self.lib.dg_peer_close(self.ctx.handle, self.C.c_void_p(q))
+            dist.barrier(group=self.group)
+            self.lib.dg_peer_free(self.ctx.handle, self.C.c_void_p(self.arena))
+            self.arena = None
         self.model.close()
         self.ctx.close()
+
+
+class _RawCuda:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _device_view(ptr: int, shape, typestr: str, device):
+    """torch tensor over raw device memory (no copy, no ownership)."""
+    import torch
+    return torch.as_tensor(_RawCuda(ptr, shape, typestr), device=device)

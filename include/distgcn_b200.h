@@ -196,8 +196,10 @@ DG_API int dg_solve_host_async(dg_context *ctx, const dg_model *model, int32_t n
  * argument below is a DEVICE pointer to a GLOBAL-sized array indexed by global vertex id (float2 arrays as
  * 2*n_global floats, bitmaps as n_global/32 words).  A call may read any vertex's entry and writes only
  * this part's rows; between calls the caller makes the written rows visible to the other ranks
- * (all-gather over NVLink, e.g. torch.distributed / NCCL - see distgcn_b200/shard.py).  The sequence for a
- * model without hidden layers (e.g. c64 l2) exchanges only scalars: y, (q,zs), utilities, bitmap words. */
+ * (all-gather over NVLink, e.g. torch.distributed / NCCL - see distgcn_b200/shard.py).  pair2 is PLANAR:
+ * q = pair2[0 .. n_global), zs = pair2[n_global .. 2 n_global); only the zs plane is read from other ranks.
+ * The sequence for a model without hidden layers (e.g. c64 l2) exchanges only scalars: y, zs, utilities,
+ * bitmap words. */
 DG_API int dg_part_create(dg_context *ctx, int32_t n_global, int32_t row0, int32_t n_local, int32_t nnz_local,
                           const int32_t *row_ptr_local, const int32_t *col_idx_global, int mem, dg_part **out);
 DG_API void dg_part_destroy(dg_part *part);
@@ -227,6 +229,35 @@ DG_API int dg_part_lgs_init(dg_part *part, const uint8_t *keep, uint32_t *remain
 DG_API int dg_part_lgs_decide(dg_part *part, const double *util, const uint32_t *remain, uint32_t *joined,
                               uint8_t *member);
 DG_API int dg_part_lgs_remove(dg_part *part, const uint32_t *joined, uint32_t *remain, int64_t *count);
+
+/* ---- exchange fused into the kernels: peer arenas over NVLink / NVSwitch (one process per GPU) ------------
+ * Instead of all-gathering after every dg_part_* call, the ranks can share one "arena" each: a device
+ * allocation of identical size and layout on every rank, exported with CUDA IPC and mapped by the others.
+ * After dg_part_set_peers, every dg_part_* call that writes a quantity other ranks read next (keep, dinv, y,
+ * (x0,s) pairs, hidden rows, zs, utilities, bitmap words) stores it to its own arena AND, at the same offset,
+ * to every peer's arena from the kernel's epilogue, provided the output pointer lies inside the own arena.
+ * dg_part_barrier then orders the ranks on their streams (flag exchange through the arenas, no host
+ * round trip); with `count` it also publishes this rank's 8-byte count into slot [rank] of every arena's
+ * count block, so that after the barrier each rank holds all ranks' counts (greedy-round termination). */
+#define DG_PEER_HANDLE_BYTES 64
+/* cudaMalloc + zero `bytes` on the context's device and export it: handle_out receives DG_PEER_HANDLE_BYTES
+ * bytes to send to the other ranks (any byte transport, e.g. torch.distributed.all_gather_object). */
+DG_API int dg_peer_alloc(dg_context *ctx, uint64_t bytes, void **dev_ptr, uint8_t *handle_out);
+/* map another rank's arena from its handle / unmap it / free an own arena */
+DG_API int dg_peer_open(dg_context *ctx, const uint8_t *handle, void **peer_ptr);
+DG_API int dg_peer_close(dg_context *ctx, void *peer_ptr);
+DG_API int dg_peer_free(dg_context *ctx, void *dev_ptr);
+/* arena_bases[r] = rank r's arena as mapped in this process (arena_bases[rank] = the own allocation);
+ * flags_offset / counts_offset: 4*world and 8*world bytes inside the arena reserved for the barrier
+ * (zero-initialised, never touched by the caller).  world <= 8. */
+DG_API int dg_part_set_peers(dg_part *part, int32_t world, int32_t rank, void *const *arena_bases,
+                             uint64_t arena_bytes, uint64_t flags_offset, uint64_t counts_offset);
+/* keep rows of this part: v < n_real (rows past the real vertex count are padding) and, with
+ * remove_zero_weight, wts[v] != 0 (mwis_dqn_call.py:203-204); wts is global-indexed, own rows valid */
+DG_API int dg_part_keep(dg_part *part, const double *wts, int remove_zero_weight, int32_t n_real, uint8_t *keep);
+/* cross-rank barrier on the stream; count may be NULL.  A rank that does not arrive within ~4 s makes the
+ * next synchronising call fail with DG_ERR_CUDA instead of hanging the GPUs. */
+DG_API int dg_part_barrier(dg_part *part, const int64_t *count);
 
 #ifdef __cplusplus
 }

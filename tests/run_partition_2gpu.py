@@ -2,6 +2,7 @@
 the CPU oracle for a 2-layer model and against the single-GPU result for a deep one."""
 import os
 import sys
+import time
 
 import numpy as np
 import scipy.sparse as sp
@@ -26,20 +27,25 @@ def main():
     w = rng.random(n)
     w[rng.random(n) < 0.05] = 0.0
     ok = True
-    for short in ("is4sat_l2_c64", "is4sat_l3_c16"):
+    cases = [(short, ex) for ex in ("nccl", "p2p") for short in ("is4sat_l2_c64", "is4sat_l3_c16", "is4sat_l20_c32")]
+    for short, exchange in cases:
+        if short == "is4sat_l20_c32" and n > 400000:
+            continue
         layers = util.load_layers(short)
         acts = E.gcn_dqn_acts(len(layers))
         per, n_pad = row_slices(n, world)
         rp, ci = slice_csr(a.indptr, a.indices, n, rank, world)
-        solver = RowPartitionedSolver(_ModelSpec(layers, acts), n, rp, ci, rank=rank, world_size=world)
+        solver = RowPartitionedSolver(_ModelSpec(layers, acts), n, rp, ci, rank=rank, world_size=world,
+                                      exchange=exchange)
         w_local = w[rank * per:min(n, (rank + 1) * per)]
+        solver.solve(w_local)   # warm-up (allocations, NCCL channels)
+        solver.exchanged_bytes = 0
         torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+        dist.barrier()
+        t0 = time.perf_counter()
         member, score, rounds = solver.solve(w_local)
-        ev1.record()
         torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1)
+        ms = 1e3 * (time.perf_counter() - t0)
         gathered = [None] * world
         dist.all_gather_object(gathered, (member, score))
         if rank == 0:
@@ -51,9 +57,16 @@ def main():
             ref = E.solve(ctx, model, batch, w, want_score=True)
             same = bool(np.array_equal(full_m, ref.member))
             err = float(np.abs(full_s - ref.score[:, 0]).max() / max(np.abs(ref.score).max(), 1e-30))
-            print("PART %s n=%d world=%d rounds=%d ms=%.2f exchanged_MB=%.1f membership_equal=%s score_err=%.2e"
-                  % (short, n, world, rounds, ms, solver.exchanged_bytes / 1e6, same, err))
-            ok = ok and same and err < 2e-6
+            print("PART %s %s n=%d world=%d rounds=%d ms=%.2f exchanged_MB=%.1f membership_equal=%s score_err=%.2e"
+                  % (short, exchange, n, world, rounds, ms, solver.exchanged_bytes / 1e6, same, err))
+            tol = 2e-6 if len(layers) < 20 else 2e-5
+            if not same:   # only near-ties flipped by fp32 summation order may differ (see test_gpu_partition.py)
+                from oracle import lgs as OL
+                keep = (w != 0).astype(np.uint8)
+                o = OL.run(a.indptr, a.indices, full_s.astype(np.float64) * w, init_remain=keep)
+                same = bool(np.array_equal(o.member, full_m)) and int((full_m != ref.member).sum()) <= 8
+                print("   exact on its own utilities: %s" % same)
+            ok = ok and same and err < tol
             batch.close(); model.close(); ctx.close()
         solver.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

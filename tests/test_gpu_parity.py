@@ -253,6 +253,51 @@ def _assert_membership(pb, r, w, ref_member, ref_util):
     assert len(bad) == 0, "graphs with membership different from the reference: %s" % bad
 
 
+@pytest.mark.parametrize("short", ["is4sat_l2_c64", "is4sat_l3_c16"])
+def test_large_single_graph_stream_path(gpu_ctx, short):
+    """One graph far above the graph-resident limit (CSR-stream scalar passes, per-layer kernel, global greedy
+    rounds, sliced weight total): a hub whose row spans many stream tiles, isolated vertices, zero weights."""
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    rng = np.random.default_rng(17)
+    n, deg, hub_deg = 150000, 14, 30000
+    m = n * deg // 2
+    u = rng.integers(0, n - 500, m)            # the last 500 vertices stay isolated
+    v = rng.integers(0, n - 500, m)
+    hub = np.full(hub_deg, 7)
+    hv = rng.choice(np.arange(8, n - 500), hub_deg, replace=False)
+    u, v = np.concatenate([u, hub]), np.concatenate([v, hv])
+    ok = u != v
+    a = sp.coo_matrix((np.ones(ok.sum()), (u[ok], v[ok])), shape=(n, n))
+    a = ((a + a.T) > 0).astype(np.float64).tocsr()
+    pb = pack_graphs([a])
+    w = rng.random(n)
+    w[rng.random(n) < 0.05] = 0.0
+    layers = util.load_layers(short)
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True, want_steps=True)
+    # yardstick: the float64 evaluation only - the fp32 numpy restatement itself is 1.4e-4 off on the hub's
+    # 30 000-term row sum, so it is no reference at this size
+    exact = util.exact_scores(pb, w, layers)
+    err = _rel_err(r.score[:, 0], exact)
+    print("%s (large graph): cuda-vs-exact %.3g" % (short, err))
+    assert err <= SCORE_RTOL
+    assert np.array_equal(r.util, r.score[:, 0].astype(np.float64) * w)
+    keep = (w != 0).astype(np.uint8)
+    o = L.run(pb.row_ptr, pb.col_idx, r.util, init_remain=keep)   # the reference rule on the GPU's utilities
+    assert np.array_equal(o.member, r.member)
+    assert int(r.steps[0]) == int(o.steps)
+    assert not r.member[w == 0].any()
+    assert abs(float(r.total[0]) - float(w[r.member == 1].sum())) <= 1e-9 * max(1.0, float(r.total[0]))
+    # against the greedy rule on the float64 scores: only near-ties that fp32 rounding flips may differ
+    o64 = L.run(pb.row_ptr, pb.col_idx, exact * w, init_remain=keep)
+    assert (r.member != o64.member).mean() < 2e-3
+    batch.close()
+    model.close()
+
+
 @pytest.mark.parametrize("short", ["is4sat_l1", "is4sat_l20_c32", "is4sat_l2_c64"])
 def test_zero_weight_removal(gpu_ctx, short):
     E = _engine()

@@ -139,20 +139,30 @@ class RowPartitionedSolver:
                                   [l.act_code for l in model.layers] if hasattr(model, "layers") else model[1])
         if self.model.n_layers < 2 or self.model.out_width != 1:
             raise NotImplementedError("row-partitioned path: >= 2 layers and one output column")
-        rp = np.ascontiguousarray(row_ptr_local, dtype=np.int32)
-        ci = np.ascontiguousarray(col_idx_global, dtype=np.int32)
-        if rp.shape[0] != self.per + 1:
+        if hasattr(row_ptr_local, "is_cuda"):   # int32 CUDA tensors: used in place
+            if not (row_ptr_local.is_cuda and col_idx_global.is_cuda and row_ptr_local.dtype == torch.int32
+                    and col_idx_global.dtype == torch.int32):
+                raise TypeError("device CSR slices must be int32 CUDA tensors")
+            self.d_rp, self.d_ci = row_ptr_local.contiguous(), col_idx_global.contiguous()
+            torch.cuda.synchronize(self.device)
+            n_rp, nnz_local = int(self.d_rp.numel()), int(self.d_ci.numel())
+        else:
+            rp = np.ascontiguousarray(row_ptr_local, dtype=np.int32)
+            ci = np.ascontiguousarray(col_idx_global, dtype=np.int32)
+            with torch.cuda.stream(self.stream):
+                self.d_rp = torch.from_numpy(rp).to(self.device)
+                self.d_ci = torch.from_numpy(ci).to(self.device)
+            self.stream.synchronize()
+            n_rp, nnz_local = int(rp.shape[0]), int(ci.shape[0])
+        if n_rp != self.per + 1:
             raise ValueError("row_ptr_local must have %d entries" % (self.per + 1))
-        with torch.cuda.stream(self.stream):
-            self.d_rp = torch.from_numpy(rp).to(self.device)
-            self.d_ci = torch.from_numpy(ci).to(self.device)
-        self.stream.synchronize()
         h = C.c_void_p()
-        self.check(self.lib.dg_part_create(self.ctx.handle, self.n_pad, self.row0, self.per, int(ci.shape[0]),
+        self.check(self.lib.dg_part_create(self.ctx.handle, self.n_pad, self.row0, self.per, nnz_local,
                                            C.c_void_p(self.d_rp.data_ptr()), C.c_void_p(self.d_ci.data_ptr()),
                                            _lib.MEM_DEVICE, C.byref(h)))
         self.part = h
         self.exchanged_bytes = 0
+        self.keep_on_device = False   # True: solve() returns CUDA tensors instead of numpy arrays
         if exchange not in ("nccl", "p2p"):
             raise ValueError("exchange must be 'nccl' or 'p2p'")
         self.exchange = exchange if self.world > 1 else "nccl"
@@ -217,11 +227,12 @@ class RowPartitionedSolver:
         torch, lib, part, m, C = self.torch, self.lib, self.part, self.model, self.C
         from . import engine
         dev, n_pad, per, r0 = self.device, self.n_pad, self.per, self.row0
-        w_local = np.zeros(per, dtype=np.float64)
-        w_in = np.asarray(wts_local, dtype=np.float64).reshape(-1)
-        w_local[: w_in.shape[0]] = w_in
         wts = torch.zeros(n_pad, dtype=torch.float64, device=dev)
-        wts[r0:r0 + per] = torch.from_numpy(w_local).to(dev)
+        if hasattr(wts_local, "is_cuda"):
+            wts[r0:r0 + wts_local.numel()] = wts_local.to(dev, torch.float64).reshape(-1)
+        else:
+            w_in = np.asarray(wts_local, dtype=np.float64).reshape(-1)
+            wts[r0:r0 + w_in.shape[0]] = torch.from_numpy(w_in).to(dev)
         F, L = m.feature_size, m.n_layers
         barrier = lambda cnt=None: self.check(lib.dg_part_barrier(part, cnt))  # noqa: E731
         barrier()   # the previous solve has drained on every rank
@@ -289,6 +300,8 @@ class RowPartitionedSolver:
             per_solve += per * (4 + 8) + sum(per * 4 * int(lib.dg_model_padded_width(m.handle, l))
                                             for l in range(1, L - 2))
         self.exchanged_bytes += (self.world - 1) * per_solve
+        if self.keep_on_device:
+            return member[r0:r0 + per], score[r0:r0 + per], rounds
         return (member[r0:r0 + per].cpu().numpy(), score[r0:r0 + per].cpu().numpy(), rounds)
 
     def _p(self, t):
@@ -317,15 +330,14 @@ class RowPartitionedSolver:
         torch, lib, part, m = self.torch, self.lib, self.part, self.model
         from . import engine
         dev, n_pad, per, r0 = self.device, self.n_pad, self.per, self.row0
-        w_local = np.zeros(per, dtype=np.float64)
-        w_in = np.asarray(wts_local, dtype=np.float64).reshape(-1)
-        w_local[: w_in.shape[0]] = w_in
-        valid = np.arange(r0, r0 + per) < self.n_global
-        keep_local = valid & ((w_local != 0) if remove_zero_weight else True)
         wts = torch.zeros(n_pad, dtype=torch.float64, device=dev)
-        wts[r0:r0 + per] = torch.from_numpy(w_local).to(dev)
+        if hasattr(wts_local, "is_cuda"):
+            wts[r0:r0 + wts_local.numel()] = wts_local.to(dev, torch.float64).reshape(-1)
+        else:
+            w_in = np.asarray(wts_local, dtype=np.float64).reshape(-1)
+            wts[r0:r0 + w_in.shape[0]] = torch.from_numpy(w_in).to(dev)
         keep = torch.zeros(n_pad, dtype=torch.uint8, device=dev)
-        keep[r0:r0 + per] = torch.from_numpy(keep_local.astype(np.uint8)).to(dev)
+        self.check(lib.dg_part_keep(part, self._p(wts), 1 if remove_zero_weight else 0, self.n_global, self._p(keep)))
         self._gather(keep)
         F = m.feature_size
         dinv = torch.zeros(n_pad, dtype=torch.float32, device=dev)
@@ -380,6 +392,8 @@ class RowPartitionedSolver:
             self.check(lib.dg_part_lgs_remove(part, self._p(joined), self._p(remain), self._p(count)))
             rounds += 1
         self.stream.synchronize()
+        if self.keep_on_device:
+            return member[r0:r0 + per], score[r0:r0 + per], rounds
         return (member[r0:r0 + per].cpu().numpy(), score[r0:r0 + per].cpu().numpy(), rounds)
 
     def _gather_words(self, words):

@@ -838,6 +838,97 @@ static int solve_device(dg_context *ctx, const dg_model *m, dg_batch *b, const d
     return DG_OK;
 }
 
+// GCN embedded into the greedy iteration (mwis_gdpg_call.py:278-318), device-space body
+static int solve_dit_device(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
+                            uint8_t *d_member, double *d_total, int32_t *d_steps) {
+    const size_t n = (size_t)b->n_nodes, G = (size_t)b->n_graphs;
+    if (n == 0 || G == 0) return DG_OK;
+    bool handled = false;
+    DG_TRY(fused_try_solve(ctx, m, b, d_wts, predict, 0, d_member, nullptr, nullptr, d_total, d_steps, &handled, true));
+    if (handled) return DG_OK;
+    // generic path: a handful of launches per iteration over the per-layer kernels
+    const int d_out = m->layers.back().c_out;
+    float *d_score = nullptr;
+    double *d_util = nullptr;
+    uint8_t *d_joined = nullptr, *d_nbis = nullptr, *saved_keep = nullptr;
+    int *d_flag = nullptr;
+    DG_TRY(scratch_as(ctx, kSlotScore, n * d_out, &d_score));
+    DG_TRY(scratch_as(ctx, kSlotUtil, n, &d_util));
+    DG_TRY(scratch_as(ctx, kSlotStageIn1, n, &d_joined));
+    DG_TRY(scratch_as(ctx, kSlotStageIn2, n, &d_nbis));
+    DG_TRY(scratch_as(ctx, kSlotStageOut0, G + 1, &d_flag));
+    int *d_any = d_flag + G;
+    const bool had_keep = b->keep != nullptr;
+    if (had_keep) {  // the caller's mask is the initial residual graph; put it back afterwards
+        DG_TRY(scratch_as(ctx, kSlotStageOut1, n, &saved_keep));
+        DG_CUDA_CHECK(cudaMemcpyAsync(saved_keep, b->keep, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        DG_CUDA_CHECK(cudaMalloc((void **)&b->keep, std::max<size_t>(b->cap_nodes, 1)));
+        DG_CUDA_CHECK(cudaMemsetAsync(b->keep, 1, n, ctx->stream));
+    }
+    DG_CUDA_CHECK(cudaMemsetAsync(d_member, 0, n, ctx->stream));
+    if (d_steps) DG_CUDA_CHECK(cudaMemsetAsync(d_steps, 0, sizeof(int32_t) * G, ctx->stream));
+    int st = DG_OK;
+    for (int it = 0; st == DG_OK; ++it) {
+        if (it >= kLgsRoundCap) {
+            set_error("iterative solve hit the round cap (NaN utilities or self-loops?)");
+            st = DG_ERR_NOT_CONVERGED;
+            break;
+        }
+        if ((st = dit_filter_device(ctx, b, d_wts, b->keep, d_flag, d_any)) != DG_OK) break;
+        if (cudaMemcpyAsync(ctx->h_flag + 1, d_any, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            set_error("CUDA error in the iterative solve: %s", cudaGetErrorString(cudaGetLastError()));
+            st = DG_ERR_CUDA;
+            break;
+        }
+        if (ctx->h_flag[1] == 0) break;
+        if ((st = dit_steps_device(ctx, (int)G, d_flag, d_steps)) != DG_OK) break;
+        if ((st = batch_compute_dinv(b)) != DG_OK) break;
+        if ((st = gcn_forward_device(ctx, m, b, d_score, d_wts, predict, d_util)) != DG_OK) break;
+        if ((st = lgs_device(ctx, b, d_util, 1, d_joined, d_nbis, nullptr, nullptr, nullptr, nullptr)) != DG_OK) break;
+        st = dit_update_device(ctx, (int)n, d_joined, d_nbis, d_member, b->keep);
+    }
+    // leave the batch as it was found
+    if (had_keep) {
+        cudaMemcpyAsync(b->keep, saved_keep, n, cudaMemcpyDeviceToDevice, ctx->stream);
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b->keep);
+        b->keep = nullptr;
+    }
+    int st2 = batch_compute_dinv(b);
+    if (st != DG_OK) return st;
+    DG_TRY(st2);
+    if (d_total) DG_TRY(member_weight_device(ctx, b, d_member, d_wts, d_total));
+    return DG_OK;
+}
+
+int dg_solve_dit(dg_context *ctx, const dg_model *m, dg_batch *b, const double *wts, int predict, uint8_t *member,
+                 double *total, int32_t *steps, int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(m && b && wts && member, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(predict == DG_PREDICT_MWIS || predict == DG_PREDICT_MIS, DG_ERR_INVALID, "unknown predict mode");
+    DG_REQUIRE(m->layers.back().c_out == 1 && m->head == DG_HEAD_LINEAR, DG_ERR_UNSUPPORTED,
+               "the iterative solve needs a one-column linear head");
+    DeviceGuard guard(ctx->device);
+    if (mem == DG_MEM_DEVICE) return solve_dit_device(ctx, m, b, wts, predict, member, total, steps);
+    const size_t n = (size_t)b->n_nodes, G = (size_t)b->n_graphs;
+    double *d_wts = nullptr, *d_total = nullptr;
+    uint8_t *d_member = nullptr;
+    int32_t *d_steps = nullptr;
+    DG_TRY(stage_in(ctx, kSlotWts, wts, n, &d_wts));
+    DG_TRY(scratch_as(ctx, kSlotMember, n, &d_member));
+    if (total) DG_TRY(scratch_as(ctx, kSlotTotal, G, &d_total));
+    if (steps) DG_TRY(scratch_as(ctx, kSlotSteps, G, &d_steps));
+    DG_TRY(solve_dit_device(ctx, m, b, d_wts, predict, d_member, d_total, d_steps));
+    DG_TRY(copy_out(ctx, member, d_member, n));
+    DG_TRY(copy_out(ctx, total, d_total, G));
+    DG_TRY(copy_out(ctx, steps, d_steps, G));
+    return finish(ctx);
+}
+
 int dg_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *wts, int predict,
              int remove_zero_weight, uint8_t *member, float *score, double *util, double *total, int32_t *steps,
              int mem) {

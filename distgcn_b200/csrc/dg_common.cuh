@@ -233,6 +233,10 @@ int part_tail(dg_context *ctx, const PartView &pv, const dg_model *m, const floa
               float *pair2);
 int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const float *dinv, const float *pair2,
               const uint8_t *keep, const double *wts, int predict, float *score, double *util);
+int dit_filter_device(dg_context *ctx, const dg_batch *b, const double *wts, uint8_t *keep, int *flag, int *any_left);
+int dit_steps_device(dg_context *ctx, int n_graphs, const int *flag, int *steps);
+int dit_update_device(dg_context *ctx, int n, const uint8_t *joined, const uint8_t *nb_is, uint8_t *member,
+                      uint8_t *keep);
 int part_keep(dg_context *ctx, const PartView &pv, const double *wts, int remove_zero_weight, int n_real,
               uint8_t *keep);
 int part_barrier(dg_context *ctx, const PeerMap &pm, unsigned long long flags_off, unsigned epoch,
@@ -247,8 +251,8 @@ int part_lgs_remove(dg_context *ctx, const PartView &pv, const uint32_t *joined,
 constexpr int kFusedMaxTileGraphs = 64;
 
 struct FusedSmemPlan {  // byte offsets into dynamic shared memory
-    size_t feat_a, feat_b, wbuf, wblob_bytes, util, mbar, dinv, sa, sb, x0s, rp, words, gstart, gcnt, gsteps, col16,
-        gid, vid, slotof, total;
+    size_t feat_a, feat_b, wbuf, wblob_bytes, util, mbar, dinv, sa, sb, x0s, rp, words, gstart, gcnt, gsteps, gpos,
+        col16, gid, vid, slotof, total;
     int n_words;
 };
 
@@ -283,13 +287,15 @@ struct FusedParams {
     int *status;
     int round_cap;
     int do_lgs;        // 0: stop after the scores (dg_gcn_forward)
+    int dit;           // 1: GCN embedded into the greedy iteration (mwis_gdpg_call.py:278-318): re-score the residual
+                       //    graph before every single greedy round
     long long *dbg;  // optional per-CTA phase timers (16 slots per CTA), see DG_FUSED_TIMING in bench tools
 };
 
 // Runs the whole solve in the fused kernel when model and batch are eligible; *handled tells.
 int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
                     int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
-                    int32_t *steps, bool *handled);
+                    int32_t *steps, bool *handled, bool dit = false);
 
 // ---- kernels / drivers implemented in dg_gcn.cu ---------------------------------------------
 int batch_compute_dinv(dg_batch *b);

@@ -120,6 +120,8 @@ __host__ __device__ inline FusedSmemPlan fused_smem_plan(int cp, int cap_n, int 
     off += sizeof(int) * kFusedMaxTileGraphs;
     p.gsteps = off;
     off += sizeof(int) * kFusedMaxTileGraphs;
+    p.gpos = off;
+    off += sizeof(int) * kFusedMaxTileGraphs;
     p.col16 = off = align_up(off, 8);
     off += sizeof(uint16_t) * (size_t)cap_nnz;
     p.gid = off = align_up(off, 4);
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
     int *gstart = reinterpret_cast<int *>(smem_raw + plan.gstart);
     int *gcnt = reinterpret_cast<int *>(smem_raw + plan.gcnt);
     int *gsteps = reinterpret_cast<int *>(smem_raw + plan.gsteps);
+    int *gpos = reinterpret_cast<int *>(smem_raw + plan.gpos);
     uint16_t *col16 = reinterpret_cast<uint16_t *>(smem_raw + plan.col16);
     uint8_t *gid = reinterpret_cast<uint8_t *>(smem_raw + plan.gid);
     uint16_t *vid = reinterpret_cast<uint16_t *>(smem_raw + plan.vid);        // slot -> local vertex id
@@ -255,6 +258,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
             for (int j2 = 0; j2 < n; ++j2) r += key[j2] > mine;
             slotof[i] = (uint16_t)r;
             vid[r] = (uint16_t)i;
+            int lo = 0, hi = ng;  // gstart[lo] <= i < gstart[hi]: the tile-local graph of vertex i
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (gstart[mid] <= i) lo = mid; else hi = mid;
+            }
+            gid[r] = (uint8_t)lo;
         }
         __syncthreads();
         {   // exclusive scan of the padded row lengths in slot order -> rp[0..n]
@@ -322,7 +331,42 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         (void)e0;
         __syncthreads();
 
-        // ---- 2. degrees on the kept sub-graph -> dinv, y = dinv * x0, per-slot graph id ---------------
+        // With P.dit the stages 2-7 repeat: the residual graph (vertices neither taken nor excluded yet) is
+        // re-scored by the network before every single greedy round (mwis_gdpg_call.py:278-318).
+        for (int dit_iter = 0;; ++dit_iter) {
+        if (P.dit) {
+            // a graph stops once its residual weights no longer sum to something positive (:296-297; weights are
+            // non-negative, so: once no residual vertex has a positive weight)
+            for (int g = tid; g < ng; g += kThreads) {
+                gpos[g] = 0;
+                gcnt[g] = 0;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += kThreads)
+                if (((keepw[i >> 5] >> (i & 31)) & 1u) && P.wts[v0 + vid[i]] > 0.0) gpos[gid[i]] = 1;
+            __syncthreads();
+            int any_left = 0;
+            for (int base = 0; base < span; base += kThreads) {
+                const int sl = base + tid;
+                const bool k = sl < n && ((keepw[sl >> 5] >> (sl & 31)) & 1u) && gpos[gid[sl]] != 0;
+                const uint32_t w = __ballot_sync(0xffffffffu, k);
+                __syncwarp();
+                if (lane == 0 && sl < span) keepw[sl >> 5] = w;
+                any_left |= k ? 1 : 0;
+            }
+            if (!__syncthreads_or(any_left)) {
+                if (dit_iter == 0 && has_hidden) {  // consume the weight fill issued at the top of the tile
+                    mbar_wait(&mbar[0], wuse & 1u);
+                    ++wuse;
+                }
+                break;
+            }
+            if (dit_iter > 0 && has_hidden && tid == 0) {  // the first hidden layer's weights again
+                mbar_expect_tx(&mbar[0], wblob_bytes);
+                bulk_g2s(wbuf, P.wall, wblob_bytes, &mbar[0]);
+            }
+        }
+        // ---- 2. degrees on the kept sub-graph -> dinv, y = dinv * x0 ----------------------------------
         for (int i = tid; i < n; i += kThreads) {
             const bool k = (keepw[i >> 5] >> (i & 31)) & 1u;
             const int vloc = vid[i];
@@ -339,13 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
             dinv[i] = di;
             x0s[i] = xi;
             sa[i] = di * xi;
-            int lo = 0, hi = ng;  // gstart[lo] <= vloc < gstart[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (gstart[mid] <= vloc) lo = mid; else hi = mid;
-            }
-            gid[i] = (uint8_t)lo;
-            if (k) atomicAdd(&gcnt[lo], 1);
+            if (k) atomicAdd(&gcnt[gid[i]], 1);
         }
         __syncthreads();
 
@@ -802,6 +840,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         int n_remain = 1;
         int rounds = 0;
         while (P.do_lgs) {
+            if (P.dit && rounds >= 1) break;  // one greedy round per re-scoring
             // per-graph round accounting (heuristics.py:119-160): a graph's step count grows while it
             // still has remaining vertices
             int any = 0;
@@ -873,6 +912,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
             ++rounds;
             __syncthreads();
         }
+        if (!P.dit) break;
+        // the residual graph of the next iteration: what is still in `remain`
+        for (int wd = tid; wd < span / 32; wd += kThreads) keepw[wd] = remain[wd];
+        __syncthreads();
+        }  // dit_iter
 
         // ---- 8. per-graph outputs ---------------------------------------------------------------------
         if (P.steps)
@@ -1065,7 +1109,7 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
 
 int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
                     int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
-                    int32_t *steps, bool *handled) {
+                    int32_t *steps, bool *handled, bool dit) {
     *handled = false;
     // member == nullptr: scores only (dg_gcn_forward); the greedy rounds are skipped
     if (member == nullptr && (d_wts == nullptr) && predict == DG_PREDICT_MWIS) return DG_OK;
@@ -1116,6 +1160,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     p.status = ctx->d_status;
     p.round_cap = kLgsRoundCap;
     p.do_lgs = member != nullptr ? 1 : 0;
+    p.dit = (dit && member != nullptr) ? 1 : 0;
     p.dbg = nullptr;
     if (getenv("DG_FUSED_TIMING")) {
         long long *dbg = nullptr;

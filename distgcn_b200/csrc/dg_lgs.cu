@@ -537,6 +537,70 @@ int part_lgs_remove(dg_context *ctx, const PartView &pv, const uint32_t *joined,
     return DG_OK;
 }
 
+// ---- GCN embedded into the greedy iteration (mwis_gdpg_call.py:278-318), generic path --------------------
+// flag[g] = 1 when graph g still has a residual vertex with a positive weight
+__global__ void dit_flag_kernel(int n, int n_graphs, const int *__restrict__ graph_ptr, const uint8_t *__restrict__ keep,
+                                const double *__restrict__ wts, int *__restrict__ flag) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    if (keep[v] && wts[v] > 0.0) flag[n_graphs == 1 ? 0 : graph_of(graph_ptr, n_graphs, v)] = 1;
+}
+
+// graphs without such a vertex stop: their residual vertices leave (:296-297); counts what is left
+__global__ void dit_filter_kernel(int n, int n_graphs, const int *__restrict__ graph_ptr, const int *__restrict__ flag,
+                                  uint8_t *__restrict__ keep, int *__restrict__ any_left) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    bool k = false;
+    if (v < n && keep[v]) {
+        k = flag[n_graphs == 1 ? 0 : graph_of(graph_ptr, n_graphs, v)] != 0;
+        if (!k) keep[v] = 0;
+    }
+    if (__syncthreads_or(k) && threadIdx.x == 0) *any_left = 1;
+}
+
+// after one greedy round: taken vertices accumulate, taken and excluded ones leave the residual graph
+__global__ void dit_update_kernel(int n, const uint8_t *__restrict__ joined, const uint8_t *__restrict__ nb_is,
+                                  uint8_t *__restrict__ member, uint8_t *__restrict__ keep) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    if (joined[v]) member[v] = 1;
+    if (joined[v] || nb_is[v]) keep[v] = 0;
+}
+
+int dit_filter_device(dg_context *ctx, const dg_batch *b, const double *wts, uint8_t *keep, int *flag, int *any_left) {
+    const int n = b->n_nodes, G = b->n_graphs;
+    if (n == 0) return DG_OK;
+    DG_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int) * (size_t)G, ctx->stream));
+    DG_CUDA_CHECK(cudaMemsetAsync(any_left, 0, sizeof(int), ctx->stream));
+    dit_flag_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, G, b->graph_ptr, keep, wts, flag);
+    dit_filter_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, G, b->graph_ptr, flag, keep, any_left);
+    ctx->launches += 2;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+__global__ void dit_steps_kernel(int n_graphs, const int *__restrict__ flag, int *__restrict__ steps) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_graphs && flag[g]) steps[g] += 1;
+}
+
+int dit_steps_device(dg_context *ctx, int n_graphs, const int *flag, int *steps) {
+    if (n_graphs == 0 || !steps) return DG_OK;
+    dit_steps_kernel<<<(n_graphs + 255) / 256, 256, 0, ctx->stream>>>(n_graphs, flag, steps);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int dit_update_device(dg_context *ctx, int n, const uint8_t *joined, const uint8_t *nb_is, uint8_t *member,
+                      uint8_t *keep) {
+    if (n == 0) return DG_OK;
+    dit_update_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, joined, nb_is, member, keep);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
 int part_barrier(dg_context *ctx, const PeerMap &pm, unsigned long long flags_off, unsigned epoch,
                  const long long *count_src, unsigned long long counts_off) {
     if (pm.world <= 1) return DG_OK;

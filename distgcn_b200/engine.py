@@ -346,6 +346,23 @@ def solve(ctx: Context, model: Model, batch: DeviceBatch, wts, predict="mwis", r
     return res
 
 
+def solve_dit(ctx: Context, model: Model, batch: DeviceBatch, wts, predict="mwis", want_total: bool = True,
+              want_steps: bool = False) -> SolveResult:
+    """GCN embedded into the greedy iteration (dg_solve_dit; MWISSolver.solve_mwis_dit, mwis_gdpg_call.py:278-318)
+    on a resident batch with host weight / result arrays."""
+    w = _np(wts, np.float64).reshape(-1)
+    if w.shape[0] != batch.n_nodes:
+        raise ValueError("weights length %d != n_nodes %d" % (w.shape[0], batch.n_nodes))
+    res = SolveResult(member=np.zeros(batch.n_nodes, dtype=np.uint8))
+    if want_total:
+        res.total = np.zeros(batch.n_graphs, dtype=np.float64)
+    if want_steps:
+        res.steps = np.zeros(batch.n_graphs, dtype=np.int32)
+    check(ctx._lib.dg_solve_dit(ctx.handle, model.handle, batch.handle, _ptr(w), predict_code(predict), _ptr(res.member),
+                                _ptr(res.total), _ptr(res.steps), MEM_HOST))
+    return res
+
+
 def solve_device(ctx: Context, model: Model, batch: DeviceBatch, wts, member, predict="mwis",
                  remove_zero_weight: bool = True, score=None, util=None, total=None, steps=None) -> None:
     """Zero-copy form: every array is a CUDA tensor on the context's device; work is only enqueued."""

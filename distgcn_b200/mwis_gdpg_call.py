@@ -3,8 +3,9 @@
 
 Differences from generation 1 that are reproduced: no zero-weight removal; features are all-ones
 row-normalised when ``predict == 'mwis'`` and ``w / (max w + 1e-9)`` otherwise; ``solve_mwis`` accepts
-``grd`` and returns (mwis, total_wt); the model is ``GCN2_DQN``.  Training, the target network, rollouts
-and the iterative variants are out of scope.
+``grd`` and returns (mwis, total_wt); the model is ``GCN2_DQN``; ``solve_mwis_dit`` (GCN inside the greedy
+iteration) runs as one device-side loop.  Training, the target network, rollouts and the centralised
+iterative variants are out of scope.
 """
 from __future__ import annotations
 
@@ -72,6 +73,34 @@ class MWISSolver(object):
     def solve_mwis(self, adj_0, wts_0, train=False, grd=1.0):
         mwis, total_wt, _, _ = self.schedule(adj_0, wts_0, train)
         return mwis, total_wt
+
+
+    def solve_mwis_dit(self, adj_0, wts_0, train=False, grd=1.0):
+        """GCN embedded into the LGS iteration (mwis_gdpg_call.py:278-318): returns (mwis, best_IS_util).  The
+        whole loop runs on the device (dg_solve_dit)."""
+        if train:
+            raise NotImplementedError("exploration belongs to training, which is out of scope")
+        wts = np.asarray(wts_0, dtype=np.float64).reshape(-1)
+        if (wts < 0).any():
+            raise ValueError("negative weights: the loop's stopping rule (np.sum(wts_nn) <= 0, :296) is only "
+                             "reproduced for non-negative weights")
+        member, total = self.solve_mwis_dit_batch(pack_graphs([adj_0]), wts)
+        return set(np.flatnonzero(member).tolist()), np.array([total[0]])
+
+    def solve_mwis_dit_batch(self, graphs, wts):
+        """Many graphs in one launch: (member uint8 [n_nodes], set weight per graph)."""
+        from .batch import PackedBatch
+        packed = graphs if isinstance(graphs, PackedBatch) else pack_graphs(graphs)
+        if self.flags.predict != "mwis":
+            raise NotImplementedError("solve_mwis_dit is built for predict == 'mwis' (constant input features)")
+        model = self.model.compile(self.ctx)
+        batch = engine.DeviceBatch(self.ctx, packed)
+        try:
+            r = engine.solve_dit(self.ctx, model, batch, np.asarray(wts, dtype=np.float64).reshape(-1),
+                                 self.flags.predict)
+        finally:
+            batch.close()
+        return r.member, r.total
 
 
 DQNAgent = MWISSolver

@@ -173,6 +173,16 @@ DG_API int dg_solve(dg_context *ctx, const dg_model *model, dg_batch *batch, con
              int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
              int32_t *steps, int mem);
 
+/* GCN embedded into the greedy iteration.  Replaces MWISSolver.solve_mwis_dit (mwis_gdpg_call.py:278-318) for a
+ * whole batch: while a graph has residual vertices whose weights sum to something positive, re-score the residual
+ * graph (degrees renormalised on it), run ONE greedy round (heuristics.local_greedy_search_nstep, nstep = 1), add
+ * the joined vertices to the set and drop them and their neighbours (nb_is).  No zero-weight removal (generation-2
+ * semantics); a mask set with dg_batch_set_keep is the initial residual graph.  member: n_nodes bytes;
+ * total (may be NULL): sum of wts over the set per graph; steps (may be NULL): iterations per graph.
+ * Small graphs run the whole loop inside the graph-resident kernel (one launch). */
+DG_API int dg_solve_dit(dg_context *ctx, const dg_model *model, dg_batch *batch, const double *wts, int predict,
+                 uint8_t *member, double *total, int32_t *steps, int mem);
+
 /* One-shot host form of dg_solve: host CSR in, host membership out; the batch lives in the
  * context's reusable device buffers.  This is what bench.py's e2e number calls. */
 DG_API int dg_solve_host(dg_context *ctx, const dg_model *model, int32_t n_graphs, int32_t n_nodes, int32_t nnz,

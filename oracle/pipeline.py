@@ -49,6 +49,34 @@ def solve_graph(adj, w, layers, predict: str = "mwis", kind: str = "gcn_dqn", re
     return score, util, member
 
 
+def solve_graph_dit(adj, w, layers, predict: str = "mwis", kind: str = "gcn_dqn", max_iter: int = 100000):
+    """GCN embedded into the LGS iteration, MWISSolver.solve_mwis_dit (mwis_gdpg_call.py:278-318), for one graph.
+    Generation-2 glue: no zero-weight removal, features from features_gen2.  Returns (member[N] uint8,
+    best_IS_util, iterations)."""
+    a0 = sp.csr_matrix(adj)
+    wts = np.asarray(w, dtype=np.float64).reshape(-1)
+    n = wts.shape[0]
+    nis = -np.ones(n)                                   # nIS_vec, :287
+    it = 0
+    while (nis == -1).sum() > 0 and it < max_iter:      # :288
+        remain = nis == -1                              # :290
+        rev = np.flatnonzero(remain)                    # :291-292
+        a = a0[remain, :][:, remain].tocsr()            # :293-295
+        wk = wts[remain]
+        if np.sum(wk) <= 0:                             # :298-299
+            break
+        it += 1
+        feats = G.features_gen2(wk, layers[0].c_in, predict)     # makestate, :82-96
+        sup = G.laplacian_supports(a, len(layers[0].weights) - 1)
+        act = G.gcn_forward(feats, sup, layers, kind)
+        u = G.utility(act[:, 0], wk, predict)           # :304-307
+        r = L.run(a.indptr, a.indices, u, nstep=1)      # local_greedy_search_nstep(..., nstep=1), :309
+        nis[rev[r.member == 1]] = 1                     # :311
+        nis[rev[r.nb_is == 1]] = 0                      # :312
+    member = (nis == 1).astype(np.uint8)
+    return member, float(np.dot(nis, wts)), it          # :313
+
+
 # ---- batch form with a process pool (the reference is single-threaded Python; graphs are
 # independent, so a fan-out over all host cores is the fairest multi-core version of it) ----------
 _POOL_STATE = {}

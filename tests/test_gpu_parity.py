@@ -345,6 +345,48 @@ def test_full_config_sets(gpu_ctx, fam, short):
     model.close()
 
 
+@pytest.mark.parametrize("path", ["fused", "layer_kernels"])
+@pytest.mark.parametrize("short,kind", [("is4sat_l1", "gcn_dqn"), ("is4sat_l20_c32", "gcn_dqn"),
+                                        ("is4sat_l2_c64", "gcn_dqn"), ("is4sat_l3_c16", "gcn2_dqn")])
+def test_solve_dit_matches_restatement(gpu_ctx, short, kind, path, monkeypatch):
+    """GCN embedded into the greedy iteration (MWISSolver.solve_mwis_dit, mwis_gdpg_call.py:278-318): the
+    device-side loop against the per-graph CPU restatement - same sets, same weights, same iteration counts."""
+    E = _engine()
+    from oracle import pipeline
+    monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    if path == "layer_kernels":
+        monkeypatch.setenv("DG_DISABLE_FUSED", "1")
+    pb, w = util.small_graphs()
+    sub = pb.slice(0, 24)
+    n = sub.n_nodes
+    rng = np.random.default_rng(5)
+    ws = w[:n].copy()
+    ws[rng.random(n) < 0.15] = 0.0                       # zero weights stay in the graph (generation 2)
+    g_all_zero = 3                                       # a graph whose weights are all zero stops at once
+    ws[int(sub.graph_ptr[g_all_zero]):int(sub.graph_ptr[g_all_zero + 1])] = 0.0
+    layers = util.load_layers(short)
+    acts = E.gcn_dqn_acts(len(layers)) if kind == "gcn_dqn" else E.gcn2_dqn_acts(len(layers))
+    model = E.Model(gpu_ctx, layers, acts)
+    batch = E.DeviceBatch(gpu_ctx, sub)
+    r = E.solve_dit(gpu_ctx, model, batch, ws, want_steps=True)
+    plain = E.solve(gpu_ctx, model, batch, ws, remove_zero_weight=False)   # the batch is left as it was found
+    differs_from_plain = 0
+    for g in range(sub.n_graphs):
+        v0, v1 = int(sub.graph_ptr[g]), int(sub.graph_ptr[g + 1])
+        member, best, iters = pipeline.solve_graph_dit(sub.graph_adj(g), ws[v0:v1], layers, "mwis", kind)
+        assert np.array_equal(r.member[v0:v1], member), "graph %d" % g
+        assert abs(r.total[g] - ws[v0:v1][member == 1].sum()) <= 1e-9
+        assert int(r.steps[g]) == iters, "graph %d: %d iterations, restatement %d" % (g, r.steps[g], iters)
+        differs_from_plain += int(not np.array_equal(r.member[v0:v1], plain.member[v0:v1]))
+    assert r.steps[g_all_zero] == 0 and not r.member[int(sub.graph_ptr[g_all_zero]):int(sub.graph_ptr[g_all_zero + 1])].any()
+    print("%s/%s: iterations per graph %s; %d of %d graphs differ from the one-shot solve"
+          % (short, path, r.steps.tolist(), differs_from_plain, sub.n_graphs))
+    a = sp.csr_matrix((np.ones(sub.nnz), sub.col_idx, sub.row_ptr), shape=(n, n))
+    assert (a @ r.member.astype(np.float64))[r.member == 1].sum() == 0   # independent
+    batch.close()
+    model.close()
+
+
 def test_graph_convolution_operator(gpu_ctx):
     """Single layer on dense inputs (GraphConvolution.__call__, gcn/layers.py:189-216)."""
     E = _engine()

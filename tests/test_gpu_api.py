@@ -177,3 +177,24 @@ def test_host_pipeline_matches_one_call_at_a_time():
             assert abs(total[g - g0] - w[a:b][ref_member[a:b] != 0].sum()) < 1e-9
     assert pipe.launch_count >= len(subs)
     pipe.close()
+
+
+def test_mwis_dqn_test_harness_ratios():
+    """distgcn_b200.mwis_dqn_test.evaluate: the 500-file loop of mwis_dqn_test.py:304-348 as two launches; the
+    normaliser equals the greedy_utility stored in the reference's own files and the ratios equal the ones
+    from the reference-LGS memberships of the golden fixture."""
+    from distgcn_b200.mwis_dqn_call import DQNAgent
+    from distgcn_b200.mwis_dqn_test import evaluate
+    pb, w, z = util.full_set("er")
+    agent = DQNAgent(1, 5000, flags=_flags(num_layer=1))
+    agent.load(util.ckpt_dir("is4sat_l1"))
+    p, total, greedy_util, member = evaluate(agent, pb, w, search="local")
+    assert np.allclose(greedy_util, z["greedy_utility"], rtol=1e-12, atol=1e-12)
+    ref_member = np.unpackbits(z["member_gcn_lgs"])[:pb.n_nodes]
+    ref_total = np.add.reduceat(np.where(ref_member == 1, w, 0.0), pb.graph_ptr[:-1])
+    agree = np.isclose(total, ref_total, rtol=1e-12)
+    assert agree.mean() > 0.995           # a near-tie flipped by fp32 rounding may change a graph or two
+    assert np.allclose(p[agree], (ref_total / z["greedy_utility"])[agree], rtol=1e-12)
+    assert 1.0 < np.nanmean(p) < 1.12     # survey-time restatement: 1.041; Gurobi optimum of the set: 1.1197
+    p2, total2, _, _ = evaluate(agent, pb, w, search="greedy")
+    assert np.isclose(total2, total, rtol=1e-12).mean() > 0.99   # the weights of this set have no zeros

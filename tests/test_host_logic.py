@@ -206,3 +206,33 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
                 assert "liblgs_oracle" not in text, fn
                 assert "/root/reference" not in text, fn
+
+
+def test_mat_dataset_ingest(tmp_path):
+    """load_mat_dataset reads the reference's .mat layout (Data_Generation.py:214-219): CSC float64 adj,
+    weights [1, N]."""
+    import scipy.io as sio
+    import scipy.sparse as sp
+    from distgcn_b200.mwis_dqn_test import load_mat_dataset
+    rng = np.random.default_rng(0)
+    ref = []
+    for k, n in enumerate((7, 12, 1)):
+        upper = np.triu(rng.random((n, n)) < 0.3, k=1)
+        adj = sp.csc_matrix((upper | upper.T).astype(np.float64))
+        w = rng.random((1, n))
+        sio.savemat(str(tmp_path / ("ER_n%d_p0.3_b%d_uni.mat" % (n, k))),
+                    {"adj": adj, "weights": w, "N": n, "p": 0.3, "greedy_utility": float(k), "mwis_utility": 1.0})
+        ref.append((adj, w.reshape(-1)))
+    names, packed, wts, extras = load_mat_dataset(str(tmp_path))
+    assert names == sorted(names) and len(names) == 3
+    order = [1, 2, 0]  # sorted file names: n12 (b1), n1 (b2), n7 (b0)
+    assert packed.n_graphs == 3 and packed.n_nodes == 20
+    off = 0
+    for g, k in enumerate(order):
+        adj, w = ref[k]
+        n = adj.shape[0]
+        assert (packed.graph_adj(g) != adj.tocsr()).nnz == 0
+        assert np.array_equal(wts[off:off + n], w)
+        off += n
+    assert np.array_equal(extras["greedy_utility"], np.array([1.0, 2.0, 0.0]))
+    packed.validate()

@@ -92,6 +92,8 @@ int copy_out(dg_context *ctx, T *host, const T *dev, size_t count) {
 
 // synchronise and surface sticky kernel-side errors
 int finish(dg_context *ctx) {
+    // the kernels' sticky status word travels with the synchronisation, not with every launch
+    DG_CUDA_CHECK(cudaMemcpyAsync(ctx->h_flag + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flag[2] != 0) {
         int code = ctx->h_flag[2];
@@ -1249,8 +1251,6 @@ int dg_part_barrier(dg_part *p, const int64_t *count) {
     p->epoch += 1;
     DG_TRY(part_barrier(p->ctx, p->peers, p->flags_off, p->epoch, reinterpret_cast<const long long *>(count),
                         p->counts_off));
-    DG_CUDA_CHECK(cudaMemcpyAsync(p->ctx->h_flag + 2, p->ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost,
-                                  p->ctx->stream));
     return DG_OK;
 }
 

@@ -142,7 +142,9 @@ __device__ __forceinline__ int swz(int row, int chunk) {
     return row * (CP + 4) + (chunk << 2);
 }
 
-template <int CP>
+// DIT: the iterative variant (P.dit) is its own instantiation so that the one-shot kernel keeps its register
+// allocation (the layer loop runs at the 128-register limit)
+template <int CP, bool DIT, bool MMA>
 __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const bool has_hidden = P.n_layers >= 3;
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         // With P.dit the stages 2-7 repeat: the residual graph (vertices neither taken nor excluded yet) is
         // re-scored by the network before every single greedy round (mwis_gdpg_call.py:278-318).
         for (int dit_iter = 0;; ++dit_iter) {
-        if (P.dit) {
+        if (DIT) {
             // a graph stops once its residual weights no longer sum to something positive (:296-297; weights are
             // non-negative, so: once no residual vertex has a positive weight)
             for (int g = tid; g < ng; g += kThreads) {
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                              &mbar[0]);
                 }
                 const float *w = wbuf;
-                const float *bias = w + (P.use_mma ? 2 * 2 * CP * (CP + 8) : 2 * CP * CP);
+                const float *bias = w + (MMA ? 2 * 2 * CP * (CP + 8) : 2 * CP * CP);
                 const int act = P.acts[h + 1];
                 bool w_ready = false;
                 for (int pbase = 0; pbase < G8; pbase += 4 * kWarps) {
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                     // -- projection of the same rows, in place.  Register-tiled FFMA GEMM: a lane owns
                     //    4 rows (one per owned group: row (gb0 + 16 e) * 8 + (lane & 7)) x 8 columns
                     //    ((lane >> 3) * 8 ..); per 4 values of k it needs 4 row loads and 8 weight loads.
-                    if (CP == 32 && !P.use_mma) {
+                    if (CP == 32 && !MMA) {
                         const int rg = lane & 7, cg = lane >> 3;
                         float acc[4][8];
                         {
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
                     //    sum), the two small correction terms are chained inside.  Weights are pre-split on
                     //    the host and stored with a row stride of 40 words so that fragment loads are
                     //    conflict-free.  An m16 tile = two of the warp's 8-row groups.
-                    if (CP == 32 && P.use_mma) {
+                    if (CP == 32 && MMA) {
                         const int g = lane >> 2, t4 = lane & 3;
                         constexpr int WS = CP + 8;            // padded row stride of the weight matrices
                         const float *whi = w, *wlo = w + 2 * CP * WS;
@@ -840,7 +842,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         int n_remain = 1;
         int rounds = 0;
         while (P.do_lgs) {
-            if (P.dit && rounds >= 1) break;  // one greedy round per re-scoring
+            if (DIT && rounds >= 1) break;  // one greedy round per re-scoring
             // per-graph round accounting (heuristics.py:119-160): a graph's step count grows while it
             // still has remaining vertices
             int any = 0;
@@ -912,10 +914,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
             ++rounds;
             __syncthreads();
         }
-        if (!P.dit) break;
-        // the residual graph of the next iteration: what is still in `remain`
-        for (int wd = tid; wd < span / 32; wd += kThreads) keepw[wd] = remain[wd];
-        __syncthreads();
+        if constexpr (!DIT) {
+            break;
+        } else {
+            // the residual graph of the next iteration: what is still in `remain`
+            for (int wd = tid; wd < span / 32; wd += kThreads) keepw[wd] = remain[wd];
+            __syncthreads();
+        }
         }  // dit_iter
 
         // ---- 8. per-graph outputs ---------------------------------------------------------------------
@@ -948,6 +953,16 @@ __global__ void __launch_bounds__(kThreads, 1) fused_solve_kernel(const FusedPar
         for (int k = 0; k < 10; ++k) P.dbg[(size_t)blockIdx.x * 16 + k] = tm[k];
     }
 #undef DG_TICK
+    // the last CTA to leave re-arms the tile counter for the next launch on this context
+    if (tid == 0) {
+        __threadfence();
+        const int done = atomicAdd(P.tile_counter + 1, 1);
+        if (done == (int)gridDim.x - 1) {
+            P.tile_counter[1] = 0;
+            __threadfence();
+            P.tile_counter[0] = 0;
+        }
+    }
 }
 
 }  // namespace
@@ -959,9 +974,9 @@ size_t fused_smem_bytes(int cp, int cap_n, int cap_nnz, bool has_hidden, size_t 
     return fused_smem_plan(cp, cap_n, cap_nnz, has_hidden, wblob_bytes).total;
 }
 
-template <int CP>
+template <int CP, bool DIT, bool MMA>
 int launch_t(dg_context *ctx, const FusedParams &p, size_t smem, int n_tiles) {
-    auto kern = fused_solve_kernel<CP>;
+    auto kern = fused_solve_kernel<CP, DIT, MMA>;
     DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     DG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -1170,7 +1185,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
         p.dbg = dbg;
     }
     const size_t smem = fused_smem_bytes(m->fused_cp, p.cap_n, p.cap_nnz, has_hidden, wblob);
-    DG_CUDA_CHECK(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), ctx->stream));
+    // the tile counter is zero on entry: the last CTA of every launch resets it (no memset between launches)
     // Work-equivalent algorithmic bytes (SURVEY.md 8d / DESIGN.md): what the same layers would move if each
     // were a streaming pass - B_layer per hidden layer, a scalar SpMV pass for the first and the last layer,
     // one pass of the greedy search.  The fused kernel itself only reads CSR + weights and writes the
@@ -1182,11 +1197,16 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
         const double scalar_passes = 2.0 * (csr + 12.0 * n);
         const double lgs = csr + 9.0 * n;
         prof_begin(ctx);
-        int st = m->fused_cp == 32 ? launch_t<32>(ctx, p, smem, p.n_tiles) : launch_t<64>(ctx, p, smem, p.n_tiles);
+        int st;
+        if (m->fused_cp != 32)
+            st = p.dit ? launch_t<64, true, false>(ctx, p, smem, p.n_tiles) : launch_t<64, false, false>(ctx, p, smem, p.n_tiles);
+        else if (p.use_mma)
+            st = p.dit ? launch_t<32, true, true>(ctx, p, smem, p.n_tiles) : launch_t<32, false, true>(ctx, p, smem, p.n_tiles);
+        else
+            st = p.dit ? launch_t<32, true, false>(ctx, p, smem, p.n_tiles) : launch_t<32, false, false>(ctx, p, smem, p.n_tiles);
         prof_end(ctx, hidden + scalar_passes + lgs);
         if (st != DG_OK) return st;
     }
-    DG_CUDA_CHECK(cudaMemcpyAsync(ctx->h_flag + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (p.dbg) {  // debugging aid: print the phase timers of this launch
         std::vector<long long> h((size_t)ctx->sm_count * 4 * 16 + (size_t)p.n_tiles * 4);
         DG_CUDA_CHECK(cudaMemcpyAsync(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));

@@ -465,7 +465,6 @@ int lgs_device(dg_context *ctx, const dg_batch *b, const double *util, int nstep
         // The status word is read back asynchronously and examined by the next synchronising call
         // (dg_context_synchronize or any HOST-space call): a non-converged graph can only come from
         // NaN utilities or self-loops, which the reference does not survive either.
-        DG_CUDA_CHECK(cudaMemcpyAsync(ctx->h_flag + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
         return DG_OK;
     }
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libdistgcn_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["dg_api.cu", "dg_gcn.cu", "dg_lgs.cu", "dg_fused.cu"]
+SOURCES = ["dg_api.cu", "dg_gcn.cu", "dg_lgs.cu", "dg_fused.cu", "dg_tc.cu"]
 HEADERS = ["dg_common.cuh", os.path.join("..", "..", "include", "distgcn_b200.h")]
 
 NVCC_FLAGS = [

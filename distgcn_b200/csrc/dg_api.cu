@@ -464,6 +464,29 @@ int dg_model_create(dg_context *ctx, int n_layers, int n_supports, const int32_t
                     status = upload(&m->fused_wall_mma, wm);
                 }
             }
+            if (status == DG_OK && has_hidden && cp == 32) {
+                // tensor-core kernel: bf16-split projection operands and the fixed-point bound factors
+                const int nh = n_layers - 2;
+                std::vector<const float *> hw0(nh), hw1(nh), hb(nh);
+                std::vector<int> hci(nh), hco(nh);
+                for (int l = 1; l + 1 < n_layers; ++l) {
+                    hw0[l - 1] = weights[2 * l];
+                    hw1[l - 1] = weights[2 * l + 1];
+                    hb[l - 1] = bias ? bias[l] : nullptr;
+                    hci[l - 1] = c_in[l];
+                    hco[l - 1] = c_out[l];
+                }
+                std::vector<unsigned char> blob;
+                tc_build_weights(nh, hw0.data(), hw1.data(), hb.data(), hci.data(), hco.data(), &blob);
+                status = [&]() -> int {
+                    DG_CUDA_CHECK(cudaMalloc((void **)&m->tc_wall, blob.size()));
+                    DG_CUDA_CHECK(cudaMemcpy(m->tc_wall, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+                    return DG_OK;
+                }();
+                double tn = 0.0;
+                for (int k = 0; k < c_in[n_layers - 1]; ++k) tn += fabs((double)weights[2 * (n_layers - 1) + 1][k]);
+                m->tc_tail_norm = (float)(tn * (1.0 + 1.0 / 1024.0));
+            }
             if (status == DG_OK) {
                 m->fused_cp = cp;
                 if (n_layers == 1) m->tail_bias = 0.f;
@@ -494,6 +517,7 @@ void dg_model_destroy(dg_model *m) {
     if (m->fused_wall) cudaFree(m->fused_wall);
     if (m->fused_wall_mma) cudaFree(m->fused_wall_mma);
     if (m->fused_tail) cudaFree(m->fused_tail);
+    if (m->tc_wall) cudaFree(m->tc_wall);
     if (m->d_acts) cudaFree(m->d_acts);
     delete m;
 }
@@ -523,6 +547,7 @@ static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nn
     DG_TRY(validate_graph_ptr(b->h_graph_ptr, n_graphs, n_nodes, &b->max_graph_nodes));
     // row_ptr at the graph boundaries (host copy): per-graph nnz for the fused kernel's tile table
     b->tiles_valid = false;
+    b->tc_tiles_valid = false;
     b->h_graph_e.resize((size_t)n_graphs + 1);
     if (mem == DG_MEM_HOST) {
         for (int g = 0; g <= n_graphs; ++g) b->h_graph_e[g] = row_ptr[b->h_graph_ptr[g]];
@@ -610,6 +635,7 @@ void dg_batch_destroy(dg_batch *b) {
     if (b->keep) cudaFree(b->keep);
     if (b->x0) cudaFree(b->x0);
     if (b->tiles_dev) cudaFree(b->tiles_dev);
+    if (b->tc_tiles_dev) cudaFree(b->tc_tiles_dev);
     delete b;
 }
 
@@ -826,6 +852,10 @@ static int solve_device(dg_context *ctx, const dg_model *m, dg_batch *b, const d
     const size_t n = (size_t)b->n_nodes;
     // small graphs: everything in one graph-resident kernel (dg_fused.cu)
     bool handled = false;
+    // ... on the tensor cores when the model has 32-wide hidden layers and every graph fits (dg_tc.cu)
+    DG_TRY(tc_try_solve(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, d_score, d_util, d_total, d_steps,
+                        &handled));
+    if (handled) return DG_OK;
     DG_TRY(fused_try_solve(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, d_score, d_util, d_total, d_steps,
                            &handled));
     if (handled) return DG_OK;

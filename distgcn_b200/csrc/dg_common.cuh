@@ -175,6 +175,9 @@ struct dg_model {
     float *fused_wall_mma = nullptr;  // same layers for the tensor-core path: TF32 hi [64x40], lo [64x40], bias [32]
     float *fused_tail = nullptr;   // [2*cp]: W_0[:,0], W_1[:,0] of the last layer
     int *d_acts = nullptr;         // [n_layers]
+    // operands of the tensor-core solve kernel (dg_tc.cu); null when the model is not eligible
+    unsigned char *tc_wall = nullptr;  // hidden layers: bf16 terms of [W_0 | W_1 r], bias, 1/r, bound factor
+    float tc_tail_norm = 0.f;          // sum |W_1[:,0]| of the last layer (fixed-point bound of its scalar aggregation)
 };
 
 struct dg_batch {
@@ -197,6 +200,11 @@ struct dg_batch {
     bool tiles_hidden = false;
     size_t tiles_wblob = 0;
     bool tiles_valid = false;
+    // tile table of the tensor-core kernel (dg_tc.cu): up to 4 graph ids per tile
+    int *tc_tiles_dev = nullptr;
+    size_t tc_tiles_cap = 0;
+    int tc_n_tiles = 0;
+    bool tc_tiles_valid = false;
 };
 
 struct dg_part {  // one rank's row slice of a single large graph (device CSR, global column ids)
@@ -296,6 +304,14 @@ struct FusedParams {
 int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
                     int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
                     int32_t *steps, bool *handled, bool dit = false);
+
+// ---- tensor-core solve kernel (dg_tc.cu) ---------------------------------------------------------
+// hidden-layer operand blobs from the layers' weights ([c_in, c_out] row-major, widths <= 32)
+void tc_build_weights(int n_hidden, const float *const *w0, const float *const *w1, const float *const *bias, const int *c_in,
+                      const int *c_out, std::vector<unsigned char> *blob);
+int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
+                 int remove_zero_weight, uint8_t *member, float *score, double *util, double *total, int32_t *steps,
+                 bool *handled);
 
 // ---- kernels / drivers implemented in dg_gcn.cu ---------------------------------------------
 int batch_compute_dinv(dg_batch *b);

@@ -761,8 +761,11 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
     if (n == 0) return DG_OK;
     {   // small graphs with a one-column linear head: the graph-resident kernel, stopped after the scores
         bool handled = false;
-        if (wts != nullptr || predict == DG_PREDICT_MIS)
-            DG_TRY(fused_try_solve(ctx, m, b, wts, predict, 0, nullptr, out, util, nullptr, nullptr, &handled));
+        if (wts != nullptr || predict == DG_PREDICT_MIS) {
+            DG_TRY(tc_try_solve(ctx, m, b, wts, predict, 0, nullptr, out, util, nullptr, nullptr, &handled));
+            if (!handled)
+                DG_TRY(fused_try_solve(ctx, m, b, wts, predict, 0, nullptr, out, util, nullptr, nullptr, &handled));
+        }
         if (handled) return DG_OK;
     }
     const int L = m->n_layers;

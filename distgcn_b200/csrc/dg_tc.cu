@@ -1,0 +1,1009 @@
+// Tensor-core solve kernel (tcgen05 / TMEM, sm_100a): the whole hot path for a tile of small graphs in one launch, like
+// dg_fused.cu, but with both heavy steps of every hidden GraphConvolution layer on the 5th-generation tensor cores.
+//
+//   reference order (gcn/layers.py:198-216):  H' = act( H.W_0 + L.(H.W_1) + b ),  L = I - D^-1/2 A D^-1/2
+//   here, per hidden layer and per 128-vertex block of a graph:
+//     (1) projection   [P0 | P1] = H . [W_0 | W_1 r]        tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M128 N64 K32.
+//         fp32 accuracy comes from a 3-term bf16 split of BOTH operands (x = hi + mid + lo, each term exact) and the 6
+//         significant cross products chained into one accumulator, smallest first (measured: 2.1e-7 of the output scale
+//         against 4.5e-7 for an fp32 FMA chain, profiles/micro/umma_probe.cu).
+//     (2) aggregation  S = A . (dinv * P1)                    tcgen05.mma kind::i8 (u8 x u8 -> s32 in TMEM), M128 N128 K=n.
+//         A is the graph's dense 0/1 adjacency, resident in shared memory as bytes for all layers; Y = dinv * P1 is
+//         quantised per graph and layer to 31-bit fixed point (scale from a bound on max |Y|, below) and its four
+//         base-256 digits are the operand columns, so the sum over neighbours is EXACT integer arithmetic.
+//         Digits are the bytes of v + 0x80808080 (unsigned, offset 128 each): sum_j A_ij v_j = sum_a 256^a (D_a - 128 deg_i).
+//     (3) epilogue     H' = act(P0 + P1 + b - dinv_i * S_i)   CUDA cores, one thread per vertex (TMEM lane), result split
+//         into bf16 terms and stored as the next projection's A operand.
+//   Fixed-point scale: |Y_jf| <= max|H| * max_f sum_k |W_1[k,f] r_f|, with r_f powers of two (exact) that equalise the
+//   column norms of W_1 (host, undone in the epilogue) and max|H| reduced per graph and layer in shared memory.  The
+//   quantisation error of an aggregated element is <= deg * 2^-31 of that bound, below fp32 rounding of the same sum.
+//   The scalar aggregations of the rank-1 first layer and of the project-first last layer use the same machinery with
+//   16 operand columns.
+//
+// Work split: 16 vertex warps (warpgroup w owns TMEM lanes of block w: thread = vertex) + 1 control warp whose lane 0
+// issues every tcgen05.mma and every weight copy (TMA bulk, 2-deep ring).  A graph is a synchronisation domain: its
+// threads arrive on the graph's `ready` mbarrier when an operand is complete, the control thread polls the graphs'
+// barriers, issues that graph's MMAs and commits them to the graph's `done` mbarrier.  Graphs of a tile therefore drift
+// apart and the tensor-core work of one overlaps the epilogue arithmetic of another.
+//
+// Reference semantics: dg_fused.cu / dg_gcn.cu / dg_lgs.cu (mwis_dqn_call.py:198-261, heuristics.py:77-116).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "dg_common.cuh"
+
+namespace dg {
+
+namespace {
+
+constexpr int kTcVertexThreads = 512;
+constexpr int kTcThreads = 544;       // + the control warp
+constexpr int kTcMaxG = 4;            // graphs per tile (every graph owns >= 1 block)
+constexpr int kTcBlocks = 4;          // 128-row blocks per tile = TMEM budget: 4 x 128 columns
+constexpr int kTcOpBlock = 24576;     // operand bytes per block: 3 bf16 terms x [4 K-chunks][128 rows][16 B]
+constexpr int kTcWBlob = 12560;       // one hidden layer: bf16 terms of [W_0 | W_1 r] (12288), bias[32], 1/r[32], bound, pad
+// shared-memory map (bytes)
+constexpr int kTcOffRing = 0;                      // 2 x kTcWBlob
+constexpr int kTcOffUtil = 25216;                  // double[512]   (aliased by the staging copy of row_ptr)
+constexpr int kTcOffDinv = kTcOffUtil + 4096;      // float[512]
+constexpr int kTcOffBits = kTcOffDinv + 2048;      // uint32[4][16]: keep, remain, joined, member
+constexpr int kTcOffGmax = kTcOffBits + 256;       // uint32[4][2] layer maxima, uint32[4] x0 maxima
+constexpr int kTcOffBar = kTcOffGmax + 64;         // full[2], ready[4], done[4]
+constexpr int kTcOffMeta = kTcOffBar + 128;        // TcMeta[4] + tile scalars
+constexpr int kTcOffPool = 32768;                  // adjacency of the tile's graphs, then the operand blocks
+static_assert(kTcOffMeta + 256 <= kTcOffPool, "shared-memory map overflows into the pool");
+
+struct TcMeta {  // one graph of the tile
+    int v0, nv, fb, nb, R, Kp, adj, e0, nnz, g;
+};
+struct TcTileInfo {
+    int ng, nblocks, adj_total, opbuf;
+};
+
+struct TcParams {
+    const int *tiles;  // 8 ints per tile: ng, g[4], -, -, -
+    int n_tiles;
+    int *tile_counter;
+    const int *graph_ptr, *row_ptr, *col_idx;
+    const double *wts;
+    const uint8_t *keep_in;
+    const float *x0;
+    float x0val;
+    int remove_zero;
+    int n_hidden;
+    const float *first;  // [3 * 32]: colsum(W_0), colsum(W_1), bias of layer 0
+    int first_act;
+    const unsigned char *wall;  // n_hidden blobs of kTcWBlob bytes
+    const int *acts;
+    const float *tail;  // [2 * 32]
+    float tail_bias, tail_norm;
+    int last_act;
+    float alpha;
+    int predict;
+    uint8_t *member;
+    float *score;
+    double *util;
+    double *total;
+    int *steps;
+    int *status;
+    int round_cap;
+    int do_lgs;
+    long long *dbg;
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(s32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// Bounded wait: a protocol error must end the launch with an error, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_test(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_test(bar, parity)) return;
+        if ((spins & 1023u) == 0u && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+                 "l"(src), "r"(bytes), "r"(s32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): start >> 4, LBO >> 4 at bit 16, SBO >> 4 at
+// bit 32, version 1 at bit 46.  K-major operand: core matrix = 8 rows x 16 B, SBO = stride between 8-row groups, LBO =
+// stride between the 16-byte K chunks.  MN-major operand: core matrix = 8 k x 16 B (16 B = consecutive MN elements),
+// LBO = stride between 8-k groups, SBO = stride between 16-byte MN runs.  (Both verified by profiles/micro/umma_probe.cu.)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptors (cute::UMMA::InstrDescriptor): c_format bit 4, a/b format bits 7/10, b MN-major bit 16, N >> 3
+// at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_u8(int M, int N) {
+    return (2u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(
+                     d_tmem),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_u8(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}" ::"r"(
+                     d_tmem),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%"
+        "30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tc_act(float v, int act, float alpha) {
+    if (act == DG_ACT_LEAKY_RELU) return v >= 0.f ? v : alpha * v;
+    if (act == DG_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+// fixed-point scale for values bounded by `bound` (>= 0): q = 2^k with |v| * q < 2^30, and its inverse
+__device__ __forceinline__ void tc_scale(float bound, float *q, float *inv_q) {
+    int eb = (__float_as_int(bound) >> 23) & 0xff;  // bound < 2^(eb - 126)
+    eb = min(max(eb, 30), 254);
+    *q = __int_as_float((283 - eb) << 23);      // 2^(156 - eb)
+    *inv_q = __int_as_float((eb - 29) << 23);   // 2^(eb - 156)
+}
+// fixed-point image of y (|y * q| < 2^30) as four offset-128 base-256 digits: the bytes of the result
+__device__ __forceinline__ uint32_t tc_digits(float y, float q) {
+    return (uint32_t)__float2int_rn(y * q) + 0x80808080u;
+}
+// sum_a 256^a (D_a - 128 deg) as a float; every D_a - 128 deg is an integer below 2^22 in magnitude
+__device__ __forceinline__ float tc_combine(const uint32_t *d, int magic_minus_off) {
+    const float m = 12582912.0f;  // 1.5 * 2^23
+    const float f0 = __int_as_float((int)d[0] + magic_minus_off) - m;
+    const float f1 = __int_as_float((int)d[1] + magic_minus_off) - m;
+    const float f2 = __int_as_float((int)d[2] + magic_minus_off) - m;
+    const float f3 = __int_as_float((int)d[3] + magic_minus_off) - m;
+    return fmaf(fmaf(fmaf(f3, 256.f, f2), 256.f, f1), 256.f, f0);
+}
+
+// 8 feature values -> three bf16 term vectors (hi, mid, lo), each 8 x bf16 = 16 B
+__device__ __forceinline__ void tc_split8(const float *h, uint4 *hi, uint4 *mid, uint4 *lo) {
+    uint32_t t0[4], t1[4], t2[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float a = h[2 * p], b = h[2 * p + 1];
+        uint32_t w;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+        t0[p] = w;
+        a -= __uint_as_float(w << 16);
+        b -= __uint_as_float(w & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+        t1[p] = w;
+        a -= __uint_as_float(w << 16);
+        b -= __uint_as_float(w & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+        t2[p] = w;
+    }
+    *hi = make_uint4(t0[0], t0[1], t0[2], t0[3]);
+    *mid = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+    *lo = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+}
+
+// 4 adjacency bytes (0/1 each) -> 4 bits (byte k -> bit k)
+__device__ __forceinline__ uint32_t tc_bits4(uint32_t w) { return (w * 0x01020408u) >> 24; }
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *wring = smem + kTcOffRing;
+    double *util_sm = reinterpret_cast<double *>(smem + kTcOffUtil);
+    int *rp_sm = reinterpret_cast<int *>(smem + kTcOffUtil);  // staging only
+    float *dinv_sm = reinterpret_cast<float *>(smem + kTcOffDinv);
+    uint32_t *keepw = reinterpret_cast<uint32_t *>(smem + kTcOffBits);
+    uint32_t *remain = keepw + 16, *joined = keepw + 32, *memb = keepw + 48;
+    uint32_t *gmax = reinterpret_cast<uint32_t *>(smem + kTcOffGmax);  // [4][2]
+    uint32_t *gmax0 = gmax + 8;                                         // [4]
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + kTcOffBar);
+    uint64_t *bar_ready = bar_full + 2, *bar_done = bar_full + 6;
+    TcMeta *meta = reinterpret_cast<TcMeta *>(smem + kTcOffMeta);
+    TcTileInfo *tinfo = reinterpret_cast<TcTileInfo *>(smem + kTcOffMeta + sizeof(TcMeta) * kTcMaxG);
+    unsigned char *pool = smem + kTcOffPool;
+    __shared__ int tile_sm;
+    __shared__ uint32_t tmem_sm;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_ctrl = warp == kTcVertexThreads / 32;
+    const int n_hidden = P.n_hidden;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) mbar_init(&bar_full[i], 1);
+        for (int i = 0; i < kTcMaxG; ++i) {
+            mbar_init(&bar_ready[i], 1);
+            mbar_init(&bar_done[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (is_ctrl) {  // the whole tensor memory of the SM: 4 blocks x 128 accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_sm)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_sm;
+    uint32_t wseq = 0;  // hidden-layer weight fills of the tiles this CTA has finished (every thread keeps its own copy)
+
+    const bool timing = P.dbg != nullptr && tid == 0;
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = timing ? clock64() : 0;
+
+    for (;;) {
+        if (tid == 0) tile_sm = atomicAdd(P.tile_counter, 1);
+        __syncthreads();
+        const int t = tile_sm;
+        if (t >= P.n_tiles) break;
+        long long tk = timing ? clock64() : 0;
+
+        // ---- tile metadata; the graphs' barriers are re-armed with this tile's thread counts -----------------
+        if (tid == 0) {
+            const int *td = P.tiles + (size_t)t * 8;
+            const int ng = td[0];
+            int fb = 0, adj = 0;
+            for (int gi = 0; gi < ng; ++gi) {
+                const int g = td[1 + gi];
+                TcMeta m;
+                m.g = g;
+                m.v0 = P.graph_ptr[g];
+                m.nv = P.graph_ptr[g + 1] - m.v0;
+                m.nb = (m.nv + 127) >> 7;
+                m.fb = fb;
+                m.R = (m.nv + 7) & ~7;
+                m.Kp = (m.nv + 31) & ~31;
+                m.adj = adj;
+                m.e0 = P.row_ptr[m.v0];
+                m.nnz = P.row_ptr[m.v0 + m.nv] - m.e0;
+                meta[gi] = m;
+                adj += m.R * m.Kp;
+                fb += m.nb;
+                mbar_inval(&bar_ready[gi]);
+                mbar_inval(&bar_done[gi]);
+                mbar_init(&bar_ready[gi], 128 * m.nb);
+                mbar_init(&bar_done[gi], 1);
+            }
+            tinfo->ng = ng;
+            tinfo->nblocks = fb;
+            tinfo->adj_total = adj;
+            tinfo->opbuf = (adj + 127) & ~127;
+            for (int i = 0; i < 12; ++i) gmax[i] = 0u;
+            fence_mbar_init();
+        }
+        __syncthreads();
+        const int ng = tinfo->ng;
+        const int opbuf = tinfo->opbuf;
+
+        // the first two hidden layers' weights start streaming in (every MMA of the previous tile has completed)
+        if (is_ctrl && lane == 0) {
+            for (int h = 0; h < n_hidden && h < 2; ++h) {
+                const uint32_t buf = (wseq + h) & 1u;
+                mbar_expect_tx(&bar_full[buf], kTcWBlob);
+                bulk_g2s(wring + buf * kTcWBlob, P.wall + (size_t)h * kTcWBlob, kTcWBlob, &bar_full[buf]);
+            }
+        }
+
+        // ---- which graph / block / row this thread is -----------------------------------------------------------
+        int gi = -1, r = 0, v = 0;
+        TcMeta G{};
+        bool valid = false, keep = false;
+        if (tid < kTcVertexThreads) {
+            const int b = tid >> 7;
+            for (int k = 0; k < ng; ++k)
+                if (b >= meta[k].fb && b < meta[k].fb + meta[k].nb) gi = k;
+            if (gi >= 0) {
+                G = meta[gi];
+                r = (b - G.fb) * 128 + (tid & 127);
+                valid = r < G.nv;
+                v = G.v0 + r;
+            }
+            if (valid) {
+                keep = P.keep_in ? P.keep_in[v] != 0 : true;
+                if (P.remove_zero) keep = keep && (P.wts[v] != 0.0);  // mwis_dqn_call.py:203
+                if (P.member) P.member[v] = 0;
+                if (keep && P.x0) atomicMax(&gmax0[gi], __float_as_uint(fabsf(P.x0[v])));
+            }
+            const uint32_t kw = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) {
+                keepw[warp] = kw;
+                memb[warp] = 0u;
+            }
+            // staging copy of the graphs' row pointers (relative to the graph's first edge)
+            for (int k = 0; k < ng; ++k) {
+                const TcMeta m = meta[k];
+                for (int i = tid; i <= m.nv; i += kTcVertexThreads) rp_sm[m.fb * 128 + k + i] = P.row_ptr[m.v0 + i] - m.e0;
+            }
+            // clear the adjacency bytes
+            const int n16 = tinfo->adj_total >> 4;
+            for (int i = tid; i < n16; i += kTcVertexThreads) reinterpret_cast<uint4 *>(pool)[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        // ---- dense adjacency of the kept sub-graph: byte (row i, column j) = 1 for every edge with both ends kept ---
+        if (tid < kTcVertexThreads) {
+            for (int k = 0; k < ng; ++k) {
+                const TcMeta m = meta[k];
+                const int *rp = rp_sm + m.fb * 128 + k;
+                unsigned char *adj = pool + m.adj;
+                for (int e = tid; e < m.nnz; e += kTcVertexThreads) {
+                    int lo = 0, hi = m.nv;  // rp[lo] <= e < rp[hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (rp[mid] <= e) lo = mid; else hi = mid;
+                    }
+                    const int j = P.col_idx[m.e0 + e] - m.v0;
+                    const uint32_t ki = (keepw[m.fb * 4 + (lo >> 5)] >> (lo & 31)) & 1u;
+                    const uint32_t kj = (keepw[m.fb * 4 + (j >> 5)] >> (j & 31)) & 1u;
+                    if (ki & kj) adj[(size_t)(j >> 4) * m.R * 16 + lo * 16 + (j & 15)] = 1;
+                }
+            }
+            fence_async_smem();
+        }
+        __syncthreads();
+        if (timing) {
+            const long long now = clock64();
+            tm[0] += now - tk;
+            tk = now;
+        }
+
+        if (is_ctrl) {
+            // ================= control thread: every tcgen05.mma and every weight copy of the tile ================
+            if (lane == 0) {
+                const int S = 2 + 2 * n_hidden;
+                int st[kTcMaxG] = {0, 0, 0, 0};
+                int passed[2] = {0, 0};
+                int remaining = ng;
+                const uint32_t pool_addr = s32(pool);
+                const long long t_ctrl = clock64();
+                uint32_t polls = 0;
+                while (remaining > 0) {
+                    if ((++polls & 4095u) == 0u && clock64() - t_ctrl > 8000000000LL) __trap();
+#pragma unroll
+                    for (int k = 0; k < kTcMaxG; ++k) {
+                        if (k >= ng || st[k] >= S) continue;
+                        if (!mbar_test(&bar_ready[k], (uint32_t)st[k] & 1u)) continue;
+                        tc_fence_after();
+                        const TcMeta m = meta[k];
+                        const int stage = st[k];
+                        const uint32_t ybase = pool_addr + opbuf + m.fb * kTcOpBlock;  // the graph's operand region
+                        if (stage == 0 || stage == S - 1 || ((stage - 1) & 1)) {
+                            // aggregation: D[block] = A[block rows, :] . Y, N = 16 (scalar) or 128 (hidden layer)
+                            const bool scalar = stage == 0 || stage == S - 1;
+                            const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
+                            const uint32_t lbo_a = (uint32_t)m.R * 16u;
+                            const uint32_t sbo_b = scalar ? 128u : (uint32_t)m.Kp * 16u;
+                            const int ksteps = m.Kp >> 5;
+                            for (int jb = 0; jb < m.nb; ++jb) {
+                                const uint32_t abase = pool_addr + m.adj + jb * 128 * 16;
+                                const uint32_t d = tmem + (uint32_t)(m.fb + jb) * 128u;
+                                for (int s = 0; s < ksteps; ++s)
+                                    mma_u8(d, umma_desc(abase + s * 2 * lbo_a, lbo_a, 128u), umma_desc(ybase + s * 512, 128u, sbo_b),
+                                           idesc, s > 0);
+                            }
+                        } else {
+                            // projection of hidden layer h: [P0 | P1] = H . [W_0 | W_1 r], 6 products x 2 K-steps
+                            const int h = (stage - 1) >> 1;
+                            if (h >= 1) {
+                                // every thread of this graph has finished layer h-1 (its epilogue reads bias / r from
+                                // the weight buffer): when all graphs have, the buffer takes layer h+1
+                                const uint32_t pbuf = (wseq + h - 1) & 1u;
+                                if (++passed[pbuf] == ng) {
+                                    passed[pbuf] = 0;
+                                    if (h + 1 < n_hidden) {
+                                        mbar_expect_tx(&bar_full[pbuf], kTcWBlob);
+                                        bulk_g2s(wring + pbuf * kTcWBlob, P.wall + (size_t)(h + 1) * kTcWBlob, kTcWBlob,
+                                                 &bar_full[pbuf]);
+                                    }
+                                }
+                            }
+                            const uint32_t seq = wseq + h;
+                            mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u);
+                            const uint32_t wbase = s32(wring + (seq & 1u) * kTcWBlob);
+                            const uint32_t idesc = idesc_bf16(128, 64);
+                            for (int jb = 0; jb < m.nb; ++jb) {
+                                const uint32_t abase = ybase + jb * kTcOpBlock;
+                                const uint32_t d = tmem + (uint32_t)(m.fb + jb) * 128u;
+                                // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
+                                const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+                                for (int p = 0; p < 6; ++p)
+#pragma unroll
+                                    for (int s = 0; s < 2; ++s)
+                                        mma_bf16(d, umma_desc(abase + ta[p] * 8192 + s * 4096, 2048u, 128u),
+                                                 umma_desc(wbase + tb[p] * 4096 + s * 2048, 1024u, 128u), idesc, (p | s) != 0);
+                            }
+                        }
+                        mma_commit(&bar_done[k]);
+                        st[k] = stage + 1;
+                        if (st[k] == S) --remaining;
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (gi >= 0) {
+            // ================= vertex threads =========================================================================
+            const int b = tid >> 7;
+            const int jb = b - G.fb;
+            const int dom_bar = 1 + G.fb, dom_cnt = 128 * G.nb;
+            const uint32_t taddr = tmem + (uint32_t)b * 128u + ((uint32_t)((warp & 3) * 32) << 16);
+            unsigned char *adj = pool + G.adj;
+            unsigned char *opg = pool + opbuf + G.fb * kTcOpBlock;  // the graph's operand region (Y digits)
+            unsigned char *opb = opg + jb * kTcOpBlock;             // this block's H terms
+            const int rb = tid & 127;                               // row within the block
+            uint32_t st = 0;                                        // stage counter -> barrier parity
+
+            // degree on the kept sub-graph, dinv, x0, and the scalar operand of the rank-1 first layer
+            unsigned deg = 0;
+            if (valid) {
+                const int nch = G.Kp >> 4;
+                for (int c = 0; c < nch; ++c) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(adj + (size_t)c * G.R * 16 + r * 16);
+                    deg = __dp4a(w.x, 0x01010101u, deg);
+                    deg = __dp4a(w.y, 0x01010101u, deg);
+                    deg = __dp4a(w.z, 0x01010101u, deg);
+                    deg = __dp4a(w.w, 0x01010101u, deg);
+                }
+            }
+            const float di = deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f;  // gcn/utils.py:122-125
+            const float xi = keep ? (P.x0 ? P.x0[v] : P.x0val) : 0.f;
+            const int moff = 0x4B400000 - 128 * (int)deg;
+            float q0, iq0;
+            tc_scale(P.x0 ? __uint_as_float(gmax0[gi]) : fabsf(P.x0val), &q0, &iq0);
+            if (valid) *reinterpret_cast<uint32_t *>(opg + (r >> 3) * 128 + (r & 7) * 16) = tc_digits(di * xi, q0);
+            fence_async_smem();
+            mbar_arrive(&bar_ready[gi]);
+
+            // -- first layer (rank 1): s = (L x0)_i, H1 = act(x0 colsum(W_0) + s colsum(W_1) + b) -----------------
+            float hmax = 0.f, t0 = 0.f, t1 = 0.f;
+            // consumes 8 new feature values of this vertex: operand terms for the next projection, or the last
+            // layer's two dot products when no hidden layer follows
+            auto emit = [&](int q, const float *hv, bool to_terms) {
+                if (to_terms) {
+                    uint4 hi, mid, lo;
+                    tc_split8(hv, &hi, &mid, &lo);
+                    *reinterpret_cast<uint4 *>(opb + 0 * 8192 + q * 2048 + rb * 16) = hi;
+                    *reinterpret_cast<uint4 *>(opb + 1 * 8192 + q * 2048 + rb * 16) = mid;
+                    *reinterpret_cast<uint4 *>(opb + 2 * 8192 + q * 2048 + rb * 16) = lo;
+                } else {
+                    const float4 wa = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q);
+                    const float4 wb = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q + 1);
+                    const float4 wc = __ldg(reinterpret_cast<const float4 *>(P.tail + 32) + 2 * q);
+                    const float4 wd = __ldg(reinterpret_cast<const float4 *>(P.tail + 32) + 2 * q + 1);
+                    t0 = fmaf(hv[0], wa.x, t0), t0 = fmaf(hv[1], wa.y, t0), t0 = fmaf(hv[2], wa.z, t0), t0 = fmaf(hv[3], wa.w, t0);
+                    t0 = fmaf(hv[4], wb.x, t0), t0 = fmaf(hv[5], wb.y, t0), t0 = fmaf(hv[6], wb.z, t0), t0 = fmaf(hv[7], wb.w, t0);
+                    t1 = fmaf(hv[0], wc.x, t1), t1 = fmaf(hv[1], wc.y, t1), t1 = fmaf(hv[2], wc.z, t1), t1 = fmaf(hv[3], wc.w, t1);
+                    t1 = fmaf(hv[4], wd.x, t1), t1 = fmaf(hv[5], wd.y, t1), t1 = fmaf(hv[6], wd.z, t1), t1 = fmaf(hv[7], wd.w, t1);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hmax = fmaxf(hmax, fabsf(hv[k]));
+            };
+            // publishes this vertex's contribution to the graph's max |H| (fixed-point bound of the next aggregation)
+            auto publish_max = [&](int slot) {
+                const uint32_t mine = (valid && keep) ? __float_as_uint(hmax) : 0u;
+                const uint32_t wmax = __reduce_max_sync(0xffffffffu, mine);
+                if (lane == 0) atomicMax(&gmax[gi * 2 + slot], wmax);
+                hmax = 0.f;
+            };
+
+            mbar_wait(&bar_done[gi], st & 1u);
+            ++st;
+            tc_fence_after();
+            {
+                uint32_t d4[4];
+                tmem_ld4(taddr, d4);
+                const float s_i = xi - di * (tc_combine(d4, moff) * iq0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float hv[8];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(P.first) + 2 * q + half);
+                        const float4 a1 = __ldg(reinterpret_cast<const float4 *>(P.first + 32) + 2 * q + half);
+                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(P.first + 64) + 2 * q + half);
+                        hv[4 * half + 0] = tc_act(fmaf(s_i, a1.x, fmaf(xi, a0.x, b0.x)), P.first_act, P.alpha);
+                        hv[4 * half + 1] = tc_act(fmaf(s_i, a1.y, fmaf(xi, a0.y, b0.y)), P.first_act, P.alpha);
+                        hv[4 * half + 2] = tc_act(fmaf(s_i, a1.z, fmaf(xi, a0.z, b0.z)), P.first_act, P.alpha);
+                        hv[4 * half + 3] = tc_act(fmaf(s_i, a1.w, fmaf(xi, a0.w, b0.w)), P.first_act, P.alpha);
+                    }
+                    emit(q, hv, n_hidden > 0);
+                }
+                publish_max(0);
+            }
+
+            // -- hidden layers -----------------------------------------------------------------------------------------
+            for (int h = 0; h < n_hidden; ++h) {
+                // H terms are in place: the projection may start
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(&bar_ready[gi]);
+                const uint32_t seq = wseq + h;
+                const unsigned char *wb = wring + (seq & 1u) * kTcWBlob;
+                const float *bias = reinterpret_cast<const float *>(wb + 12288);
+                const float *rinv = bias + 32;
+                mbar_wait(&bar_done[gi], st & 1u);
+                ++st;
+                tc_fence_after();
+                mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u);  // (already complete: the projection has read it)
+                float qs, iqs;
+                tc_scale(__uint_as_float(gmax[gi * 2 + (h & 1)]) * bias[64], &qs, &iqs);
+                const float dq = di * qs, ndq = -di * iqs;
+                float c[32];
+                uint32_t p[32];
+                tmem_ld32(taddr + 32, p);  // P1 (columns scaled by r)
+#pragma unroll
+                for (int f4 = 0; f4 < 8; ++f4) {
+                    const float4 ri = *reinterpret_cast<const float4 *>(rinv + 4 * f4);
+                    const float4 bi = *reinterpret_cast<const float4 *>(bias + 4 * f4);
+                    const float p0 = __uint_as_float(p[4 * f4]), p1 = __uint_as_float(p[4 * f4 + 1]);
+                    const float p2 = __uint_as_float(p[4 * f4 + 2]), p3 = __uint_as_float(p[4 * f4 + 3]);
+                    c[4 * f4 + 0] = fmaf(p0, ri.x, bi.x);
+                    c[4 * f4 + 1] = fmaf(p1, ri.y, bi.y);
+                    c[4 * f4 + 2] = fmaf(p2, ri.z, bi.z);
+                    c[4 * f4 + 3] = fmaf(p3, ri.w, bi.w);
+                    // run f4 of the MN-major operand = features 4 f4 .. 4 f4 + 3, digit a of feature f at column 4 f + a
+                    const uint4 dg4 = make_uint4(tc_digits(p0, dq), tc_digits(p1, dq), tc_digits(p2, dq), tc_digits(p3, dq));
+                    if (valid)
+                        *reinterpret_cast<uint4 *>(opg + (size_t)f4 * G.Kp * 16 + (r >> 3) * 128 + (r & 7) * 16) = dg4;
+                }
+                tmem_ld32(taddr, p);  // P0
+#pragma unroll
+                for (int f = 0; f < 32; ++f) c[f] += __uint_as_float(p[f]);
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(&bar_ready[gi]);
+                const int act = __ldg(P.acts + h + 1);
+                const bool more = h + 1 < n_hidden;
+                mbar_wait(&bar_done[gi], st & 1u);
+                ++st;
+                tc_fence_after();
+                if (r == 0) gmax[gi * 2 + (h & 1)] = 0u;  // every thread of the graph has read it (see header)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tmem_ld32(taddr + 32 * q, p);
+                    const float4 ra = *reinterpret_cast<const float4 *>(rinv + 8 * q);
+                    const float4 rb4 = *reinterpret_cast<const float4 *>(rinv + 8 * q + 4);
+                    const float rv[8] = {ra.x, ra.y, ra.z, ra.w, rb4.x, rb4.y, rb4.z, rb4.w};
+                    float hv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        hv[k] = tc_act(fmaf(tc_combine(p + 4 * k, moff), ndq * rv[k], c[8 * q + k]), act, P.alpha);
+                    emit(q, hv, more);
+                }
+                publish_max((h + 1) & 1);
+            }
+
+            // -- last layer, projected first: q = H.w_0 + z, z = H.w_1, score = act(q - dinv_i sum_j A_ij dinv_j z_j + b)
+            float score;
+            {
+                bar_sync(dom_bar, dom_cnt);  // the graph's max |H| is complete
+                float qs, iqs;
+                tc_scale(__uint_as_float(gmax[gi * 2 + (n_hidden & 1)]) * P.tail_norm, &qs, &iqs);
+                if (valid) *reinterpret_cast<uint32_t *>(opg + (r >> 3) * 128 + (r & 7) * 16) = tc_digits(di * t1, qs);
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(&bar_ready[gi]);
+                mbar_wait(&bar_done[gi], st & 1u);
+                ++st;
+                tc_fence_after();
+                uint32_t d4[4];
+                tmem_ld4(taddr, d4);
+                tc_fence_before();
+                score = tc_act((t0 + t1) - di * (tc_combine(d4, moff) * iqs) + P.tail_bias, P.last_act, P.alpha);
+                if (!keep) score = 0.f;
+            }
+            // -- utility (mwis_dqn_call.py:230-235) ------------------------------------------------------------------
+            {
+                const double u = !valid ? 0.0 : (P.predict == DG_PREDICT_MWIS) ? (double)score * P.wts[v] : (double)score;
+                util_sm[tid] = u;
+                if (valid) {
+                    if (P.score) P.score[v] = score;
+                    if (P.util) P.util[v] = u;
+                }
+            }
+            if (P.do_lgs) {
+                // -- local greedy search (heuristics.py:77-116); neighbour sets as bit rows in registers -----------
+                uint32_t nbm[12];
+#pragma unroll
+                for (int w = 0; w < 12; ++w) nbm[w] = 0u;
+                if (valid) {
+                    const int nch = G.Kp >> 4;
+#pragma unroll
+                    for (int c = 0; c < 24; ++c) {
+                        if (c < nch) {
+                            const uint4 w = *reinterpret_cast<const uint4 *>(adj + (size_t)c * G.R * 16 + r * 16);
+                            const uint32_t m16 = tc_bits4(w.x) | (tc_bits4(w.y) << 4) | (tc_bits4(w.z) << 8) | (tc_bits4(w.w) << 12);
+                            nbm[c >> 1] |= m16 << ((c & 1) * 16);
+                        }
+                    }
+                }
+                const int w0 = G.fb * 4, nw = G.nb * 4;
+                if (lane == 0) remain[warp] = keepw[warp];
+                bar_sync(dom_bar, dom_cnt);
+                const double wv = util_sm[tid];
+                int rounds = 0, steps = 0;
+                for (;;) {
+                    uint32_t any = 0u;
+#pragma unroll
+                    for (int w = 0; w < 12; ++w)
+                        if (w < nw) any |= remain[w0 + w];
+                    if (!any) break;
+                    ++steps;
+                    if (rounds >= P.round_cap) {
+                        if (r == 0) atomicExch(P.status, DG_ERR_NOT_CONVERGED);
+                        break;
+                    }
+                    const bool active = (remain[warp] >> lane) & 1u;
+                    bool join = active;
+                    if (active) {
+#pragma unroll
+                        for (int w = 0; w < 12; ++w) {
+                            if (w < nw) {
+                                uint32_t cand = nbm[w] & remain[w0 + w];
+                                while (cand) {
+                                    const int bit = __ffs(cand) - 1;
+                                    cand &= cand - 1;
+                                    const int us = (w0 + w) * 32 + bit;  // the neighbour's slot
+                                    const double wu = util_sm[us];
+                                    if (!((wv > wu) || (wv == wu && tid < us))) {
+                                        join = false;
+                                        cand = 0u;
+                                    }
+                                }
+                            }
+                        }
+                        if (join && P.member) P.member[v] = 1;
+                    }
+                    const uint32_t jw = __ballot_sync(0xffffffffu, join);
+                    if (lane == 0) {
+                        joined[warp] = jw;
+                        memb[warp] |= jw;
+                    }
+                    bar_sync(dom_bar, dom_cnt);
+                    bool still = active && !join;
+                    if (still) {
+#pragma unroll
+                        for (int w = 0; w < 12; ++w)
+                            if (w < nw && (nbm[w] & joined[w0 + w])) still = false;
+                    }
+                    const uint32_t rw = __ballot_sync(0xffffffffu, still);
+                    if (lane == 0) remain[warp] = rw;
+                    ++rounds;
+                    bar_sync(dom_bar, dom_cnt);
+                }
+                if (r == 0 && P.steps) P.steps[G.g] = steps;
+                if (P.total && jb == 0 && (warp & 3) == 0) {  // the graph's first warp: vertex order, as dg_fused.cu
+                    double acc = 0.0;
+                    for (int i = lane; i < G.nv; i += 32) {
+                        const int sl = G.fb * 128 + i;
+                        if ((memb[sl >> 5] >> (sl & 31)) & 1u) acc += P.wts[G.v0 + i];  // mwis_dqn_call.py:241
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                    if (lane == 0) P.total[G.g] = acc;
+                }
+            }
+        }
+        wseq += (uint32_t)n_hidden;
+        tc_fence_before();
+        __syncthreads();  // shared memory, tensor memory and the barriers are recycled by the next tile
+        tc_fence_after();
+        if (timing) {
+            const long long now = clock64();
+            tm[1] += now - tk;
+            tm[2] += 1;
+        }
+    }
+    if (timing) {
+        tm[7] = clock64() - t_begin;
+        for (int k = 0; k < 8; ++k) P.dbg[(size_t)blockIdx.x * 8 + k] = tm[k];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (is_ctrl) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    // the last CTA to leave re-arms the tile counter for the next launch on this context
+    if (tid == 0) {
+        __threadfence();
+        const int done = atomicAdd(P.tile_counter + 1, 1);
+        if (done == (int)gridDim.x - 1) {
+            P.tile_counter[1] = 0;
+            __threadfence();
+            P.tile_counter[0] = 0;
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+uint16_t bf16_rne(float x) {
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    if ((b & 0x7f800000u) == 0x7f800000u) return (uint16_t)(b >> 16);
+    b += 0x7fffu + ((b >> 16) & 1u);
+    return (uint16_t)(b >> 16);
+}
+float bf16_to_f(uint16_t h) {
+    const uint32_t b = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+struct TcGraph {
+    int g, nv, nb;
+    size_t bytes;   // adjacency + operand blocks
+    long long cost;
+};
+
+}  // namespace
+
+// Operand blobs of the hidden layers (dg_model_create): per layer the bf16 terms of [W_0 | W_1 r] in the K-major core
+// matrix layout of the projection's B operand, then bias[32], 1/r[32] and the layer's fixed-point bound factor.
+void tc_build_weights(int n_hidden, const float *const *w0, const float *const *w1, const float *const *bias, const int *c_in,
+                      const int *c_out, std::vector<unsigned char> *blob) {
+    blob->assign((size_t)n_hidden * kTcWBlob, 0);
+    for (int h = 0; h < n_hidden; ++h) {
+        unsigned char *dst = blob->data() + (size_t)h * kTcWBlob;
+        float *fb = reinterpret_cast<float *>(dst + 12288);
+        float norm[32], rscale[32];
+        float maxnorm = 0.f;
+        for (int f = 0; f < 32; ++f) {
+            double s = 0.0;
+            if (f < c_out[h])
+                for (int k = 0; k < c_in[h]; ++k) s += fabs((double)w1[h][(size_t)k * c_out[h] + f]);
+            norm[f] = (float)s;
+            maxnorm = std::max(maxnorm, norm[f]);
+        }
+        for (int f = 0; f < 32; ++f) {
+            rscale[f] = 1.f;
+            if (norm[f] > 0.f && maxnorm > 0.f) {
+                int e;
+                frexp((double)maxnorm / (double)norm[f], &e);  // ratio = m 2^e, m in [0.5, 1)
+                rscale[f] = (float)ldexp(1.0, e - 1);           // largest power of two <= ratio
+            }
+        }
+        for (int n = 0; n < 64; ++n)
+            for (int k = 0; k < 32; ++k) {
+                float w = 0.f;
+                const int f = n & 31;
+                if (f < c_out[h] && k < c_in[h])
+                    w = n < 32 ? w0[h][(size_t)k * c_out[h] + f] : w1[h][(size_t)k * c_out[h] + f] * rscale[f];
+                const uint16_t t0 = bf16_rne(w);
+                const float r1 = w - bf16_to_f(t0);
+                const uint16_t t1 = bf16_rne(r1);
+                const float r2 = r1 - bf16_to_f(t1);
+                const uint16_t t2 = bf16_rne(r2);
+                const uint16_t terms[3] = {t0, t1, t2};
+                for (int term = 0; term < 3; ++term)
+                    memcpy(dst + term * 4096 + (k >> 3) * 1024 + n * 16 + (k & 7) * 2, &terms[term], 2);
+            }
+        for (int f = 0; f < 32; ++f) {
+            fb[f] = (bias && bias[h] && f < c_out[h]) ? bias[h][f] : 0.f;
+            fb[32 + f] = 1.f / rscale[f];
+        }
+        fb[64] = maxnorm * (1.f + 1.f / 1024.f);
+    }
+}
+
+namespace {
+
+// tiles: first-fit over a window of open tiles, graphs in order of decreasing cost
+int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
+    *ok = false;
+    if (b->tc_tiles_valid) {
+        *ok = b->tc_n_tiles > 0;
+        return DG_OK;
+    }
+    b->tc_tiles_valid = true;
+    b->tc_n_tiles = 0;
+    const size_t pool = (size_t)ctx->max_smem_optin - 1024 - kTcOffPool;
+    const auto &gp = b->h_graph_ptr;
+    std::vector<TcGraph> gs((size_t)b->n_graphs);
+    for (int g = 0; g < b->n_graphs; ++g) {
+        TcGraph t;
+        t.g = g;
+        t.nv = gp[g + 1] - gp[g];
+        t.nb = std::max(1, (t.nv + 127) / 128);
+        const size_t R = (size_t)((t.nv + 7) & ~7), Kp = (size_t)((t.nv + 31) & ~31);
+        t.bytes = ((R * Kp + 127) & ~(size_t)127) + (size_t)t.nb * kTcOpBlock;
+        // per layer: projection ~650 cycles per block, aggregation ~65 per block and 32 columns, epilogue ~900 per block
+        t.cost = (long long)t.nb * (1600 + 2 * (long long)Kp);
+        if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + 128 > pool) return DG_OK;  // not eligible: the caller falls back
+        gs[(size_t)g] = t;
+    }
+    std::stable_sort(gs.begin(), gs.end(), [](const TcGraph &a, const TcGraph &c) { return a.cost > c.cost; });
+    struct Open {
+        int ng, blocks, g[kTcMaxG];
+        size_t bytes;
+        long long cost;
+    };
+    std::vector<Open> tiles;
+    std::vector<int> open;  // indices of tiles that can still take a graph
+    for (const TcGraph &t : gs) {
+        int chosen = -1;
+        for (size_t oi = 0; oi < open.size() && chosen < 0; ++oi) {
+            const Open &o = tiles[(size_t)open[oi]];
+            if (o.ng < kTcMaxG && o.blocks + t.nb <= kTcBlocks && o.bytes + t.bytes + 128 <= pool) chosen = (int)oi;
+        }
+        if (chosen < 0) {
+            if (open.size() >= 64) open.erase(open.begin());  // bounded window: the oldest open tile is closed
+            tiles.push_back(Open{});
+            open.push_back((int)tiles.size() - 1);
+            chosen = (int)open.size() - 1;
+        }
+        Open &o = tiles[(size_t)open[(size_t)chosen]];
+        o.g[o.ng++] = t.g;
+        o.blocks += t.nb;
+        o.bytes += t.bytes;
+        o.cost += t.cost;
+        if (o.ng == kTcMaxG || o.blocks == kTcBlocks) open.erase(open.begin() + chosen);
+    }
+    std::stable_sort(tiles.begin(), tiles.end(), [](const Open &a, const Open &c) { return a.cost > c.cost; });
+    std::vector<int> flat(tiles.size() * 8, 0);
+    for (size_t i = 0; i < tiles.size(); ++i) {
+        flat[i * 8] = tiles[i].ng;
+        for (int k = 0; k < tiles[i].ng; ++k) flat[i * 8 + 1 + k] = tiles[i].g[k];
+    }
+    if (b->tc_tiles_cap < flat.size() || !b->tc_tiles_dev) {
+        if (b->tc_tiles_dev) {
+            DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(b->tc_tiles_dev);
+            b->tc_tiles_dev = nullptr;
+        }
+        b->tc_tiles_cap = flat.size() + flat.size() / 4 + 8;
+        DG_CUDA_CHECK(cudaMalloc((void **)&b->tc_tiles_dev, sizeof(int) * b->tc_tiles_cap));
+    }
+    if (!flat.empty())
+        DG_CUDA_CHECK(cudaMemcpyAsync(b->tc_tiles_dev, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    b->tc_n_tiles = (int)tiles.size();
+    if (getenv("DG_FUSED_TIMING")) fprintf(stderr, "[tc tiles] %d tiles for %d graphs\n", b->tc_n_tiles, b->n_graphs);
+    *ok = b->tc_n_tiles > 0;
+    return DG_OK;
+}
+
+}  // namespace
+
+int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict, int remove_zero_weight,
+                 uint8_t *member, float *score, double *util, double *total, int32_t *steps, bool *handled) {
+    *handled = false;
+    if (getenv("DG_DISABLE_TC") || getenv("DG_DISABLE_FUSED")) return DG_OK;
+    if (!m->tc_wall || m->n_layers < 3 || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
+    if (member == nullptr && d_wts == nullptr && predict == DG_PREDICT_MWIS) return DG_OK;
+    bool ok = false;
+    DG_TRY(tc_build_tiles(ctx, b, &ok));
+    if (!ok) return DG_OK;
+    TcParams p{};
+    p.tiles = b->tc_tiles_dev;
+    p.n_tiles = b->tc_n_tiles;
+    p.tile_counter = ctx->d_status + 1;
+    p.graph_ptr = b->graph_ptr;
+    p.row_ptr = b->row_ptr;
+    p.col_idx = b->col_idx;
+    p.wts = d_wts;
+    p.keep_in = remove_zero_weight ? nullptr : b->keep;
+    p.x0 = b->x0;
+    p.x0val = 1.0f / (float)m->layers[0].c_in;
+    p.remove_zero = remove_zero_weight ? 1 : 0;
+    p.n_hidden = m->n_layers - 2;
+    p.first = m->fused_first;
+    p.first_act = m->layers[0].act;
+    p.wall = m->tc_wall;
+    p.acts = m->d_acts;
+    p.tail = m->fused_tail;
+    p.tail_bias = m->tail_bias;
+    p.tail_norm = m->tc_tail_norm;
+    p.last_act = m->layers.back().act;
+    p.alpha = m->alpha;
+    p.predict = predict;
+    p.member = member;
+    p.score = score;
+    p.util = util;
+    p.total = total;
+    p.steps = steps;
+    p.status = ctx->d_status;
+    p.round_cap = kLgsRoundCap;
+    p.do_lgs = member != nullptr ? 1 : 0;
+    p.dbg = nullptr;
+    const size_t smem = (size_t)ctx->max_smem_optin - 1024;
+    if (getenv("DG_FUSED_TIMING")) {
+        long long *dbg = nullptr;
+        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * 8, &dbg));
+        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * (size_t)ctx->sm_count * 8, ctx->stream));
+        p.dbg = dbg;
+    }
+    DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(ctx->sm_count, p.n_tiles);
+    {
+        // work-equivalent algorithmic bytes, the same figure dg_fused.cu reports (SURVEY.md 8d / DESIGN.md)
+        const double n = (double)b->n_nodes, nnz = (double)b->nnz, cp = 32.0;
+        const double csr = 4.0 * (n + 1) + 4.0 * nnz;
+        const double hidden = (double)p.n_hidden * (csr + 4.0 * n + 8.0 * n * cp + 8.0 * cp * cp);
+        const double scalar_passes = 2.0 * (csr + 12.0 * n);
+        const double lgs = csr + 9.0 * n;
+        prof_begin(ctx);
+        tc_solve_kernel<<<grid, kTcThreads, smem, ctx->stream>>>(p);
+        ctx->launches++;
+        prof_end(ctx, hidden + scalar_passes + lgs);
+        DG_CUDA_CHECK(cudaGetLastError());
+    }
+    if (p.dbg) {
+        std::vector<long long> h((size_t)ctx->sm_count * 8);
+        DG_CUDA_CHECK(cudaMemcpyAsync(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const char *names[8] = {"stage", "solve", "tiles", "-", "-", "-", "-", "total"};
+        for (int k : {0, 1, 2, 7}) {
+            long long mn = -1, mx = 0;
+            double sum = 0;
+            int cnt = 0;
+            for (int c = 0; c < grid; ++c) {
+                const long long vv = h[(size_t)c * 8 + k];
+                mn = mn < 0 ? vv : std::min(mn, vv);
+                mx = std::max(mx, vv);
+                sum += (double)vv;
+                ++cnt;
+            }
+            fprintf(stderr, "[tc timing] %-6s min %10lld avg %12.0f max %10lld (%d CTAs)\n", names[k], mn, cnt ? sum / cnt : 0.0,
+                    mx, cnt);
+        }
+    }
+    *handled = true;
+    return DG_OK;
+}
+
+}  // namespace dg

@@ -176,14 +176,16 @@ def test_lgs_global_path_large_graph(gpu_ctx):
 # ------------------------------------------------------------------------------------------------
 # GCN forward
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("path", ["fused", "layer_kernels"])
+@pytest.mark.parametrize("path", ["tensor_core", "fused", "layer_kernels"])
 @pytest.mark.parametrize("short", list(util.CKPTS))
 def test_gcn_forward_matches_oracle(gpu_ctx, short, path, monkeypatch):
     E = _engine()
+    monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    monkeypatch.delenv("DG_DISABLE_TC", raising=False)
     if path == "layer_kernels":
         monkeypatch.setenv("DG_DISABLE_FUSED", "1")  # force the streaming per-layer kernels
-    else:
-        monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    elif path == "fused":
+        monkeypatch.setenv("DG_DISABLE_TC", "1")     # graph-resident CUDA-core kernel instead of the tcgen05 one
     gold = util.load_npz("gcn_oracle_small.npz")
     pb, w = util.small_graphs()
     layers = util.load_layers(short)
@@ -202,18 +204,23 @@ def test_gcn_forward_matches_oracle(gpu_ctx, short, path, monkeypatch):
     model.close()
 
 
-@pytest.mark.parametrize("path", ["fused", "layer_kernels", "fused_mma"])
+@pytest.mark.parametrize("path", ["tensor_core", "fused", "layer_kernels", "fused_mma"])
 @pytest.mark.parametrize("short", ["is4sat_l1", "is4sat_l20_c32", "is4sat_l2_c64", "dqnba_l20_c32"])
 def test_solve_membership_matches_reference_lgs(gpu_ctx, short, path, monkeypatch):
     """End to end (GCN -> utility -> LGS) against memberships the reference's LGS produced from the
-    oracle's utilities; through the graph-resident kernel, the per-layer kernels, and the optional
-    tensor-core projection."""
+    oracle's utilities; through the tcgen05 kernel (32-wide hidden layers; other models fall through to the
+    graph-resident kernel), the graph-resident CUDA-core kernel, the per-layer kernels, and the optional
+    mma.sync projection."""
     E = _engine()
     monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
     monkeypatch.delenv("DG_FUSED_MMA", raising=False)
+    monkeypatch.delenv("DG_DISABLE_TC", raising=False)
     if path == "layer_kernels":
         monkeypatch.setenv("DG_DISABLE_FUSED", "1")
+    elif path == "fused":
+        monkeypatch.setenv("DG_DISABLE_TC", "1")
     elif path == "fused_mma":
+        monkeypatch.setenv("DG_DISABLE_TC", "1")
         monkeypatch.setenv("DG_FUSED_MMA", "1")
     gold = util.load_npz("gcn_oracle_small.npz")
     pb, w = util.small_graphs()

@@ -419,11 +419,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     for (int k = 0; k < kTcMaxG; ++k) {
                         if (k >= ng || st[k] >= S) continue;
                         if (!mbar_test(&bar_ready[k], (uint32_t)st[k] & 1u)) continue;
+                        const int stage = st[k];
+                        const bool is_agg = stage == 0 || stage == S - 1 || ((stage - 1) & 1);
+                        if (!is_agg) {
+                            // The layer's weights must have landed.  Never block here: the copy may be waiting for
+                            // ANOTHER graph of the tile to finish with the buffer, and that graph's events are
+                            // served by this same thread - come back to this graph on a later poll.
+                            const uint32_t seq = wseq + (uint32_t)((stage - 1) >> 1);
+                            if (!mbar_test(&bar_full[seq & 1u], (seq >> 1) & 1u)) continue;
+                        }
                         tc_fence_after();
                         const TcMeta m = meta[k];
-                        const int stage = st[k];
                         const uint32_t ybase = pool_addr + opbuf + m.fb * kTcOpBlock;  // the graph's operand region
-                        if (stage == 0 || stage == S - 1 || ((stage - 1) & 1)) {
+                        if (is_agg) {
                             // aggregation: D[block] = A[block rows, :] . Y, N = 16 (scalar) or 128 (hidden layer)
                             const bool scalar = stage == 0 || stage == S - 1;
                             const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
@@ -454,7 +462,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                                 }
                             }
                             const uint32_t seq = wseq + h;
-                            mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u);
                             const uint32_t wbase = s32(wring + (seq & 1u) * kTcWBlob);
                             const uint32_t idesc = idesc_bf16(128, 64);
                             for (int jb = 0; jb < m.nb; ++jb) {

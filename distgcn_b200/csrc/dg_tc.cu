@@ -11,7 +11,7 @@
 //         A is the graph's dense 0/1 adjacency, resident in shared memory as bytes for all layers; Y = dinv * P1 is
 //         quantised per graph and layer to 31-bit fixed point (scale from a bound on max |Y|, below) and its four
 //         base-256 digits are the operand columns, so the sum over neighbours is EXACT integer arithmetic.
-//         Digits are the bytes of v + 0x80808080 (unsigned, offset 128 each): sum_j A_ij v_j = sum_a 256^a (D_a - 128 deg_i).
+//         Digits are balanced (signed bytes): sum_j A_ij v_j = sum_a 256^a D_a with |D_a| <= 128 deg_i.
 //     (3) epilogue     H' = act(P0 + P1 + b - dinv_i * S_i)   CUDA cores, one thread per vertex (TMEM lane), result split
 //         into bf16 terms and stored as the next projection's A operand.
 //   Fixed-point scale: |Y_jf| <= max|H| * max_f sum_k |W_1[k,f] r_f|, with r_f powers of two (exact) that equalise the
@@ -33,6 +33,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <vector>
 
 #include "dg_common.cuh"
@@ -45,7 +46,6 @@ constexpr int kTcVertexThreads = 512;
 constexpr int kTcThreads = 544;       // + the control warp
 constexpr int kTcMaxG = 4;            // graphs per tile (every graph owns >= 1 block)
 constexpr int kTcBlocks = 4;          // 128-row blocks per tile = TMEM budget: 4 x 128 columns
-constexpr int kTcOpBlock = 24576;     // operand bytes per block: 3 bf16 terms x [4 K-chunks][128 rows][16 B]
 constexpr int kTcWBlob = 12560;       // one hidden layer: bf16 terms of [W_0 | W_1 r] (12288), bias[32], 1/r[32], bound, pad
 // shared-memory map (bytes)
 constexpr int kTcOffRing = 0;                      // 2 x kTcWBlob
@@ -53,16 +53,22 @@ constexpr int kTcOffUtil = 25216;                  // double[512]   (aliased by 
 constexpr int kTcOffDinv = kTcOffUtil + 4096;      // float[512]
 constexpr int kTcOffBits = kTcOffDinv + 2048;      // uint32[4][16]: keep, remain, joined, member
 constexpr int kTcOffGmax = kTcOffBits + 256;       // uint32[4][2] layer maxima, uint32[4] x0 maxima
-constexpr int kTcOffBar = kTcOffGmax + 64;         // full[2], ready[4], done[4]
-constexpr int kTcOffMeta = kTcOffBar + 128;        // TcMeta[4] + tile scalars
-constexpr int kTcOffPool = 32768;                  // adjacency of the tile's graphs, then the operand blocks
+constexpr int kTcOffBar = kTcOffGmax + 64;         // 22 mbarriers, see the kernel
+constexpr int kTcOffMeta = kTcOffBar + 256;        // TcMeta[4] + tile scalars
+// Pool, per graph of the tile (R = rows padded to 8, Kp = columns padded to 32):
+//   adjacency  u8  [Kp/16 chunks][R rows][16 B]        K-major A operand of the aggregation  (R Kp bytes)
+//   H terms    bf16 [3 terms][4 chunks][R rows][16 B]   K-major A operand of the projection   (192 R bytes)
+//   Y digits   u8  [8 runs][Kp/8 groups][8 k][16 B]     MN-major B operand of the aggregation (128 Kp bytes)
+// A 128-row block of a graph whose last block is partial reads past row R: those reads stay inside the pool (the next
+// region) and only feed accumulator rows nobody looks at.
+constexpr int kTcOffPool = 32768;
 static_assert(kTcOffMeta + 256 <= kTcOffPool, "shared-memory map overflows into the pool");
 
-struct TcMeta {  // one graph of the tile
-    int v0, nv, fb, nb, R, Kp, adj, e0, nnz, g;
+struct TcMeta {  // one graph of the tile; adj / hoff / yoff: byte offsets of its three regions in the pool
+    int v0, nv, fb, nb, R, Kp, adj, hoff, yoff, e0, nnz, g;
 };
 struct TcTileInfo {
-    int ng, nblocks, adj_total, opbuf;
+    int ng, nblocks, pool_used, blkg[4];
 };
 
 struct TcParams {
@@ -154,8 +160,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// A unsigned 8-bit (the 0/1 adjacency), B signed 8-bit (balanced base-256 digits), B MN-major, s32 accumulators
 __host__ __device__ constexpr uint32_t idesc_u8(int M, int N) {
-    return (2u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (2u << 4) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(
@@ -184,6 +191,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// split form: issue a 16-column load, do other work, then wait (the wait names the registers so that no use of them can
+// be scheduled above it)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t *r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -204,18 +227,17 @@ __device__ __forceinline__ void tc_scale(float bound, float *q, float *inv_q) {
     *q = __int_as_float((283 - eb) << 23);      // 2^(156 - eb)
     *inv_q = __int_as_float((eb - 29) << 23);   // 2^(eb - 156)
 }
-// fixed-point image of y (|y * q| < 2^30) as four offset-128 base-256 digits: the bytes of the result
+// fixed-point image v of y (|y * q| < 2^30) as four balanced base-256 digits d_a in [-128, 127], v = sum_a 256^a d_a:
+// the bytes of (v + 0x80808080) are the digits offset by 128; flipping each byte's top bit makes them two's complement
 __device__ __forceinline__ uint32_t tc_digits(float y, float q) {
-    return (uint32_t)__float2int_rn(y * q) + 0x80808080u;
+    return ((uint32_t)__float2int_rn(y * q) + 0x80808080u) ^ 0x80808080u;
 }
-// sum_a 256^a (D_a - 128 deg) as a float; every D_a - 128 deg is an integer below 2^22 in magnitude
-__device__ __forceinline__ float tc_combine(const uint32_t *d, int magic_minus_off) {
-    const float m = 12582912.0f;  // 1.5 * 2^23
-    const float f0 = __int_as_float((int)d[0] + magic_minus_off) - m;
-    const float f1 = __int_as_float((int)d[1] + magic_minus_off) - m;
-    const float f2 = __int_as_float((int)d[2] + magic_minus_off) - m;
-    const float f3 = __int_as_float((int)d[3] + magic_minus_off) - m;
-    return fmaf(fmaf(fmaf(f3, 256.f, f2), 256.f, f1), 256.f, f0);
+// sum_a 256^a D_a as a float: the two digit pairs are combined exactly in integers (|D_a| <= 128 deg), converted, and
+// joined with one FMA
+__device__ __forceinline__ float tc_combine(const uint32_t *d) {
+    const int lo = (int)d[1] * 256 + (int)d[0];
+    const int hi = (int)d[3] * 256 + (int)d[2];
+    return fmaf((float)hi, 65536.f, (float)lo);
 }
 
 // 8 feature values -> three bf16 term vectors (hi, mid, lo), each 8 x bf16 = 16 B
@@ -248,14 +270,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *wring = smem + kTcOffRing;
     double *util_sm = reinterpret_cast<double *>(smem + kTcOffUtil);
-    int *rp_sm = reinterpret_cast<int *>(smem + kTcOffUtil);  // staging only
-    float *dinv_sm = reinterpret_cast<float *>(smem + kTcOffDinv);
     uint32_t *keepw = reinterpret_cast<uint32_t *>(smem + kTcOffBits);
     uint32_t *remain = keepw + 16, *joined = keepw + 32, *memb = keepw + 48;
     uint32_t *gmax = reinterpret_cast<uint32_t *>(smem + kTcOffGmax);  // [4][2]
     uint32_t *gmax0 = gmax + 8;                                         // [4]
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + kTcOffBar);
-    uint64_t *bar_ready = bar_full + 2, *bar_done = bar_full + 6;
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + kTcOffBar);  // [2]  weight ring
+    uint64_t *bar_rp = bar_full + 2;    // [4] per block: the projection's A operand (H terms) is complete
+    uint64_t *bar_dp = bar_full + 6;    // [4] per block: projection MMAs complete
+    uint64_t *bar_da = bar_full + 10;   // [4] per block: aggregation MMAs complete
+    uint64_t *bar_ra = bar_full + 14;   // [4] per graph: the aggregation's B operand (Y digits) is complete
+    uint64_t *bar_mx = bar_full + 18;   // [4] per graph: every vertex has published its max |H|
     TcMeta *meta = reinterpret_cast<TcMeta *>(smem + kTcOffMeta);
     TcTileInfo *tinfo = reinterpret_cast<TcTileInfo *>(smem + kTcOffMeta + sizeof(TcMeta) * kTcMaxG);
     unsigned char *pool = smem + kTcOffPool;
@@ -267,11 +291,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     const int n_hidden = P.n_hidden;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init(&bar_full[i], 1);
-        for (int i = 0; i < kTcMaxG; ++i) {
-            mbar_init(&bar_ready[i], 1);
-            mbar_init(&bar_done[i], 1);
-        }
+        for (int i = 0; i < 22; ++i) mbar_init(&bar_full[i], 1);
         fence_mbar_init();
     }
     if (is_ctrl) {  // the whole tensor memory of the SM: 4 blocks x 128 accumulator columns
@@ -295,11 +315,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         if (t >= P.n_tiles) break;
         long long tk = timing ? clock64() : 0;
 
-        // ---- tile metadata; the graphs' barriers are re-armed with this tile's thread counts -----------------
+        // ---- tile metadata; the barriers are re-armed with this tile's thread counts ---------------------------
         if (tid == 0) {
             const int *td = P.tiles + (size_t)t * 8;
             const int ng = td[0];
-            int fb = 0, adj = 0;
+            int fb = 0, off = 0;
             for (int gi = 0; gi < ng; ++gi) {
                 const int g = td[1 + gi];
                 TcMeta m;
@@ -310,27 +330,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 m.fb = fb;
                 m.R = (m.nv + 7) & ~7;
                 m.Kp = (m.nv + 31) & ~31;
-                m.adj = adj;
+                m.adj = off;
+                m.hoff = off + m.R * m.Kp;
+                m.yoff = m.hoff + 192 * m.R;
+                off = m.yoff + 128 * m.Kp;
                 m.e0 = P.row_ptr[m.v0];
                 m.nnz = P.row_ptr[m.v0 + m.nv] - m.e0;
                 meta[gi] = m;
-                adj += m.R * m.Kp;
+                for (int jb = 0; jb < m.nb; ++jb) tinfo->blkg[fb + jb] = gi;
                 fb += m.nb;
-                mbar_inval(&bar_ready[gi]);
-                mbar_inval(&bar_done[gi]);
-                mbar_init(&bar_ready[gi], 128 * m.nb);
-                mbar_init(&bar_done[gi], 1);
+                mbar_inval(&bar_ra[gi]);
+                mbar_inval(&bar_mx[gi]);
+                mbar_init(&bar_ra[gi], 128 * m.nb);
+                mbar_init(&bar_mx[gi], 128 * m.nb);
+            }
+            for (int b = 0; b < fb; ++b) {
+                mbar_inval(&bar_rp[b]);
+                mbar_inval(&bar_dp[b]);
+                mbar_inval(&bar_da[b]);
+                mbar_init(&bar_rp[b], 128);
+                mbar_init(&bar_dp[b], 1);
+                mbar_init(&bar_da[b], 1);
             }
             tinfo->ng = ng;
             tinfo->nblocks = fb;
-            tinfo->adj_total = adj;
-            tinfo->opbuf = (adj + 127) & ~127;
+            tinfo->pool_used = off;
             for (int i = 0; i < 12; ++i) gmax[i] = 0u;
             fence_mbar_init();
         }
         __syncthreads();
         const int ng = tinfo->ng;
-        const int opbuf = tinfo->opbuf;
+        const int nblocks = tinfo->nblocks;
 
         // the first two hidden layers' weights start streaming in (every MMA of the previous tile has completed)
         if (is_ctrl && lane == 0) {
@@ -347,8 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         bool valid = false, keep = false;
         if (tid < kTcVertexThreads) {
             const int b = tid >> 7;
-            for (int k = 0; k < ng; ++k)
-                if (b >= meta[k].fb && b < meta[k].fb + meta[k].nb) gi = k;
+            if (b < nblocks) gi = tinfo->blkg[b];
             if (gi >= 0) {
                 G = meta[gi];
                 r = (b - G.fb) * 128 + (tid & 127);
@@ -366,27 +395,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 keepw[warp] = kw;
                 memb[warp] = 0u;
             }
-            // staging copy of the graphs' row pointers (relative to the graph's first edge)
             for (int k = 0; k < ng; ++k) {
                 const TcMeta m = meta[k];
-                for (int i = tid; i <= m.nv; i += kTcVertexThreads) rp_sm[m.fb * 128 + k + i] = P.row_ptr[m.v0 + i] - m.e0;
+                // clear the adjacency bytes
+                uint4 *a16 = reinterpret_cast<uint4 *>(pool + m.adj);
+                const int n16 = (m.R * m.Kp) >> 4;
+                for (int i = tid; i < n16; i += kTcVertexThreads) a16[i] = make_uint4(0u, 0u, 0u, 0u);
             }
-            // clear the adjacency bytes
-            const int n16 = tinfo->adj_total >> 4;
-            for (int i = tid; i < n16; i += kTcVertexThreads) reinterpret_cast<uint4 *>(pool)[i] = make_uint4(0u, 0u, 0u, 0u);
+            // Edge -> row table of this thread's vertex, parked in the graph's H / Y regions (free until the first layer):
+            // the scatter below then needs one shared-memory load per edge instead of a binary search in row_ptr.
+            if (valid) {
+                uint16_t *rowof = reinterpret_cast<uint16_t *>(pool + G.hoff);
+                if (2 * G.nnz <= 192 * G.R + 128 * G.Kp) {
+                    const int beg = P.row_ptr[v] - G.e0, end = P.row_ptr[v + 1] - G.e0;
+                    for (int e = beg; e < end; ++e) rowof[e] = (uint16_t)r;
+                }
+            }
         }
         __syncthreads();
         // ---- dense adjacency of the kept sub-graph: byte (row i, column j) = 1 for every edge with both ends kept ---
         if (tid < kTcVertexThreads) {
             for (int k = 0; k < ng; ++k) {
                 const TcMeta m = meta[k];
-                const int *rp = rp_sm + m.fb * 128 + k;
                 unsigned char *adj = pool + m.adj;
+                const uint16_t *rowof = reinterpret_cast<const uint16_t *>(pool + m.hoff);
+                const bool table = 2 * m.nnz <= 192 * m.R + 128 * m.Kp;
                 for (int e = tid; e < m.nnz; e += kTcVertexThreads) {
-                    int lo = 0, hi = m.nv;  // rp[lo] <= e < rp[hi]
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (rp[mid] <= e) lo = mid; else hi = mid;
+                    int lo;
+                    if (table) {
+                        lo = rowof[e];
+                    } else {  // (a nearly complete graph: the table does not fit)
+                        lo = 0;
+                        int hi = m.nv;  // row_ptr[lo] <= e < row_ptr[hi]
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (P.row_ptr[m.v0 + mid] - m.e0 <= e) lo = mid; else hi = mid;
+                        }
                     }
                     const int j = P.col_idx[m.e0 + e] - m.v0;
                     const uint32_t ki = (keepw[m.fb * 4 + (lo >> 5)] >> (lo & 31)) & 1u;
@@ -404,82 +448,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         }
 
         if (is_ctrl) {
-            // ================= control thread: every tcgen05.mma and every weight copy of the tile ================
-            if (lane == 0) {
-                const int S = 2 + 2 * n_hidden;
-                int st[kTcMaxG] = {0, 0, 0, 0};
+            // ================= control warp: every tcgen05.mma and every weight copy of the tile ===================
+            // The whole warp runs the loop with identical values (uniform registers feed the MMA operands directly);
+            // lane 0 alone issues.
+            {
+                const bool leader = lane == 0;
+                int pst[kTcBlocks] = {0, 0, 0, 0};  // projections issued per block
+                int ast[kTcMaxG] = {0, 0, 0, 0};    // aggregations issued per graph (0 first layer, 1..n_hidden, n_hidden+1 tail)
                 int passed[2] = {0, 0};
-                int remaining = ng;
+                int remaining = ng * (n_hidden + 2) + nblocks * n_hidden;
                 const uint32_t pool_addr = s32(pool);
+                const uint32_t ring_addr = s32(wring);
                 const long long t_ctrl = clock64();
                 uint32_t polls = 0;
                 while (remaining > 0) {
                     if ((++polls & 4095u) == 0u && clock64() - t_ctrl > 8000000000LL) __trap();
 #pragma unroll
                     for (int k = 0; k < kTcMaxG; ++k) {
-                        if (k >= ng || st[k] >= S) continue;
-                        if (!mbar_test(&bar_ready[k], (uint32_t)st[k] & 1u)) continue;
-                        const int stage = st[k];
-                        const bool is_agg = stage == 0 || stage == S - 1 || ((stage - 1) & 1);
-                        if (!is_agg) {
-                            // The layer's weights must have landed.  Never block here: the copy may be waiting for
-                            // ANOTHER graph of the tile to finish with the buffer, and that graph's events are
-                            // served by this same thread - come back to this graph on a later poll.
-                            const uint32_t seq = wseq + (uint32_t)((stage - 1) >> 1);
-                            if (!mbar_test(&bar_full[seq & 1u], (seq >> 1) & 1u)) continue;
-                        }
+                        // aggregation of graph k: D[block] = A[block rows, :] . Y, N = 16 (scalar) or 128 (hidden layer)
+                        if (k >= ng || ast[k] > n_hidden + 1) continue;
+                        if (!mbar_test(&bar_ra[k], (uint32_t)ast[k] & 1u)) continue;
                         tc_fence_after();
                         const TcMeta m = meta[k];
-                        const uint32_t ybase = pool_addr + opbuf + m.fb * kTcOpBlock;  // the graph's operand region
-                        if (is_agg) {
-                            // aggregation: D[block] = A[block rows, :] . Y, N = 16 (scalar) or 128 (hidden layer)
-                            const bool scalar = stage == 0 || stage == S - 1;
-                            const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
-                            const uint32_t lbo_a = (uint32_t)m.R * 16u;
-                            const uint32_t sbo_b = scalar ? 128u : (uint32_t)m.Kp * 16u;
-                            const int ksteps = m.Kp >> 5;
-                            for (int jb = 0; jb < m.nb; ++jb) {
-                                const uint32_t abase = pool_addr + m.adj + jb * 128 * 16;
-                                const uint32_t d = tmem + (uint32_t)(m.fb + jb) * 128u;
-                                for (int s = 0; s < ksteps; ++s)
-                                    mma_u8(d, umma_desc(abase + s * 2 * lbo_a, lbo_a, 128u), umma_desc(ybase + s * 512, 128u, sbo_b),
-                                           idesc, s > 0);
+                        const bool scalar = ast[k] == 0 || ast[k] == n_hidden + 1;
+                        const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
+                        const uint32_t lbo_a = (uint32_t)m.R * 16u;
+                        const uint64_t bdesc0 = umma_desc(pool_addr + m.yoff, 128u, scalar ? 128u : (uint32_t)m.Kp * 16u);
+                        const uint64_t adesc0 = umma_desc(pool_addr + m.adj, lbo_a, 128u);
+                        const uint32_t a_step = (2u * lbo_a) >> 4;  // one K-step (32 columns = 2 chunks) in descriptor units
+                        const int ksteps = m.Kp >> 5;
+                        for (int jb = 0; jb < m.nb; ++jb) {
+                            uint64_t adesc = adesc0 + (uint64_t)(jb * 128);  // 128 rows x 16 B >> 4
+                            uint64_t bdesc = bdesc0;
+                            const uint32_t d = tmem + (uint32_t)(m.fb + jb) * 128u;
+                            for (int s = 0; s < ksteps; ++s) {
+                                if (leader) mma_u8(d, adesc, bdesc, idesc, s > 0);
+                                adesc += a_step;
+                                bdesc += 32u;  // 4 k-groups x 128 B >> 4
                             }
-                        } else {
-                            // projection of hidden layer h: [P0 | P1] = H . [W_0 | W_1 r], 6 products x 2 K-steps
-                            const int h = (stage - 1) >> 1;
-                            if (h >= 1) {
-                                // every thread of this graph has finished layer h-1 (its epilogue reads bias / r from
-                                // the weight buffer): when all graphs have, the buffer takes layer h+1
-                                const uint32_t pbuf = (wseq + h - 1) & 1u;
-                                if (++passed[pbuf] == ng) {
-                                    passed[pbuf] = 0;
-                                    if (h + 1 < n_hidden) {
-                                        mbar_expect_tx(&bar_full[pbuf], kTcWBlob);
-                                        bulk_g2s(wring + pbuf * kTcWBlob, P.wall + (size_t)(h + 1) * kTcWBlob, kTcWBlob,
-                                                 &bar_full[pbuf]);
-                                    }
+                            if (leader) mma_commit(&bar_da[m.fb + jb]);
+                        }
+                        ++ast[k];
+                        --remaining;
+                    }
+#pragma unroll
+                    for (int b = 0; b < kTcBlocks; ++b) {
+                        // projection of block b, hidden layer h: [P0 | P1] = H . [W_0 | W_1 r], 6 products x 2 K-steps
+                        if (b >= nblocks || pst[b] >= n_hidden) continue;
+                        if (!mbar_test(&bar_rp[b], (uint32_t)pst[b] & 1u)) continue;
+                        const int h = pst[b];
+                        const uint32_t seq = wseq + (uint32_t)h;
+                        // The layer's weights must have landed.  Never block here: the copy may be waiting for ANOTHER
+                        // block of the tile to finish with the buffer, and that block's events are served by this same
+                        // warp - come back on a later poll.
+                        if (!mbar_test(&bar_full[seq & 1u], (seq >> 1) & 1u)) continue;
+                        tc_fence_after();
+                        if (h >= 1) {
+                            // every thread of this block has finished layer h-1 (its epilogue reads bias / r from the
+                            // weight buffer): when all blocks have, the buffer takes layer h+1
+                            const uint32_t pbuf = (seq - 1u) & 1u;
+                            if (++passed[pbuf] == nblocks) {
+                                passed[pbuf] = 0;
+                                if (h + 1 < n_hidden && leader) {
+                                    mbar_expect_tx(&bar_full[pbuf], kTcWBlob);
+                                    bulk_g2s(wring + pbuf * kTcWBlob, P.wall + (size_t)(h + 1) * kTcWBlob, kTcWBlob,
+                                             &bar_full[pbuf]);
                                 }
                             }
-                            const uint32_t seq = wseq + h;
-                            const uint32_t wbase = s32(wring + (seq & 1u) * kTcWBlob);
-                            const uint32_t idesc = idesc_bf16(128, 64);
-                            for (int jb = 0; jb < m.nb; ++jb) {
-                                const uint32_t abase = ybase + jb * kTcOpBlock;
-                                const uint32_t d = tmem + (uint32_t)(m.fb + jb) * 128u;
-                                // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
-                                const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
-#pragma unroll
-                                for (int p = 0; p < 6; ++p)
-#pragma unroll
-                                    for (int s = 0; s < 2; ++s)
-                                        mma_bf16(d, umma_desc(abase + ta[p] * 8192 + s * 4096, 2048u, 128u),
-                                                 umma_desc(wbase + tb[p] * 4096 + s * 2048, 1024u, 128u), idesc, (p | s) != 0);
-                            }
                         }
-                        mma_commit(&bar_done[k]);
-                        st[k] = stage + 1;
-                        if (st[k] == S) --remaining;
+                        const TcMeta m = meta[tinfo->blkg[b]];
+                        const uint32_t lbo_a = (uint32_t)m.R * 16u;  // H terms: [term][chunk][R rows][16 B]
+                        const uint64_t a0 = umma_desc(pool_addr + m.hoff + (uint32_t)(b - m.fb) * 2048u, lbo_a, 128u);
+                        const uint64_t b0 = umma_desc(ring_addr + (seq & 1u) * kTcWBlob, 1024u, 128u);
+                        const uint32_t a_chunk = lbo_a >> 4;  // one 16-byte K chunk of all rows, in descriptor units
+                        const uint32_t idesc = idesc_bf16(128, 64);
+                        const uint32_t d = tmem + (uint32_t)b * 128u;
+                        // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi); A term t starts
+                        // 4 t chunks in, W term t starts 4096 t bytes in; the second K-step is 2 chunks further
+                        const uint64_t at[3] = {a0, a0 + 4u * a_chunk, a0 + 8u * a_chunk};
+                        const uint64_t bt[3] = {b0, b0 + 256u, b0 + 512u};
+                        const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+                        if (leader) {
+#pragma unroll
+                            for (int p = 0; p < 6; ++p) {
+                                mma_bf16(d, at[ta[p]], bt[tb[p]], idesc, p != 0);
+                                mma_bf16(d, at[ta[p]] + 2u * a_chunk, bt[tb[p]] + 128u, idesc, 1u);
+                            }
+                            mma_commit(&bar_dp[b]);
+                        }
+                        ++pst[b];
+                        --remaining;
                     }
                 }
             }
@@ -488,13 +546,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             // ================= vertex threads =========================================================================
             const int b = tid >> 7;
             const int jb = b - G.fb;
+            const int lastb = G.fb + G.nb - 1;
             const int dom_bar = 1 + G.fb, dom_cnt = 128 * G.nb;
             const uint32_t taddr = tmem + (uint32_t)b * 128u + ((uint32_t)((warp & 3) * 32) << 16);
             unsigned char *adj = pool + G.adj;
-            unsigned char *opg = pool + opbuf + G.fb * kTcOpBlock;  // the graph's operand region (Y digits)
-            unsigned char *opb = opg + jb * kTcOpBlock;             // this block's H terms
-            const int rb = tid & 127;                               // row within the block
-            uint32_t st = 0;                                        // stage counter -> barrier parity
+            unsigned char *hrow = pool + G.hoff + r * 16;  // this vertex's 16-byte slots in the H-term chunks
+            unsigned char *yrow = pool + G.yoff + (r >> 3) * 128 + (r & 7) * 16;  // ... and in the Y digit runs
+            const int hterm = 4 * G.R * 16, hchunk = G.R * 16;
+            uint32_t ea = 0, ep = 0, em = 0;  // aggregation / projection / max events consumed -> barrier parities
 
             // degree on the kept sub-graph, dinv, x0, and the scalar operand of the rank-1 first layer
             unsigned deg = 0;
@@ -510,14 +569,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             }
             const float di = deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f;  // gcn/utils.py:122-125
             const float xi = keep ? (P.x0 ? P.x0[v] : P.x0val) : 0.f;
-            const int moff = 0x4B400000 - 128 * (int)deg;
             float q0, iq0;
             tc_scale(P.x0 ? __uint_as_float(gmax0[gi]) : fabsf(P.x0val), &q0, &iq0);
-            if (valid) *reinterpret_cast<uint32_t *>(opg + (r >> 3) * 128 + (r & 7) * 16) = tc_digits(di * xi, q0);
+            if (valid) *reinterpret_cast<uint32_t *>(yrow) = tc_digits(di * xi, q0);
             fence_async_smem();
-            mbar_arrive(&bar_ready[gi]);
+            mbar_arrive(&bar_ra[gi]);
 
-            // -- first layer (rank 1): s = (L x0)_i, H1 = act(x0 colsum(W_0) + s colsum(W_1) + b) -----------------
             float hmax = 0.f, t0 = 0.f, t1 = 0.f;
             // consumes 8 new feature values of this vertex: operand terms for the next projection, or the last
             // layer's two dot products when no hidden layer follows
@@ -525,9 +582,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 if (to_terms) {
                     uint4 hi, mid, lo;
                     tc_split8(hv, &hi, &mid, &lo);
-                    *reinterpret_cast<uint4 *>(opb + 0 * 8192 + q * 2048 + rb * 16) = hi;
-                    *reinterpret_cast<uint4 *>(opb + 1 * 8192 + q * 2048 + rb * 16) = mid;
-                    *reinterpret_cast<uint4 *>(opb + 2 * 8192 + q * 2048 + rb * 16) = lo;
+                    if (valid) {  // rows past the graph's last vertex stay whatever they are: their outputs are ignored
+                        *reinterpret_cast<uint4 *>(hrow + 0 * hterm + q * hchunk) = hi;
+                        *reinterpret_cast<uint4 *>(hrow + 1 * hterm + q * hchunk) = mid;
+                        *reinterpret_cast<uint4 *>(hrow + 2 * hterm + q * hchunk) = lo;
+                    }
                 } else {
                     const float4 wa = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q);
                     const float4 wb = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q + 1);
@@ -547,15 +606,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 const uint32_t wmax = __reduce_max_sync(0xffffffffu, mine);
                 if (lane == 0) atomicMax(&gmax[gi * 2 + slot], wmax);
                 hmax = 0.f;
+                mbar_arrive(&bar_mx[gi]);
+            };
+            // the graph's max |H|, once every vertex of the graph has published
+            auto graph_max = [&](int slot) -> float {
+                mbar_wait(&bar_mx[gi], em & 1u);
+                ++em;
+                return __uint_as_float(gmax[gi * 2 + slot]);
+            };
+            // Y may be overwritten once EVERY block's MMAs of the graph's previous aggregation have completed (this
+            // block's have; commits complete in issue order, so the graph's last block tells)
+            auto y_free = [&]() {
+                if (b != lastb) mbar_wait(&bar_da[lastb], (ea - 1u) & 1u);
             };
 
-            mbar_wait(&bar_done[gi], st & 1u);
-            ++st;
+            // -- first layer (rank 1): s = (L x0)_i, H1 = act(x0 colsum(W_0) + s colsum(W_1) + b) -----------------
+            mbar_wait(&bar_da[b], ea & 1u);
+            ++ea;
             tc_fence_after();
             {
                 uint32_t d4[4];
                 tmem_ld4(taddr, d4);
-                const float s_i = xi - di * (tc_combine(d4, moff) * iq0);
+                const float s_i = xi - di * (tc_combine(d4) * iq0);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float hv[8];
@@ -571,88 +643,126 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     }
                     emit(q, hv, n_hidden > 0);
                 }
-                publish_max(0);
             }
 
             // -- hidden layers -----------------------------------------------------------------------------------------
             for (int h = 0; h < n_hidden; ++h) {
-                // H terms are in place: the projection may start
+                // this block's H terms are in place: its projection may start
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(&bar_ready[gi]);
+                mbar_arrive(&bar_rp[b]);
+                publish_max(h & 1);
                 const uint32_t seq = wseq + h;
                 const unsigned char *wb = wring + (seq & 1u) * kTcWBlob;
                 const float *bias = reinterpret_cast<const float *>(wb + 12288);
                 const float *rinv = bias + 32;
-                mbar_wait(&bar_done[gi], st & 1u);
-                ++st;
+                long long tq = timing ? clock64() : 0;
+                mbar_wait(&bar_dp[b], ep & 1u);
+                ++ep;
                 tc_fence_after();
+                if (timing) {
+                    const long long now = clock64();
+                    tm[3] += now - tq;
+                    tq = now;
+                }
                 mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u);  // (already complete: the projection has read it)
                 float qs, iqs;
-                tc_scale(__uint_as_float(gmax[gi * 2 + (h & 1)]) * bias[64], &qs, &iqs);
+                tc_scale(graph_max(h & 1) * bias[64], &qs, &iqs);
                 const float dq = di * qs, ndq = -di * iqs;
+                y_free();
                 float c[32];
-                uint32_t p[32];
-                tmem_ld32(taddr + 32, p);  // P1 (columns scaled by r)
+                uint32_t pa[16], pb[16];
+                // TMEM loads run one 16-column piece ahead of the arithmetic: P1 (columns 32..63, scaled by r), then P0
+                auto half_b = [&](const uint32_t *pp, int f0) {
 #pragma unroll
-                for (int f4 = 0; f4 < 8; ++f4) {
-                    const float4 ri = *reinterpret_cast<const float4 *>(rinv + 4 * f4);
-                    const float4 bi = *reinterpret_cast<const float4 *>(bias + 4 * f4);
-                    const float p0 = __uint_as_float(p[4 * f4]), p1 = __uint_as_float(p[4 * f4 + 1]);
-                    const float p2 = __uint_as_float(p[4 * f4 + 2]), p3 = __uint_as_float(p[4 * f4 + 3]);
-                    c[4 * f4 + 0] = fmaf(p0, ri.x, bi.x);
-                    c[4 * f4 + 1] = fmaf(p1, ri.y, bi.y);
-                    c[4 * f4 + 2] = fmaf(p2, ri.z, bi.z);
-                    c[4 * f4 + 3] = fmaf(p3, ri.w, bi.w);
-                    // run f4 of the MN-major operand = features 4 f4 .. 4 f4 + 3, digit a of feature f at column 4 f + a
-                    const uint4 dg4 = make_uint4(tc_digits(p0, dq), tc_digits(p1, dq), tc_digits(p2, dq), tc_digits(p3, dq));
-                    if (valid)
-                        *reinterpret_cast<uint4 *>(opg + (size_t)f4 * G.Kp * 16 + (r >> 3) * 128 + (r & 7) * 16) = dg4;
-                }
-                tmem_ld32(taddr, p);  // P0
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const int f = f0 + 4 * g4;
+                        const float4 ri = *reinterpret_cast<const float4 *>(rinv + f);
+                        const float4 bi = *reinterpret_cast<const float4 *>(bias + f);
+                        const float p0 = __uint_as_float(pp[4 * g4]), p1 = __uint_as_float(pp[4 * g4 + 1]);
+                        const float p2 = __uint_as_float(pp[4 * g4 + 2]), p3 = __uint_as_float(pp[4 * g4 + 3]);
+                        c[f + 0] = fmaf(p0, ri.x, bi.x);
+                        c[f + 1] = fmaf(p1, ri.y, bi.y);
+                        c[f + 2] = fmaf(p2, ri.z, bi.z);
+                        c[f + 3] = fmaf(p3, ri.w, bi.w);
+                        // run f / 4 of the MN-major operand = features f .. f + 3, digit a of feature f at column 4 f + a
+                        const uint4 dg4 = make_uint4(tc_digits(p0, dq), tc_digits(p1, dq), tc_digits(p2, dq), tc_digits(p3, dq));
+                        if (valid) *reinterpret_cast<uint4 *>(yrow + (size_t)(f >> 2) * G.Kp * 16) = dg4;
+                    }
+                };
+                tmem_ld16_issue(taddr + 32, pa);
+                tmem_ld16_wait(pa);
+                tmem_ld16_issue(taddr + 48, pb);
+                half_b(pa, 0);
+                tmem_ld16_wait(pb);
+                tmem_ld16_issue(taddr, pa);
+                half_b(pb, 16);
+                tmem_ld16_wait(pa);
+                tmem_ld16_issue(taddr + 16, pb);
 #pragma unroll
-                for (int f = 0; f < 32; ++f) c[f] += __uint_as_float(p[f]);
+                for (int f = 0; f < 16; ++f) c[f] += __uint_as_float(pa[f]);
+                tmem_ld16_wait(pb);
+#pragma unroll
+                for (int f = 0; f < 16; ++f) c[16 + f] += __uint_as_float(pb[f]);
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(&bar_ready[gi]);
+                mbar_arrive(&bar_ra[gi]);
                 const int act = __ldg(P.acts + h + 1);
                 const bool more = h + 1 < n_hidden;
-                mbar_wait(&bar_done[gi], st & 1u);
-                ++st;
+                if (timing) {
+                    const long long now = clock64();
+                    tm[4] += now - tq;
+                    tq = now;
+                }
+                mbar_wait(&bar_da[b], ea & 1u);
+                ++ea;
                 tc_fence_after();
-                if (r == 0) gmax[gi * 2 + (h & 1)] = 0u;  // every thread of the graph has read it (see header)
+                if (timing) {
+                    const long long now = clock64();
+                    tm[5] += now - tq;
+                    tq = now;
+                }
+                if (r == 0) gmax[gi * 2 + (h & 1)] = 0u;  // every block of the graph has read it: all of Y was needed
+                auto half_c = [&](const uint32_t *pp, int f0, float *hv) {
+                    const float4 ra = *reinterpret_cast<const float4 *>(rinv + f0);
+                    const float rv[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        hv[k] = tc_act(fmaf(tc_combine(pp + 4 * k), ndq * rv[k], c[f0 + k]), act, P.alpha);
+                };
+                tmem_ld16_issue(taddr, pa);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    tmem_ld32(taddr + 32 * q, p);
-                    const float4 ra = *reinterpret_cast<const float4 *>(rinv + 8 * q);
-                    const float4 rb4 = *reinterpret_cast<const float4 *>(rinv + 8 * q + 4);
-                    const float rv[8] = {ra.x, ra.y, ra.z, ra.w, rb4.x, rb4.y, rb4.z, rb4.w};
                     float hv[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        hv[k] = tc_act(fmaf(tc_combine(p + 4 * k, moff), ndq * rv[k], c[8 * q + k]), act, P.alpha);
+                    tmem_ld16_wait(pa);
+                    tmem_ld16_issue(taddr + 32 * q + 16, pb);
+                    half_c(pa, 8 * q, hv);
+                    tmem_ld16_wait(pb);
+                    if (q < 3) tmem_ld16_issue(taddr + 32 * (q + 1), pa);
+                    half_c(pb, 8 * q + 4, hv + 4);
                     emit(q, hv, more);
                 }
-                publish_max((h + 1) & 1);
+                if (timing) tm[6] += clock64() - tq;
             }
 
             // -- last layer, projected first: q = H.w_0 + z, z = H.w_1, score = act(q - dinv_i sum_j A_ij dinv_j z_j + b)
             float score;
             {
-                bar_sync(dom_bar, dom_cnt);  // the graph's max |H| is complete
+                publish_max(n_hidden & 1);
                 float qs, iqs;
-                tc_scale(__uint_as_float(gmax[gi * 2 + (n_hidden & 1)]) * P.tail_norm, &qs, &iqs);
-                if (valid) *reinterpret_cast<uint32_t *>(opg + (r >> 3) * 128 + (r & 7) * 16) = tc_digits(di * t1, qs);
+                tc_scale(graph_max(n_hidden & 1) * P.tail_norm, &qs, &iqs);
+                y_free();
+                if (valid) *reinterpret_cast<uint32_t *>(yrow) = tc_digits(di * t1, qs);
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(&bar_ready[gi]);
-                mbar_wait(&bar_done[gi], st & 1u);
-                ++st;
+                mbar_arrive(&bar_ra[gi]);
+                mbar_wait(&bar_da[b], ea & 1u);
+                ++ea;
                 tc_fence_after();
                 uint32_t d4[4];
                 tmem_ld4(taddr, d4);
                 tc_fence_before();
-                score = tc_act((t0 + t1) - di * (tc_combine(d4, moff) * iqs) + P.tail_bias, P.last_act, P.alpha);
+                score = tc_act((t0 + t1) - di * (tc_combine(d4) * iqs) + P.tail_bias, P.last_act, P.alpha);
                 if (!keep) score = 0.f;
             }
             // -- utility (mwis_dqn_call.py:230-235) ------------------------------------------------------------------
@@ -793,7 +903,7 @@ float bf16_to_f(uint16_t h) {
 
 struct TcGraph {
     int g, nv, nb;
-    size_t bytes;   // adjacency + operand blocks
+    size_t bytes;   // adjacency + H terms + Y digits
     long long cost;
 };
 
@@ -867,38 +977,47 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         t.nv = gp[g + 1] - gp[g];
         t.nb = std::max(1, (t.nv + 127) / 128);
         const size_t R = (size_t)((t.nv + 7) & ~7), Kp = (size_t)((t.nv + 31) & ~31);
-        t.bytes = ((R * Kp + 127) & ~(size_t)127) + (size_t)t.nb * kTcOpBlock;
+        t.bytes = R * Kp + 192 * R + 128 * Kp;
         // per layer: projection ~650 cycles per block, aggregation ~65 per block and 32 columns, epilogue ~900 per block
         t.cost = (long long)t.nb * (1600 + 2 * (long long)Kp);
         if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + 128 > pool) return DG_OK;  // not eligible: the caller falls back
         gs[(size_t)g] = t;
     }
-    std::stable_sort(gs.begin(), gs.end(), [](const TcGraph &a, const TcGraph &c) { return a.cost > c.cost; });
+    // Largest graph first; every tile is then topped up with the largest remaining graphs that still fit (blocks, bytes
+    // and cost all grow with the vertex count, so "largest that fits" is a lookup in the size-ordered remainder).
     struct Open {
         int ng, blocks, g[kTcMaxG];
         size_t bytes;
         long long cost;
     };
     std::vector<Open> tiles;
-    std::vector<int> open;  // indices of tiles that can still take a graph
-    for (const TcGraph &t : gs) {
-        int chosen = -1;
-        for (size_t oi = 0; oi < open.size() && chosen < 0; ++oi) {
-            const Open &o = tiles[(size_t)open[oi]];
-            if (o.ng < kTcMaxG && o.blocks + t.nb <= kTcBlocks && o.bytes + t.bytes + 128 <= pool) chosen = (int)oi;
+    std::map<int, std::vector<const TcGraph *>> by_size;  // vertex count -> graphs of that size still unplaced
+    for (const TcGraph &t : gs) by_size[t.nv].push_back(&t);
+    while (!by_size.empty()) {
+        Open o{};
+        for (;;) {
+            // the largest size whose graph fits into what is left of the tile
+            auto it = by_size.end();
+            bool found = false;
+            while (it != by_size.begin()) {
+                --it;
+                const TcGraph *c = it->second.back();
+                if (o.ng < kTcMaxG && o.blocks + c->nb <= kTcBlocks && o.bytes + c->bytes + 128 <= pool) {
+                    found = true;
+                    break;
+                }
+            }
+            if (!found) break;
+            const TcGraph *c = it->second.back();
+            it->second.pop_back();
+            if (it->second.empty()) by_size.erase(it);
+            o.g[o.ng++] = c->g;
+            o.blocks += c->nb;
+            o.bytes += c->bytes;
+            o.cost += c->cost;
+            if (by_size.empty()) break;
         }
-        if (chosen < 0) {
-            if (open.size() >= 64) open.erase(open.begin());  // bounded window: the oldest open tile is closed
-            tiles.push_back(Open{});
-            open.push_back((int)tiles.size() - 1);
-            chosen = (int)open.size() - 1;
-        }
-        Open &o = tiles[(size_t)open[(size_t)chosen]];
-        o.g[o.ng++] = t.g;
-        o.blocks += t.nb;
-        o.bytes += t.bytes;
-        o.cost += t.cost;
-        if (o.ng == kTcMaxG || o.blocks == kTcBlocks) open.erase(open.begin() + chosen);
+        tiles.push_back(o);
     }
     std::stable_sort(tiles.begin(), tiles.end(), [](const Open &a, const Open &c) { return a.cost > c.cost; });
     std::vector<int> flat(tiles.size() * 8, 0);
@@ -993,8 +1112,8 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         std::vector<long long> h((size_t)ctx->sm_count * 8);
         DG_CUDA_CHECK(cudaMemcpyAsync(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
         DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        const char *names[8] = {"stage", "solve", "tiles", "-", "-", "-", "-", "total"};
-        for (int k : {0, 1, 2, 7}) {
+        const char *names[8] = {"stage", "solve", "tiles", "w_proj", "phaseB", "w_agg", "phaseC", "total"};
+        for (int k : {0, 1, 2, 3, 4, 5, 6, 7}) {
             long long mn = -1, mx = 0;
             double sum = 0;
             int cnt = 0;

@@ -205,6 +205,7 @@ struct dg_batch {
     size_t tc_tiles_cap = 0;
     int tc_n_tiles = 0;
     bool tc_tiles_valid = false;
+    std::vector<int> tc_tiles_host;  // host copy of the table (scheduling diagnostics)
 };
 
 struct dg_part {  // one rank's row slice of a single large graph (device CSR, global column ids)

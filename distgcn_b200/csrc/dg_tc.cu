@@ -20,11 +20,12 @@
 //   The scalar aggregations of the rank-1 first layer and of the project-first last layer use the same machinery with
 //   16 operand columns.
 //
-// Work split: 16 vertex warps (warpgroup w owns TMEM lanes of block w: thread = vertex) + 1 control warp whose lane 0
-// issues every tcgen05.mma and every weight copy (TMA bulk, 2-deep ring).  A graph is a synchronisation domain: its
-// threads arrive on the graph's `ready` mbarrier when an operand is complete, the control thread polls the graphs'
-// barriers, issues that graph's MMAs and commits them to the graph's `done` mbarrier.  Graphs of a tile therefore drift
-// apart and the tensor-core work of one overlaps the epilogue arithmetic of another.
+// Work split: 16 warps, warpgroup w owns the TMEM lanes of block w (thread = vertex).  A graph is a synchronisation
+// domain and there is no dedicated MMA warp: when a warp finishes writing an operand it bumps a shared-memory counter,
+// and the warp that completes the count (the last of the block for a projection, the last of the graph for an
+// aggregation) issues that step's tcgen05.mma chain from its lane 0 and commits it to the mbarrier the consumers wait
+// on.  Weight blobs stream through a 2-deep TMA ring, refilled by whichever warp retires the previous user.  Blocks and
+// graphs of a tile therefore drift apart and the tensor-core work of one overlaps the epilogue arithmetic of another.
 //
 // Reference semantics: dg_fused.cu / dg_gcn.cu / dg_lgs.cu (mwis_dqn_call.py:198-261, heuristics.py:77-116).
 #include <math.h>
@@ -43,9 +44,11 @@ namespace dg {
 namespace {
 
 constexpr int kTcVertexThreads = 512;
-constexpr int kTcThreads = 544;       // + the control warp
+constexpr int kTcThreads = 512;       // 16 warps: 128 registers per thread
 constexpr int kTcMaxG = 4;            // graphs per tile (every graph owns >= 1 block)
 constexpr int kTcBlocks = 4;          // 128-row blocks per tile = TMEM budget: 4 x 128 columns
+// a partial last block reads up to 127 rows x 16 B past its graph's last region: the tile keeps that much of the pool free
+constexpr int kTcOverread = 2048 + 128;
 constexpr int kTcWBlob = 12560;       // one hidden layer: bf16 terms of [W_0 | W_1 r] (12288), bias[32], 1/r[32], bound, pad
 // shared-memory map (bytes)
 constexpr int kTcOffRing = 0;                      // 2 x kTcWBlob
@@ -58,7 +61,9 @@ constexpr int kTcOffMeta = kTcOffBar + 256;        // TcMeta[4] + tile scalars
 // Pool, per graph of the tile (R = rows padded to 8, Kp = columns padded to 32):
 //   adjacency  u8  [Kp/16 chunks][R rows][16 B]        K-major A operand of the aggregation  (R Kp bytes)
 //   H terms    bf16 [3 terms][4 chunks][R rows][16 B]   K-major A operand of the projection   (192 R bytes)
-//   Y digits   u8  [8 runs][Kp/8 groups][8 k][16 B]     MN-major B operand of the aggregation (128 Kp bytes)
+//   Y digits   u8  [8 runs][Kp/8 groups][8 k][16 B]     MN-major B operand of the aggregation (128 Kp bytes), in the SAME
+//              bytes as the H terms: Y is written only after every projection of the graph that reads H has completed, H
+//              only after every aggregation that reads Y has
 // A 128-row block of a graph whose last block is partial reads past row R: those reads stay inside the pool (the next
 // region) and only feed accumulator rows nobody looks at.
 constexpr int kTcOffPool = 32768;
@@ -72,7 +77,7 @@ struct TcTileInfo {
 };
 
 struct TcParams {
-    const int *tiles;  // 8 ints per tile: ng, g[4], -, -, -
+    const int *tiles;  // 32 ints per tile: ng, then per graph (g, v0, nv, e0, nnz, -)
     int n_tiles;
     int *tile_counter;
     const int *graph_ptr, *row_ptr, *col_idx;
@@ -126,13 +131,31 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
-// Bounded wait: a protocol error must end the launch with an error, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Bounded wait: a protocol error must end the launch with an error, never hang the GPU.  The wait site that gave up is
+// left in pinned host memory (dg_context::h_flag[3]) for the post-mortem.
+__device__ int *g_tc_watchdog = nullptr;
+__device__ int g_tc_watchdog_wide = 0;  // DG_TC_DEBUG: the pointer is a wide table, every stuck thread logs its site
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int site = 0) {
     if (mbar_test(bar, parity)) return;
     const long long t0 = clock64();
+    bool logged = false;
     for (uint32_t spins = 1;; ++spins) {
         if (mbar_test(bar, parity)) return;
-        if ((spins & 1023u) == 0u && clock64() - t0 > 4000000000LL) __trap();
+        if ((spins & 1023u) == 0u) {
+            const long long dt = clock64() - t0;
+            if (!logged && dt > 1000000000LL && g_tc_watchdog && g_tc_watchdog_wide) {
+                g_tc_watchdog[1 + blockIdx.x * 512 + threadIdx.x] = site;
+                __threadfence_system();
+                logged = true;
+            }
+            if (dt > 3000000000LL) {
+                if (g_tc_watchdog) {
+                    *g_tc_watchdog = site | ((int)threadIdx.x << 8) | ((int)blockIdx.x << 20);
+                    __threadfence_system();
+                }
+                __trap();
+            }
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -214,10 +237,14 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float tc_act(float v, int act, float alpha) {
-    if (act == DG_ACT_LEAKY_RELU) return v >= 0.f ? v : alpha * v;
-    if (act == DG_ACT_RELU) return fmaxf(v, 0.f);
-    return v;
+// Every activation of the path is v >= 0 ? v : slope * v with slope = alpha (leaky ReLU), 0 (ReLU) or 1 (none); as
+// max(v, slope v) for slope <= 1 and min(v, slope v) otherwise it is branch-free and bit-identical to the select form.
+__device__ __forceinline__ float tc_slope(int act, float alpha) {
+    return act == DG_ACT_LEAKY_RELU ? alpha : act == DG_ACT_RELU ? 0.f : 1.f;
+}
+__device__ __forceinline__ float tc_act(float v, float slope, bool use_max) {
+    const float t = v * slope;
+    return use_max ? fmaxf(v, t) : fminf(v, t);
 }
 
 // fixed-point scale for values bounded by `bound` (>= 0): q = 2^k with |v| * q < 2^30, and its inverse
@@ -227,10 +254,12 @@ __device__ __forceinline__ void tc_scale(float bound, float *q, float *inv_q) {
     *q = __int_as_float((283 - eb) << 23);      // 2^(156 - eb)
     *inv_q = __int_as_float((eb - 29) << 23);   // 2^(eb - 156)
 }
-// fixed-point image v of y (|y * q| < 2^30) as four balanced base-256 digits d_a in [-128, 127], v = sum_a 256^a d_a:
-// the bytes of (v + 0x80808080) are the digits offset by 128; flipping each byte's top bit makes them two's complement
+// fixed-point image v = rn(y q) (|v| < 2^30) as four balanced base-256 digits d_a in [-128, 127], v = sum_a 256^a d_a:
+// the low three bytes of v + 0x808080 are d_0..d_2 offset by 128 (flip their top bits), its top byte is d_3 as it stands.
+// The offset rides on the multiply: y q + 8421504 rounds to the same integer as rn(y q) + 8421504 (the constant is a
+// multiple of every ulp involved), so the conversion is one FMA, one F2I and one XOR.
 __device__ __forceinline__ uint32_t tc_digits(float y, float q) {
-    return ((uint32_t)__float2int_rn(y * q) + 0x80808080u) ^ 0x80808080u;
+    return (uint32_t)__float2int_rn(fmaf(y, q, 8421504.f)) ^ 0x00808080u;
 }
 // sum_a 256^a D_a as a float: the two digit pairs are combined exactly in integers (|D_a| <= 128 deg), converted, and
 // joined with one FMA
@@ -275,10 +304,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     uint32_t *gmax = reinterpret_cast<uint32_t *>(smem + kTcOffGmax);  // [4][2]
     uint32_t *gmax0 = gmax + 8;                                         // [4]
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + kTcOffBar);  // [2]  weight ring
-    uint64_t *bar_rp = bar_full + 2;    // [4] per block: the projection's A operand (H terms) is complete
+    uint32_t *cnt_p = reinterpret_cast<uint32_t *>(bar_full + 22);     // [4] per block: warps whose H terms are in place
+    uint32_t *cnt_a = cnt_p + 4;                                        // [4] per graph: warps whose Y digits are in place
+    uint32_t *cnt_w = cnt_p + 8;                                        // [2] per ring buffer: blocks done with its layer
     uint64_t *bar_dp = bar_full + 6;    // [4] per block: projection MMAs complete
     uint64_t *bar_da = bar_full + 10;   // [4] per block: aggregation MMAs complete
-    uint64_t *bar_ra = bar_full + 14;   // [4] per graph: the aggregation's B operand (Y digits) is complete
+    uint64_t *bar_ra = bar_full + 14;   // [4] per graph: the aggregation's B operand (Y digits) is complete (one arrival per warp)
     uint64_t *bar_mx = bar_full + 18;   // [4] per graph: every vertex has published its max |H|
     TcMeta *meta = reinterpret_cast<TcMeta *>(smem + kTcOffMeta);
     TcTileInfo *tinfo = reinterpret_cast<TcTileInfo *>(smem + kTcOffMeta + sizeof(TcMeta) * kTcMaxG);
@@ -287,14 +318,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     __shared__ uint32_t tmem_sm;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_ctrl = warp == kTcVertexThreads / 32;
     const int n_hidden = P.n_hidden;
 
     if (tid == 0) {
-        for (int i = 0; i < 22; ++i) mbar_init(&bar_full[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&bar_full[i], 1);
+        for (int i = 0; i < kTcBlocks; ++i) {
+            mbar_init(&bar_dp[i], 1);
+            mbar_init(&bar_da[i], 1);
+            mbar_init(&bar_mx[i], 1);
+            mbar_init(&bar_ra[i], 1);
+        }
         fence_mbar_init();
     }
-    if (is_ctrl) {  // the whole tensor memory of the SM: 4 blocks x 128 accumulator columns
+    if (warp == 0) {  // the whole tensor memory of the SM: 4 blocks x 128 accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_sm)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -305,7 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     uint32_t wseq = 0;  // hidden-layer weight fills of the tiles this CTA has finished (every thread keeps its own copy)
 
     const bool timing = P.dbg != nullptr && tid == 0;
-    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tm[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = timing ? clock64() : 0;
 
     for (;;) {
@@ -314,41 +350,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         const int t = tile_sm;
         if (t >= P.n_tiles) break;
         long long tk = timing ? clock64() : 0;
+        const long long t_tile = tk;
 
         // ---- tile metadata; the barriers are re-armed with this tile's thread counts ---------------------------
         if (tid == 0) {
-            const int *td = P.tiles + (size_t)t * 8;
+            const int *td = P.tiles + (size_t)t * 32;
             const int ng = td[0];
             int fb = 0, off = 0;
             for (int gi = 0; gi < ng; ++gi) {
-                const int g = td[1 + gi];
+                const int *gd = td + 1 + 6 * gi;  // (the host knows every graph's extent: no dependent loads here)
                 TcMeta m;
-                m.g = g;
-                m.v0 = P.graph_ptr[g];
-                m.nv = P.graph_ptr[g + 1] - m.v0;
+                m.g = gd[0];
+                m.v0 = gd[1];
+                m.nv = gd[2];
                 m.nb = (m.nv + 127) >> 7;
                 m.fb = fb;
                 m.R = (m.nv + 7) & ~7;
                 m.Kp = (m.nv + 31) & ~31;
                 m.adj = off;
                 m.hoff = off + m.R * m.Kp;
+#ifdef DG_TC_NO_ALIAS
                 m.yoff = m.hoff + 192 * m.R;
                 off = m.yoff + 128 * m.Kp;
-                m.e0 = P.row_ptr[m.v0];
-                m.nnz = P.row_ptr[m.v0 + m.nv] - m.e0;
+#else
+                m.yoff = m.hoff;  // Y digits and H terms are never live together (see the hazard waits below)
+                off = m.hoff + max(192 * m.R, 128 * m.Kp);
+#endif
+                m.e0 = gd[3];
+                m.nnz = gd[4];
                 meta[gi] = m;
                 for (int jb = 0; jb < m.nb; ++jb) tinfo->blkg[fb + jb] = gi;
                 fb += m.nb;
-                mbar_inval(&bar_ra[gi]);
                 mbar_inval(&bar_mx[gi]);
-                mbar_init(&bar_ra[gi], 128 * m.nb);
+                mbar_inval(&bar_ra[gi]);
                 mbar_init(&bar_mx[gi], 128 * m.nb);
+                mbar_init(&bar_ra[gi], 4 * m.nb);
             }
             for (int b = 0; b < fb; ++b) {
-                mbar_inval(&bar_rp[b]);
                 mbar_inval(&bar_dp[b]);
                 mbar_inval(&bar_da[b]);
-                mbar_init(&bar_rp[b], 128);
                 mbar_init(&bar_dp[b], 1);
                 mbar_init(&bar_da[b], 1);
             }
@@ -356,6 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             tinfo->nblocks = fb;
             tinfo->pool_used = off;
             for (int i = 0; i < 12; ++i) gmax[i] = 0u;
+            for (int i = 0; i < 10; ++i) cnt_p[i] = 0u;
             fence_mbar_init();
         }
         __syncthreads();
@@ -363,7 +404,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         const int nblocks = tinfo->nblocks;
 
         // the first two hidden layers' weights start streaming in (every MMA of the previous tile has completed)
-        if (is_ctrl && lane == 0) {
+        if (tid == 0) {
             for (int h = 0; h < n_hidden && h < 2; ++h) {
                 const uint32_t buf = (wseq + h) & 1u;
                 mbar_expect_tx(&bar_full[buf], kTcWBlob);
@@ -375,6 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         int gi = -1, r = 0, v = 0;
         TcMeta G{};
         bool valid = false, keep = false;
+        double wt_v = 0.0;
         if (tid < kTcVertexThreads) {
             const int b = tid >> 7;
             if (b < nblocks) gi = tinfo->blkg[b];
@@ -385,8 +427,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 v = G.v0 + r;
             }
             if (valid) {
+                if (P.wts) wt_v = P.wts[v];
                 keep = P.keep_in ? P.keep_in[v] != 0 : true;
-                if (P.remove_zero) keep = keep && (P.wts[v] != 0.0);  // mwis_dqn_call.py:203
+                if (P.remove_zero) keep = keep && (wt_v != 0.0);  // mwis_dqn_call.py:203
                 if (P.member) P.member[v] = 0;
                 if (keep && P.x0) atomicMax(&gmax0[gi], __float_as_uint(fabsf(P.x0[v])));
             }
@@ -406,7 +449,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             // the scatter below then needs one shared-memory load per edge instead of a binary search in row_ptr.
             if (valid) {
                 uint16_t *rowof = reinterpret_cast<uint16_t *>(pool + G.hoff);
-                if (2 * G.nnz <= 192 * G.R + 128 * G.Kp) {
+                if (2 * G.nnz <= max(192 * G.R, 128 * G.Kp)) {
                     const int beg = P.row_ptr[v] - G.e0, end = P.row_ptr[v + 1] - G.e0;
                     for (int e = beg; e < end; ++e) rowof[e] = (uint16_t)r;
                 }
@@ -419,7 +462,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 const TcMeta m = meta[k];
                 unsigned char *adj = pool + m.adj;
                 const uint16_t *rowof = reinterpret_cast<const uint16_t *>(pool + m.hoff);
-                const bool table = 2 * m.nnz <= 192 * m.R + 128 * m.Kp;
+                const bool table = 2 * m.nnz <= max(192 * m.R, 128 * m.Kp);
                 for (int e = tid; e < m.nnz; e += kTcVertexThreads) {
                     int lo;
                     if (table) {
@@ -447,102 +490,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             tk = now;
         }
 
-        if (is_ctrl) {
-            // ================= control warp: every tcgen05.mma and every weight copy of the tile ===================
-            // The whole warp runs the loop with identical values (uniform registers feed the MMA operands directly);
-            // lane 0 alone issues.
-            {
-                const bool leader = lane == 0;
-                int pst[kTcBlocks] = {0, 0, 0, 0};  // projections issued per block
-                int ast[kTcMaxG] = {0, 0, 0, 0};    // aggregations issued per graph (0 first layer, 1..n_hidden, n_hidden+1 tail)
-                int passed[2] = {0, 0};
-                int remaining = ng * (n_hidden + 2) + nblocks * n_hidden;
-                const uint32_t pool_addr = s32(pool);
-                const uint32_t ring_addr = s32(wring);
-                const long long t_ctrl = clock64();
-                uint32_t polls = 0;
-                while (remaining > 0) {
-                    if ((++polls & 4095u) == 0u && clock64() - t_ctrl > 8000000000LL) __trap();
-#pragma unroll
-                    for (int k = 0; k < kTcMaxG; ++k) {
-                        // aggregation of graph k: D[block] = A[block rows, :] . Y, N = 16 (scalar) or 128 (hidden layer)
-                        if (k >= ng || ast[k] > n_hidden + 1) continue;
-                        if (!mbar_test(&bar_ra[k], (uint32_t)ast[k] & 1u)) continue;
-                        tc_fence_after();
-                        const TcMeta m = meta[k];
-                        const bool scalar = ast[k] == 0 || ast[k] == n_hidden + 1;
-                        const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
-                        const uint32_t lbo_a = (uint32_t)m.R * 16u;
-                        const uint64_t bdesc0 = umma_desc(pool_addr + m.yoff, 128u, scalar ? 128u : (uint32_t)m.Kp * 16u);
-                        const uint64_t adesc0 = umma_desc(pool_addr + m.adj, lbo_a, 128u);
-                        const uint32_t a_step = (2u * lbo_a) >> 4;  // one K-step (32 columns = 2 chunks) in descriptor units
-                        const int ksteps = m.Kp >> 5;
-                        for (int jb = 0; jb < m.nb; ++jb) {
-                            uint64_t adesc = adesc0 + (uint64_t)(jb * 128);  // 128 rows x 16 B >> 4
-                            uint64_t bdesc = bdesc0;
-                            const uint32_t d = tmem + (uint32_t)(m.fb + jb) * 128u;
-                            for (int s = 0; s < ksteps; ++s) {
-                                if (leader) mma_u8(d, adesc, bdesc, idesc, s > 0);
-                                adesc += a_step;
-                                bdesc += 32u;  // 4 k-groups x 128 B >> 4
-                            }
-                            if (leader) mma_commit(&bar_da[m.fb + jb]);
-                        }
-                        ++ast[k];
-                        --remaining;
-                    }
-#pragma unroll
-                    for (int b = 0; b < kTcBlocks; ++b) {
-                        // projection of block b, hidden layer h: [P0 | P1] = H . [W_0 | W_1 r], 6 products x 2 K-steps
-                        if (b >= nblocks || pst[b] >= n_hidden) continue;
-                        if (!mbar_test(&bar_rp[b], (uint32_t)pst[b] & 1u)) continue;
-                        const int h = pst[b];
-                        const uint32_t seq = wseq + (uint32_t)h;
-                        // The layer's weights must have landed.  Never block here: the copy may be waiting for ANOTHER
-                        // block of the tile to finish with the buffer, and that block's events are served by this same
-                        // warp - come back on a later poll.
-                        if (!mbar_test(&bar_full[seq & 1u], (seq >> 1) & 1u)) continue;
-                        tc_fence_after();
-                        if (h >= 1) {
-                            // every thread of this block has finished layer h-1 (its epilogue reads bias / r from the
-                            // weight buffer): when all blocks have, the buffer takes layer h+1
-                            const uint32_t pbuf = (seq - 1u) & 1u;
-                            if (++passed[pbuf] == nblocks) {
-                                passed[pbuf] = 0;
-                                if (h + 1 < n_hidden && leader) {
-                                    mbar_expect_tx(&bar_full[pbuf], kTcWBlob);
-                                    bulk_g2s(wring + pbuf * kTcWBlob, P.wall + (size_t)(h + 1) * kTcWBlob, kTcWBlob,
-                                             &bar_full[pbuf]);
-                                }
-                            }
-                        }
-                        const TcMeta m = meta[tinfo->blkg[b]];
-                        const uint32_t lbo_a = (uint32_t)m.R * 16u;  // H terms: [term][chunk][R rows][16 B]
-                        const uint64_t a0 = umma_desc(pool_addr + m.hoff + (uint32_t)(b - m.fb) * 2048u, lbo_a, 128u);
-                        const uint64_t b0 = umma_desc(ring_addr + (seq & 1u) * kTcWBlob, 1024u, 128u);
-                        const uint32_t a_chunk = lbo_a >> 4;  // one 16-byte K chunk of all rows, in descriptor units
-                        const uint32_t idesc = idesc_bf16(128, 64);
-                        const uint32_t d = tmem + (uint32_t)b * 128u;
-                        // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi); A term t starts
-                        // 4 t chunks in, W term t starts 4096 t bytes in; the second K-step is 2 chunks further
-                        const uint64_t at[3] = {a0, a0 + 4u * a_chunk, a0 + 8u * a_chunk};
-                        const uint64_t bt[3] = {b0, b0 + 256u, b0 + 512u};
-                        const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
-                        if (leader) {
-#pragma unroll
-                            for (int p = 0; p < 6; ++p) {
-                                mma_bf16(d, at[ta[p]], bt[tb[p]], idesc, p != 0);
-                                mma_bf16(d, at[ta[p]] + 2u * a_chunk, bt[tb[p]] + 128u, idesc, 1u);
-                            }
-                            mma_commit(&bar_dp[b]);
-                        }
-                        ++pst[b];
-                        --remaining;
-                    }
-                }
-            }
-            __syncwarp();
-        } else if (gi >= 0) {
+        if (gi >= 0) {
             // ================= vertex threads =========================================================================
             const int b = tid >> 7;
             const int jb = b - G.fb;
@@ -554,6 +502,88 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             unsigned char *yrow = pool + G.yoff + (r >> 3) * 128 + (r & 7) * 16;  // ... and in the Y digit runs
             const int hterm = 4 * G.R * 16, hchunk = G.R * 16;
             uint32_t ea = 0, ep = 0, em = 0;  // aggregation / projection / max events consumed -> barrier parities
+
+            // ---- hand-off to the tensor cores: the warp that completes an operand issues the MMAs that consume it ----
+            const uint32_t pool_addr = s32(pool);
+            // true for the warp whose arrival completes `total` (other warps' operand stores are then visible to it)
+            auto last_warp = [&](uint32_t *cnt, uint32_t total) -> bool {
+                __syncwarp();
+                uint32_t old = 0u;
+                if (lane == 0) {
+                    __threadfence_block();
+                    old = atomicAdd(cnt, 1u);
+                }
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old != total - 1u) return false;
+                if (lane == 0) *cnt = 0u;  // next use follows the completion of the MMAs issued now
+                __threadfence_block();
+                return true;
+            };
+            // Aggregation D[block] = A[block rows, :] . Y, N = 16 (scalar) or 128 (hidden layer), for every block of the
+            // graph, issued by the warp that completes Y (one issuer: the commits of the blocks then complete in order,
+            // which is what agg_drained() relies on).
+            auto hand_off_agg = [&](bool scalar) {
+                if (!last_warp(&cnt_a[gi], 4u * (uint32_t)G.nb)) return;
+                if (lane == 0) {
+                    tc_fence_after();
+                    const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
+                    const uint32_t lbo_a = (uint32_t)G.R * 16u;
+                    const uint64_t bdesc0 = umma_desc(pool_addr + G.yoff, 128u, scalar ? 128u : (uint32_t)G.Kp * 16u);
+                    const uint64_t adesc0 = umma_desc(pool_addr + G.adj, lbo_a, 128u);
+                    const uint32_t a_step = (2u * lbo_a) >> 4;  // one K-step (32 columns = 2 chunks) in descriptor units
+                    const int ksteps = G.Kp >> 5;
+                    for (int k = 0; k < G.nb; ++k) {
+                        uint64_t adesc = adesc0 + (uint64_t)(k * 128);  // 128 rows x 16 B >> 4
+                        uint64_t bdesc = bdesc0;
+                        const uint32_t d = tmem + (uint32_t)(G.fb + k) * 128u;
+                        for (int s2 = 0; s2 < ksteps; ++s2) {
+                            mma_u8(d, adesc, bdesc, idesc, s2 > 0);
+                            adesc += a_step;
+                            bdesc += 32u;  // 4 k-groups x 128 B >> 4
+                        }
+                        mma_commit(&bar_da[G.fb + k]);
+                    }
+                }
+                __syncwarp();
+            };
+            // projection of this block, hidden layer h: [P0 | P1] = H . [W_0 | W_1 r], 6 products x 2 K-steps
+            auto issue_proj = [&](int h) {
+                if (lane == 0) {
+                    const uint32_t seq = wseq + (uint32_t)h;
+                    if (h >= 1) {
+                        // every thread of this block has finished layer h-1 (its epilogue reads bias / r from the weight
+                        // buffer): when all blocks of the tile have, the buffer takes layer h+1
+                        const uint32_t pbuf = (seq - 1u) & 1u;
+                        if (atomicAdd(&cnt_w[pbuf], 1u) == (uint32_t)nblocks - 1u) {
+                            cnt_w[pbuf] = 0u;
+                            if (h + 1 < n_hidden) {
+                                mbar_expect_tx(&bar_full[pbuf], kTcWBlob);
+                                bulk_g2s(wring + pbuf * kTcWBlob, P.wall + (size_t)(h + 1) * kTcWBlob, kTcWBlob, &bar_full[pbuf]);
+                            }
+                        }
+                    }
+                    mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u, 2);  // the layer's weights have landed
+                    tc_fence_after();
+                    const uint32_t lbo_a = (uint32_t)G.R * 16u;  // H terms: [term][chunk][R rows][16 B]
+                    const uint64_t a0 = umma_desc(pool_addr + G.hoff + (uint32_t)jb * 2048u, lbo_a, 128u);
+                    const uint64_t b0 = umma_desc(s32(wring) + (seq & 1u) * kTcWBlob, 1024u, 128u);
+                    const uint32_t a_chunk = lbo_a >> 4;  // one 16-byte K chunk of all rows, in descriptor units
+                    const uint32_t idesc = idesc_bf16(128, 64);
+                    const uint32_t d = tmem + (uint32_t)b * 128u;
+                    // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi); A term t starts 4 t
+                    // chunks in, W term t starts 4096 t bytes in; the second K-step is 2 chunks further
+                    const uint64_t at[3] = {a0, a0 + 4u * a_chunk, a0 + 8u * a_chunk};
+                    const uint64_t bt[3] = {b0, b0 + 256u, b0 + 512u};
+                    const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+                    for (int pp = 0; pp < 6; ++pp) {
+                        mma_bf16(d, at[ta[pp]], bt[tb[pp]], idesc, pp != 0);
+                        mma_bf16(d, at[ta[pp]] + 2u * a_chunk, bt[tb[pp]] + 128u, idesc, 1u);
+                    }
+                    mma_commit(&bar_dp[b]);
+                }
+                __syncwarp();
+            };
 
             // degree on the kept sub-graph, dinv, x0, and the scalar operand of the rank-1 first layer
             unsigned deg = 0;
@@ -573,7 +603,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             tc_scale(P.x0 ? __uint_as_float(gmax0[gi]) : fabsf(P.x0val), &q0, &iq0);
             if (valid) *reinterpret_cast<uint32_t *>(yrow) = tc_digits(di * xi, q0);
             fence_async_smem();
-            mbar_arrive(&bar_ra[gi]);
+            hand_off_agg(true);
 
             float hmax = 0.f, t0 = 0.f, t1 = 0.f;
             // consumes 8 new feature values of this vertex: operand terms for the next projection, or the last
@@ -610,24 +640,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             };
             // the graph's max |H|, once every vertex of the graph has published
             auto graph_max = [&](int slot) -> float {
-                mbar_wait(&bar_mx[gi], em & 1u);
+                mbar_wait(&bar_mx[gi], em & 1u, 3);
                 ++em;
                 return __uint_as_float(gmax[gi * 2 + slot]);
             };
-            // Y may be overwritten once EVERY block's MMAs of the graph's previous aggregation have completed (this
-            // block's have; commits complete in issue order, so the graph's last block tells)
-            auto y_free = [&]() {
-                if (b != lastb) mbar_wait(&bar_da[lastb], (ea - 1u) & 1u);
+            // The operand region changes hands: it takes new H terms once EVERY block's MMAs of the graph's last
+            // aggregation have completed (commits complete in issue order, so the graph's last block tells), and new Y
+            // digits once every block's last projection has.
+            auto agg_drained = [&]() {
+                if (b != lastb) mbar_wait(&bar_da[lastb], (ea - 1u) & 1u, 4);
+            };
+            auto proj_drained = [&]() {
+                for (int k = G.fb; k <= lastb; ++k)
+                    if (k != b) mbar_wait(&bar_dp[k], (ep - 1u) & 1u, 5);
             };
 
             // -- first layer (rank 1): s = (L x0)_i, H1 = act(x0 colsum(W_0) + s colsum(W_1) + b) -----------------
-            mbar_wait(&bar_da[b], ea & 1u);
+            mbar_wait(&bar_da[b], ea & 1u, 6);
             ++ea;
             tc_fence_after();
             {
                 uint32_t d4[4];
                 tmem_ld4(taddr, d4);
                 const float s_i = xi - di * (tc_combine(d4) * iq0);
+                const float sl0 = tc_slope(P.first_act, P.alpha);
+                agg_drained();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float hv[8];
@@ -636,28 +673,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                         const float4 a0 = __ldg(reinterpret_cast<const float4 *>(P.first) + 2 * q + half);
                         const float4 a1 = __ldg(reinterpret_cast<const float4 *>(P.first + 32) + 2 * q + half);
                         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(P.first + 64) + 2 * q + half);
-                        hv[4 * half + 0] = tc_act(fmaf(s_i, a1.x, fmaf(xi, a0.x, b0.x)), P.first_act, P.alpha);
-                        hv[4 * half + 1] = tc_act(fmaf(s_i, a1.y, fmaf(xi, a0.y, b0.y)), P.first_act, P.alpha);
-                        hv[4 * half + 2] = tc_act(fmaf(s_i, a1.z, fmaf(xi, a0.z, b0.z)), P.first_act, P.alpha);
-                        hv[4 * half + 3] = tc_act(fmaf(s_i, a1.w, fmaf(xi, a0.w, b0.w)), P.first_act, P.alpha);
+                        hv[4 * half + 0] = tc_act(fmaf(s_i, a1.x, fmaf(xi, a0.x, b0.x)), sl0, sl0 <= 1.f);
+                        hv[4 * half + 1] = tc_act(fmaf(s_i, a1.y, fmaf(xi, a0.y, b0.y)), sl0, sl0 <= 1.f);
+                        hv[4 * half + 2] = tc_act(fmaf(s_i, a1.z, fmaf(xi, a0.z, b0.z)), sl0, sl0 <= 1.f);
+                        hv[4 * half + 3] = tc_act(fmaf(s_i, a1.w, fmaf(xi, a0.w, b0.w)), sl0, sl0 <= 1.f);
                     }
                     emit(q, hv, n_hidden > 0);
                 }
             }
 
+            if (timing) {
+                const long long now = clock64();
+                tm[8] += now - tk;
+                tk = now;
+            }
             // -- hidden layers -----------------------------------------------------------------------------------------
             for (int h = 0; h < n_hidden; ++h) {
                 // this block's H terms are in place: its projection may start
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(&bar_rp[b]);
+                if (last_warp(&cnt_p[b], 4u)) issue_proj(h);
                 publish_max(h & 1);
                 const uint32_t seq = wseq + h;
                 const unsigned char *wb = wring + (seq & 1u) * kTcWBlob;
                 const float *bias = reinterpret_cast<const float *>(wb + 12288);
                 const float *rinv = bias + 32;
                 long long tq = timing ? clock64() : 0;
-                mbar_wait(&bar_dp[b], ep & 1u);
+                mbar_wait(&bar_dp[b], ep & 1u, 7);
                 ++ep;
                 tc_fence_after();
                 if (timing) {
@@ -665,11 +707,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     tm[3] += now - tq;
                     tq = now;
                 }
-                mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u);  // (already complete: the projection has read it)
+                mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u, 8);  // (already complete: the projection has read it)
                 float qs, iqs;
                 tc_scale(graph_max(h & 1) * bias[64], &qs, &iqs);
                 const float dq = di * qs, ndq = -di * iqs;
-                y_free();
+                proj_drained();
                 float c[32];
                 uint32_t pa[16], pb[16];
                 // TMEM loads run one 16-column piece ahead of the arithmetic: P1 (columns 32..63, scaled by r), then P0
@@ -706,15 +748,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 for (int f = 0; f < 16; ++f) c[16 + f] += __uint_as_float(pb[f]);
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(&bar_ra[gi]);
-                const int act = __ldg(P.acts + h + 1);
+                hand_off_agg(false);
+                const float slope = tc_slope(__ldg(P.acts + h + 1), P.alpha);
+                const bool act_max = slope <= 1.f;
                 const bool more = h + 1 < n_hidden;
                 if (timing) {
                     const long long now = clock64();
                     tm[4] += now - tq;
                     tq = now;
                 }
-                mbar_wait(&bar_da[b], ea & 1u);
+                mbar_wait(&bar_da[b], ea & 1u, 9);
                 ++ea;
                 tc_fence_after();
                 if (timing) {
@@ -723,12 +766,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     tq = now;
                 }
                 if (r == 0) gmax[gi * 2 + (h & 1)] = 0u;  // every block of the graph has read it: all of Y was needed
+                agg_drained();
                 auto half_c = [&](const uint32_t *pp, int f0, float *hv) {
                     const float4 ra = *reinterpret_cast<const float4 *>(rinv + f0);
                     const float rv[4] = {ra.x, ra.y, ra.z, ra.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        hv[k] = tc_act(fmaf(tc_combine(pp + 4 * k), ndq * rv[k], c[f0 + k]), act, P.alpha);
+                        hv[k] = tc_act(fmaf(tc_combine(pp + 4 * k), ndq * rv[k], c[f0 + k]), slope, act_max);
                 };
                 tmem_ld16_issue(taddr, pa);
 #pragma unroll
@@ -747,32 +791,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
 
             // -- last layer, projected first: q = H.w_0 + z, z = H.w_1, score = act(q - dinv_i sum_j A_ij dinv_j z_j + b)
             float score;
+            if (timing) tk = clock64();
             {
                 publish_max(n_hidden & 1);
                 float qs, iqs;
                 tc_scale(graph_max(n_hidden & 1) * P.tail_norm, &qs, &iqs);
-                y_free();
+                agg_drained();
                 if (valid) *reinterpret_cast<uint32_t *>(yrow) = tc_digits(di * t1, qs);
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(&bar_ra[gi]);
-                mbar_wait(&bar_da[b], ea & 1u);
+                hand_off_agg(true);
+                mbar_wait(&bar_da[b], ea & 1u, 10);
                 ++ea;
                 tc_fence_after();
                 uint32_t d4[4];
                 tmem_ld4(taddr, d4);
                 tc_fence_before();
-                score = tc_act((t0 + t1) - di * (tc_combine(d4) * iqs) + P.tail_bias, P.last_act, P.alpha);
+                const float sll = tc_slope(P.last_act, P.alpha);
+                score = tc_act((t0 + t1) - di * (tc_combine(d4) * iqs) + P.tail_bias, sll, sll <= 1.f);
                 if (!keep) score = 0.f;
             }
             // -- utility (mwis_dqn_call.py:230-235) ------------------------------------------------------------------
             {
-                const double u = !valid ? 0.0 : (P.predict == DG_PREDICT_MWIS) ? (double)score * P.wts[v] : (double)score;
+                const double u = !valid ? 0.0 : (P.predict == DG_PREDICT_MWIS) ? (double)score * wt_v : (double)score;
                 util_sm[tid] = u;
                 if (valid) {
                     if (P.score) P.score[v] = score;
                     if (P.util) P.util[v] = u;
                 }
+            }
+            if (timing) {
+                const long long now = clock64();
+                tm[9] += now - tk;
+                tk = now;
             }
             if (P.do_lgs) {
                 // -- local greedy search (heuristics.py:77-116); neighbour sets as bit rows in registers -----------
@@ -790,10 +841,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                         }
                     }
                 }
+                uint32_t nbr[12];
+#pragma unroll
+                for (int w = 0; w < 12; ++w) nbr[w] = nbm[w];
                 const int w0 = G.fb * 4, nw = G.nb * 4;
                 if (lane == 0) remain[warp] = keepw[warp];
                 bar_sync(dom_bar, dom_cnt);
-                const double wv = util_sm[tid];
+                // nbm := the neighbours that beat this vertex (larger utility, or equal and smaller id - heuristics.py:
+                // 96-111), found once; a round is then a handful of word operations: the vertex joins iff none of them
+                // is still there.  NaN utilities beat and are beaten by nobody's rule: they block, as np.max does.
+                {
+                    const double wv = util_sm[tid];
+#pragma unroll
+                    for (int w = 0; w < 12; ++w) {
+                        if (w < nw) {
+                            uint32_t cand = nbm[w] & remain[w0 + w], beat = 0u;
+                            while (cand) {
+                                const int bit = __ffs(cand) - 1;
+                                cand &= cand - 1;
+                                const int us = (w0 + w) * 32 + bit;  // the neighbour's slot
+                                const double wu = util_sm[us];
+                                if (!((wv > wu) || (wv == wu && tid < us))) beat |= 1u << bit;
+                            }
+                            nbm[w] = beat;
+                        }
+                    }
+                }
+                // nbr := all kept neighbours (for the removal of a joined vertex's neighbourhood)
                 int rounds = 0, steps = 0;
                 for (;;) {
                     uint32_t any = 0u;
@@ -808,25 +882,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     }
                     const bool active = (remain[warp] >> lane) & 1u;
                     bool join = active;
-                    if (active) {
 #pragma unroll
-                        for (int w = 0; w < 12; ++w) {
-                            if (w < nw) {
-                                uint32_t cand = nbm[w] & remain[w0 + w];
-                                while (cand) {
-                                    const int bit = __ffs(cand) - 1;
-                                    cand &= cand - 1;
-                                    const int us = (w0 + w) * 32 + bit;  // the neighbour's slot
-                                    const double wu = util_sm[us];
-                                    if (!((wv > wu) || (wv == wu && tid < us))) {
-                                        join = false;
-                                        cand = 0u;
-                                    }
-                                }
-                            }
-                        }
-                        if (join && P.member) P.member[v] = 1;
-                    }
+                    for (int w = 0; w < 12; ++w)
+                        if (w < nw && (nbm[w] & remain[w0 + w])) join = false;
+                    if (join && P.member) P.member[v] = 1;
                     const uint32_t jw = __ballot_sync(0xffffffffu, join);
                     if (lane == 0) {
                         joined[warp] = jw;
@@ -837,7 +896,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     if (still) {
 #pragma unroll
                         for (int w = 0; w < 12; ++w)
-                            if (w < nw && (nbm[w] & joined[w0 + w])) still = false;
+                            if (w < nw && (nbr[w] & joined[w0 + w])) still = false;
                     }
                     const uint32_t rw = __ballot_sync(0xffffffffu, still);
                     if (lane == 0) remain[warp] = rw;
@@ -845,17 +904,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     bar_sync(dom_bar, dom_cnt);
                 }
                 if (r == 0 && P.steps) P.steps[G.g] = steps;
-                if (P.total && jb == 0 && (warp & 3) == 0) {  // the graph's first warp: vertex order, as dg_fused.cu
-                    double acc = 0.0;
-                    for (int i = lane; i < G.nv; i += 32) {
-                        const int sl = G.fb * 128 + i;
-                        if ((memb[sl >> 5] >> (sl & 31)) & 1u) acc += P.wts[G.v0 + i];  // mwis_dqn_call.py:241
-                    }
+                if (P.total) {  // member weights through shared memory, summed in the order dg_fused.cu uses
+                    util_sm[tid] = (valid && ((memb[warp] >> lane) & 1u)) ? wt_v : 0.0;  // mwis_dqn_call.py:241
+                    bar_sync(dom_bar, dom_cnt);
+                    if (jb == 0 && (warp & 3) == 0) {
+                        double acc = 0.0;
+                        for (int i = lane; i < G.nv; i += 32) acc += util_sm[G.fb * 128 + i];
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                    if (lane == 0) P.total[G.g] = acc;
+                        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                        if (lane == 0) P.total[G.g] = acc;
+                    }
                 }
             }
+        }
+        if (timing) {
+            const long long now = clock64();
+            tm[10] += now - tk;
+            tk = now;
         }
         wseq += (uint32_t)n_hidden;
         tc_fence_before();
@@ -863,17 +928,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         tc_fence_after();
         if (timing) {
             const long long now = clock64();
-            tm[1] += now - tk;
+            tm[11] += now - tk;
             tm[2] += 1;
+            long long *td2 = P.dbg + (size_t)gridDim.x * 12 + (size_t)t * 2;
+            td2[0] = now - t_tile;
+            td2[1] = t;
         }
     }
     if (timing) {
         tm[7] = clock64() - t_begin;
-        for (int k = 0; k < 8; ++k) P.dbg[(size_t)blockIdx.x * 8 + k] = tm[k];
+        for (int k = 0; k < 12; ++k) P.dbg[(size_t)blockIdx.x * 12 + k] = tm[k];
     }
     tc_fence_before();
     __syncthreads();
-    if (is_ctrl) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     // the last CTA to leave re-arms the tile counter for the next launch on this context
     if (tid == 0) {
         __threadfence();
@@ -903,7 +971,7 @@ float bf16_to_f(uint16_t h) {
 
 struct TcGraph {
     int g, nv, nb;
-    size_t bytes;   // adjacency + H terms + Y digits
+    size_t bytes;   // adjacency + max(H terms, Y digits)
     long long cost;
 };
 
@@ -977,10 +1045,14 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         t.nv = gp[g + 1] - gp[g];
         t.nb = std::max(1, (t.nv + 127) / 128);
         const size_t R = (size_t)((t.nv + 7) & ~7), Kp = (size_t)((t.nv + 31) & ~31);
+#ifdef DG_TC_NO_ALIAS
         t.bytes = R * Kp + 192 * R + 128 * Kp;
+#else
+        t.bytes = R * Kp + std::max<size_t>(192 * R, 128 * Kp);
+#endif
         // per layer: projection ~650 cycles per block, aggregation ~65 per block and 32 columns, epilogue ~900 per block
         t.cost = (long long)t.nb * (1600 + 2 * (long long)Kp);
-        if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + 128 > pool) return DG_OK;  // not eligible: the caller falls back
+        if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + kTcOverread > pool) return DG_OK;  // not eligible: the caller falls back
         gs[(size_t)g] = t;
     }
     // Largest graph first; every tile is then topped up with the largest remaining graphs that still fit (blocks, bytes
@@ -1002,7 +1074,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
             while (it != by_size.begin()) {
                 --it;
                 const TcGraph *c = it->second.back();
-                if (o.ng < kTcMaxG && o.blocks + c->nb <= kTcBlocks && o.bytes + c->bytes + 128 <= pool) {
+                if (o.ng < kTcMaxG && o.blocks + c->nb <= kTcBlocks && o.bytes + c->bytes + kTcOverread <= pool) {
                     found = true;
                     break;
                 }
@@ -1020,10 +1092,15 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         tiles.push_back(o);
     }
     std::stable_sort(tiles.begin(), tiles.end(), [](const Open &a, const Open &c) { return a.cost > c.cost; });
-    std::vector<int> flat(tiles.size() * 8, 0);
+    const auto &ge = b->h_graph_e;
+    std::vector<int> flat(tiles.size() * 32, 0);
     for (size_t i = 0; i < tiles.size(); ++i) {
-        flat[i * 8] = tiles[i].ng;
-        for (int k = 0; k < tiles[i].ng; ++k) flat[i * 8 + 1 + k] = tiles[i].g[k];
+        flat[i * 32] = tiles[i].ng;
+        for (int k = 0; k < tiles[i].ng; ++k) {
+            const int g = tiles[i].g[k];
+            int *d = &flat[i * 32 + 1 + 6 * k];
+            d[0] = g, d[1] = gp[g], d[2] = gp[g + 1] - gp[g], d[3] = ge[g], d[4] = ge[g + 1] - ge[g];
+        }
     }
     if (b->tc_tiles_cap < flat.size() || !b->tc_tiles_dev) {
         if (b->tc_tiles_dev) {
@@ -1038,6 +1115,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         DG_CUDA_CHECK(cudaMemcpyAsync(b->tc_tiles_dev, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice,
                                       ctx->stream));
     b->tc_n_tiles = (int)tiles.size();
+    b->tc_tiles_host = flat;
     if (getenv("DG_FUSED_TIMING")) fprintf(stderr, "[tc tiles] %d tiles for %d graphs\n", b->tc_n_tiles, b->n_graphs);
     *ok = b->tc_n_tiles > 0;
     return DG_OK;
@@ -1045,11 +1123,14 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
 
 }  // namespace
 
+static int *g_wide_buf = nullptr;  // DG_TC_DEBUG: pinned table the stuck threads log their wait sites into
+
 int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict, int remove_zero_weight,
                  uint8_t *member, float *score, double *util, double *total, int32_t *steps, bool *handled) {
     *handled = false;
     if (getenv("DG_DISABLE_TC") || getenv("DG_DISABLE_FUSED")) return DG_OK;
     if (!m->tc_wall || m->n_layers < 3 || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
+    if ((int)b->h_graph_e.size() != b->n_graphs + 1) return DG_OK;
     if (member == nullptr && d_wts == nullptr && predict == DG_PREDICT_MWIS) return DG_OK;
     bool ok = false;
     DG_TRY(tc_build_tiles(ctx, b, &ok));
@@ -1089,12 +1170,24 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     const size_t smem = (size_t)ctx->max_smem_optin - 1024;
     if (getenv("DG_FUSED_TIMING")) {
         long long *dbg = nullptr;
-        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * 8, &dbg));
-        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * (size_t)ctx->sm_count * 8, ctx->stream));
+        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * 12 + (size_t)p.n_tiles * 2, &dbg));
+        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * 12 + (size_t)p.n_tiles * 2), ctx->stream));
         p.dbg = dbg;
     }
     DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(ctx->sm_count, p.n_tiles);
+    {
+        int *wd = ctx->h_flag + 3;  // pinned host memory: readable after a device-side trap
+        int wide = 0;
+        if (getenv("DG_TC_DEBUG")) {
+            if (!g_wide_buf) DG_CUDA_CHECK(cudaHostAlloc((void **)&g_wide_buf, sizeof(int) * (1 + 148 * 512), cudaHostAllocDefault));
+            memset(g_wide_buf, 0, sizeof(int) * (1 + 148 * 512));
+            wd = g_wide_buf;
+            wide = 1;
+        }
+        DG_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_tc_watchdog, &wd, sizeof(wd), 0, cudaMemcpyHostToDevice, ctx->stream));
+        DG_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_tc_watchdog_wide, &wide, sizeof(wide), 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
     {
         // work-equivalent algorithmic bytes, the same figure dg_fused.cu reports (SURVEY.md 8d / DESIGN.md)
         const double n = (double)b->n_nodes, nnz = (double)b->nnz, cp = 32.0;
@@ -1108,17 +1201,31 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         prof_end(ctx, hidden + scalar_passes + lgs);
         DG_CUDA_CHECK(cudaGetLastError());
     }
+    if (getenv("DG_TC_DEBUG")) {
+        const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess && g_wide_buf) {
+            const int w = g_wide_buf[0];
+            const int cta = w >> 20;
+            fprintf(stderr, "[tc debug] %s; first to give up: site %d, thread %d, CTA %d; stuck threads of that CTA (site x count):",
+                    cudaGetErrorString(e), w & 0xff, (w >> 8) & 0xfff, cta);
+            for (int wp = 0; wp < 16; ++wp) {
+                fprintf(stderr, "\n  warp %2d:", wp);
+                for (int l = 0; l < 32; ++l) fprintf(stderr, " %d", g_wide_buf[1 + cta * 512 + wp * 32 + l]);
+            }
+            fprintf(stderr, "\n");
+        }
+    }
     if (p.dbg) {
-        std::vector<long long> h((size_t)ctx->sm_count * 8);
+        std::vector<long long> h((size_t)ctx->sm_count * 12 + (size_t)p.n_tiles * 2);
         DG_CUDA_CHECK(cudaMemcpyAsync(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
         DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        const char *names[8] = {"stage", "solve", "tiles", "w_proj", "phaseB", "w_agg", "phaseC", "total"};
-        for (int k : {0, 1, 2, 3, 4, 5, 6, 7}) {
+        const char *names[12] = {"stage", "-", "tiles", "w_proj", "phaseB", "w_agg", "phaseC", "total", "first", "tail", "greedy", "endwait"};
+        for (int k : {0, 8, 3, 4, 5, 6, 9, 10, 11, 2, 7}) {
             long long mn = -1, mx = 0;
             double sum = 0;
             int cnt = 0;
             for (int c = 0; c < grid; ++c) {
-                const long long vv = h[(size_t)c * 8 + k];
+                const long long vv = h[(size_t)c * 12 + k];
                 mn = mn < 0 ? vv : std::min(mn, vv);
                 mx = std::max(mx, vv);
                 sum += (double)vv;
@@ -1126,6 +1233,17 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
             }
             fprintf(stderr, "[tc timing] %-6s min %10lld avg %12.0f max %10lld (%d CTAs)\n", names[k], mn, cnt ? sum / cnt : 0.0,
                     mx, cnt);
+        }
+        if (const char *path = getenv("DG_TC_TILE_DUMP")) {  // per tile: cycles, then the vertex counts of its graphs
+            if (FILE *f = fopen(path, "w")) {
+                for (int t = 0; t < p.n_tiles; ++t) {
+                    const int *td = &b->tc_tiles_host[(size_t)t * 32];
+                    fprintf(f, "%lld", h[(size_t)grid * 12 + (size_t)t * 2]);
+                    for (int k = 0; k < td[0]; ++k) fprintf(f, " %d", td[1 + 6 * k + 2]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
         }
     }
     *handled = true;

@@ -36,6 +36,17 @@ ROTATING_COPIES = 16  # distinct resident input sets cycled through the timed st
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu
 # capture of the same command (profiles/r01_fused_ncu.md); None where no capture exists
 TRAFFIC_NCU = {"ba500": 9.12e6}
+KERNEL_NOTES = {
+    "tc_solve_kernel": ("tc_solve_kernel (graph-resident, tcgen05: bf16-split projection + exact u8 aggregation MMAs, "
+                        "utility and greedy rounds in one launch)",
+                        "The kernel keeps adjacency, operands and accumulators in shared / tensor memory: its real DRAM "
+                        "traffic is `traffic` (ncu, profiles/); it is bound by the hand-off latency between tensor-core and "
+                        "CUDA-core phases of a layer, not by HBM."),
+    "fused_solve_kernel": ("fused_solve_kernel (graph-resident: all GCN layers + utility + greedy rounds in one launch)",
+                           "The fused kernel keeps features in shared memory, its real DRAM traffic is `traffic` (ncu, "
+                           "profiles/) - it is shared-memory-bandwidth bound, not HBM bound."),
+    "gc_layer_kernel": ("gc_layer_kernel (fused GraphConvolution layer)", "Streaming per-layer kernel."),
+}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -324,6 +335,7 @@ def run_ours(args):
     dev_ms = ev.stop()  # synchronises the library's stream
     wall_ms = 1e3 * (time.perf_counter() - t0)
     launches = ctx.launch_count - launches0
+    kernel_name = ctx.last_kernel
     tot_ms, n_launch, alg_bytes = C.c_double(), C.c_uint64(), C.c_double()
     E.check(lib.dg_profile_collect(ctx.handle, C.byref(tot_ms), C.byref(n_launch), C.byref(alg_bytes)))
     lib.dg_profile_enable(ctx.handle, 0)
@@ -411,11 +423,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm",
-                         "kernel": "fused_solve_kernel (graph-resident: all GCN layers + utility + greedy rounds in one launch)"
-                                   if launches <= 2 * args.steps else "gc_layer_kernel (fused GraphConvolution layer)",
+                         "kernel": KERNEL_NOTES.get(kernel_name, (kernel_name, ""))[0],
                          "note": "achieved = work-equivalent algorithmic bytes (per-layer B_layer of DESIGN.md summed over the "
-                                 "fused layers) / kernel time; the fused kernel keeps features in shared memory, its real DRAM "
-                                 "traffic is `traffic` (ncu, profiles/) - it is shared-memory-bandwidth bound, not HBM bound",
+                                 "fused layers) / kernel time. " + KERNEL_NOTES.get(kernel_name, ("", ""))[1],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_NCU.get(args.workload), "launches_timed": kern_launches,
                          "avg_launch_us": 1e3 * tot_ms.value / max(kern_launches, 1),

@@ -44,6 +44,7 @@ SIGNATURES = {
     "dg_host_alloc": (_p, [C.c_uint64]),
     "dg_host_free": (None, [_p]),
     "dg_context_launch_count": (C.c_uint64, [_p]),
+    "dg_context_last_kernel": (C.c_char_p, [_p]),
     "dg_timer_start": (C.c_int, [_p]),
     "dg_timer_stop": (C.c_int, [_p, _p]),
     "dg_profile_enable": (C.c_int, [_p, C.c_int]),

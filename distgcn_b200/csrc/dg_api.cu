@@ -242,6 +242,8 @@ void dg_host_free(void *p) {
 
 uint64_t dg_context_launch_count(const dg_context *ctx) { return ctx ? ctx->launches : 0; }
 
+const char *dg_context_last_kernel(const dg_context *ctx) { return ctx ? ctx->last_kernel : ""; }
+
 int dg_timer_start(dg_context *ctx) {
     clear_error();
     DG_TRY(check_ctx(ctx));

@@ -98,6 +98,7 @@ struct dg_context {
     std::vector<cudaEvent_t> prof_events;  // pairs: [2k] start, [2k+1] stop
     size_t prof_used = 0;                  // events recorded since the last collect
     double prof_bytes = 0.0;               // algorithmic bytes of the recorded launches
+    const char *last_kernel = "";          // dominant kernel of the most recent solve (dg_context_last_kernel)
 };
 
 namespace dg {

@@ -1196,6 +1196,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
         const double hidden = (double)std::max(0, m->n_layers - 2) * (csr + 4.0 * n + 8.0 * n * cp + 8.0 * cp * cp);
         const double scalar_passes = 2.0 * (csr + 12.0 * n);
         const double lgs = csr + 9.0 * n;
+        ctx->last_kernel = "fused_solve_kernel";
         prof_begin(ctx);
         int st;
         if (m->fused_cp != 32)

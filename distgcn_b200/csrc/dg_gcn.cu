@@ -499,7 +499,8 @@ int launch_layer_t(dg_context *ctx, const LayerArgs &args) {
     const double nnz = (double)args.nnz;
     const double bytes = 4.0 * (n + 1) + 4.0 * nnz + 4.0 * n + 4.0 * n * (IMPLICIT_IN ? 2 : CPI) +
                          4.0 * n * (TAIL ? 2 : CPO) + 4.0 * (2 * CPI * CPO + CPO);
-    prof_begin(ctx);
+    ctx->last_kernel = "gc_layer_kernel";
+        prof_begin(ctx);
     kern<<<grid, kWarpsPerCta * 32, smem, ctx->stream>>>(args);
     prof_end(ctx, bytes);
     ctx->launches++;

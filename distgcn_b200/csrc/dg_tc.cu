@@ -239,6 +239,16 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
 
 // Every activation of the path is v >= 0 ? v : slope * v with slope = alpha (leaky ReLU), 0 (ReLU) or 1 (none); as
 // max(v, slope v) for slope <= 1 and min(v, slope v) otherwise it is branch-free and bit-identical to the select form.
+// one lane of a converged warp (the lane that issues tcgen05.mma / commit for it)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0u;
+}
+// a value every lane holds identically, handed to the compiler as warp-uniform (so that it can live in a uniform register
+// and feed the MMA operands without a per-instruction broadcast)
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ float tc_slope(int act, float alpha) {
     return act == DG_ACT_LEAKY_RELU ? alpha : act == DG_ACT_RELU ? 0.f : 1.f;
 }
@@ -524,32 +534,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             // which is what agg_drained() relies on).
             auto hand_off_agg = [&](bool scalar) {
                 if (!last_warp(&cnt_a[gi], 4u * (uint32_t)G.nb)) return;
-                if (lane == 0) {
-                    tc_fence_after();
-                    const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
-                    const uint32_t lbo_a = (uint32_t)G.R * 16u;
-                    const uint64_t bdesc0 = umma_desc(pool_addr + G.yoff, 128u, scalar ? 128u : (uint32_t)G.Kp * 16u);
-                    const uint64_t adesc0 = umma_desc(pool_addr + G.adj, lbo_a, 128u);
-                    const uint32_t a_step = (2u * lbo_a) >> 4;  // one K-step (32 columns = 2 chunks) in descriptor units
-                    const int ksteps = G.Kp >> 5;
-                    for (int k = 0; k < G.nb; ++k) {
-                        uint64_t adesc = adesc0 + (uint64_t)(k * 128);  // 128 rows x 16 B >> 4
-                        uint64_t bdesc = bdesc0;
-                        const uint32_t d = tmem + (uint32_t)(G.fb + k) * 128u;
-                        for (int s2 = 0; s2 < ksteps; ++s2) {
-                            mma_u8(d, adesc, bdesc, idesc, s2 > 0);
-                            adesc += a_step;
-                            bdesc += 32u;  // 4 k-groups x 128 B >> 4
-                        }
-                        mma_commit(&bar_da[G.fb + k]);
+                // the whole (converged) warp runs the loop on warp-uniform values; one elected lane issues
+                tc_fence_after();
+                const uint32_t u_r = uniform((uint32_t)G.R), u_kp = uniform((uint32_t)G.Kp), u_nb = uniform((uint32_t)G.nb);
+                const uint32_t u_adj = uniform(pool_addr + (uint32_t)G.adj), u_y = uniform(pool_addr + (uint32_t)G.yoff);
+                const uint32_t u_d = uniform(tmem + (uint32_t)G.fb * 128u), u_bar = uniform(s32(&bar_da[G.fb]));
+                const uint32_t idesc = scalar ? idesc_u8(128, 16) : idesc_u8(128, 128);
+                const uint32_t lbo_a = u_r * 16u;
+                const uint64_t bdesc0 = umma_desc(u_y, 128u, scalar ? 128u : u_kp * 16u);
+                const uint64_t adesc0 = umma_desc(u_adj, lbo_a, 128u);
+                const uint32_t a_step = (2u * lbo_a) >> 4;  // one K-step (32 columns = 2 chunks) in descriptor units
+                const uint32_t ksteps = u_kp >> 5;
+                const bool leader = elect_one();
+                for (uint32_t k = 0; k < u_nb; ++k) {
+                    uint64_t adesc = adesc0 + (uint64_t)(k * 128u);  // 128 rows x 16 B >> 4
+                    uint64_t bdesc = bdesc0;
+                    const uint32_t d = u_d + k * 128u;
+                    for (uint32_t s2 = 0; s2 < ksteps; ++s2) {
+                        if (leader) mma_u8(d, adesc, bdesc, idesc, s2 > 0u);
+                        adesc += a_step;
+                        bdesc += 32u;  // 4 k-groups x 128 B >> 4
                     }
+                    if (leader)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_bar + k * 8u)
+                                     : "memory");
                 }
                 __syncwarp();
             };
             // projection of this block, hidden layer h: [P0 | P1] = H . [W_0 | W_1 r], 6 products x 2 K-steps
             auto issue_proj = [&](int h) {
+                const uint32_t seq = wseq + (uint32_t)h;
                 if (lane == 0) {
-                    const uint32_t seq = wseq + (uint32_t)h;
                     if (h >= 1) {
                         // every thread of this block has finished layer h-1 (its epilogue reads bias / r from the weight
                         // buffer): when all blocks of the tile have, the buffer takes layer h+1
@@ -563,24 +578,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                         }
                     }
                     mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u, 2);  // the layer's weights have landed
-                    tc_fence_after();
-                    const uint32_t lbo_a = (uint32_t)G.R * 16u;  // H terms: [term][chunk][R rows][16 B]
-                    const uint64_t a0 = umma_desc(pool_addr + G.hoff + (uint32_t)jb * 2048u, lbo_a, 128u);
-                    const uint64_t b0 = umma_desc(s32(wring) + (seq & 1u) * kTcWBlob, 1024u, 128u);
-                    const uint32_t a_chunk = lbo_a >> 4;  // one 16-byte K chunk of all rows, in descriptor units
-                    const uint32_t idesc = idesc_bf16(128, 64);
-                    const uint32_t d = tmem + (uint32_t)b * 128u;
-                    // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi); A term t starts 4 t
-                    // chunks in, W term t starts 4096 t bytes in; the second K-step is 2 chunks further
-                    const uint64_t at[3] = {a0, a0 + 4u * a_chunk, a0 + 8u * a_chunk};
-                    const uint64_t bt[3] = {b0, b0 + 256u, b0 + 512u};
-                    const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+                }
+                __syncwarp();
+                tc_fence_after();
+                // warp-uniform operands, one elected lane issues (see hand_off_agg)
+                const uint32_t u_r = uniform((uint32_t)G.R);
+                const uint32_t u_h = uniform(pool_addr + (uint32_t)G.hoff + (uint32_t)jb * 2048u);
+                const uint32_t u_w = uniform(s32(wring) + (seq & 1u) * kTcWBlob);
+                const uint32_t d = uniform(tmem + (uint32_t)b * 128u);
+                const uint32_t u_bar = uniform(s32(&bar_dp[b]));
+                const uint32_t lbo_a = u_r * 16u;  // H terms: [term][chunk][R rows][16 B]
+                const uint64_t a0 = umma_desc(u_h, lbo_a, 128u);
+                const uint64_t b0 = umma_desc(u_w, 1024u, 128u);
+                const uint32_t a_chunk = lbo_a >> 4;  // one 16-byte K chunk of all rows, in descriptor units
+                const uint32_t idesc = idesc_bf16(128, 64);
+                // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi); A term t starts 4 t chunks
+                // in, W term t starts 4096 t bytes in; the second K-step is 2 chunks further
+                const uint64_t at[3] = {a0, a0 + 4u * a_chunk, a0 + 8u * a_chunk};
+                const uint64_t bt[3] = {b0, b0 + 256u, b0 + 512u};
+                const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+                if (elect_one()) {
 #pragma unroll
                     for (int pp = 0; pp < 6; ++pp) {
                         mma_bf16(d, at[ta[pp]], bt[tb[pp]], idesc, pp != 0);
                         mma_bf16(d, at[ta[pp]] + 2u * a_chunk, bt[tb[pp]] + 128u, idesc, 1u);
                     }
-                    mma_commit(&bar_dp[b]);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_bar) : "memory");
                 }
                 __syncwarp();
             };
@@ -1195,6 +1218,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         const double hidden = (double)p.n_hidden * (csr + 4.0 * n + 8.0 * n * cp + 8.0 * cp * cp);
         const double scalar_passes = 2.0 * (csr + 12.0 * n);
         const double lgs = csr + 9.0 * n;
+        ctx->last_kernel = "tc_solve_kernel";
         prof_begin(ctx);
         tc_solve_kernel<<<grid, kTcThreads, smem, ctx->stream>>>(p);
         ctx->launches++;

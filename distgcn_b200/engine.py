@@ -67,6 +67,11 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.dg_context_launch_count(self.handle))
 
+    @property
+    def last_kernel(self) -> str:
+        """Kernel that carried the most recent solve on this context (which of the three GPU paths ran)."""
+        return (self._lib.dg_context_last_kernel(self.handle) or b"").decode()
+
     def close(self) -> None:
         if self._h is not None:
             self._lib.dg_context_destroy(self._h)

@@ -90,6 +90,10 @@ DG_API void *dg_host_alloc(uint64_t bytes);
 DG_API void dg_host_free(void *p);
 /* Number of kernel launches this context has enqueued so far (bench.py's gpu_launches). */
 DG_API uint64_t dg_context_launch_count(const dg_context *ctx);
+/* Name of the kernel that carried the most recent profiled launch on this context (the solve kernel of
+ * dg_solve* / dg_gcn_forward: "tc_solve_kernel", "fused_solve_kernel" or "gc_layer_kernel"); "" before
+ * the first launch.  The string is static. */
+DG_API const char *dg_context_last_kernel(const dg_context *ctx);
 
 /* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,
  * waits for it and returns the elapsed device time between the two in milliseconds. */

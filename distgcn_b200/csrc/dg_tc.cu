@@ -135,8 +135,32 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 // left in pinned host memory (dg_context::h_flag[3]) for the post-mortem.
 __device__ int *g_tc_watchdog = nullptr;
 __device__ int g_tc_watchdog_wide = 0;  // DG_TC_DEBUG: the pointer is a wide table, every stuck thread logs its site
+// The fast path is a tight loop around try_wait (a suspend-time hint made wake-ups slower and bought nothing:
+// profiles/r01_notes.md); only after ~64 K failed attempts does the instrumented loop run.
+__device__ __forceinline__ bool mbar_wait_fast(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "TC_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "@p bra TC_WAIT_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 65536;\n"
+        "@p bra TC_WAIT_LOOP;\n"
+        "setp.ne.u32 p, n, n;\n"
+        "TC_WAIT_DONE:\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(s32(bar)), "r"(parity)
+        : "memory");
+    return done != 0u;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int site = 0) {
-    if (mbar_test(bar, parity)) return;
+    if (mbar_wait_fast(bar, parity)) return;
     const long long t0 = clock64();
     bool logged = false;
     for (uint32_t spins = 1;; ++spins) {

@@ -476,6 +476,106 @@ def test_other_heads_and_gen2(gpu_ctx):
     batch.close()
 
 
+def test_tensor_core_kernel_edge_cases(gpu_ctx, monkeypatch):
+    """tc_solve_kernel (dg_tc.cu) on the shapes its tiling has to get right: graphs of 1..304 vertices around the 128-row block
+    boundaries, isolated vertices and empty edge sets, zero weights (kept sub-graph), a per-vertex x0, ReLU / identity / leaky
+    activations with bias, hidden widths below 32.  Scores against the float64 evaluation of the oracle's network, memberships
+    against the reference rule on the GPU's own utilities and against the CUDA-core kernel; a batch with one graph above the
+    limit must fall back as a whole."""
+    E = _engine()
+    from oracle import gcn_oracle as G
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    from distgcn_b200.ckpt import LayerWeights
+    monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    monkeypatch.delenv("DG_DISABLE_TC", raising=False)
+    rng = np.random.default_rng(7)
+    sizes = [1, 2, 3, 31, 33, 64, 100, 127, 128, 129, 150, 200, 255, 256, 257, 300, 304, 17, 5, 288]
+    adjs = []
+    for k, n in enumerate(sizes):
+        p = [0.0, 0.03, 0.1, 0.3][k % 4] if n > 3 else 1.0
+        upper = np.triu(rng.random((n, n)) < p, k=1)
+        adjs.append(sp.csr_matrix((upper | upper.T).astype(np.float64)))
+    pb = pack_graphs(adjs)
+    n = pb.n_nodes
+    w = rng.random(n)
+    w[rng.random(n) < 0.1] = 0.0   # removed vertices
+    w[rng.random(n) < 0.2] = 0.5   # ties: the index rule decides
+
+    def rand_layers(dims, bias):
+        out = []
+        for ci, co in zip(dims[:-1], dims[1:]):
+            lw = LayerWeights(weights=[(rng.standard_normal((ci, co)) / np.sqrt(ci + co)).astype(np.float32) for _ in range(2)])
+            if bias:
+                lw.bias = (0.1 * rng.standard_normal(co)).astype(np.float32)
+            out.append(lw)
+        return out
+
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    cases = [((1, 32, 32, 32, 1), False, [1, 1, 1, 0]),          # GCN_DQN wiring: leaky ... identity
+             ((1, 32, 32, 32, 1), True, [2, 0, 1, 1]),            # ReLU / identity / leaky, bias, activation on the last layer
+             ((1, 16, 24, 16, 8, 1), True, [1, 1, 1, 1, 0])]      # widths below 32 (zero padded)
+    for dims, bias, acts in cases:
+        layers = rand_layers(dims, bias)
+        model = E.Model(gpu_ctx, layers, acts)
+        r = E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True, want_score=True, want_util=True, want_steps=True)
+        assert gpu_ctx.last_kernel == "tc_solve_kernel", dims
+        exact = np.zeros(n)
+        for g in range(pb.n_graphs):
+            v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+            keep = np.where(w[v0:v1] > 0)[0]
+            if keep.shape[0] == 0:
+                continue
+            a = pb.graph_adj(g)[keep][:, keep].tocsr()
+            feats = G.features_gen1(w[v0:v1][keep], 1)
+            exact[v0 + keep] = G.gcn_forward_fp64(feats, G.laplacian_supports(a, 1), layers, acts=acts)[:, 0]
+        assert _rel_err(r.score[:, 0], exact) <= SCORE_RTOL, dims
+        for g in range(pb.n_graphs):   # no graph may hide behind another graph's scale
+            v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+            assert np.abs(r.score[v0:v1, 0] - exact[v0:v1]).max() <= 2 * SCORE_RTOL * max(np.abs(exact[v0:v1]).max(), 1e-3), (dims, g)
+        assert np.all(r.score[w == 0, 0] == 0) and r.member[w == 0].sum() == 0
+        assert np.array_equal(r.util, r.score[:, 0].astype(np.float64) * w)
+        o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, r.util, init_remain=(w > 0).astype(np.uint8))
+        assert np.array_equal(o.member, r.member) and np.array_equal(o.steps, r.steps)
+        tot = np.array([w[pb.graph_ptr[g]:pb.graph_ptr[g + 1]][r.member[pb.graph_ptr[g]:pb.graph_ptr[g + 1]] == 1].sum()
+                        for g in range(pb.n_graphs)])
+        assert np.allclose(r.total, tot, rtol=1e-12, atol=1e-300)
+        # the CUDA-core graph-resident kernel on the same inputs
+        monkeypatch.setenv("DG_DISABLE_TC", "1")
+        r2 = E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True, want_score=True)
+        assert gpu_ctx.last_kernel == "fused_solve_kernel"
+        monkeypatch.delenv("DG_DISABLE_TC")
+        assert _rel_err(r2.score[:, 0], r.score[:, 0]) <= 2 * SCORE_RTOL
+        model.close()
+    # per-vertex x0 and a caller-supplied keep mask, scores only
+    layers = rand_layers((1, 32, 32, 1), True)
+    model = E.Model(gpu_ctx, layers, E.gcn2_dqn_acts(3))
+    x0 = rng.random(n).astype(np.float32)
+    batch.set_x0(x0)
+    out = E.gcn_forward(gpu_ctx, model, batch)
+    assert gpu_ctx.last_kernel == "tc_solve_kernel"
+    ref = np.zeros(n)
+    for g in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        feats = sp.csr_matrix(x0[v0:v1].astype(np.float64).reshape(-1, 1))
+        ref[v0:v1] = G.gcn_forward_fp64(feats, G.laplacian_supports(pb.graph_adj(g), 1), layers, "gcn2_dqn")[:, 0]
+    assert _rel_err(out[:, 0], ref) <= SCORE_RTOL
+    batch.set_x0(None)
+    batch.close()
+    # one graph above the size limit (~352 vertices): the whole batch takes the CUDA-core kernel, same answers
+    up = np.triu(rng.random((400, 400)) < 0.05, k=1)
+    big = pack_graphs(adjs + [sp.csr_matrix((up | up.T).astype(np.float64))])
+    wb = np.concatenate([w, rng.random(400)])
+    bbatch = E.DeviceBatch(gpu_ctx, big)
+    rb = E.solve(gpu_ctx, model, bbatch, wb, remove_zero_weight=True, want_score=True)
+    assert gpu_ctx.last_kernel == "fused_solve_kernel"
+    rs = E.solve(gpu_ctx, model, E.DeviceBatch(gpu_ctx, pb), w, remove_zero_weight=True, want_score=True)
+    assert gpu_ctx.last_kernel == "tc_solve_kernel"
+    assert _rel_err(rb.score[:n, 0], rs.score[:, 0]) <= 2 * SCORE_RTOL
+    bbatch.close()
+    model.close()
+
+
 def test_error_reporting(gpu_ctx):
     E = _engine()
     from distgcn_b200 import _lib

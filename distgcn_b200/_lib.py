@@ -61,6 +61,7 @@ SIGNATURES = {
     "dg_gcn_forward": (C.c_int, [_p, _p, _p, _p, C.c_int]),
     "dg_utility": (C.c_int, [_p, _p, _p, _i32, _p, C.c_int, _p, C.c_int]),
     "dg_lgs": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, C.c_int]),
+    "dg_dist_greedy": (C.c_int, [_p, _p, _p, C.c_double, _p, _p, C.c_int]),
     "dg_member_weight": (C.c_int, [_p, _p, _p, _p, _p, C.c_int]),
     "dg_solve": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, _p, _p, C.c_int]),
     "dg_part_create": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, C.c_int, C.POINTER(_p)]),

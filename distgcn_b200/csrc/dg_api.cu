@@ -830,6 +830,28 @@ int dg_lgs(dg_context *ctx, const dg_batch *b, const double *util, int32_t nstep
     return finish(ctx);
 }
 
+int dg_dist_greedy(dg_context *ctx, const dg_batch *b, const double *wts, double epsilon, uint8_t *member,
+                   int32_t *steps, int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(b && wts && member, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(epsilon > 0.0, DG_ERR_INVALID, "epsilon must be positive (heuristics.py:43)");
+    DeviceGuard guard(ctx->device);
+    const double alpha = 1.0 + (epsilon / 3.0);  // heuristics.py:46
+    const size_t n = (size_t)b->n_nodes, G = (size_t)b->n_graphs;
+    if (mem == DG_MEM_DEVICE) return dist_greedy_device(ctx, b, wts, alpha, member, steps);
+    double *d_wts = nullptr;
+    uint8_t *d_member = nullptr;
+    int32_t *d_steps = nullptr;
+    DG_TRY(stage_in(ctx, kSlotUtil, wts, n, &d_wts));
+    DG_TRY(scratch_as(ctx, kSlotMember, n, &d_member));
+    if (steps) DG_TRY(scratch_as(ctx, kSlotSteps, G, &d_steps));
+    DG_TRY(dist_greedy_device(ctx, b, d_wts, alpha, d_member, d_steps));
+    DG_TRY(copy_out(ctx, member, d_member, n));
+    DG_TRY(copy_out(ctx, steps, d_steps, G));
+    return finish(ctx);
+}
+
 int dg_member_weight(dg_context *ctx, const dg_batch *b, const uint8_t *member, const double *wts, double *total,
                      int mem) {
     clear_error();

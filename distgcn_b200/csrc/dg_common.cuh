@@ -328,6 +328,8 @@ int keep_from_weights_device(dg_context *ctx, int n, const double *wts, uint8_t 
 // ---- implemented in dg_lgs.cu ------------------------------------------------------------------
 int lgs_device(dg_context *ctx, const dg_batch *b, const double *util, int nstep, uint8_t *member,
                uint8_t *nb_is, int32_t *steps, int64_t *p2p, int64_t *bst, double *oh_vec);
+int dist_greedy_device(dg_context *ctx, const dg_batch *b, const double *wts, double alpha, uint8_t *member,
+                       int32_t *steps);
 int member_weight_device(dg_context *ctx, const dg_batch *b, const uint8_t *member, const double *wts,
                          double *total);
 

@@ -167,6 +167,146 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
 }
 
 // -------------------------------------------------------------------------------------------------
+// Threshold distributed greedy (heuristics.py:38-74, dist_greedy_search), one CTA per graph.
+// Per round: (1) seta = remaining vertices with no remaining neighbour, or whose weight reaches
+// max(remaining neighbours' weights) / alpha (:54-63); (2) mis_i = the vertices of seta taken one
+// after the other unless a neighbour was taken before (:64-69) - the reference walks seta in the
+// iteration order of a Python set, here the order is ascending vertex id (the two agree whenever no
+// two vertices of seta are adjacent), and that sequential scan is evaluated as
+// the lexicographically-first maximal independent set of seta by parallel sub-rounds: an undecided
+// vertex is dropped once a smaller-id neighbour is in, and joins once no smaller-id neighbour is
+// undecided or in; (3) mis_i joins the result, mis_i and its neighbours leave `remain` (:70-71).
+// A NaN among the weights compared keeps the vertex out of seta (np.max / >= semantics).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLgsCtaThreads)
+dgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+               const double *__restrict__ wts, const uint8_t *__restrict__ keep, double alpha, int round_cap,
+               int words_cap, uint8_t *__restrict__ member, int *__restrict__ steps, int *__restrict__ status) {
+    extern __shared__ uint32_t lgs_words[];
+    uint32_t *remain = lgs_words;
+    uint32_t *seta = lgs_words + words_cap;       // this round's candidates
+    uint32_t *und = lgs_words + 2 * words_cap;    // candidates not decided yet
+    uint32_t *mis = lgs_words + 3 * words_cap;    // candidates taken this round
+
+    const int g = blockIdx.x;
+    const int v0 = graph_ptr[g];
+    const int n = graph_ptr[g + 1] - v0;
+    const int lane = threadIdx.x & 31;
+    const int span = ((n + 31) / 32) * 32;
+    auto bit = [](const uint32_t *w, int u) -> bool { return (w[u >> 5] >> (u & 31)) & 1u; };
+
+    int n_remain = 0;
+    for (int base = 0; base < span; base += kLgsCtaThreads) {
+        const int v = base + threadIdx.x;
+        bool alive = false;
+        if (v < n) {
+            alive = keep ? keep[v0 + v] != 0 : true;
+            member[v0 + v] = 0;
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0 && v < span) remain[v >> 5] = w;
+        n_remain += __syncthreads_count(alive);
+    }
+
+    int rounds = 0;
+    while (n_remain > 0) {
+        if (rounds >= round_cap) {
+            if (threadIdx.x == 0) atomicExch(status, DG_ERR_NOT_CONVERGED);
+            break;
+        }
+        // ---- (1) candidates ------------------------------------------------------------------------
+        for (int base = 0; base < span; base += kLgsCtaThreads) {
+            const int v = base + threadIdx.x;
+            bool cand = false;
+            if (v < span && bit(remain, v)) {
+                const int beg = row_ptr[v0 + v], end = row_ptr[v0 + v + 1];
+                bool any = false, has_nan = false;
+                double w_bar = 0.0;
+                for (int e = beg; e < end; ++e) {
+                    const int u = col_idx[e] - v0;
+                    if (!bit(remain, u)) continue;
+                    const double wu = wts[v0 + u];
+                    has_nan |= wu != wu;
+                    if (!any || wu > w_bar) w_bar = wu;
+                    any = true;
+                }
+                cand = !any || (!has_nan && wts[v0 + v] >= w_bar / alpha);
+            }
+            const uint32_t cw = __ballot_sync(0xffffffffu, cand);
+            if (lane == 0 && v < span) {
+                seta[v >> 5] = cw;
+                und[v >> 5] = cw;
+                mis[v >> 5] = 0u;
+            }
+        }
+        __syncthreads();
+        // ---- (2) ascending-id scan of seta as parallel sub-rounds -----------------------------------
+        for (int sub = 0;; ++sub) {
+            int left = 0;
+            for (int base = 0; base < span; base += kLgsCtaThreads) {
+                const int v = base + threadIdx.x;
+                bool take = false, drop = false;
+                if (v < span && bit(und, v)) {
+                    const int beg = row_ptr[v0 + v], end = row_ptr[v0 + v + 1];
+                    bool wait = false;
+                    for (int e = beg; e < end; ++e) {
+                        const int u = col_idx[e] - v0;
+                        if (u >= v) continue;
+                        if (bit(mis, u)) {
+                            drop = true;
+                            break;
+                        }
+                        wait |= bit(und, u);
+                    }
+                    take = !drop && !wait;
+                }
+                const uint32_t tw = __ballot_sync(0xffffffffu, take);
+                const uint32_t dw = __ballot_sync(0xffffffffu, take || drop);
+                // every thread of the CTA has read the round-start words before any of them changes
+                const int undecided = __syncthreads_count(v < span && bit(und, v) && !(take || drop));
+                if (lane == 0 && v < span) {
+                    mis[v >> 5] |= tw;
+                    und[v >> 5] &= ~dw;
+                }
+                left += undecided;
+                __syncthreads();
+            }
+            if (left == 0) break;
+            if (sub > n) {  // cannot happen: the smallest undecided vertex is decided in every sub-round
+                if (threadIdx.x == 0) atomicExch(status, DG_ERR_NOT_CONVERGED);
+                break;
+            }
+        }
+        // ---- (3) the taken vertices join; they and their neighbours leave ---------------------------
+        n_remain = 0;
+        for (int base = 0; base < span; base += kLgsCtaThreads) {
+            const int v = base + threadIdx.x;
+            bool still = false;
+            if (v < span && bit(remain, v)) {
+                if (bit(mis, v)) {
+                    member[v0 + v] = 1;
+                } else {
+                    const int beg = row_ptr[v0 + v], end = row_ptr[v0 + v + 1];
+                    still = true;
+                    for (int e = beg; e < end; ++e) {
+                        if (bit(mis, col_idx[e] - v0)) {
+                            still = false;
+                            break;
+                        }
+                    }
+                }
+            }
+            const uint32_t rw = __ballot_sync(0xffffffffu, still);
+            __syncwarp();
+            if (lane == 0 && v < span) remain[v >> 5] = rw;
+            n_remain += __syncthreads_count(still);
+        }
+        ++rounds;
+    }
+    if (threadIdx.x == 0 && steps) steps[g] = rounds;
+}
+
+// -------------------------------------------------------------------------------------------------
 // global path
 // -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int graph_of(const int *__restrict__ graph_ptr, int n_graphs, int v) {
@@ -504,6 +644,21 @@ int lgs_device(dg_context *ctx, const dg_batch *b, const double *util, int nstep
         DG_CUDA_CHECK(cudaGetLastError());
         ++rounds;
     }
+    return DG_OK;
+}
+
+int dist_greedy_device(dg_context *ctx, const dg_batch *b, const double *wts, double alpha, uint8_t *member,
+                       int32_t *steps) {
+    const int G = b->n_graphs;
+    if (G == 0) return DG_OK;
+    DG_REQUIRE(b->max_graph_nodes <= kLgsCtaMaxNodes, DG_ERR_UNSUPPORTED,
+               "dist_greedy_search runs one CTA per graph: graphs above %d vertices are not supported", kLgsCtaMaxNodes);
+    const int words_cap = (b->max_graph_nodes + 31) / 32 + 1;
+    const size_t smem = sizeof(uint32_t) * 4 * (size_t)words_cap;
+    dgs_cta_kernel<<<G, kLgsCtaThreads, smem, ctx->stream>>>(b->graph_ptr, b->row_ptr, b->col_idx, wts, b->keep, alpha,
+                                                             kLgsRoundCap, words_cap, member, steps, ctx->d_status);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;
 }
 

@@ -320,6 +320,19 @@ def lgs(ctx: Context, batch: DeviceBatch, util, nstep: int = -1, want_nb_is: boo
     return res
 
 
+def dist_greedy(ctx: Context, batch: DeviceBatch, wts, epsilon: float = 0.5, want_steps: bool = True) -> LgsResult:
+    """Threshold distributed greedy (heuristics.py:38-74) on every graph of the batch (dg_dist_greedy)."""
+    w = _np(wts, np.float64).reshape(-1)
+    if w.shape[0] != batch.n_nodes:
+        raise ValueError("weights length %d != n_nodes %d" % (w.shape[0], batch.n_nodes))
+    res = LgsResult(member=np.zeros(batch.n_nodes, dtype=np.uint8))
+    if want_steps:
+        res.steps = np.zeros(batch.n_graphs, dtype=np.int32)
+    check(ctx._lib.dg_dist_greedy(ctx.handle, batch.handle, _ptr(w), float(epsilon), _ptr(res.member), _ptr(res.steps),
+                                  MEM_HOST))
+    return res
+
+
 def member_weight(ctx: Context, batch: DeviceBatch, member, wts) -> np.ndarray:
     m = _np(member, np.uint8)
     w = _np(wts, np.float64).reshape(-1)

@@ -95,6 +95,26 @@ def greedy_search(adj, wts):
     return local_greedy_search(adj, wts)
 
 
+def dist_greedy_search(adj, wts, epislon=0.5):
+    """Threshold distributed greedy (heuristics.py:38-74; the misspelt keyword is the reference's).  Per round the
+    remaining vertices within a factor alpha = 1 + epislon / 3 of their heaviest remaining neighbour are candidates,
+    and a maximal independent subset of the candidates joins.  The reference picks that subset by walking a Python
+    set; here the candidates are walked in ascending vertex id - the same result whenever no two candidates of a
+    round are adjacent, one of the reference's possible results otherwise."""
+    batch, owned = _as_batch(adj)
+    try:
+        if batch.n_graphs != 1:
+            raise ValueError("the per-graph entry points take one graph; use dist_greedy_search_batch for %d graphs"
+                             % batch.n_graphs)
+        w = _flat_weights(wts, batch.n_nodes)
+        res = engine.dist_greedy(batch.ctx, batch, w, epsilon=epislon, want_steps=False)
+    finally:
+        if owned:
+            batch.close()
+    mwis = _member_set(res.member)
+    return mwis, np.sum(w[list(mwis)])
+
+
 # ---- batched forms --------------------------------------------------------------------------------
 def local_greedy_search_batch(graphs, wts, nstep=-1, stats=False, overhead=False, nb_is=False):
     """Many graphs at once.  `graphs`: PackedBatch, DeviceBatch or a list of adjacency matrices.
@@ -106,6 +126,19 @@ def local_greedy_search_batch(graphs, wts, nstep=-1, stats=False, overhead=False
         w = _flat_weights(wts, batch.n_nodes)
         return engine.lgs(batch.ctx, batch, w, nstep=nstep, want_nb_is=nb_is, want_steps=True,
                           want_stats=stats or overhead, want_overhead=overhead)
+    finally:
+        if owned:
+            batch.close()
+
+
+def dist_greedy_search_batch(graphs, wts, epislon=0.5):
+    """dist_greedy_search on many graphs at once -> engine.LgsResult (membership vector, rounds per graph)."""
+    if isinstance(graphs, (list, tuple)):
+        graphs = pack_graphs(graphs)
+    batch, owned = _as_batch(graphs)
+    try:
+        w = _flat_weights(wts, batch.n_nodes)
+        return engine.dist_greedy(batch.ctx, batch, w, epsilon=epislon, want_steps=True)
     finally:
         if owned:
             batch.close()

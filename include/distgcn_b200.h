@@ -166,6 +166,17 @@ DG_API int dg_utility(dg_context *ctx, const dg_batch *batch, const float *score
 DG_API int dg_lgs(dg_context *ctx, const dg_batch *batch, const double *util, int32_t nstep, uint8_t *member,
            uint8_t *nb_is, int32_t *steps, int64_t *p2p, int64_t *bst, double *oh_vec, int mem);
 
+/* Threshold distributed greedy on every graph of the batch.  Replaces heuristics.dist_greedy_search
+ * (heuristics.py:38-74; call sites wireless_dqn_test_mc.py:252, wireless_dqn_test.py:242 with epsilon 0.1).
+ *   wts      fp64 weights (n_nodes); a vertex is a candidate of a round when it has no remaining neighbour
+ *            or wts[v] >= max(remaining neighbours' wts) / (1 + epsilon / 3)
+ *   member   out, n_nodes bytes;  steps  out or NULL, n_graphs int32, rounds executed
+ * Each round's candidates are scanned in ascending vertex id (the reference scans them in Python-set
+ * iteration order; identical whenever no two candidates of a round are adjacent).  Graphs above 8192
+ * vertices: DG_ERR_UNSUPPORTED.  Vertices removed by dg_batch_set_keep start outside `remain`. */
+DG_API int dg_dist_greedy(dg_context *ctx, const dg_batch *batch, const double *wts, double epsilon, uint8_t *member,
+                   int32_t *steps, int mem);
+
 /* total[g] = sum of wts over the members of graph g (mwis_dqn_call.py:241). */
 DG_API int dg_member_weight(dg_context *ctx, const dg_batch *batch, const uint8_t *member, const double *wts,
                      double *total, int mem);

@@ -40,6 +40,9 @@ def _load():
                                              c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
         lib.greedy_oracle_run.restype = None
         lib.greedy_oracle_run.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+        lib.dgs_oracle_run.restype = c.c_longlong
+        lib.dgs_oracle_run.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_double,
+                                       c.c_longlong, c.c_void_p, c.c_void_p]
         _lib = lib
     return _lib
 
@@ -110,3 +113,23 @@ def greedy(row_ptr, col_idx, order) -> np.ndarray:
     member = np.zeros(n, dtype=np.uint8)
     lib.greedy_oracle_run(n, _ptr(rp), _ptr(ci), _ptr(od), _ptr(member))
     return member
+
+
+def dist_greedy(row_ptr, col_idx, wts, epislon: float = 0.5, init_remain=None, max_rounds: int = -1):
+    """heuristics.py:38-74 with the per-round scan in ascending vertex id (see dgs_oracle_run).
+    -> (member uint8[n], rounds, order_free)"""
+    lib = _load()
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    ci = np.ascontiguousarray(col_idx, dtype=np.int32)
+    w = np.ascontiguousarray(np.asarray(wts, dtype=np.float64).reshape(-1))
+    n = rp.shape[0] - 1
+    assert w.shape[0] == n
+    ir = None if init_remain is None else np.ascontiguousarray(init_remain, dtype=np.uint8)
+    alpha = 1.0 + (epislon / 3.0)  # heuristics.py:46
+    member = np.zeros(n, dtype=np.uint8)
+    free_order = ctypes.c_int(1)
+    r = lib.dgs_oracle_run(n, _ptr(rp), _ptr(ci), _ptr(w), _ptr(ir), float(alpha), int(max_rounds), _ptr(member),
+                           ctypes.byref(free_order))
+    if r < 0:
+        raise RuntimeError("dgs_oracle_run failed with %d (-2 = did not converge)" % r)
+    return member, int(r), bool(free_order.value)

@@ -11,6 +11,7 @@
  *   local_greedy_search_overhead   heuristics.py:212-263   (+ per-vertex overhead vector)
  *   local_greedy_search_nstep      heuristics.py:266-305   (stop after nstep rounds, return nb_is)
  *   greedy_search                  heuristics.py:13-35     (centralised greedy, distinct weights)
+ *   dist_greedy_search             heuristics.py:38-74     (threshold greedy; scan order canonicalised, see dgs_oracle_run)
  *
  * Parity status: PINNED.  tests/golden/make_golden.py imports the reference's own heuristics.py
  * (unmodified; three unused third-party imports stubbed) and stores its outputs; this file is
@@ -165,6 +166,83 @@ void greedy_oracle_run(int n, const long long *row_ptr, const int *col_idx, cons
         for (long long e = row_ptr[v]; e < row_ptr[v + 1]; ++e) blocked[col_idx[e]] = 1;
     }
     free(blocked);
+}
+
+/*
+ * Threshold ("epsilon") distributed greedy, heuristics.py:38-74.  Per round over `remain`:
+ *   seta  = remaining vertices without remaining neighbours, or with wts[v] >= max(wts[N(v) & remain]) / alpha
+ *           (heuristics.py:54-63; alpha = 1 + epsilon / 3 is computed by the caller exactly as :46 does);
+ *   mis_i = vertices of seta taken one after the other unless a neighbour was taken before (:64-69);
+ *   mis_i joins the result, mis_i and all its neighbours leave `remain` (:70-71).
+ * The reference walks seta in the iteration order of a CPython set, an implementation accident that
+ * this restatement does not model: it walks seta in ASCENDING VERTEX ID.  The two agree whenever
+ * no two vertices of a round's seta are adjacent (then mis_i = seta whatever the order);
+ * `*order_free` reports whether that held in every round, and the parity fixtures compare with
+ * the reference's output only on such instances (tests/golden/make_golden.py, "dgs_ref").
+ * np.max / >= semantics: a NaN among the remaining neighbours' weights or in wts[v] keeps v out.
+ * Returns the number of rounds, -1 on allocation failure, -2 when max_rounds passed (negative or
+ * NaN weights can leave seta empty for ever; the reference then never returns).
+ */
+long long dgs_oracle_run(int n, const long long *row_ptr, const int *col_idx, const double *wts,
+                         const unsigned char *init_remain, double alpha, long long max_rounds,
+                         unsigned char *member, int *order_free)
+{
+    unsigned char *remain = (unsigned char *)malloc((size_t)(n > 0 ? n : 1));
+    unsigned char *seta = (unsigned char *)malloc((size_t)(n > 0 ? n : 1));
+    unsigned char *mis = (unsigned char *)malloc((size_t)(n > 0 ? n : 1));
+    if (!remain || !seta || !mis) { free(remain); free(seta); free(mis); return -1; }
+    long long n_remain = 0, rounds = 0;
+    int free_order = 1;
+    for (int v = 0; v < n; ++v) {
+        remain[v] = init_remain ? (init_remain[v] != 0) : 1;
+        n_remain += remain[v];
+        member[v] = 0;
+    }
+    while (n_remain > 0) {
+        if (max_rounds >= 0 && rounds >= max_rounds) { free(remain); free(seta); free(mis); return -2; }
+        for (int v = 0; v < n; ++v) {
+            seta[v] = 0;
+            mis[v] = 0;
+            if (!remain[v]) continue;
+            int cnt = 0, has_nan = 0;
+            double w_bar = 0.0;
+            for (long long e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+                int u = col_idx[e];
+                if (!remain[u]) continue;
+                double wu = wts[u];
+                if (wu != wu) has_nan = 1;
+                if (cnt == 0 || wu > w_bar) w_bar = wu;
+                ++cnt;
+            }
+            if (cnt == 0) seta[v] = 1;                                   /* heuristics.py:58-60 */
+            else if (!has_nan && wts[v] >= w_bar / alpha) seta[v] = 1;   /* heuristics.py:61-63 */
+        }
+        for (int v = 0; v < n; ++v) {                                    /* ascending id, see above */
+            if (!seta[v]) continue;
+            int taken_nb = 0;
+            for (long long e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+                int u = col_idx[e];
+                if (seta[u]) free_order = 0;
+                if (mis[u]) taken_nb = 1;
+            }
+            if (!taken_nb) mis[v] = 1;                                   /* heuristics.py:67-69 */
+        }
+        for (int v = 0; v < n; ++v) {
+            if (!mis[v]) continue;
+            member[v] = 1;
+            if (remain[v]) { remain[v] = 0; --n_remain; }
+            for (long long e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+                int u = col_idx[e];
+                if (remain[u]) { remain[u] = 0; --n_remain; }            /* heuristics.py:69,71 */
+            }
+        }
+        ++rounds;
+    }
+    if (order_free) *order_free = free_order;
+    free(remain);
+    free(seta);
+    free(mis);
+    return rounds;
 }
 
 #ifdef __cplusplus

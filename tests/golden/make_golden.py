@@ -134,12 +134,66 @@ def special_graphs():
     return out
 
 
+
+def make_dgs(ref_h):
+    """dgs_ref.npz: the reference's own dist_greedy_search (heuristics.py:38-74) on the committed small
+    graph set (file weights and tie-heavy variants) and the special graphs, epsilon 0.1 (the value every
+    reference call site uses, e.g. wireless_dqn_test_mc.py:252) and 0.5 (the default).  The reference walks
+    each round's candidate set in CPython set order; the fixtures keep every instance, the tests compare
+    memberships on those the oracle reports as order-free and check the defining properties on the rest."""
+    z = np.load(os.path.join(HERE, "graphs_small.npz"))
+    gp, rp, ci, w_all = z["graph_ptr"], z["row_ptr"], z["col_idx"], z["weights"]
+    rng = np.random.default_rng(77)
+    inst = []
+    names = []
+    for g in range(len(gp) - 1):
+        v0, v1 = int(gp[g]), int(gp[g + 1])
+        e0, e1 = int(rp[v0]), int(rp[v1])
+        n = v1 - v0
+        adj = sp.csr_matrix((np.ones(e1 - e0), ci[e0:e1].astype(np.int64) - v0, rp[v0:v1 + 1].astype(np.int64) - e0),
+                            shape=(n, n))
+        w = w_all[v0:v1]
+        inst.append((adj, w.copy()))
+        names.append("g%d|file" % g)
+        if g % 5 == 0:
+            for vn, wv in (("int0to5", rng.integers(0, 6, n).astype(np.float64)),
+                           ("withzeros", np.where(rng.random(n) < 0.25, 0.0, w)),
+                           ("spread", np.exp(8.0 * rng.random(n))),
+                           ("allequal", np.full(n, 0.75))):
+                inst.append((adj, wv))
+                names.append("g%d|%s" % (g, vn))
+    for gname, adj in special_graphs():
+        n = adj.shape[0]
+        for vn, wv in (("equal", np.ones(n)), ("ramp", np.arange(n, dtype=np.float64)),
+                       ("rramp", np.arange(n, 0, -1).astype(np.float64)), ("zeros", np.zeros(n)),
+                       ("pow", 3.0 ** np.arange(n, dtype=np.float64))):
+            inst.append((adj, wv))
+            names.append("%s|%s" % (gname, vn))
+    out = pack(inst)
+    eps_list = (0.1, 0.5)
+    for eps in eps_list:
+        members, totals = [], []
+        for adj, w in inst:
+            s, tot = ref_h.dist_greedy_search(sp.csr_matrix(adj), w, eps)
+            members.append(member_vec(s, adj.shape[0]))
+            totals.append(float(tot))
+        tag = ("%g" % eps).replace(".", "p")
+        out["member_eps%s" % tag] = np.concatenate(members)
+        out["total_eps%s" % tag] = np.asarray(totals)
+    np.savez_compressed(os.path.join(HERE, "dgs_ref.npz"), names=np.asarray(names), eps=np.asarray(eps_list), **out)
+    print("dgs_ref.npz: %d instances" % len(inst))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--full", action="store_true", help="also write the full 500-graph ER/BA test2 fixtures")
+    ap.add_argument("--only", default=None, choices=["dgs"], help="regenerate just one fixture family")
     args = ap.parse_args()
     ref_h, ref_u = import_reference(args.reference)
+    if args.only == "dgs":
+        make_dgs(ref_h)
+        return
     from distgcn_b200 import ckpt as ckpt_reader
     from oracle import gcn_oracle as G
 

@@ -84,6 +84,21 @@ def test_heuristics_entry_points_match_reference_vectors():
         assert mwis2 == want
     res = H.local_greedy_search_batch(pb, w, stats=True)
     assert np.array_equal(res.member, ref["member"]) and np.array_equal(res.p2p, ref["p2p"])
+    # dist_greedy_search(adj, wts, epislon) as the wireless scripts call it (wireless_dqn_test_mc.py:252)
+    from oracle import lgs as L
+    dref = util.load_npz("dgs_ref.npz")
+    dpb, dw = util.packed_from_npz(dref), dref["weights"]
+    for g in (0, 3, 57):
+        v0, v1 = int(dpb.graph_ptr[g]), int(dpb.graph_ptr[g + 1])
+        sub = dpb.slice(g, g + 1)
+        member, _, order_free = L.dist_greedy(sub.row_ptr, sub.col_idx, dw[v0:v1], 0.1)
+        mwis, total = H.dist_greedy_search(dpb.graph_adj(g), dw[v0:v1], 0.1)
+        assert mwis == set(np.flatnonzero(member).tolist())
+        assert abs(total - float(dw[v0:v1][member.astype(bool)].sum())) < 1e-9
+        if order_free:
+            assert mwis == set(np.flatnonzero(dref["member_eps0p1"][v0:v1]).tolist())
+    resd = H.dist_greedy_search_batch(dpb, dw, 0.5)
+    assert resd.member.shape == (dpb.n_nodes,) and resd.steps.shape == (dpb.n_graphs,)
 
 
 def test_graph_convolution_layer_call():

@@ -135,6 +135,91 @@ def test_lgs_nan_reports_not_converged(gpu_ctx, monkeypatch):
     batch.close()
 
 
+# ------------------------------------------------------------------------------------------------
+# threshold distributed greedy (heuristics.dist_greedy_search)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("eps,tag", [(0.1, "0p1"), (0.5, "0p5")])
+def test_dist_greedy_matches_oracle_and_reference(gpu_ctx, eps, tag):
+    """Bit-exact against the C restatement on every instance (same ascending-id scan), and against the
+    reference's own dist_greedy_search output on the order-free instances (tests/golden/dgs_ref.npz)."""
+    E = _engine()
+    from oracle import lgs as L
+    ref = util.load_npz("dgs_ref.npz")
+    pb, w = util.packed_from_npz(ref), ref["weights"]
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    r = E.dist_greedy(gpu_ctx, batch, w, epsilon=eps)
+    n_free = 0
+    for g in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        sub = pb.slice(g, g + 1)
+        member, rounds, order_free = L.dist_greedy(sub.row_ptr, sub.col_idx, w[v0:v1], eps)
+        assert np.array_equal(r.member[v0:v1], member), "graph %d (%s)" % (g, ref["names"][g])
+        assert int(r.steps[g]) == rounds
+        if order_free:
+            n_free += 1
+            assert np.array_equal(r.member[v0:v1], ref["member_eps" + tag][v0:v1])
+    assert n_free >= 20
+    tot = E.member_weight(gpu_ctx, batch, r.member, w)
+    free_tot = [g for g in range(pb.n_graphs) if np.array_equal(
+        r.member[pb.graph_ptr[g]:pb.graph_ptr[g + 1]], ref["member_eps" + tag][pb.graph_ptr[g]:pb.graph_ptr[g + 1]])]
+    assert np.allclose(tot[free_tot], ref["total_eps" + tag][free_tot], rtol=1e-12, atol=1e-12)
+    batch.close()
+
+
+def test_dist_greedy_keep_mask_edge_cases_and_full_sets(gpu_ctx):
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200 import _lib
+    from distgcn_b200.batch import PackedBatch, pack_graphs
+    # keep mask == removal
+    pb, w = util.small_graphs()
+    rng = np.random.default_rng(19)
+    keep = (rng.random(pb.n_nodes) < 0.7).astype(np.uint8)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    batch.set_keep(keep)
+    r = E.dist_greedy(gpu_ctx, batch, w, epsilon=0.1)
+    for g in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        sub = pb.slice(g, g + 1)
+        member, rounds, _ = L.dist_greedy(sub.row_ptr, sub.col_idx, w[v0:v1], 0.1, init_remain=keep[v0:v1])
+        assert np.array_equal(r.member[v0:v1], member) and int(r.steps[g]) == rounds
+    batch.close()
+    # empty batch, empty graph, single vertex, edgeless graph, one edge with equal weights (lower id first)
+    batch = E.DeviceBatch(gpu_ctx, PackedBatch(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32)))
+    assert E.dist_greedy(gpu_ctx, batch, np.zeros(0)).member.shape == (0,)
+    batch.close()
+    adjs = [sp.csr_matrix((0, 0)), sp.csr_matrix((1, 1)), sp.csr_matrix((5, 5)),
+            sp.csr_matrix(np.array([[0, 1], [1, 0]], dtype=float))]
+    batch = E.DeviceBatch(gpu_ctx, pack_graphs(adjs))
+    r = E.dist_greedy(gpu_ctx, batch, np.array([1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 2.0, 2.0]))
+    assert r.member.tolist() == [1, 1, 1, 1, 1, 1, 1, 0] and r.steps.tolist() == [0, 1, 1, 1]
+    batch.close()
+    # a long path with equal weights: every vertex is a candidate of round 1, the ascending scan takes every other one
+    n = 1000
+    path = sp.diags([np.ones(n - 1), np.ones(n - 1)], [-1, 1], format="csr")
+    batch = E.DeviceBatch(gpu_ctx, pack_graphs([path]))
+    r = E.dist_greedy(gpu_ctx, batch, np.ones(n))
+    assert np.array_equal(r.member, (np.arange(n) % 2 == 0).astype(np.uint8)) and r.steps.tolist() == [1]
+    batch.close()
+    # negative weights leave the candidate set empty for ever (the reference never returns): reported
+    batch = E.DeviceBatch(gpu_ctx, pack_graphs([adjs[3]]))
+    with pytest.raises(_lib.DistGCNError) as ei:
+        E.dist_greedy(gpu_ctx, batch, np.array([-1.0, -1.0]))
+    assert ei.value.code == _lib.ERR_NOT_CONVERGED
+    batch.close()
+    # the reference's full test sets at epsilon 0.1 (the value its call sites use)
+    for fam in ("er", "ba"):
+        pb, w, _ = util.full_set(fam)
+        batch = E.DeviceBatch(gpu_ctx, pb)
+        r = E.dist_greedy(gpu_ctx, batch, w, epsilon=0.1)
+        for g in range(0, pb.n_graphs, 7):
+            v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+            sub = pb.slice(g, g + 1)
+            member, rounds, _ = L.dist_greedy(sub.row_ptr, sub.col_idx, w[v0:v1], 0.1)
+            assert np.array_equal(r.member[v0:v1], member) and int(r.steps[g]) == rounds
+        batch.close()
+
+
 def test_lgs_global_path_large_graph(gpu_ctx):
     """Graphs above the one-CTA limit take the per-round global-bitmap kernels."""
     E = _engine()

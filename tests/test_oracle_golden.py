@@ -139,3 +139,47 @@ def test_l1_model_closed_form():
         lap = G.laplacian_supports(adj, 1)[1]
         s = np.asarray(lap @ np.ones(v1 - v0))
         assert np.allclose(score, w0 + w1 * s, rtol=0, atol=2e-6)
+
+
+def _dgs_checks(pb, g, w, member, alpha):
+    """Defining properties of a dist_greedy_search result (heuristics.py:38-74), whatever the scan order: the set is
+    independent and maximal."""
+    a = pb.graph_adj(g)
+    m = member.astype(bool)
+    assert a[m][:, m].nnz == 0, "graph %d: adjacent members" % g
+    covered = m | (np.asarray(a[:, m].sum(axis=1)).reshape(-1) > 0)
+    assert covered.all(), "graph %d: not maximal" % g
+
+
+@pytest.mark.parametrize("eps,tag", [(0.1, "0p1"), (0.5, "0p5")])
+def test_dist_greedy_oracle_matches_reference(eps, tag):
+    """The reference scans every round's candidates in Python-set order, the restatement in ascending vertex id: on
+    the instances where no round has adjacent candidates (order-free) the memberships must be those of the reference's
+    own dist_greedy_search; on the others both must be maximal independent sets."""
+    ref = util.load_npz("dgs_ref.npz")
+    pb, w = util.packed_from_npz(ref), ref["weights"]
+    want = ref["member_eps" + tag]
+    n_free = 0
+    for g, v0, v1, sub in _per_graph(pb, None):
+        member, rounds, order_free = L.dist_greedy(sub.row_ptr, sub.col_idx, w[v0:v1], eps)
+        _dgs_checks(pb, g, w[v0:v1], member, 1.0 + eps / 3.0)
+        _dgs_checks(pb, g, w[v0:v1], want[v0:v1], 1.0 + eps / 3.0)
+        if order_free:
+            n_free += 1
+            assert np.array_equal(member, want[v0:v1]), "graph %d (%s)" % (g, ref["names"][g])
+            assert abs(float(w[v0:v1][member.astype(bool)].sum()) - float(ref["total_eps" + tag][g])) < 1e-9
+    assert n_free >= 20, "too few order-free instances pin the restatement: %d" % n_free
+
+
+def test_dist_greedy_oracle_spread_weights_equal_local_greedy():
+    """Weights further apart than alpha on every edge: every round's candidates are exactly the vertices that dominate
+    their remaining neighbourhood, i.e. the rounds of local_greedy_search (heuristics.py:77-116)."""
+    pb, _ = util.small_graphs()
+    rng = np.random.default_rng(3)
+    for g in (0, 13, 27, 41):
+        sub = pb.slice(g, g + 1)
+        n = sub.n_nodes
+        w = 1.2 ** (2.0 * rng.permutation(n))
+        member, rounds, order_free = L.dist_greedy(sub.row_ptr, sub.col_idx, w, 0.5)
+        r = L.run(sub.row_ptr, sub.col_idx, w)
+        assert order_free and np.array_equal(member, r.member) and rounds == r.steps

@@ -43,6 +43,11 @@ namespace dg {
 
 namespace {
 
+#ifdef DG_TC_HOLD
+#define DG_TC_HOLD_ON true
+#else
+#define DG_TC_HOLD_ON false
+#endif
 constexpr int kTcVertexThreads = 512;
 constexpr int kTcThreads = 512;       // 16 warps: 128 registers per thread
 constexpr int kTcMaxG = 4;            // graphs per tile (every graph owns >= 1 block)
@@ -60,17 +65,22 @@ constexpr int kTcOffBar = kTcOffGmax + 64;         // 22 mbarriers, see the kern
 constexpr int kTcOffMeta = kTcOffBar + 256;        // TcMeta[4] + tile scalars
 // Pool, per graph of the tile (R = rows padded to 8, Kp = columns padded to 32):
 //   adjacency  u8  [Kp/16 chunks][R rows][16 B]        K-major A operand of the aggregation  (R Kp bytes)
-//   H terms    bf16 [3 terms][4 chunks][R rows][16 B]   K-major A operand of the projection   (192 R bytes)
+//   H terms    bf16 [3 terms][4 chunks][hs rows][16 B]  K-major A operand of the projection   (192 hs bytes; hs = Kp for a
+//              graph of several blocks, R for a one-block graph)
 //   Y digits   u8  [8 runs][Kp/8 groups][8 k][16 B]     MN-major B operand of the aggregation (128 Kp bytes), in the SAME
-//              bytes as the H terms: Y is written only after every projection of the graph that reads H has completed, H
-//              only after every aggregation that reads Y has
+//              bytes as the H terms.  Both are "plane x vertex x 16 B", and with hs = Kp plane p of H (hi and mid terms) and run
+//              p of Y hold a vertex at the same address: a block's Y digits overwrite only the H rows its OWN projection read
+//              (complete before the digits exist), so blocks need not wait for each other there.  The other way round a
+//              block's new H rows overwrite Y rows that EVERY block's aggregation reads: the hi / mid terms are held in
+//              registers until the graph's last aggregation has completed (agg_drained), the lo terms (planes 8..11, beyond
+//              Y) are stored at once
 // A 128-row block of a graph whose last block is partial reads past row R: those reads stay inside the pool (the next
 // region) and only feed accumulator rows nobody looks at.
 constexpr int kTcOffPool = 32768;
 static_assert(kTcOffMeta + 256 <= kTcOffPool, "shared-memory map overflows into the pool");
 
 struct TcMeta {  // one graph of the tile; adj / hoff / yoff: byte offsets of its three regions in the pool
-    int v0, nv, fb, nb, R, Kp, adj, hoff, yoff, e0, nnz, g;
+    int v0, nv, fb, nb, R, Kp, adj, hoff, yoff, e0, nnz, g, hs;
 };
 struct TcTileInfo {
     int ng, nblocks, pool_used, blkg[4];
@@ -303,22 +313,48 @@ __device__ __forceinline__ float tc_combine(const uint32_t *d) {
     return fmaf((float)hi, 65536.f, (float)lo);
 }
 
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2 of sm_100): the same IEEE result per element as the scalar instruction, half
+// the issue slots - the epilogues are bound by instruction issue (profiles/r01_notes.md).
+__device__ __forceinline__ uint64_t pk(float lo, float hi) {
+    return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float pk_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float pk_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // 8 feature values -> three bf16 term vectors (hi, mid, lo), each 8 x bf16 = 16 B
 __device__ __forceinline__ void tc_split8(const float *h, uint4 *hi, uint4 *mid, uint4 *lo) {
     uint32_t t0[4], t1[4], t2[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        float a = h[2 * p], b = h[2 * p + 1];
+        uint64_t ab = pk(h[2 * p], h[2 * p + 1]);
         uint32_t w;
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(pk_hi(ab)), "f"(pk_lo(ab)));
         t0[p] = w;
-        a -= __uint_as_float(w << 16);
-        b -= __uint_as_float(w & 0xffff0000u);
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+        ab = sub2(ab, (uint64_t)(w << 16) | ((uint64_t)(w & 0xffff0000u) << 32));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(pk_hi(ab)), "f"(pk_lo(ab)));
         t1[p] = w;
-        a -= __uint_as_float(w << 16);
-        b -= __uint_as_float(w & 0xffff0000u);
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+        ab = sub2(ab, (uint64_t)(w << 16) | ((uint64_t)(w & 0xffff0000u) << 32));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(pk_hi(ab)), "f"(pk_lo(ab)));
         t2[p] = w;
     }
     *hi = make_uint4(t0[0], t0[1], t0[2], t0[3]);
@@ -377,6 +413,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     const bool timing = P.dbg != nullptr && tid == 0;
     long long tm[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = timing ? clock64() : 0;
+    unsigned long long ns_begin = 0;
+    if (timing) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin));
 
     for (;;) {
         if (tid == 0) tile_sm = atomicAdd(P.tile_counter, 1);
@@ -401,14 +439,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 m.fb = fb;
                 m.R = (m.nv + 7) & ~7;
                 m.Kp = (m.nv + 31) & ~31;
+                m.hs = m.nb >= 2 ? m.Kp : m.R;  // row stride of the H-term planes (see the pool layout above)
                 m.adj = off;
                 m.hoff = off + m.R * m.Kp;
 #ifdef DG_TC_NO_ALIAS
-                m.yoff = m.hoff + 192 * m.R;
+                m.yoff = m.hoff + 192 * m.hs;
                 off = m.yoff + 128 * m.Kp;
 #else
                 m.yoff = m.hoff;  // Y digits and H terms are never live together (see the hazard waits below)
-                off = m.hoff + max(192 * m.R, 128 * m.Kp);
+                off = m.hoff + max(192 * m.hs, 128 * m.Kp);
 #endif
                 m.e0 = gd[3];
                 m.nnz = gd[4];
@@ -483,7 +522,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             // the scatter below then needs one shared-memory load per edge instead of a binary search in row_ptr.
             if (valid) {
                 uint16_t *rowof = reinterpret_cast<uint16_t *>(pool + G.hoff);
-                if (2 * G.nnz <= max(192 * G.R, 128 * G.Kp)) {
+                if (2 * G.nnz <= max(192 * G.hs, 128 * G.Kp)) {
                     const int beg = P.row_ptr[v] - G.e0, end = P.row_ptr[v + 1] - G.e0;
                     for (int e = beg; e < end; ++e) rowof[e] = (uint16_t)r;
                 }
@@ -496,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 const TcMeta m = meta[k];
                 unsigned char *adj = pool + m.adj;
                 const uint16_t *rowof = reinterpret_cast<const uint16_t *>(pool + m.hoff);
-                const bool table = 2 * m.nnz <= max(192 * m.R, 128 * m.Kp);
+                const bool table = 2 * m.nnz <= max(192 * m.hs, 128 * m.Kp);
                 for (int e = tid; e < m.nnz; e += kTcVertexThreads) {
                     int lo;
                     if (table) {
@@ -534,7 +573,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             unsigned char *adj = pool + G.adj;
             unsigned char *hrow = pool + G.hoff + r * 16;  // this vertex's 16-byte slots in the H-term chunks
             unsigned char *yrow = pool + G.yoff + (r >> 3) * 128 + (r & 7) * 16;  // ... and in the Y digit runs
-            const int hterm = 4 * G.R * 16, hchunk = G.R * 16;
+            const int hterm = 4 * G.hs * 16, hchunk = G.hs * 16;
             uint32_t ea = 0, ep = 0, em = 0;  // aggregation / projection / max events consumed -> barrier parities
 
             // ---- hand-off to the tensor cores: the warp that completes an operand issues the MMAs that consume it ----
@@ -606,7 +645,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 __syncwarp();
                 tc_fence_after();
                 // warp-uniform operands, one elected lane issues (see hand_off_agg)
-                const uint32_t u_r = uniform((uint32_t)G.R);
+                const uint32_t u_r = uniform((uint32_t)G.hs);
                 const uint32_t u_h = uniform(pool_addr + (uint32_t)G.hoff + (uint32_t)jb * 2048u);
                 const uint32_t u_w = uniform(s32(wring) + (seq & 1u) * kTcWBlob);
                 const uint32_t d = uniform(tmem + (uint32_t)b * 128u);
@@ -655,15 +694,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             float hmax = 0.f, t0 = 0.f, t1 = 0.f;
             // consumes 8 new feature values of this vertex: operand terms for the next projection, or the last
             // layer's two dot products when no hidden layer follows
-            auto emit = [&](int q, const float *hv, bool to_terms) {
+            uint4 held_hi[4], held_mid[4];  // epilogue C: terms parked until the operand region may take them
+            auto emit = [&](int q, const float *hv, bool to_terms, bool hold) {
                 if (to_terms) {
                     uint4 hi, mid, lo;
                     tc_split8(hv, &hi, &mid, &lo);
                     if (valid) {  // rows past the graph's last vertex stay whatever they are: their outputs are ignored
-                        *reinterpret_cast<uint4 *>(hrow + 0 * hterm + q * hchunk) = hi;
-                        *reinterpret_cast<uint4 *>(hrow + 1 * hterm + q * hchunk) = mid;
+                        if (!hold) {
+                            *reinterpret_cast<uint4 *>(hrow + 0 * hterm + q * hchunk) = hi;
+                            *reinterpret_cast<uint4 *>(hrow + 1 * hterm + q * hchunk) = mid;
+                        }
                         *reinterpret_cast<uint4 *>(hrow + 2 * hterm + q * hchunk) = lo;
                     }
+                    if (hold) held_hi[q] = hi, held_mid[q] = mid;
                 } else {
                     const float4 wa = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q);
                     const float4 wb = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q + 1);
@@ -697,10 +740,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             auto agg_drained = [&]() {
                 if (b != lastb) mbar_wait(&bar_da[lastb], (ea - 1u) & 1u, 4);
             };
-            auto proj_drained = [&]() {
-                for (int k = G.fb; k <= lastb; ++k)
-                    if (k != b) mbar_wait(&bar_dp[k], (ep - 1u) & 1u, 5);
-            };
 
             // -- first layer (rank 1): s = (L x0)_i, H1 = act(x0 colsum(W_0) + s colsum(W_1) + b) -----------------
             mbar_wait(&bar_da[b], ea & 1u, 6);
@@ -725,7 +764,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                         hv[4 * half + 2] = tc_act(fmaf(s_i, a1.z, fmaf(xi, a0.z, b0.z)), sl0, sl0 <= 1.f);
                         hv[4 * half + 3] = tc_act(fmaf(s_i, a1.w, fmaf(xi, a0.w, b0.w)), sl0, sl0 <= 1.f);
                     }
-                    emit(q, hv, n_hidden > 0);
+                    emit(q, hv, n_hidden > 0, false);
                 }
             }
 
@@ -758,24 +797,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 float qs, iqs;
                 tc_scale(graph_max(h & 1) * bias[64], &qs, &iqs);
                 const float dq = di * qs, ndq = -di * iqs;
-                proj_drained();
                 float c[32];
                 uint32_t pa[16], pb[16];
                 // TMEM loads run one 16-column piece ahead of the arithmetic: P1 (columns 32..63, scaled by r), then P0
+                const uint64_t dq2 = pk(dq, dq);
                 auto half_b = [&](const uint32_t *pp, int f0) {
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4) {
                         const int f = f0 + 4 * g4;
                         const float4 ri = *reinterpret_cast<const float4 *>(rinv + f);
                         const float4 bi = *reinterpret_cast<const float4 *>(bias + f);
-                        const float p0 = __uint_as_float(pp[4 * g4]), p1 = __uint_as_float(pp[4 * g4 + 1]);
-                        const float p2 = __uint_as_float(pp[4 * g4 + 2]), p3 = __uint_as_float(pp[4 * g4 + 3]);
-                        c[f + 0] = fmaf(p0, ri.x, bi.x);
-                        c[f + 1] = fmaf(p1, ri.y, bi.y);
-                        c[f + 2] = fmaf(p2, ri.z, bi.z);
-                        c[f + 3] = fmaf(p3, ri.w, bi.w);
+                        const uint64_t p01 = (uint64_t)pp[4 * g4] | ((uint64_t)pp[4 * g4 + 1] << 32);
+                        const uint64_t p23 = (uint64_t)pp[4 * g4 + 2] | ((uint64_t)pp[4 * g4 + 3] << 32);
+                        const uint64_t c01 = fma2(p01, pk(ri.x, ri.y), pk(bi.x, bi.y));
+                        const uint64_t c23 = fma2(p23, pk(ri.z, ri.w), pk(bi.z, bi.w));
+                        c[f + 0] = pk_lo(c01), c[f + 1] = pk_hi(c01), c[f + 2] = pk_lo(c23), c[f + 3] = pk_hi(c23);
                         // run f / 4 of the MN-major operand = features f .. f + 3, digit a of feature f at column 4 f + a
-                        const uint4 dg4 = make_uint4(tc_digits(p0, dq), tc_digits(p1, dq), tc_digits(p2, dq), tc_digits(p3, dq));
+                        const uint64_t y01 = fma2(p01, dq2, pk(8421504.f, 8421504.f));  // tc_digits, two at a time
+                        const uint64_t y23 = fma2(p23, dq2, pk(8421504.f, 8421504.f));
+                        const uint4 dg4 = make_uint4((uint32_t)__float2int_rn(pk_lo(y01)) ^ 0x00808080u,
+                                                     (uint32_t)__float2int_rn(pk_hi(y01)) ^ 0x00808080u,
+                                                     (uint32_t)__float2int_rn(pk_lo(y23)) ^ 0x00808080u,
+                                                     (uint32_t)__float2int_rn(pk_hi(y23)) ^ 0x00808080u);
                         if (valid) *reinterpret_cast<uint4 *>(yrow + (size_t)(f >> 2) * G.Kp * 16) = dg4;
                     }
                 };
@@ -789,10 +832,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 tmem_ld16_wait(pa);
                 tmem_ld16_issue(taddr + 16, pb);
 #pragma unroll
-                for (int f = 0; f < 16; ++f) c[f] += __uint_as_float(pa[f]);
+                for (int f = 0; f < 16; f += 2) {
+                    const uint64_t t2 = add2(pk(c[f], c[f + 1]), (uint64_t)pa[f] | ((uint64_t)pa[f + 1] << 32));
+                    c[f] = pk_lo(t2), c[f + 1] = pk_hi(t2);
+                }
                 tmem_ld16_wait(pb);
 #pragma unroll
-                for (int f = 0; f < 16; ++f) c[16 + f] += __uint_as_float(pb[f]);
+                for (int f = 0; f < 16; f += 2) {
+                    const uint64_t t2 = add2(pk(c[16 + f], c[17 + f]), (uint64_t)pb[f] | ((uint64_t)pb[f + 1] << 32));
+                    c[16 + f] = pk_lo(t2), c[17 + f] = pk_hi(t2);
+                }
                 fence_async_smem();
                 tc_fence_before();
                 hand_off_agg(false);
@@ -813,13 +862,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     tq = now;
                 }
                 if (r == 0) gmax[gi * 2 + (h & 1)] = 0u;  // every block of the graph has read it: all of Y was needed
+#ifndef DG_TC_HOLD
                 agg_drained();
+#endif
+                const uint64_t ndq2 = pk(ndq, ndq), slope2 = pk(slope, slope);
                 auto half_c = [&](const uint32_t *pp, int f0, float *hv) {
                     const float4 ra = *reinterpret_cast<const float4 *>(rinv + f0);
-                    const float rv[4] = {ra.x, ra.y, ra.z, ra.w};
+                    const uint64_t rv2[2] = {pk(ra.x, ra.y), pk(ra.z, ra.w)};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        hv[k] = tc_act(fmaf(tc_combine(pp + 4 * k), ndq * rv[k], c[f0 + k]), slope, act_max);
+                    for (int k = 0; k < 4; k += 2) {  // two features per packed instruction; per element as tc_combine / tc_act
+                        const uint32_t *d = pp + 4 * k;
+                        const int lo0 = (int)d[1] * 256 + (int)d[0], hi0 = (int)d[3] * 256 + (int)d[2];
+                        const int lo1 = (int)d[5] * 256 + (int)d[4], hi1 = (int)d[7] * 256 + (int)d[6];
+                        const uint64_t comb = fma2(pk((float)hi0, (float)hi1), pk(65536.f, 65536.f), pk((float)lo0, (float)lo1));
+                        const uint64_t v2 = fma2(comb, mul2(ndq2, rv2[k >> 1]), pk(c[f0 + k], c[f0 + k + 1]));
+                        const uint64_t t2 = mul2(v2, slope2);
+                        hv[k] = act_max ? fmaxf(pk_lo(v2), pk_lo(t2)) : fminf(pk_lo(v2), pk_lo(t2));
+                        hv[k + 1] = act_max ? fmaxf(pk_hi(v2), pk_hi(t2)) : fminf(pk_hi(v2), pk_hi(t2));
+                    }
                 };
                 tmem_ld16_issue(taddr, pa);
 #pragma unroll
@@ -831,7 +891,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     tmem_ld16_wait(pb);
                     if (q < 3) tmem_ld16_issue(taddr + 32 * (q + 1), pa);
                     half_c(pb, 8 * q + 4, hv + 4);
-                    emit(q, hv, more);
+#ifdef DG_TC_HOLD
+                    emit(q, hv, more, true);
+#else
+                    emit(q, hv, more, false);
+#endif
+                }
+                // the sibling blocks' aggregations ran while this block did its arithmetic; now the hi / mid terms land
+#ifdef DG_TC_HOLD
+                agg_drained();
+#endif
+                if (DG_TC_HOLD_ON && more && valid) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        *reinterpret_cast<uint4 *>(hrow + 0 * hterm + q * hchunk) = held_hi[q];
+                        *reinterpret_cast<uint4 *>(hrow + 1 * hterm + q * hchunk) = held_mid[q];
+                    }
                 }
                 if (timing) tm[6] += clock64() - tq;
             }
@@ -984,6 +1059,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     }
     if (timing) {
         tm[7] = clock64() - t_begin;
+        unsigned long long ns_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+        tm[1] = (long long)(ns_end - ns_begin);  // wall time of the same interval: tm[7] / tm[1] = SM clock in GHz
         for (int k = 0; k < 12; ++k) P.dbg[(size_t)blockIdx.x * 12 + k] = tm[k];
     }
     tc_fence_before();
@@ -1095,7 +1173,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
 #ifdef DG_TC_NO_ALIAS
         t.bytes = R * Kp + 192 * R + 128 * Kp;
 #else
-        t.bytes = R * Kp + std::max<size_t>(192 * R, 128 * Kp);
+        t.bytes = R * Kp + std::max<size_t>(192 * (t.nb >= 2 ? Kp : R), 128 * Kp);
 #endif
         // per layer: projection ~650 cycles per block, aggregation ~65 per block and 32 columns, epilogue ~900 per block
         t.cost = (long long)t.nb * (1600 + 2 * (long long)Kp);
@@ -1267,8 +1345,8 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         std::vector<long long> h((size_t)ctx->sm_count * 12 + (size_t)p.n_tiles * 2);
         DG_CUDA_CHECK(cudaMemcpyAsync(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
         DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        const char *names[12] = {"stage", "-", "tiles", "w_proj", "phaseB", "w_agg", "phaseC", "total", "first", "tail", "greedy", "endwait"};
-        for (int k : {0, 8, 3, 4, 5, 6, 9, 10, 11, 2, 7}) {
+        const char *names[12] = {"stage", "wall_ns", "tiles", "w_proj", "phaseB", "w_agg", "phaseC", "total", "first", "tail", "greedy", "endwait"};
+        for (int k : {0, 8, 3, 4, 5, 6, 9, 10, 11, 2, 7, 1}) {
             long long mn = -1, mx = 0;
             double sum = 0;
             int cnt = 0;

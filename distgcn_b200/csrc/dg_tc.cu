@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <map>
+#include <type_traits>
 #include <vector>
 
 #include "dg_common.cuh"
@@ -43,11 +44,6 @@ namespace dg {
 
 namespace {
 
-#ifdef DG_TC_HOLD
-#define DG_TC_HOLD_ON true
-#else
-#define DG_TC_HOLD_ON false
-#endif
 constexpr int kTcVertexThreads = 512;
 constexpr int kTcThreads = 512;       // 16 warps: 128 registers per thread
 constexpr int kTcMaxG = 4;            // graphs per tile (every graph owns >= 1 block)
@@ -65,22 +61,23 @@ constexpr int kTcOffBar = kTcOffGmax + 64;         // 22 mbarriers, see the kern
 constexpr int kTcOffMeta = kTcOffBar + 256;        // TcMeta[4] + tile scalars
 // Pool, per graph of the tile (R = rows padded to 8, Kp = columns padded to 32):
 //   adjacency  u8  [Kp/16 chunks][R rows][16 B]        K-major A operand of the aggregation  (R Kp bytes)
-//   H terms    bf16 [3 terms][4 chunks][hs rows][16 B]  K-major A operand of the projection   (192 hs bytes; hs = Kp for a
-//              graph of several blocks, R for a one-block graph)
-//   Y digits   u8  [8 runs][Kp/8 groups][8 k][16 B]     MN-major B operand of the aggregation (128 Kp bytes), in the SAME
-//              bytes as the H terms.  Both are "plane x vertex x 16 B", and with hs = Kp plane p of H (hi and mid terms) and run
-//              p of Y hold a vertex at the same address: a block's Y digits overwrite only the H rows its OWN projection read
-//              (complete before the digits exist), so blocks need not wait for each other there.  The other way round a
-//              block's new H rows overwrite Y rows that EVERY block's aggregation reads: the hi / mid terms are held in
-//              registers until the graph's last aggregation has completed (agg_drained), the lo terms (planes 8..11, beyond
-//              Y) are stored at once
-// A 128-row block of a graph whose last block is partial reads past row R: those reads stay inside the pool (the next
-// region) and only feed accumulator rows nobody looks at.
+//   Y digits   u8  [8 runs][Kp/8 groups][8 k][16 B]     MN-major B operand of the aggregation (128 Kp bytes)
+// A 128-row block of a graph whose last block is partial reads adjacency rows past R: those reads stay inside the pool (the
+// next chunk / the Y region) and only feed accumulator rows nobody looks at.
+// The projection's A operand (the bf16 terms of H) lives in TENSOR memory, see the column map in the kernel.
 constexpr int kTcOffPool = 32768;
+// Tensor-memory columns of a block (128 of the 512; base = block * 128):
+//   0..63    [P0 | P1]  fp32 accumulators of the projection                  (written by the projection, read by epilogue B)
+//   0..127   S          s32 accumulators of the aggregation, column 4 f + a  (written after epilogue B, read by epilogue C)
+//   64..111  H terms    bf16 A operand of the NEXT projection: term t of K step s (features 16 s .. 16 s + 15) in the 8
+//            columns kTcHCol(t, s).  Epilogue C reads S in the feature order 16..31, 0..15 and writes the terms of the
+//            features it has finished into S columns it has already consumed: features 16..31 (columns 64..127 of S) free
+//            64..127, of which 64..87 take K step 1; K step 0 goes to 88..111 once features 24..31 are done.
+__host__ __device__ constexpr uint32_t kTcHCol(int term, int kstep) { return (kstep ? 64u : 88u) + 8u * (uint32_t)term; }
 static_assert(kTcOffMeta + 256 <= kTcOffPool, "shared-memory map overflows into the pool");
 
 struct TcMeta {  // one graph of the tile; adj / hoff / yoff: byte offsets of its three regions in the pool
-    int v0, nv, fb, nb, R, Kp, adj, hoff, yoff, e0, nnz, g, hs;
+    int v0, nv, fb, nb, R, Kp, adj, hoff, yoff, e0, nnz, g;
 };
 struct TcTileInfo {
     int ng, nblocks, pool_used, blkg[4];
@@ -227,6 +224,19 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b
                  "l"(a), "l"(b), "r"(idesc), "r"(acc)
                  : "memory");
 }
+// A operand in tensor memory (lane = row, 8 columns per 16-element K step, element 2j / 2j+1 in the low / high half of
+// column j: profiles/micro/umma_ts_probe.cu), B from shared memory
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(
+                     d_tmem),
+                 "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4 &v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_u8(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}" ::"r"(
                      d_tmem),
@@ -439,16 +449,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 m.fb = fb;
                 m.R = (m.nv + 7) & ~7;
                 m.Kp = (m.nv + 31) & ~31;
-                m.hs = m.nb >= 2 ? m.Kp : m.R;  // row stride of the H-term planes (see the pool layout above)
                 m.adj = off;
                 m.hoff = off + m.R * m.Kp;
-#ifdef DG_TC_NO_ALIAS
-                m.yoff = m.hoff + 192 * m.hs;
+                m.yoff = m.hoff;
                 off = m.yoff + 128 * m.Kp;
-#else
-                m.yoff = m.hoff;  // Y digits and H terms are never live together (see the hazard waits below)
-                off = m.hoff + max(192 * m.hs, 128 * m.Kp);
-#endif
                 m.e0 = gd[3];
                 m.nnz = gd[4];
                 meta[gi] = m;
@@ -518,11 +522,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 const int n16 = (m.R * m.Kp) >> 4;
                 for (int i = tid; i < n16; i += kTcVertexThreads) a16[i] = make_uint4(0u, 0u, 0u, 0u);
             }
-            // Edge -> row table of this thread's vertex, parked in the graph's H / Y regions (free until the first layer):
+            // Edge -> row table of this thread's vertex, parked in the graph's Y region (free until the first layer):
             // the scatter below then needs one shared-memory load per edge instead of a binary search in row_ptr.
             if (valid) {
                 uint16_t *rowof = reinterpret_cast<uint16_t *>(pool + G.hoff);
-                if (2 * G.nnz <= max(192 * G.hs, 128 * G.Kp)) {
+                if (2 * G.nnz <= 128 * G.Kp) {
                     const int beg = P.row_ptr[v] - G.e0, end = P.row_ptr[v + 1] - G.e0;
                     for (int e = beg; e < end; ++e) rowof[e] = (uint16_t)r;
                 }
@@ -535,7 +539,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 const TcMeta m = meta[k];
                 unsigned char *adj = pool + m.adj;
                 const uint16_t *rowof = reinterpret_cast<const uint16_t *>(pool + m.hoff);
-                const bool table = 2 * m.nnz <= max(192 * m.hs, 128 * m.Kp);
+                const bool table = 2 * m.nnz <= 128 * m.Kp;
                 for (int e = tid; e < m.nnz; e += kTcVertexThreads) {
                     int lo;
                     if (table) {
@@ -571,9 +575,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             const int dom_bar = 1 + G.fb, dom_cnt = 128 * G.nb;
             const uint32_t taddr = tmem + (uint32_t)b * 128u + ((uint32_t)((warp & 3) * 32) << 16);
             unsigned char *adj = pool + G.adj;
-            unsigned char *hrow = pool + G.hoff + r * 16;  // this vertex's 16-byte slots in the H-term chunks
             unsigned char *yrow = pool + G.yoff + (r >> 3) * 128 + (r & 7) * 16;  // ... and in the Y digit runs
-            const int hterm = 4 * G.hs * 16, hchunk = G.hs * 16;
             uint32_t ea = 0, ep = 0, em = 0;  // aggregation / projection / max events consumed -> barrier parities
 
             // ---- hand-off to the tensor cores: the warp that completes an operand issues the MMAs that consume it ----
@@ -645,26 +647,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 __syncwarp();
                 tc_fence_after();
                 // warp-uniform operands, one elected lane issues (see hand_off_agg)
-                const uint32_t u_r = uniform((uint32_t)G.hs);
-                const uint32_t u_h = uniform(pool_addr + (uint32_t)G.hoff + (uint32_t)jb * 2048u);
                 const uint32_t u_w = uniform(s32(wring) + (seq & 1u) * kTcWBlob);
                 const uint32_t d = uniform(tmem + (uint32_t)b * 128u);
                 const uint32_t u_bar = uniform(s32(&bar_dp[b]));
-                const uint32_t lbo_a = u_r * 16u;  // H terms: [term][chunk][R rows][16 B]
-                const uint64_t a0 = umma_desc(u_h, lbo_a, 128u);
                 const uint64_t b0 = umma_desc(u_w, 1024u, 128u);
-                const uint32_t a_chunk = lbo_a >> 4;  // one 16-byte K chunk of all rows, in descriptor units
                 const uint32_t idesc = idesc_bf16(128, 64);
-                // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi); A term t starts 4 t chunks
-                // in, W term t starts 4096 t bytes in; the second K-step is 2 chunks further
-                const uint64_t at[3] = {a0, a0 + 4u * a_chunk, a0 + 8u * a_chunk};
+                // smallest products first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi); the H terms are this block's
+                // tensor-memory columns kTcHCol(term, K step), W term t starts 4096 t bytes in, its second K step 2 chunks on
                 const uint64_t bt[3] = {b0, b0 + 256u, b0 + 512u};
                 const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
                 if (elect_one()) {
 #pragma unroll
                     for (int pp = 0; pp < 6; ++pp) {
-                        mma_bf16(d, at[ta[pp]], bt[tb[pp]], idesc, pp != 0);
-                        mma_bf16(d, at[ta[pp]] + 2u * a_chunk, bt[tb[pp]] + 128u, idesc, 1u);
+                        mma_bf16_ts(d, d + kTcHCol(ta[pp], 0), bt[tb[pp]], idesc, pp != 0);
+                        mma_bf16_ts(d, d + kTcHCol(ta[pp], 1), bt[tb[pp]] + 128u, idesc, 1u);
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_bar) : "memory");
                 }
@@ -694,19 +690,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             float hmax = 0.f, t0 = 0.f, t1 = 0.f;
             // consumes 8 new feature values of this vertex: operand terms for the next projection, or the last
             // layer's two dot products when no hidden layer follows
-            uint4 held_hi[4], held_mid[4];  // epilogue C: terms parked until the operand region may take them
-            auto emit = [&](int q, const float *hv, bool to_terms, bool hold) {
+            auto emit = [&](int q, const float *hv, bool to_terms) {
                 if (to_terms) {
+                    // (rows past the graph's last vertex write whatever they hold: their outputs are ignored)
                     uint4 hi, mid, lo;
                     tc_split8(hv, &hi, &mid, &lo);
-                    if (valid) {  // rows past the graph's last vertex stay whatever they are: their outputs are ignored
-                        if (!hold) {
-                            *reinterpret_cast<uint4 *>(hrow + 0 * hterm + q * hchunk) = hi;
-                            *reinterpret_cast<uint4 *>(hrow + 1 * hterm + q * hchunk) = mid;
-                        }
-                        *reinterpret_cast<uint4 *>(hrow + 2 * hterm + q * hchunk) = lo;
-                    }
-                    if (hold) held_hi[q] = hi, held_mid[q] = mid;
+                    const uint32_t col = taddr + 4u * (uint32_t)(q & 1);
+                    tmem_st4(col + kTcHCol(0, q >> 1), hi);
+                    tmem_st4(col + kTcHCol(1, q >> 1), mid);
+                    tmem_st4(col + kTcHCol(2, q >> 1), lo);
                 } else {
                     const float4 wa = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q);
                     const float4 wb = __ldg(reinterpret_cast<const float4 *>(P.tail) + 2 * q + 1);
@@ -734,9 +726,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 ++em;
                 return __uint_as_float(gmax[gi * 2 + slot]);
             };
-            // The operand region changes hands: it takes new H terms once EVERY block's MMAs of the graph's last
-            // aggregation have completed (commits complete in issue order, so the graph's last block tells), and new Y
-            // digits once every block's last projection has.
+            // Every block's MMAs of the graph's last aggregation have completed (commits complete in issue order, so the
+            // graph's last block tells): the Y region may take the last layer's scalar operand.  (Between hidden layers no
+            // such wait is needed: a block writes new Y digits only after its own next projection has completed, and the
+            // tensor pipe runs the MMAs in issue order, so every aggregation issued before that projection is done.)
             auto agg_drained = [&]() {
                 if (b != lastb) mbar_wait(&bar_da[lastb], (ea - 1u) & 1u, 4);
             };
@@ -750,7 +743,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 tmem_ld4(taddr, d4);
                 const float s_i = xi - di * (tc_combine(d4) * iq0);
                 const float sl0 = tc_slope(P.first_act, P.alpha);
-                agg_drained();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float hv[8];
@@ -764,7 +756,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                         hv[4 * half + 2] = tc_act(fmaf(s_i, a1.z, fmaf(xi, a0.z, b0.z)), sl0, sl0 <= 1.f);
                         hv[4 * half + 3] = tc_act(fmaf(s_i, a1.w, fmaf(xi, a0.w, b0.w)), sl0, sl0 <= 1.f);
                     }
-                    emit(q, hv, n_hidden > 0, false);
+                    emit(q, hv, n_hidden > 0);
                 }
             }
 
@@ -775,8 +767,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
             }
             // -- hidden layers -----------------------------------------------------------------------------------------
             for (int h = 0; h < n_hidden; ++h) {
-                // this block's H terms are in place: its projection may start
-                fence_async_smem();
+                // this block's H terms are in place (tensor memory): its projection may start
+                tmem_st_wait();
                 tc_fence_before();
                 if (last_warp(&cnt_p[b], 4u)) issue_proj(h);
                 publish_max(h & 1);
@@ -862,9 +854,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                     tq = now;
                 }
                 if (r == 0) gmax[gi * 2 + (h & 1)] = 0u;  // every block of the graph has read it: all of Y was needed
-#ifndef DG_TC_HOLD
-                agg_drained();
-#endif
                 const uint64_t ndq2 = pk(ndq, ndq), slope2 = pk(slope, slope);
                 auto half_c = [&](const uint32_t *pp, int f0, float *hv) {
                     const float4 ra = *reinterpret_cast<const float4 *>(rinv + f0);
@@ -881,33 +870,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                         hv[k + 1] = act_max ? fmaxf(pk_hi(v2), pk_hi(t2)) : fminf(pk_hi(v2), pk_hi(t2));
                     }
                 };
-                tmem_ld16_issue(taddr, pa);
+                // feature groups in the order 2, 3, 0, 1 when H terms follow (see the column map); 0..3 for the last hidden
+                // layer, whose dot products keep their summation order
+                auto run_c = [&](auto qx_c) {
+                    constexpr int qx = decltype(qx_c)::value;  // compile-time: c[] must stay in registers
+                    tmem_ld16_issue(taddr + 32 * qx, pa);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float hv[8];
-                    tmem_ld16_wait(pa);
-                    tmem_ld16_issue(taddr + 32 * q + 16, pb);
-                    half_c(pa, 8 * q, hv);
-                    tmem_ld16_wait(pb);
-                    if (q < 3) tmem_ld16_issue(taddr + 32 * (q + 1), pa);
-                    half_c(pb, 8 * q + 4, hv + 4);
-#ifdef DG_TC_HOLD
-                    emit(q, hv, more, true);
-#else
-                    emit(q, hv, more, false);
-#endif
-                }
-                // the sibling blocks' aggregations ran while this block did its arithmetic; now the hi / mid terms land
-#ifdef DG_TC_HOLD
-                agg_drained();
-#endif
-                if (DG_TC_HOLD_ON && more && valid) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        *reinterpret_cast<uint4 *>(hrow + 0 * hterm + q * hchunk) = held_hi[q];
-                        *reinterpret_cast<uint4 *>(hrow + 1 * hterm + q * hchunk) = held_mid[q];
+                    for (int qi = 0; qi < 4; ++qi) {
+                        const int q = qi ^ qx;
+                        float hv[8];
+                        tmem_ld16_wait(pa);
+                        tmem_ld16_issue(taddr + 32 * q + 16, pb);
+                        half_c(pa, 8 * q, hv);
+                        tmem_ld16_wait(pb);
+                        if (qi < 3) tmem_ld16_issue(taddr + 32 * ((qi + 1) ^ qx), pa);
+                        half_c(pb, 8 * q + 4, hv + 4);
+                        emit(q, hv, qx != 0);
                     }
-                }
+                };
+                if (more) run_c(std::integral_constant<int, 2>{}); else run_c(std::integral_constant<int, 0>{});
                 if (timing) tm[6] += clock64() - tq;
             }
 
@@ -1096,7 +1077,7 @@ float bf16_to_f(uint16_t h) {
 
 struct TcGraph {
     int g, nv, nb;
-    size_t bytes;   // adjacency + max(H terms, Y digits)
+    size_t bytes;   // adjacency + Y digits
     long long cost;
 };
 
@@ -1170,11 +1151,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         t.nv = gp[g + 1] - gp[g];
         t.nb = std::max(1, (t.nv + 127) / 128);
         const size_t R = (size_t)((t.nv + 7) & ~7), Kp = (size_t)((t.nv + 31) & ~31);
-#ifdef DG_TC_NO_ALIAS
-        t.bytes = R * Kp + 192 * R + 128 * Kp;
-#else
-        t.bytes = R * Kp + std::max<size_t>(192 * (t.nb >= 2 ? Kp : R), 128 * Kp);
-#endif
+        t.bytes = R * Kp + 128 * Kp;
         // per layer: projection ~650 cycles per block, aggregation ~65 per block and 32 columns, epilogue ~900 per block
         t.cost = (long long)t.nb * (1600 + 2 * (long long)Kp);
         if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + kTcOverread > pool) return DG_OK;  // not eligible: the caller falls back

@@ -34,6 +34,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <type_traits>
 #include <vector>
@@ -540,22 +541,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
                 unsigned char *adj = pool + m.adj;
                 const uint16_t *rowof = reinterpret_cast<const uint16_t *>(pool + m.hoff);
                 const bool table = 2 * m.nnz <= 128 * m.Kp;
-                for (int e = tid; e < m.nnz; e += kTcVertexThreads) {
-                    int lo;
-                    if (table) {
-                        lo = rowof[e];
-                    } else {  // (a nearly complete graph: the table does not fit)
-                        lo = 0;
-                        int hi = m.nv;  // row_ptr[lo] <= e < row_ptr[hi]
-                        while (hi - lo > 1) {
-                            const int mid = (lo + hi) >> 1;
-                            if (P.row_ptr[m.v0 + mid] - m.e0 <= e) lo = mid; else hi = mid;
+                // four edges per thread and pass, their global loads issued back to back (the loop is latency bound)
+                for (int eb = tid; eb < m.nnz; eb += 4 * kTcVertexThreads) {
+                    int jj[4], ll[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = eb + u * kTcVertexThreads;
+                        jj[u] = e < m.nnz ? __ldg(P.col_idx + m.e0 + e) - m.v0 : -1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = eb + u * kTcVertexThreads;
+                        int lo = 0;
+                        if (e < m.nnz) {
+                            if (table) {
+                                lo = rowof[e];
+                            } else {  // (a nearly complete graph: the table does not fit)
+                                int hi = m.nv;  // row_ptr[lo] <= e < row_ptr[hi]
+                                while (hi - lo > 1) {
+                                    const int mid = (lo + hi) >> 1;
+                                    if (__ldg(P.row_ptr + m.v0 + mid) - m.e0 <= e) lo = mid; else hi = mid;
+                                }
+                            }
+                        }
+                        ll[u] = lo;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = jj[u], lo = ll[u];
+                        if (j >= 0) {
+                            const uint32_t ki = (keepw[m.fb * 4 + (lo >> 5)] >> (lo & 31)) & 1u;
+                            const uint32_t kj = (keepw[m.fb * 4 + (j >> 5)] >> (j & 31)) & 1u;
+                            if (ki & kj) adj[(size_t)(j >> 4) * m.R * 16 + lo * 16 + (j & 15)] = 1;
                         }
                     }
-                    const int j = P.col_idx[m.e0 + e] - m.v0;
-                    const uint32_t ki = (keepw[m.fb * 4 + (lo >> 5)] >> (lo & 31)) & 1u;
-                    const uint32_t kj = (keepw[m.fb * 4 + (j >> 5)] >> (j & 31)) & 1u;
-                    if (ki & kj) adj[(size_t)(j >> 4) * m.R * 16 + lo * 16 + (j & 15)] = 1;
                 }
             }
             fence_async_smem();
@@ -1134,6 +1153,76 @@ void tc_build_weights(int n_hidden, const float *const *w0, const float *const *
 namespace {
 
 // tiles: first-fit over a window of open tiles, graphs in order of decreasing cost
+struct Open {  // a tile being filled
+    int ng, blocks, g[kTcMaxG];
+    size_t bytes;
+    long long cost;
+};
+
+// Fitted cost model of a tile in cycles (profiles/r01_notes.md r01-j: 1610 tiles of the BA set in five packings, rms error
+// 2.2 %): 92.9 k per tile - the dependent hand-offs of the 20 layers, whatever the tile holds - plus, per graph,
+// 8.6 k per 128-row block + 43.6 per block and adjacency column + 2.3 per edge.
+constexpr long long kTcTileFixedCost = 92900;
+inline long long tc_graph_cost(int nb, int Kp, int nnz) {
+    return 8574LL * nb + (436LL * nb * Kp) / 10 + (23LL * nnz) / 10;
+}
+
+// `bins` tiles filled longest-processing-time first: every graph, heaviest first, goes to the lightest tile that can take it
+bool tc_pack_lpt(const std::vector<TcGraph> &gs, int bins, size_t pool, std::vector<Open> *out) {
+    std::vector<const TcGraph *> order;
+    order.reserve(gs.size());
+    for (const TcGraph &t : gs) order.push_back(&t);
+    std::sort(order.begin(), order.end(), [](const TcGraph *a, const TcGraph *c) { return a->cost != c->cost ? a->cost > c->cost : a->g < c->g; });
+    std::vector<Open> tiles((size_t)bins, Open{});
+    typedef std::pair<long long, int> Key;  // (cost so far, tile)
+    std::vector<Key> heap;
+    heap.reserve((size_t)bins);
+    for (int i = 0; i < bins; ++i) heap.push_back(Key(0, i));
+    auto cmp = std::greater<Key>();
+    std::vector<Key> aside;
+    for (const TcGraph *c : order) {
+        int best = -1;
+        aside.clear();
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            const Key k = heap.back();
+            heap.pop_back();
+            const Open &o = tiles[(size_t)k.second];
+            if (o.ng < kTcMaxG && o.blocks + c->nb <= kTcBlocks && o.bytes + c->bytes + kTcOverread <= pool) {
+                best = k.second;
+                break;
+            }
+            if (o.ng < kTcMaxG && o.blocks < kTcBlocks) aside.push_back(k);  // (a full tile never comes back)
+        }
+        for (const Key &k : aside) {
+            heap.push_back(k);
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+        if (best < 0) return false;
+        Open &o = tiles[(size_t)best];
+        o.g[o.ng++] = c->g;
+        o.blocks += c->nb;
+        o.bytes += c->bytes;
+        o.cost += c->cost;
+        heap.push_back(Key(o.cost, best));
+        std::push_heap(heap.begin(), heap.end(), cmp);
+    }
+    tiles.erase(std::remove_if(tiles.begin(), tiles.end(), [](const Open &o) { return o.ng == 0; }), tiles.end());
+    out->swap(tiles);
+    return true;
+}
+
+// makespan of heaviest-first list scheduling on `workers` CTAs (what the kernel's atomic tile counter does); `tiles` sorted
+long long tc_makespan(const std::vector<Open> &tiles, int workers) {
+    std::vector<long long> load((size_t)workers, 0);
+    for (const Open &t : tiles) {
+        std::pop_heap(load.begin(), load.end(), std::greater<long long>());
+        load.back() += t.cost + kTcTileFixedCost;
+        std::push_heap(load.begin(), load.end(), std::greater<long long>());
+    }
+    return *std::max_element(load.begin(), load.end());
+}
+
 int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     *ok = false;
     if (b->tc_tiles_valid) {
@@ -1144,6 +1233,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     b->tc_n_tiles = 0;
     const size_t pool = (size_t)ctx->max_smem_optin - 1024 - kTcOffPool;
     const auto &gp = b->h_graph_ptr;
+    const auto &ge = b->h_graph_e;
     std::vector<TcGraph> gs((size_t)b->n_graphs);
     for (int g = 0; g < b->n_graphs; ++g) {
         TcGraph t;
@@ -1152,18 +1242,12 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         t.nb = std::max(1, (t.nv + 127) / 128);
         const size_t R = (size_t)((t.nv + 7) & ~7), Kp = (size_t)((t.nv + 31) & ~31);
         t.bytes = R * Kp + 128 * Kp;
-        // per layer: projection ~650 cycles per block, aggregation ~65 per block and 32 columns, epilogue ~900 per block
-        t.cost = (long long)t.nb * (1600 + 2 * (long long)Kp);
+        t.cost = tc_graph_cost(t.nb, (int)Kp, ge[g + 1] - ge[g]);
         if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + kTcOverread > pool) return DG_OK;  // not eligible: the caller falls back
         gs[(size_t)g] = t;
     }
     // Largest graph first; every tile is then topped up with the largest remaining graphs that still fit (blocks, bytes
     // and cost all grow with the vertex count, so "largest that fits" is a lookup in the size-ordered remainder).
-    struct Open {
-        int ng, blocks, g[kTcMaxG];
-        size_t bytes;
-        long long cost;
-    };
     std::vector<Open> tiles;
     std::map<int, std::vector<const TcGraph *>> by_size;  // vertex count -> graphs of that size still unplaced
     for (const TcGraph &t : gs) by_size[t.nv].push_back(&t);
@@ -1194,7 +1278,22 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         tiles.push_back(o);
     }
     std::stable_sort(tiles.begin(), tiles.end(), [](const Open &a, const Open &c) { return a.cost > c.cost; });
-    const auto &ge = b->h_graph_e;
+    // With few tiles per SM the dense packing leaves some SMs a whole tile short (250 tiles on 148 SMs: 102 run two, 46 one).
+    // A tile costs a large fixed time whatever it holds, so a multiple of the SM count of lighter tiles, balanced by
+    // cost, finishes earlier; both plans are simulated and the shorter one is kept.  (Large batches: no difference, skipped.)
+    {
+        const int sms = ctx->sm_count;
+        const int k = ((int)tiles.size() + sms - 1) / sms;
+        int want = k * sms;
+        if (const char *e = getenv("DG_TC_TILES")) want = atoi(e);  // (experiments)
+        if (k <= 8 && want > (int)tiles.size() && want <= b->n_graphs) {
+            std::vector<Open> lpt;
+            if (tc_pack_lpt(gs, want, pool, &lpt)) {
+                std::stable_sort(lpt.begin(), lpt.end(), [](const Open &a, const Open &c) { return a.cost > c.cost; });
+                if (tc_makespan(lpt, sms) < tc_makespan(tiles, sms)) tiles.swap(lpt);
+            }
+        }
+    }
     std::vector<int> flat(tiles.size() * 32, 0);
     for (size_t i = 0; i < tiles.size(); ++i) {
         flat[i * 32] = tiles[i].ng;
@@ -1342,7 +1441,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
                 for (int t = 0; t < p.n_tiles; ++t) {
                     const int *td = &b->tc_tiles_host[(size_t)t * 32];
                     fprintf(f, "%lld", h[(size_t)grid * 12 + (size_t)t * 2]);
-                    for (int k = 0; k < td[0]; ++k) fprintf(f, " %d", td[1 + 6 * k + 2]);
+                    for (int k = 0; k < td[0]; ++k) fprintf(f, " %d:%d", td[1 + 6 * k + 2], td[1 + 6 * k + 4]);
                     fprintf(f, "\n");
                 }
                 fclose(f);

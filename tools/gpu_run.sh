@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -5
-timeout 300 python bench.py --no-cpu-baseline --steps 100 --warmup 10 2>gpurun_out/ts.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('bench', d['ms_per_step'], d['e2e']['ms_per_step'], d['config']['paths_agree'], d['roofline']['kernel'][:12])"
-tail -3 gpurun_out/ts.err
-DG_FUSED_TIMING=1 DG_TC_TILE_DUMP=gpurun_out/tiles_ts.txt timeout 300 python bench.py --no-cpu-baseline --steps 3 --warmup 3 2>gpurun_out/timing_ts.err >/dev/null
-grep "tc t" gpurun_out/timing_ts.err | tail -13
+timeout 300 python bench.py --workload synth-er-16384 --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/synth.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('synth16k', d['ms_per_step'], d['wall_ms_per_step'], d['roofline']['avg_launch_us'], d['roofline']['kernel'][:20], d['gpu_launches'], d['e2e']['ms_per_step'], d['config']['paths_agree'])"
+tail -3 gpurun_out/synth.err
+DG_FUSED_TIMING=1 timeout 300 python bench.py --workload synth-er-16384 --steps 2 --warmup 1 --no-cpu-baseline 2>&1 >/dev/null | grep "tc t" | head -14

@@ -34,14 +34,14 @@ METRIC = "graphs_per_sec_gcn_lgs"
 UNIT = "graphs/s"
 ROTATING_COPIES = 16  # distinct resident input sets cycled through the timed steps (> L2 in total)
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu
-# capture of the same command (profiles/r01_fused_ncu.md); None where no capture exists
-TRAFFIC_NCU = {"ba500": 9.12e6}
+# capture of the same command (profiles/r01_tc2_ncu.md); None where no capture exists
+TRAFFIC_NCU = {"ba500": 9.29e6}
 KERNEL_NOTES = {
     "tc_solve_kernel": ("tc_solve_kernel (graph-resident, tcgen05: bf16-split projection + exact u8 aggregation MMAs, "
                         "utility and greedy rounds in one launch)",
                         "The kernel keeps adjacency, operands and accumulators in shared / tensor memory: its real DRAM "
-                        "traffic is `traffic` (ncu, profiles/); it is bound by the hand-off latency between tensor-core and "
-                        "CUDA-core phases of a layer, not by HBM."),
+                        "traffic is `traffic` (ncu, profiles/r01_tc2_ncu.md); it is bound by the dependent tensor-core / CUDA-core "
+                        "phases of a layer (tensor pipe 29 % active, issue slots 40 %), not by HBM."),
     "fused_solve_kernel": ("fused_solve_kernel (graph-resident: all GCN layers + utility + greedy rounds in one launch)",
                            "The fused kernel keeps features in shared memory, its real DRAM traffic is `traffic` (ncu, "
                            "profiles/) - it is shared-memory-bandwidth bound, not HBM bound."),

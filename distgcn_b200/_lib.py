@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdistgcn_b200.so")
+LIB_PATH = os.environ.get("DISTGCN_B200_LIB") or os.path.join(HERE, "libdistgcn_b200.so")  # (override: experiments)
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_CONVERGED, ERR_NO_DEVICE = 1, 2, 3, 4, 5

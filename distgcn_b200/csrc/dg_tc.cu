@@ -45,10 +45,20 @@ namespace dg {
 
 namespace {
 
+#ifdef DG_TC_HALF  // experiment: two CTAs per SM, each with half the tensor memory / shared memory / warps
+constexpr int kTcVertexThreads = 256;
+constexpr int kTcThreads = 256;
+constexpr int kTcMaxG = 2;
+constexpr int kTcBlocks = 2;
+constexpr int kTcCtasPerSm = 2;
+#else
 constexpr int kTcVertexThreads = 512;
 constexpr int kTcThreads = 512;       // 16 warps: 128 registers per thread
 constexpr int kTcMaxG = 4;            // graphs per tile (every graph owns >= 1 block)
 constexpr int kTcBlocks = 4;          // 128-row blocks per tile = TMEM budget: 4 x 128 columns
+constexpr int kTcCtasPerSm = 1;
+#endif
+constexpr int kTcTmemCols = 128 * kTcBlocks;
 // a partial last block reads up to 127 rows x 16 B past its graph's last region: the tile keeps that much of the pool free
 constexpr int kTcOverread = 2048 + 128;
 constexpr int kTcWBlob = 12560;       // one hidden layer: bf16 terms of [W_0 | W_1 r] (12288), bias[32], 1/r[32], bound, pad
@@ -376,7 +386,7 @@ __device__ __forceinline__ void tc_split8(const float *h, uint4 *hi, uint4 *mid,
 // 4 adjacency bytes (0/1 each) -> 4 bits (byte k -> bit k)
 __device__ __forceinline__ uint32_t tc_bits4(uint32_t w) { return (w * 0x01020408u) >> 24; }
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams P) {
+__global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *wring = smem + kTcOffRing;
     double *util_sm = reinterpret_cast<double *>(smem + kTcOffUtil);
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
         fence_mbar_init();
     }
     if (warp == 0) {  // the whole tensor memory of the SM: 4 blocks x 128 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_sm)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_sm)), "r"(kTcTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -1066,7 +1076,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_solve_kernel(const TcParams 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
     // the last CTA to leave re-arms the tile counter for the next launch on this context
     if (tid == 0) {
         __threadfence();
@@ -1153,6 +1163,11 @@ void tc_build_weights(int n_hidden, const float *const *w0, const float *const *
 namespace {
 
 // tiles: first-fit over a window of open tiles, graphs in order of decreasing cost
+// dynamic shared memory of one CTA
+inline size_t tc_smem_bytes(const dg_context *ctx) {
+    return kTcCtasPerSm == 1 ? (size_t)ctx->max_smem_optin - 1024 : (size_t)112 * 1024;
+}
+
 struct Open {  // a tile being filled
     int ng, blocks, g[kTcMaxG];
     size_t bytes;
@@ -1231,7 +1246,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     }
     b->tc_tiles_valid = true;
     b->tc_n_tiles = 0;
-    const size_t pool = (size_t)ctx->max_smem_optin - 1024 - kTcOffPool;
+    const size_t pool = tc_smem_bytes(ctx) - kTcOffPool;
     const auto &gp = b->h_graph_ptr;
     const auto &ge = b->h_graph_e;
     std::vector<TcGraph> gs((size_t)b->n_graphs);
@@ -1282,7 +1297,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     // A tile costs a large fixed time whatever it holds, so a multiple of the SM count of lighter tiles, balanced by
     // cost, finishes earlier; both plans are simulated and the shorter one is kept.  (Large batches: no difference, skipped.)
     {
-        const int sms = ctx->sm_count;
+        const int sms = ctx->sm_count * kTcCtasPerSm;
         const int k = ((int)tiles.size() + sms - 1) / sms;
         int want = k * sms;
         if (const char *e = getenv("DG_TC_TILES")) want = atoi(e);  // (experiments)
@@ -1368,15 +1383,15 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     p.round_cap = kLgsRoundCap;
     p.do_lgs = member != nullptr ? 1 : 0;
     p.dbg = nullptr;
-    const size_t smem = (size_t)ctx->max_smem_optin - 1024;
+    const size_t smem = tc_smem_bytes(ctx);
     if (getenv("DG_FUSED_TIMING")) {
         long long *dbg = nullptr;
-        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * 12 + (size_t)p.n_tiles * 2, &dbg));
-        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * 12 + (size_t)p.n_tiles * 2), ctx->stream));
+        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2, &dbg));
+        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2), ctx->stream));
         p.dbg = dbg;
     }
     DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(ctx->sm_count, p.n_tiles);
+    const int grid = std::min(ctx->sm_count * kTcCtasPerSm, p.n_tiles);
     {
         int *wd = ctx->h_flag + 3;  // pinned host memory: readable after a device-side trap
         int wide = 0;
@@ -1418,7 +1433,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         }
     }
     if (p.dbg) {
-        std::vector<long long> h((size_t)ctx->sm_count * 12 + (size_t)p.n_tiles * 2);
+        std::vector<long long> h((size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2);
         DG_CUDA_CHECK(cudaMemcpyAsync(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
         DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         const char *names[12] = {"stage", "wall_ns", "tiles", "w_proj", "phaseB", "w_agg", "phaseC", "total", "first", "tail", "greedy", "endwait"};

@@ -51,7 +51,8 @@ SIM_RI = 4.0          # :94
 P_OVERLAP = 0.8       # :96
 RATE_HI = 100         # :98
 RATE_LO = 0           # :99
-ALGOS = ("Greedy", "DGCN-LGS", "LGS-Seq", "DGCN-LGS-Seq")
+ALGOS = ("Greedy", "Greedy-Th", "DGCN-LGS", "DGCN-LGS-it", "LGS-Seq", "DGCN-LGS-Seq")
+GREEDY_TH_EPSILON = 0.1   # dist_greedy_search(adj_gK, wts, 0.1), wireless_dqn_test_mc.py:252
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -208,6 +209,10 @@ class BatchedScheduler:
 
     def _solve(self, k: int, w: np.ndarray) -> np.ndarray:
         self.solver_calls += 1
+        if self.algo == "DGCN-LGS-it":   # solve_mwis_dit on the joint graph (wireless_dqn_test_mc.py:264)
+            return engine.solve_dit(self.ctx, self.model, self.batches[k], w, predict=self.predict, want_total=False).member
+        if self.algo == "Greedy-Th":     # threshold distributed greedy on the joint graph (:252)
+            return engine.dist_greedy(self.ctx, self.batches[k], w, epsilon=GREEDY_TH_EPSILON, want_steps=False).member
         if self.algo.startswith("DGCN"):
             return engine.solve(self.ctx, self.model, self.batches[k], w, predict=self.predict,
                                 remove_zero_weight=True, want_total=False).member

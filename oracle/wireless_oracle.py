@@ -40,8 +40,13 @@ def run_instance(adj_list, adj_gK, arrivals, rates, algo, layers=None, predict="
         wts1 = np.reshape(wts0, nflows * n_ch, order="F")                                # :240
         if algo == "Greedy":
             mwis = _lgs_set(adj_gK, wts1)                                                # :244
+        elif algo == "Greedy-Th":
+            a = sp.csr_matrix(adj_gK)
+            mwis = np.flatnonzero(L.dist_greedy(a.indptr, a.indices, wts1, 0.1)[0])      # :252 (ascending-id scan, lgs_oracle.c)
         elif algo == "DGCN-LGS":
             mwis = _dgcn_set(adj_gK, wts1, layers, predict)                              # :289
+        elif algo == "DGCN-LGS-it":
+            mwis = np.flatnonzero(pipeline.solve_graph_dit(adj_gK, wts1, layers, predict)[0])   # :264
         elif algo in ("LGS-Seq", "DGCN-LGS-Seq"):
             parts = []
             for ic in range(n_ch):

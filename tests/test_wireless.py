@@ -57,13 +57,13 @@ def test_traffic_follows_the_reference_draw_order():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("algo", ["Greedy", "DGCN-LGS", "LGS-Seq", "DGCN-LGS-Seq"])
+@pytest.mark.parametrize("algo", ["Greedy", "Greedy-Th", "DGCN-LGS", "DGCN-LGS-it", "LGS-Seq", "DGCN-LGS-Seq"])
 @pytest.mark.parametrize("ck", ["is4sat_l1", "is4sat_l20_c32"])
 def test_batched_slot_loop_matches_per_instance_restatement(algo, ck):
     from distgcn_b200 import engine as E
     from distgcn_b200 import wireless as W
     from oracle import wireless_oracle as WO
-    if algo in ("Greedy", "LGS-Seq") and ck != "is4sat_l1":
+    if algo in ("Greedy", "Greedy-Th", "LGS-Seq") and ck != "is4sat_l1":
         pytest.skip("no model involved")
     n_slots = 14
     insts = W.make_instances(n_networks=3, loads=[0.2, 0.9], n_ch=3, timeslots=n_slots + 1, seed=11, n_nodes=60,

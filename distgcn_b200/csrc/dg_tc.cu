@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
     TcTileInfo *tinfo = reinterpret_cast<TcTileInfo *>(smem + kTcOffMeta + sizeof(TcMeta) * kTcMaxG);
     unsigned char *pool = smem + kTcOffPool;
     __shared__ int tile_sm;
+    __shared__ int trec[32];
     __shared__ uint32_t tmem_sm;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -446,8 +447,10 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
         const long long t_tile = tk;
 
         // ---- tile metadata; the barriers are re-armed with this tile's thread counts ---------------------------
+        if (warp == 0) trec[lane] = __ldg(P.tiles + (size_t)t * 32 + lane);  // the tile's record in one coalesced load
+        __syncwarp();
         if (tid == 0) {
-            const int *td = P.tiles + (size_t)t * 32;
+            const int *td = trec;
             const int ng = td[0];
             int fb = 0, off = 0;
             for (int gi = 0; gi < ng; ++gi) {
@@ -551,16 +554,16 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 unsigned char *adj = pool + m.adj;
                 const uint16_t *rowof = reinterpret_cast<const uint16_t *>(pool + m.hoff);
                 const bool table = 2 * m.nnz <= 128 * m.Kp;
-                // four edges per thread and pass, their global loads issued back to back (the loop is latency bound)
-                for (int eb = tid; eb < m.nnz; eb += 4 * kTcVertexThreads) {
-                    int jj[4], ll[4];
+                // eight edges per thread and pass, their global loads issued back to back (the loop is latency bound)
+                for (int eb = tid; eb < m.nnz; eb += 8 * kTcVertexThreads) {
+                    int jj[8], ll[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int e = eb + u * kTcVertexThreads;
                         jj[u] = e < m.nnz ? __ldg(P.col_idx + m.e0 + e) - m.v0 : -1;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int e = eb + u * kTcVertexThreads;
                         int lo = 0;
                         if (e < m.nnz) {
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         ll[u] = lo;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int j = jj[u], lo = ll[u];
                         if (j >= 0) {
                             const uint32_t ki = (keepw[m.fb * 4 + (lo >> 5)] >> (lo & 31)) & 1u;

@@ -254,7 +254,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -290,14 +290,15 @@ def run_ours(args):
         d_w = torch.from_numpy(w).to("cuda:%d" % local_rank)
         d_member = torch.empty(pb.n_nodes, dtype=torch.uint8, device=d_w.device)
         d_total = torch.empty(pb.n_graphs, dtype=torch.float64, device=d_w.device)
+        c16 = pb.local_columns()  # the compact host format: 16-bit graph-local column ids (dg_solve_host_compact)
         h = {k: E.pinned_empty(a.shape, a.dtype) for k, a in
-             (("gp", pb.graph_ptr), ("rp", pb.row_ptr), ("ci", pb.col_idx), ("w", w))}
-        h["gp"][:], h["rp"][:], h["ci"][:], h["w"][:] = pb.graph_ptr, pb.row_ptr, pb.col_idx, w
+             (("gp", pb.graph_ptr), ("rp", pb.row_ptr), ("ci", pb.col_idx), ("w", w), ("c16", c16))}
+        h["gp"][:], h["rp"][:], h["ci"][:], h["w"][:], h["c16"][:] = pb.graph_ptr, pb.row_ptr, pb.col_idx, w, c16
         h_member = E.pinned_empty(pb.n_nodes, np.uint8)
         h_total = E.pinned_empty(pb.n_graphs, np.float64)
         from distgcn_b200.batch import PackedBatch
         copies.append(dict(pb=pb, w=w, dev=dev_batch, d_w=d_w, d_member=d_member, d_total=d_total,
-                           h_pb=PackedBatch(h["gp"], h["rp"], h["ci"]), h_w=h["w"], h_member=h_member,
+                           h_pb=PackedBatch(h["gp"], h["rp"], h["ci"]), h_w=h["w"], h_c16=h["c16"], h_member=h_member,
                            h_total=h_total))
         input_bytes += 4 * (pb.n_graphs + 1) + 4 * (pb.n_nodes + 1) + 4 * pb.nnz + 8 * pb.n_nodes
     n_graphs = pb0.n_graphs
@@ -358,7 +359,8 @@ def run_ours(args):
 
     def pipe_step(i):
         c = copies[i % R]
-        pipe.submit(c["h_pb"], c["h_w"], c["h_member"], c["h_total"], predict="mwis", remove_zero_weight=True)
+        pipe.submit(c["h_pb"], c["h_w"], c["h_member"], c["h_total"], predict="mwis", remove_zero_weight=True,
+                    col_local16=c["h_c16"])
 
     for i in range(max(4, args.warmup // 2)):
         pipe_step(i)
@@ -398,7 +400,8 @@ def run_ours(args):
         value = world * n_graphs * args.steps / (dev_ms / 1e3)
         e2e_value = world * n_graphs * args.steps / (e2e_ms / 1e3)
         c0 = copies[0]["pb"]
-        h2d = 4 * (c0.n_graphs + 1) + 4 * (c0.n_nodes + 1) + 4 * c0.nnz + 8 * c0.n_nodes
+        h2d = 4 * (c0.n_graphs + 1) + 4 * (c0.n_nodes + 1) + 2 * c0.nnz + 8 * c0.n_nodes  # compact: 16-bit column ids
+        h2d_packed = 4 * (c0.n_graphs + 1) + 4 * (c0.n_nodes + 1) + 4 * c0.nnz + 8 * c0.n_nodes
         d2h = c0.n_nodes + 8 * c0.n_graphs
         kern_launches = int(n_launch.value)
         achieved = (alg_bytes.value / 1e9) / (tot_ms.value / 1e3) if tot_ms.value > 0 else 0.0
@@ -415,11 +418,13 @@ def run_ours(args):
                        "paths_agree": bool(same and pipe_same)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps,
-                    "api": "engine.HostPipeline.submit (dg_solve_host_async, 2 contexts in turn): pinned host CSR + "
-                           "weights in, membership + totals out, every step; wall clock over the K steps",
+                    "api": "engine.HostPipeline.submit (dg_solve_host_compact, 2 contexts in turn): pinned host CSR with "
+                           "16-bit graph-local column ids + weights in, membership + totals out, every step; wall clock "
+                           "over the K steps",
                     "gpu_launches": int(pipe_launches),
                     "one_call_at_a_time": {"value": world * n_graphs * args.steps / (e2e_sync_ms / 1e3),
-                                           "ms_per_step": e2e_sync_ms / args.steps, "api": "dg_solve_host"}},
+                                           "ms_per_step": e2e_sync_ms / args.steps, "api": "dg_solve_host (packed int32 "
+                                           "column ids)", "h2d_bytes_per_step": int(h2d_packed)}},
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm",
@@ -441,7 +446,7 @@ def run_ours(args):
                                     "sample": "%d graphs of the same workload, best of 3 passes, %d worker processes "
                                               "(numpy/scipy GCN restatement + C local greedy search; the reference's own "
                                               "Python/TensorFlow code cannot run on this box)" % (sample, cores)}
-        print(json.dumps(line))
+        emit_line(line)
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -467,6 +472,25 @@ class DeviceTimer:
         return float(ms.value)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Native libraries (NCCL prints its version line) write to file descriptor 1: from here on fd 1 is stderr and the
+    one JSON line goes to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,6 +501,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

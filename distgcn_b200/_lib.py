@@ -86,6 +86,7 @@ SIGNATURES = {
     "dg_solve_host": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
     "dg_solve_dit": (C.c_int, [_p, _p, _p, _p, C.c_int, _p, _p, _p, C.c_int]),
     "dg_solve_host_async": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
+    "dg_solve_host_compact": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_int]),
 }
 
 _lib = None

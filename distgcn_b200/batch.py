@@ -54,6 +54,15 @@ class PackedBatch:
     def graph_nnz(self) -> np.ndarray:
         return np.diff(self.row_ptr[self.graph_ptr])
 
+    def local_columns(self) -> np.ndarray:
+        """uint16 [nnz]: column ids local to their graph (what each per-graph scipy matrix of the reference holds) -
+        the compact host format of ``engine.solve_host(..., col_local16=...)`` / dg_solve_host_compact, half the
+        host->device bytes of ``col_idx``.  Graphs of at most 65536 vertices."""
+        if self.n_graphs and int(self.graph_sizes().max()) > 65536:
+            raise ValueError("16-bit local column ids need graphs of at most 65536 vertices")
+        base = np.repeat(self.graph_ptr[:-1].astype(np.int64), self.graph_nnz())
+        return (self.col_idx.astype(np.int64) - base).astype(np.uint16)
+
     def slice(self, g0: int, g1: int) -> "PackedBatch":
         """Graphs g0 .. g1-1 as their own batch (vertex ids re-based)."""
         v0, v1 = int(self.graph_ptr[g0]), int(self.graph_ptr[g1])

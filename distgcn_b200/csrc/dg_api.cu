@@ -527,14 +527,38 @@ void dg_model_destroy(dg_model *m) {
 int dg_model_out_width(const dg_model *m) { return m ? m->layers.back().c_out : 0; }
 
 // -------------------------------------------------------------------------------------------------
+// graph-local 16-bit column ids -> batch-global int32 ids, one CTA per graph (the compact host format of dg_solve_host_compact)
+__global__ void __launch_bounds__(256)
+expand_cols16_kernel(const int32_t *__restrict__ graph_ptr, const int32_t *__restrict__ row_ptr,
+                     const uint16_t *__restrict__ col16, int32_t *__restrict__ col_idx) {
+    const int v0 = graph_ptr[blockIdx.x], v1 = graph_ptr[blockIdx.x + 1];
+    const int e1 = row_ptr[v1];
+    for (int e = row_ptr[v0] + (int)threadIdx.x; e < e1; e += (int)blockDim.x) col_idx[e] = (int32_t)col16[e] + v0;
+}
+
+// batch-global int32 column ids of a batch that arrived in the compact format (no-op otherwise)
+static int batch_ensure_cols(dg_batch *b) {
+    if (!b->cols_pending) return DG_OK;
+    if (b->n_graphs > 0 && b->nnz > 0) {
+        expand_cols16_kernel<<<b->n_graphs, 256, 0, b->ctx->stream>>>(b->graph_ptr, b->row_ptr, b->col16, b->col_idx);
+        b->ctx->launches++;
+        DG_CUDA_CHECK(cudaGetLastError());
+    }
+    b->cols_pending = false;
+    return DG_OK;
+}
+
 static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nnz, const int32_t *graph_ptr,
-                      const int32_t *row_ptr, const int32_t *col_idx, int mem, bool compute_dinv = true) {
+                      const int32_t *row_ptr, const int32_t *col_idx, int mem, bool compute_dinv = true,
+                      const uint16_t *col_local16 = nullptr) {
     dg_context *ctx = b->ctx;
     DG_REQUIRE(n_graphs >= 0 && n_nodes >= 0 && nnz >= 0, DG_ERR_INVALID, "negative size");
-    DG_REQUIRE(graph_ptr && row_ptr && (col_idx || nnz == 0), DG_ERR_INVALID, "null CSR pointer");
+    DG_REQUIRE(graph_ptr && row_ptr && (col_idx || col_local16 || nnz == 0), DG_ERR_INVALID, "null CSR pointer");
+    DG_REQUIRE(!col_local16 || mem == DG_MEM_HOST, DG_ERR_INVALID, "the compact column format is a host format");
     b->n_graphs = n_graphs;
     b->n_nodes = n_nodes;
     b->nnz = nnz;
+    b->cols_pending = false;
     b->h_graph_ptr.resize((size_t)n_graphs + 1);
     if (mem == DG_MEM_HOST) {
         std::copy(graph_ptr, graph_ptr + n_graphs + 1, b->h_graph_ptr.begin());
@@ -581,18 +605,27 @@ static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nn
         }
         if (b->cap_nnz < (size_t)nnz || !b->col_idx) {
             if (b->col_idx) cudaFree(b->col_idx);
+            if (b->col16) cudaFree(b->col16);
             b->col_idx = nullptr;
+            b->col16 = nullptr;
             b->cap_nnz = (size_t)nnz + (size_t)nnz / 4 + 1;
             DG_CUDA_CHECK(cudaMalloc((void **)&b->col_idx, sizeof(int32_t) * b->cap_nnz));
         }
+        if (col_local16 && !b->col16) DG_CUDA_CHECK(cudaMalloc((void **)&b->col16, sizeof(uint16_t) * b->cap_nnz));
         b->owns_csr = true;
         DG_CUDA_CHECK(cudaMemcpyAsync(b->graph_ptr, graph_ptr, sizeof(int32_t) * ((size_t)n_graphs + 1),
                                       cudaMemcpyHostToDevice, ctx->stream));
         DG_CUDA_CHECK(cudaMemcpyAsync(b->row_ptr, row_ptr, sizeof(int32_t) * ((size_t)n_nodes + 1),
                                       cudaMemcpyHostToDevice, ctx->stream));
-        if (nnz)
+        if (nnz && col_local16) {
+            DG_REQUIRE(b->max_graph_nodes <= 65536, DG_ERR_INVALID, "16-bit column ids need graphs of at most 65536 vertices");
+            DG_CUDA_CHECK(cudaMemcpyAsync(b->col16, col_local16, sizeof(uint16_t) * (size_t)nnz, cudaMemcpyHostToDevice,
+                                          ctx->stream));
+            b->cols_pending = true;  // the tensor-core kernel reads the 16-bit ids as they are; others expand them first
+        } else if (nnz) {
             DG_CUDA_CHECK(cudaMemcpyAsync(b->col_idx, col_idx, sizeof(int32_t) * (size_t)nnz,
                                           cudaMemcpyHostToDevice, ctx->stream));
+        }
     } else {
         b->owns_csr = false;
         b->graph_ptr = const_cast<int32_t *>(graph_ptr);
@@ -633,6 +666,7 @@ void dg_batch_destroy(dg_batch *b) {
         if (b->row_ptr) cudaFree(b->row_ptr);
         if (b->col_idx) cudaFree(b->col_idx);
     }
+    if (b->col16) cudaFree(b->col16);
     if (b->dinv) cudaFree(b->dinv);
     if (b->keep) cudaFree(b->keep);
     if (b->x0) cudaFree(b->x0);
@@ -880,6 +914,7 @@ static int solve_device(dg_context *ctx, const dg_model *m, dg_batch *b, const d
     DG_TRY(tc_try_solve(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, d_score, d_util, d_total, d_steps,
                         &handled));
     if (handled) return DG_OK;
+    DG_TRY(batch_ensure_cols(b));
     DG_TRY(fused_try_solve(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, d_score, d_util, d_total, d_steps,
                            &handled));
     if (handled) return DG_OK;
@@ -1019,7 +1054,7 @@ int dg_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *wts,
 static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
                            const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
                            const double *wts, int predict, int remove_zero_weight, uint8_t *member, double *total,
-                           bool wait) {
+                           bool wait, const uint16_t *col_local16 = nullptr) {
     clear_error();
     DG_TRY(check_ctx(ctx));
     DG_REQUIRE(m && wts && member, DG_ERR_INVALID, "null argument");
@@ -1041,7 +1076,7 @@ static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs,
         b->keep = nullptr;
     }
     // with zero-weight removal the degrees are computed once the keep mask is known (solve_device)
-    DG_TRY(batch_fill(b, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, DG_MEM_HOST, !remove_zero_weight));
+    DG_TRY(batch_fill(b, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, DG_MEM_HOST, !remove_zero_weight, col_local16));
     const size_t n = (size_t)n_nodes, G = (size_t)n_graphs;
     double *d_wts = nullptr, *d_total = nullptr;
     uint8_t *d_member = nullptr;
@@ -1066,6 +1101,14 @@ int dg_solve_host_async(dg_context *ctx, const dg_model *m, int32_t n_graphs, in
                         int predict, int remove_zero_weight, uint8_t *member, double *total) {
     return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, wts, predict,
                            remove_zero_weight, member, total, false);
+}
+
+int dg_solve_host_compact(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                          const int32_t *graph_ptr, const int32_t *row_ptr, const uint16_t *col_local, const double *wts,
+                          int predict, int remove_zero_weight, uint8_t *member, double *total, int wait) {
+    DG_REQUIRE(col_local || nnz == 0, DG_ERR_INVALID, "null column array");
+    return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, nullptr, wts, predict, remove_zero_weight,
+                           member, total, wait != 0, col_local);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -187,6 +187,8 @@ struct dg_batch {
     int max_graph_nodes = 0;
     bool owns_csr = false;
     int32_t *graph_ptr = nullptr, *row_ptr = nullptr, *col_idx = nullptr;  // device
+    uint16_t *col16 = nullptr;  // device copy of graph-local 16-bit column ids (compact host format), cap_nnz entries
+    bool cols_pending = false;  // col16 holds the batch's columns and col_idx has not been expanded from it yet
     std::vector<int32_t> h_graph_ptr;  // host copy (small) for launch planning
     float *dinv = nullptr;     // [n_nodes] fp32(deg^-1/2) on the kept sub-graph, 0 for isolated/removed
     uint8_t *keep = nullptr;   // [n_nodes] or nullptr = all kept

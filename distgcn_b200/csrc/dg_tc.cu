@@ -99,6 +99,7 @@ struct TcParams {
     int n_tiles;
     int *tile_counter;
     const int *graph_ptr, *row_ptr, *col_idx;
+    const uint16_t *col16;  // graph-local column ids (compact host format) or nullptr: then col_idx, batch-global
     const double *wts;
     const uint8_t *keep_in;
     const float *x0;
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int e = eb + u * kTcVertexThreads;
-                        jj[u] = e < m.nnz ? __ldg(P.col_idx + m.e0 + e) - m.v0 : -1;
+                        jj[u] = e >= m.nnz ? -1 : P.col16 ? (int)__ldg(P.col16 + m.e0 + e) : __ldg(P.col_idx + m.e0 + e) - m.v0;
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -1361,6 +1362,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     p.graph_ptr = b->graph_ptr;
     p.row_ptr = b->row_ptr;
     p.col_idx = b->col_idx;
+    p.col16 = b->cols_pending ? b->col16 : nullptr;
     p.wts = d_wts;
     p.keep_in = remove_zero_weight ? nullptr : b->keep;
     p.x0 = b->x0;

@@ -393,12 +393,14 @@ def solve_device(ctx: Context, model: Model, batch: DeviceBatch, wts, member, pr
 
 
 def solve_host(ctx: Context, model: Model, packed: PackedBatch, wts, predict="mwis", remove_zero_weight: bool = True,
-               member: Optional[np.ndarray] = None, total: Optional[np.ndarray] = None, wait: bool = True):
+               member: Optional[np.ndarray] = None, total: Optional[np.ndarray] = None, wait: bool = True,
+               col_local16: Optional[np.ndarray] = None):
     """One-shot host CSR in / host membership out (dg_solve_host): H2D, kernels and D2H in one call.
     ``wait=False`` only enqueues (dg_solve_host_async): the arrays must stay alive (and should be pinned,
-    see ``pinned_empty``) until ``ctx.synchronize()``."""
+    see ``pinned_empty``) until ``ctx.synchronize()``.  ``col_local16`` (``PackedBatch.local_columns()``, uint16):
+    the compact host format - it crosses PCIe instead of ``packed.col_idx`` (dg_solve_host_compact)."""
     gp, rp, ci = packed.graph_ptr, packed.row_ptr, packed.col_idx
-    for a in (gp, rp, ci):
+    for a in (gp, rp) + (() if col_local16 is not None else (ci,)):
         if a.dtype != np.int32 or not a.flags.c_contiguous:
             raise TypeError("PackedBatch arrays must be contiguous int32")
     w = wts if (isinstance(wts, np.ndarray) and wts.dtype == np.float64 and wts.flags.c_contiguous) else _np(wts, np.float64)
@@ -407,6 +409,13 @@ def solve_host(ctx: Context, model: Model, packed: PackedBatch, wts, predict="mw
         member = np.empty(n, dtype=np.uint8)
     if total is None:
         total = np.empty(g, dtype=np.float64)
+    if col_local16 is not None:
+        if col_local16.dtype != np.uint16 or not col_local16.flags.c_contiguous or col_local16.shape[0] != packed.nnz:
+            raise TypeError("col_local16 must be a contiguous uint16 array of nnz entries")
+        check(ctx._lib.dg_solve_host_compact(ctx.handle, model.handle, g, n, packed.nnz, _ptr(gp), _ptr(rp), _ptr(col_local16),
+                                             _ptr(w), predict_code(predict), 1 if remove_zero_weight else 0, _ptr(member),
+                                             _ptr(total), 1 if wait else 0))
+        return member, total
     fn = ctx._lib.dg_solve_host if wait else ctx._lib.dg_solve_host_async
     check(fn(ctx.handle, model.handle, g, n, packed.nnz, _ptr(gp), _ptr(rp), _ptr(ci), _ptr(w),
              predict_code(predict), 1 if remove_zero_weight else 0, _ptr(member), _ptr(total)))
@@ -435,13 +444,13 @@ class HostPipeline:
         return sum(c.launch_count for c in self.ctxs)
 
     def submit(self, packed: PackedBatch, wts, member: np.ndarray, total: Optional[np.ndarray] = None,
-               predict="mwis", remove_zero_weight: bool = True) -> int:
+               predict="mwis", remove_zero_weight: bool = True, col_local16: Optional[np.ndarray] = None) -> int:
         slot = self._next
         self._next = (slot + 1) % len(self.ctxs)
         self.wait(slot)
         solve_host(self.ctxs[slot], self.models[slot], packed, wts, predict, remove_zero_weight, member, total,
-                   wait=False)
-        self._busy[slot] = (packed, wts, member, total)  # keep the arrays alive
+                   wait=False, col_local16=col_local16)
+        self._busy[slot] = (packed, wts, member, total, col_local16)  # keep the arrays alive
         return slot
 
     def wait(self, slot: Optional[int] = None) -> None:

@@ -214,6 +214,15 @@ DG_API int dg_solve_host_async(dg_context *ctx, const dg_model *model, int32_t n
                         const double *wts, int predict, int remove_zero_weight, uint8_t *member,
                         double *total);
 
+/* The same with the compact host format: col_local[e] = column id LOCAL to the graph (what every per-graph scipy
+ * matrix of the reference holds, mwis_dqn_call.py:198), 16 bits - half the host->device bytes of the packed int32
+ * form, which is what bounds the streaming path once the kernels are fast (PCIe).  Expanded to batch-global ids on
+ * the device.  Graphs of at most 65536 vertices.  wait != 0: return after the results have landed (dg_solve_host),
+ * wait == 0: enqueue only (dg_solve_host_async). */
+DG_API int dg_solve_host_compact(dg_context *ctx, const dg_model *model, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                          const int32_t *graph_ptr, const int32_t *row_ptr, const uint16_t *col_local, const double *wts,
+                          int predict, int remove_zero_weight, uint8_t *member, double *total, int wait);
+
 /* ---- one giant graph, row-partitioned over several GPUs (no reference counterpart: the
  * reference handles one 100-300 vertex graph per call) ------------------------------------------------
  * A dg_part is one rank's slice: rows row0 .. row0+n_local-1 of a graph with n_global vertices (row0 and

@@ -194,6 +194,48 @@ def test_host_pipeline_matches_one_call_at_a_time():
     pipe.close()
 
 
+def test_compact_host_format_matches_the_packed_one():
+    """dg_solve_host_compact (16-bit graph-local column ids, expanded on the device) gives what dg_solve_host gives,
+    one call at a time and through the pipeline; graphs above 65536 vertices are refused."""
+    from distgcn_b200 import engine as E
+    from distgcn_b200 import _lib
+    from distgcn_b200.batch import PackedBatch, pack_graphs
+    pb, w = util.small_graphs()
+    c16 = pb.local_columns()
+    assert c16.dtype == np.uint16 and c16.shape == pb.col_idx.shape
+    base = np.repeat(pb.graph_ptr[:-1], pb.graph_nnz())
+    assert np.array_equal(c16.astype(np.int64) + base, pb.col_idx)
+    layers = util.load_layers("is4sat_l20_c32")
+    ctx = E.Context(0)
+    model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
+    m0, t0 = E.solve_host(ctx, model, pb, w)
+    m1, t1 = E.solve_host(ctx, model, pb, w, col_local16=c16)
+    assert np.array_equal(m0, m1) and np.array_equal(t0, t1)
+    for short in ("is4sat_l1", "is4sat_l2_c64"):          # the other kernels read the expanded ids too
+        lay = util.load_layers(short)
+        mod = E.Model(ctx, lay, E.gcn_dqn_acts(len(lay)))
+        a, _ = E.solve_host(ctx, mod, pb, w)
+        b, _ = E.solve_host(ctx, mod, pb, w, col_local16=c16)
+        assert np.array_equal(a, b)
+        mod.close()
+    pipe = E.HostPipeline(0, layers, E.gcn_dqn_acts(len(layers)), depth=2)
+    outs = []
+    for g0, g1 in ((0, 50), (3, 29), (29, 50)):
+        sub = pb.slice(g0, g1)
+        v0, v1 = int(pb.graph_ptr[g0]), int(pb.graph_ptr[g1])
+        member = E.pinned_empty(sub.n_nodes, np.uint8)
+        pipe.submit(sub, np.ascontiguousarray(w[v0:v1]), member, None, col_local16=sub.local_columns())
+        outs.append((v0, v1, member))
+    pipe.wait()
+    for v0, v1, member in outs:
+        assert np.array_equal(np.asarray(member), m0[v0:v1])
+    pipe.close()
+    with pytest.raises(TypeError):
+        E.solve_host(ctx, model, pb, w, col_local16=c16.astype(np.int32))
+    model.close()
+    ctx.close()
+
+
 def test_mwis_dqn_test_harness_ratios():
     """distgcn_b200.mwis_dqn_test.evaluate: the 500-file loop of mwis_dqn_test.py:304-348 as two launches; the
     normaliser equals the greedy_utility stored in the reference's own files and the ratios equal the ones

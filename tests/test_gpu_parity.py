@@ -201,6 +201,14 @@ def test_dist_greedy_keep_mask_edge_cases_and_full_sets(gpu_ctx):
     r = E.dist_greedy(gpu_ctx, batch, np.ones(n))
     assert np.array_equal(r.member, (np.arange(n) % 2 == 0).astype(np.uint8)) and r.steps.tolist() == [1]
     batch.close()
+    # one CTA per graph: graphs above 8192 vertices are refused, not mis-solved
+    nbig = 9000
+    big = sp.diags([np.ones(nbig - 1), np.ones(nbig - 1)], [-1, 1], format="csr")
+    batch = E.DeviceBatch(gpu_ctx, pack_graphs([big]))
+    with pytest.raises(_lib.DistGCNError) as ei:
+        E.dist_greedy(gpu_ctx, batch, np.ones(nbig))
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    batch.close()
     # negative weights leave the candidate set empty for ever (the reference never returns): reported
     batch = E.DeviceBatch(gpu_ctx, pack_graphs([adjs[3]]))
     with pytest.raises(_lib.DistGCNError) as ei:

@@ -558,10 +558,18 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 // eight edges per thread and pass, their global loads issued back to back (the loop is latency bound)
                 for (int eb = tid; eb < m.nnz; eb += 8 * kTcVertexThreads) {
                     int jj[8], ll[8];
+                    if (P.col16) {  // (uniform branch outside the loads: they must issue back to back)
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int e = eb + u * kTcVertexThreads;
-                        jj[u] = e >= m.nnz ? -1 : P.col16 ? (int)__ldg(P.col16 + m.e0 + e) : __ldg(P.col_idx + m.e0 + e) - m.v0;
+                        for (int u = 0; u < 8; ++u) {
+                            const int e = eb + u * kTcVertexThreads;
+                            jj[u] = e < m.nnz ? (int)__ldg(P.col16 + m.e0 + e) : -1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int e = eb + u * kTcVertexThreads;
+                            jj[u] = e < m.nnz ? __ldg(P.col_idx + m.e0 + e) - m.v0 : -1;
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {

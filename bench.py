@@ -191,6 +191,33 @@ def measured_peak_gbs():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
 
 
+def tensor_view(kernel_name, pb, layers, launch_us):
+    """The same launch against the tensor roofline (only tc_solve_kernel issues MMAs): algorithmic flops of the sparse
+    formulation and the dense MMA work the kernel actually issues, against the measured bf16 peak."""
+    if kernel_name != "tc_solve_kernel" or launch_us <= 0:
+        return None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["bf16_tflops"])
+    except Exception:
+        peak = 2250.0
+    n, nnz = float(pb.n_nodes), float(pb.nnz)
+    hidden = [l for l in layers[1:-1]]
+    alg = sum(2.0 * 2 * n * l.c_in * l.c_out + 2.0 * (nnz + n) * l.c_out + n * l.c_out for l in hidden)
+    sizes = pb.graph_sizes().astype(np.int64)
+    nb = (sizes + 127) // 128
+    kp = (sizes + 31) // 32 * 32
+    proj = float(nb.sum()) * 12 * 2 * 128 * 64 * 16 * len(hidden)          # 6 split products x 2 K steps, bf16
+    agg = float((nb * kp).sum()) * 2 * 128 * 128 * len(hidden)             # u8 x s8 digits, N = 128
+    t = launch_us * 1e-6
+    return {"algorithmic_tflops": alg / t / 1e12, "issued_bf16_tflops": proj / t / 1e12, "issued_int8_tops": agg / t / 1e12,
+            "peak_bf16_tflops": peak,
+            "frac_of_tensor_time": (proj / (peak * 1e12) + agg / (2 * peak * 1e12)) / t,
+            "note": "issued = dense MMA work (bf16 3-term split projection, int8 digit aggregation over the dense adjacency); "
+                    "frac_of_tensor_time = time those MMAs need at the measured bf16 peak (int8 at twice it) / kernel time; "
+                    "ncu: sm__pipe_tensor_cycles_active 29 % (profiles/r01_tc2_ncu.md)"}
+
+
 def dist_env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
             int(os.environ.get("WORLD_SIZE", "1")))
@@ -436,7 +463,8 @@ def run_ours(args):
                          "avg_launch_us": 1e3 * tot_ms.value / max(kern_launches, 1),
                          "algorithmic_bytes_per_launch": alg_bytes.value / max(kern_launches, 1),
                          "share_of_step": tot_ms.value / dev_ms if dev_ms > 0 else None,
-                         "peak_source": peak_src},
+                         "peak_source": peak_src,
+                         "tensor": tensor_view(kernel_name, c0, layers, 1e3 * tot_ms.value / max(kern_launches, 1))},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

@@ -76,6 +76,7 @@ constexpr int kTcOffMeta = kTcOffBar + 256;        // TcMeta[4] + tile scalars
 // A 128-row block of a graph whose last block is partial reads adjacency rows past R: those reads stay inside the pool (the
 // next chunk / the Y region) and only feed accumulator rows nobody looks at.
 // The projection's A operand (the bf16 terms of H) lives in TENSOR memory, see the column map in the kernel.
+constexpr int kTcOffWatch = kTcOffMeta + 224;     // TcWatch (16 bytes)
 constexpr int kTcOffPool = 32768;
 // Tensor-memory columns of a block (128 of the 512; base = block * 128):
 //   0..63    [P0 | P1]  fp32 accumulators of the projection                  (written by the projection, read by epilogue B)
@@ -124,6 +125,8 @@ struct TcParams {
     int round_cap;
     int do_lgs;
     long long *dbg;
+    int *watchdog;      // pinned host memory the wait site of a protocol error is left in
+    int watchdog_wide;
 };
 
 // ---- PTX helpers ----------------------------------------------------------------------------------------------------
@@ -152,8 +155,12 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 }
 // Bounded wait: a protocol error must end the launch with an error, never hang the GPU.  The wait site that gave up is
 // left in pinned host memory (dg_context::h_flag[3]) for the post-mortem.
-__device__ int *g_tc_watchdog = nullptr;
-__device__ int g_tc_watchdog_wide = 0;  // DG_TC_DEBUG: the pointer is a wide table, every stuck thread logs its site
+// (the pointer and the "wide table" flag of DG_TC_DEBUG travel as kernel parameters and are parked in shared memory at
+// kTcOffWatch, where the slow path of mbar_wait finds them: no per-launch symbol copies on the stream)
+struct TcWatch {
+    int *ptr;
+    int wide;  // DG_TC_DEBUG: the pointer is a wide table, every stuck thread logs its site
+};
 // The fast path is a tight loop around try_wait (a suspend-time hint made wake-ups slower and bought nothing:
 // profiles/r01_notes.md); only after ~64 K failed attempts does the instrumented loop run.
 __device__ __forceinline__ bool mbar_wait_fast(uint64_t *bar, uint32_t parity) {
@@ -182,6 +189,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int si
     if (mbar_wait_fast(bar, parity)) return;
     const long long t0 = clock64();
     bool logged = false;
+    extern __shared__ __align__(1024) unsigned char tc_smem_base[];
+    int *const g_tc_watchdog = reinterpret_cast<const TcWatch *>(tc_smem_base + kTcOffWatch)->ptr;
+    const int g_tc_watchdog_wide = reinterpret_cast<const TcWatch *>(tc_smem_base + kTcOffWatch)->wide;
     for (uint32_t spins = 1;; ++spins) {
         if (mbar_test(bar, parity)) return;
         if ((spins & 1023u) == 0u) {
@@ -414,6 +424,9 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
     const int n_hidden = P.n_hidden;
 
     if (tid == 0) {
+        TcWatch *w = reinterpret_cast<TcWatch *>(smem + kTcOffWatch);
+        w->ptr = P.watchdog;
+        w->wide = P.watchdog_wide;
         for (int i = 0; i < 2; ++i) mbar_init(&bar_full[i], 1);
         for (int i = 0; i < kTcBlocks; ++i) {
             mbar_init(&bar_dp[i], 1);
@@ -1403,7 +1416,10 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2), ctx->stream));
         p.dbg = dbg;
     }
-    DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!ctx->tc_attr_set) {  // once per context (the attribute is per device)
+        DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->tc_attr_set = true;
+    }
     const int grid = std::min(ctx->sm_count * kTcCtasPerSm, p.n_tiles);
     {
         int *wd = ctx->h_flag + 3;  // pinned host memory: readable after a device-side trap
@@ -1414,8 +1430,8 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
             wd = g_wide_buf;
             wide = 1;
         }
-        DG_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_tc_watchdog, &wd, sizeof(wd), 0, cudaMemcpyHostToDevice, ctx->stream));
-        DG_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_tc_watchdog_wide, &wide, sizeof(wide), 0, cudaMemcpyHostToDevice, ctx->stream));
+        p.watchdog = wd;
+        p.watchdog_wide = wide;
     }
     {
         // work-equivalent algorithmic bytes, the same figure dg_fused.cu reports (SURVEY.md 8d / DESIGN.md)

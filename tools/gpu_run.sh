@@ -1,3 +1,4 @@
-for i in 1 2 3; do
-timeout 300 python bench.py --no-cpu-baseline --steps 100 --warmup 20 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('bench', d['ms_per_step'], d['roofline']['avg_launch_us'], d['e2e']['ms_per_step'], d['config']['paths_agree'])"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor_core or full_config" 2>&1 | tail -2
+for i in 1 2; do
+timeout 300 python bench.py --no-cpu-baseline --steps 100 --warmup 20 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('bench', d['ms_per_step'], d['roofline']['avg_launch_us'], d['e2e']['ms_per_step'], d['config']['paths_agree'], d['roofline']['tensor']['frac_of_tensor_time'])"
 done

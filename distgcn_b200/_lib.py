@@ -45,6 +45,7 @@ SIGNATURES = {
     "dg_host_free": (None, [_p]),
     "dg_context_launch_count": (C.c_uint64, [_p]),
     "dg_context_last_kernel": (C.c_char_p, [_p]),
+    "dg_context_wait": (C.c_int, [_p, _p]),
     "dg_timer_start": (C.c_int, [_p]),
     "dg_timer_stop": (C.c_int, [_p, _p]),
     "dg_profile_enable": (C.c_int, [_p, C.c_int]),

@@ -216,6 +216,7 @@ void dg_context_destroy(dg_context *ctx) {
     for (auto e : ctx->prof_events) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k)
         if (ctx->timer_ev[k]) cudaEventDestroy(ctx->timer_ev[k]);
+    if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -264,6 +265,19 @@ int dg_timer_stop(dg_context *ctx, double *elapsed_ms) {
     float ms = 0.f;
     DG_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->timer_ev[0], ctx->timer_ev[1]));
     if (elapsed_ms) *elapsed_ms = ms;
+    return DG_OK;
+}
+
+int dg_context_wait(dg_context *ctx, dg_context *other) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_TRY(check_ctx(other));
+    DG_REQUIRE(ctx->device == other->device, DG_ERR_INVALID, "both contexts must live on the same device");
+    if (ctx == other) return DG_OK;
+    DeviceGuard guard(ctx->device);
+    if (!other->order_ev) DG_CUDA_CHECK(cudaEventCreateWithFlags(&other->order_ev, cudaEventDisableTiming));
+    DG_CUDA_CHECK(cudaEventRecord(other->order_ev, other->stream));
+    DG_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, other->order_ev, 0));
     return DG_OK;
 }
 

@@ -89,6 +89,7 @@ struct dg_context {
     int max_smem_optin = 0;
     uint64_t launches = 0;
     std::vector<dg::Buffer> slots;  // named scratch, see dg::Slot
+    cudaEvent_t order_ev = nullptr;  // dg_context_wait: marks this context's stream for another context to wait on
     bool tc_attr_set = false;       // tc_solve_kernel's shared-memory attribute has been set on this context's device
     int *h_flag = nullptr;          // pinned, 4 ints: [0] LGS round read-back, [2] copy of *d_status
     int *d_status = nullptr;        // device, sticky error status written by kernels

@@ -97,6 +97,9 @@ DG_API const char *dg_context_last_kernel(const dg_context *ctx);
 
 /* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,
  * waits for it and returns the elapsed device time between the two in milliseconds. */
+/* Work enqueued on `ctx` after this call starts only when everything enqueued on `other` so far has completed (an
+ * event on other's stream, no host synchronisation).  For callers that drive two contexts of one device in turn. */
+DG_API int dg_context_wait(dg_context *ctx, dg_context *other);
 DG_API int dg_timer_start(dg_context *ctx);
 DG_API int dg_timer_stop(dg_context *ctx, double *elapsed_ms);
 

@@ -205,6 +205,8 @@ struct dg_batch {
     bool tiles_hidden = false;
     size_t tiles_wblob = 0;
     bool tiles_valid = false;
+    int tiles_hint_n = 0, tiles_hint_graphs = 0, tiles_hint_min_n = 0, tiles_hint_cp = 0;  // the previous plan's shape
+    bool tiles_hint_hidden = false;
     // tile table of the tensor-core kernel (dg_tc.cu): up to 4 graph ids per tile
     int *tc_tiles_dev = nullptr;
     size_t tc_tiles_cap = 0;

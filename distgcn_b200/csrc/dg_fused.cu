@@ -977,9 +977,19 @@ size_t fused_smem_bytes(int cp, int cap_n, int cap_nnz, bool has_hidden, size_t 
 template <int CP, bool DIT, bool MMA>
 int launch_t(dg_context *ctx, const FusedParams &p, size_t smem, int n_tiles) {
     auto kern = fused_solve_kernel<CP, DIT, MMA>;
-    DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // attribute and occupancy are queried once per (device, instantiation, shared-memory size): they cost microseconds
+    // of host time that the streaming path would pay on every call
+    static thread_local int c_dev = -1;
+    static thread_local size_t c_smem = 0;
+    static thread_local int c_per_sm = 0;
     int per_sm = 0;
-    DG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (c_dev == ctx->device && c_smem == smem) {
+        per_sm = c_per_sm;
+    } else {
+        DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+        c_dev = ctx->device, c_smem = smem, c_per_sm = per_sm;
+    }
     DG_REQUIRE(per_sm > 0, DG_ERR_UNSUPPORTED, "fused kernel does not fit on an SM with %zu bytes of shared memory",
                smem);
     int grid = ctx->sm_count * per_sm;
@@ -1067,8 +1077,14 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
     std::vector<Tile> best_tiles, tiles;
     int best_n = 0, best_nnz = 0;
     long long best_span = -1;
+    // A context that solves a stream of similar batches (dg_solve_host*) re-plans on every call: when the previous plan
+    // was made for a batch of the same shape (graph count, largest graph), only its capacity and the two neighbouring
+    // ones are simulated again.
+    const bool hinted = b->tiles_hint_n > 0 && b->tiles_hint_graphs == b->n_graphs && b->tiles_hint_min_n == min_n &&
+                        b->tiles_hint_cp == cp && b->tiles_hint_hidden == has_hidden;
     for (int cap_n = min_n; cap_n <= 1024; cap_n += 32) {
         if (forced_rows > 0 && cap_n != std::max(min_n, (forced_rows + 31) / 32 * 32)) continue;
+        if (forced_rows <= 0 && hinted && (cap_n < b->tiles_hint_n - 32 || cap_n > b->tiles_hint_n + 32)) continue;
         // give the neighbour lists whatever shared memory is left (bounded by 48 padded entries per row)
         const size_t fixed = fused_smem_bytes(cp, cap_n, 0, has_hidden, wblob);
         if (fixed + sizeof(uint16_t) * (size_t)min_nnz > budget) break;
@@ -1086,6 +1102,8 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
         }
     }
     if (best_span < 0) return DG_OK;
+    b->tiles_hint_n = best_n, b->tiles_hint_graphs = b->n_graphs, b->tiles_hint_min_n = min_n;
+    b->tiles_hint_cp = cp, b->tiles_hint_hidden = has_hidden;
     std::vector<int> flat(best_tiles.size() * 8, 0);
     for (size_t t = 0; t < best_tiles.size(); ++t) {
         int *d = &flat[t * 8];

@@ -1013,12 +1013,24 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                     for (int w = 0; w < 12; ++w) {
                         if (w < nw) {
                             uint32_t cand = nbm[w] & remain[w0 + w], beat = 0u;
+                            const int base = (w0 + w) * 32;  // the word's first slot
                             while (cand) {
-                                const int bit = __ffs(cand) - 1;
-                                cand &= cand - 1;
-                                const int us = (w0 + w) * 32 + bit;  // the neighbour's slot
-                                const double wu = util_sm[us];
-                                if (!((wv > wu) || (wv == wu && tid < us))) beat |= 1u << bit;
+                                // up to four neighbours per pass, their utilities loaded back to back (the loop is bound
+                                // by the shared-memory round trip, and a warp runs as many passes as its busiest lane)
+                                int bit[4];
+                                double wu[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    bit[k] = cand ? __ffs(cand) - 1 : -1;
+                                    cand &= cand - 1;  // (0 stays 0)
+                                }
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) wu[k] = util_sm[bit[k] >= 0 ? base + bit[k] : tid];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int us = base + bit[k];
+                                    if (bit[k] >= 0 && !((wv > wu[k]) || (wv == wu[k] && tid < us))) beat |= 1u << bit[k];
+                                }
                             }
                             nbm[w] = beat;
                         }

@@ -1,3 +1,5 @@
-python tools/host_cost.py 2>&1 | tail -2
-timeout 600 python -m pytest tests -m gpu -x -q -k "fused or full_config or host or heuristics or dit" 2>&1 | tail -2
-timeout 300 python bench.py --workload er500 --steps 100 --warmup 20 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('er500', d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['config']['paths_agree'])"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor_core or full_config or zero_weight or solve_membership" 2>&1 | tail -2
+for i in 1 2; do
+timeout 300 python bench.py --no-cpu-baseline --steps 100 --warmup 20 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('bench', d['ms_per_step'], d['roofline']['avg_launch_us'], d['e2e']['ms_per_step'], d['config']['paths_agree'])"
+done
+DG_FUSED_TIMING=1 timeout 300 python bench.py --no-cpu-baseline --steps 3 --warmup 3 2>&1 >/dev/null | grep "tc timing\] greedy\|tc timing\] total" | tail -2

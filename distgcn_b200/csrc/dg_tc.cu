@@ -59,6 +59,10 @@ constexpr int kTcBlocks = 4;          // 128-row blocks per tile = TMEM budget: 
 constexpr int kTcCtasPerSm = 1;
 #endif
 constexpr int kTcTmemCols = 128 * kTcBlocks;
+#ifndef DG_BEAT_UNROLL
+#define DG_BEAT_UNROLL 4
+#endif
+constexpr int kBeatUnroll = DG_BEAT_UNROLL;  // neighbours per pass of the greedy phase's 'who beats me' scan
 // a partial last block reads up to 127 rows x 16 B past its graph's last region: the tile keeps that much of the pool free
 constexpr int kTcOverread = 2048 + 128;
 constexpr int kTcWBlob = 12560;       // one hidden layer: bf16 terms of [W_0 | W_1 r] (12288), bias[32], 1/r[32], bound, pad
@@ -1015,19 +1019,19 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                             uint32_t cand = nbm[w] & remain[w0 + w], beat = 0u;
                             const int base = (w0 + w) * 32;  // the word's first slot
                             while (cand) {
-                                // up to four neighbours per pass, their utilities loaded back to back (the loop is bound
+                                // up to kBeatUnroll neighbours per pass, their utilities loaded back to back (the loop is bound
                                 // by the shared-memory round trip, and a warp runs as many passes as its busiest lane)
-                                int bit[4];
-                                double wu[4];
+                                int bit[kBeatUnroll];
+                                double wu[kBeatUnroll];
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
+                                for (int k = 0; k < kBeatUnroll; ++k) {
                                     bit[k] = cand ? __ffs(cand) - 1 : -1;
                                     cand &= cand - 1;  // (0 stays 0)
                                 }
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) wu[k] = util_sm[bit[k] >= 0 ? base + bit[k] : tid];
+                                for (int k = 0; k < kBeatUnroll; ++k) wu[k] = util_sm[bit[k] >= 0 ? base + bit[k] : tid];
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
+                                for (int k = 0; k < kBeatUnroll; ++k) {
                                     const int us = base + bit[k];
                                     if (bit[k] >= 0 && !((wv > wu[k]) || (wv == wu[k] && tid < us))) beat |= 1u << bit[k];
                                 }

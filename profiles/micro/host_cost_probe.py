@@ -1,7 +1,7 @@
 """Host-side cost of one dg_solve_host_async submit (enqueue only) per workload."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import bench
 from distgcn_b200 import engine as E
 for wl in ("ba500", "er500"):

@@ -1,7 +1,7 @@
 """Throughput of tc_solve_kernel on synthetic graphs of n_lo..n_hi vertices (device-resident, CUDA events)."""
 import os, sys, ctypes as C
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import bench
 from distgcn_b200 import engine as E
 from tests import util

@@ -35,7 +35,6 @@
 
 #include <algorithm>
 #include <functional>
-#include <map>
 #include <type_traits>
 #include <vector>
 
@@ -1305,31 +1304,43 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     // Largest graph first; every tile is then topped up with the largest remaining graphs that still fit (blocks, bytes
     // and cost all grow with the vertex count, so "largest that fits" is a lookup in the size-ordered remainder).
     std::vector<Open> tiles;
-    std::map<int, std::vector<const TcGraph *>> by_size;  // vertex count -> graphs of that size still unplaced
-    for (const TcGraph &t : gs) by_size[t.nv].push_back(&t);
-    while (!by_size.empty()) {
+    // Unplaced graphs as one stack per vertex count (LIFO: the last graph of a size goes first); prev_size[s] leads to the
+    // largest non-empty size <= s (removals only: pointer jumping with path compression), so a fill is O(1) - this planner
+    // runs on the host for every streamed batch, 16 k graphs at a time in the large configurations.
+    const int max_size = kTcBlocks * 128;
+    std::vector<int> head((size_t)max_size + 1, -1), next_same((size_t)b->n_graphs, -1), prev_size((size_t)max_size + 1);
+    for (const TcGraph &t : gs) {
+        next_same[(size_t)t.g] = head[(size_t)t.nv];
+        head[(size_t)t.nv] = t.g;
+    }
+    prev_size[0] = 0;
+    for (int sz = 1; sz <= max_size; ++sz) prev_size[(size_t)sz] = head[(size_t)sz] >= 0 ? sz : prev_size[(size_t)sz - 1];
+    auto largest_at_most = [&](int sz) {
+        int r = sz;
+        while (r > 0 && prev_size[(size_t)r] != r) r = prev_size[(size_t)r];
+        for (int q = sz; q > 0 && prev_size[(size_t)q] != q;) {  // path compression
+            const int nq = prev_size[(size_t)q];
+            prev_size[(size_t)q] = r;
+            q = nq;
+        }
+        return r;
+    };
+    int remaining = b->n_graphs;
+    while (remaining > 0) {
         Open o{};
-        for (;;) {
-            // the largest size whose graph fits into what is left of the tile
-            auto it = by_size.end();
-            bool found = false;
-            while (it != by_size.begin()) {
-                --it;
-                const TcGraph *c = it->second.back();
-                if (o.ng < kTcMaxG && o.blocks + c->nb <= kTcBlocks && o.bytes + c->bytes + kTcOverread <= pool) {
-                    found = true;
-                    break;
-                }
-            }
-            if (!found) break;
-            const TcGraph *c = it->second.back();
-            it->second.pop_back();
-            if (it->second.empty()) by_size.erase(it);
+        while (o.ng < kTcMaxG && o.blocks < kTcBlocks) {
+            // the largest graph that fits into what is left of the tile: blocks bound its size, then the pool bytes
+            int sz = largest_at_most((kTcBlocks - o.blocks) * 128);
+            while (sz > 0 && o.bytes + gs[(size_t)head[(size_t)sz]].bytes + kTcOverread > pool) sz = largest_at_most(sz - 1);
+            if (sz == 0) break;
+            const TcGraph *c = &gs[(size_t)head[(size_t)sz]];
+            head[(size_t)sz] = next_same[(size_t)c->g];
+            if (head[(size_t)sz] < 0) prev_size[(size_t)sz] = sz - 1;
             o.g[o.ng++] = c->g;
             o.blocks += c->nb;
             o.bytes += c->bytes;
             o.cost += c->cost;
-            if (by_size.empty()) break;
+            --remaining;
         }
         tiles.push_back(o);
     }

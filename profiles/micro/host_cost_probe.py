@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import bench
 from distgcn_b200 import engine as E
-for wl in ("ba500", "er500"):
+for wl in (sys.argv[1:] or ["ba500", "er500"]):
     pb, w, layers, desc = bench.load_workload(wl, 0)
     ctx = E.Context(0)
     model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))

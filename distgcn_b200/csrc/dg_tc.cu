@@ -61,7 +61,11 @@ constexpr int kTcTmemCols = 128 * kTcBlocks;
 #ifndef DG_BEAT_UNROLL
 #define DG_BEAT_UNROLL 4
 #endif
-constexpr int kBeatUnroll = DG_BEAT_UNROLL;  // neighbours per pass of the greedy phase's 'who beats me' scan
+constexpr int kBeatUnroll = DG_BEAT_UNROLL;
+#ifndef DG_STAGE_EDGES
+#define DG_STAGE_EDGES 8
+#endif
+constexpr int kStageEdges = DG_STAGE_EDGES;  // edges per thread and staging pass (global loads in flight)  // neighbours per pass of the greedy phase's 'who beats me' scan
 // a partial last block reads up to 127 rows x 16 B past its graph's last region: the tile keeps that much of the pool free
 constexpr int kTcOverread = 2048 + 128;
 constexpr int kTcWBlob = 12560;       // one hidden layer: bf16 terms of [W_0 | W_1 r] (12288), bias[32], 1/r[32], bound, pad
@@ -571,24 +575,24 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 unsigned char *adj = pool + m.adj;
                 const uint16_t *rowof = reinterpret_cast<const uint16_t *>(pool + m.hoff);
                 const bool table = 2 * m.nnz <= 128 * m.Kp;
-                // eight edges per thread and pass, their global loads issued back to back (the loop is latency bound)
-                for (int eb = tid; eb < m.nnz; eb += 8 * kTcVertexThreads) {
-                    int jj[8], ll[8];
+                // kStageEdges edges per thread and pass, their global loads issued back to back (the loop is latency bound)
+                for (int eb = tid; eb < m.nnz; eb += kStageEdges * kTcVertexThreads) {
+                    int jj[kStageEdges], ll[kStageEdges];
                     if (P.col16) {  // (uniform branch outside the loads: they must issue back to back)
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
+                        for (int u = 0; u < kStageEdges; ++u) {
                             const int e = eb + u * kTcVertexThreads;
                             jj[u] = e < m.nnz ? (int)__ldg(P.col16 + m.e0 + e) : -1;
                         }
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
+                        for (int u = 0; u < kStageEdges; ++u) {
                             const int e = eb + u * kTcVertexThreads;
                             jj[u] = e < m.nnz ? __ldg(P.col_idx + m.e0 + e) - m.v0 : -1;
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < kStageEdges; ++u) {
                         const int e = eb + u * kTcVertexThreads;
                         int lo = 0;
                         if (e < m.nnz) {
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         ll[u] = lo;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < kStageEdges; ++u) {
                         const int j = jj[u], lo = ll[u];
                         if (j >= 0) {
                             const uint32_t ki = (keepw[m.fb * 4 + (lo >> 5)] >> (lo & 31)) & 1u;

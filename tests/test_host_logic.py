@@ -236,3 +236,23 @@ def test_mat_dataset_ingest(tmp_path):
         off += n
     assert np.array_equal(extras["greedy_utility"], np.array([1.0, 2.0, 0.0]))
     packed.validate()
+
+
+def test_local_columns_compact_format():
+    """PackedBatch.local_columns(): 16-bit graph-local column ids (the compact host format of dg_solve_host_compact)."""
+    pb, _ = util.small_graphs()
+    c16 = pb.local_columns()
+    assert c16.dtype == np.uint16 and c16.flags.c_contiguous and c16.shape == pb.col_idx.shape
+    base = np.repeat(pb.graph_ptr[:-1].astype(np.int64), pb.graph_nnz())
+    assert np.array_equal(c16.astype(np.int64) + base, pb.col_idx)
+    sizes = np.repeat(pb.graph_sizes().astype(np.int64), pb.graph_nnz())
+    assert (c16 < sizes).all()
+    sub = pb.slice(7, 19)                      # slices re-base their ids: the local form is unchanged
+    e0, e1 = int(pb.row_ptr[pb.graph_ptr[7]]), int(pb.row_ptr[pb.graph_ptr[19]])
+    assert np.array_equal(sub.local_columns(), c16[e0:e1])
+    from distgcn_b200.batch import PackedBatch
+    empty = PackedBatch(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    assert empty.local_columns().shape == (0,)
+    big = PackedBatch(np.array([0, 70000], np.int32), np.zeros(70001, np.int32), np.zeros(0, np.int32))
+    with pytest.raises(ValueError):
+        big.local_columns()

@@ -213,6 +213,10 @@ struct dg_batch {
     int tc_n_tiles = 0;
     bool tc_tiles_valid = false;
     std::vector<int> tc_tiles_host;  // host copy of the table (scheduling diagnostics)
+    std::vector<uint8_t> tc_skip;    // per graph: 1 = beyond the tensor-core kernel's limits (left to the CUDA-core kernel)
+    int tc_n_skipped = 0;
+    bool tc_ran_partial = false;     // the tensor-core kernel has just solved the batch except the tc_skip graphs
+    bool tiles_subset = false;       // the fused kernel's cached tile table covers only the tc_skip graphs
 };
 
 struct dg_part {  // one rank's row slice of a single large graph (device CSR, global column ids)

@@ -1013,12 +1013,18 @@ inline long long tile_cost(const Tile &t) {
     return 41LL * ((long long)t.nnz + 3LL * t.n / 2) + 300LL * t.n + 200000LL;
 }
 
-void pack_tiles(const dg_batch *b, int cap_n, int cap_nnz, std::vector<Tile> *out) {
+// `subset`: only the graphs the tensor-core kernel left out (dg_batch::tc_skip); a tile never spans a gap
+void pack_tiles(const dg_batch *b, int cap_n, int cap_nnz, bool subset, std::vector<Tile> *out) {
     out->clear();
     const auto &gp = b->h_graph_ptr;
     const auto &ge = b->h_graph_e;
     Tile cur{0, 0, 0, 0, 0, 0};
     for (int g = 0; g < b->n_graphs; ++g) {
+        if (subset && !b->tc_skip[(size_t)g]) {
+            if (cur.ng > 0) out->push_back(cur);
+            cur = Tile{0, 0, 0, 0, 0, 0};
+            continue;
+        }
         const int gn = gp[g + 1] - gp[g], gz = ge[g + 1] - ge[g];
         // cap_nnz bounds the PADDED neighbour lists (each row rounded up to a multiple of 4)
         if (cur.ng > 0 && (cur.n + gn > cap_n || cur.nnz + gz + 3 * (cur.n + gn) > cap_nnz ||
@@ -1057,10 +1063,10 @@ long long simulate_makespan(const std::vector<Tile> &tiles, int workers) {
 // among the feasible ones by simulating that schedule: with a few hundred graphs on 148 SMs the
 // number of tiles per CTA is small and a capacity that leaves a few CTAs with one tile more than the
 // others costs tens of percent.
-int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wblob, bool *ok) {
+int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wblob, bool subset, bool *ok) {
     *ok = false;
-    if (b->tiles_valid) {  // the plan depends only on the batch and on (cp, has_hidden)
-        if (b->tiles_cp == cp && b->tiles_hidden == has_hidden && b->tiles_wblob == wblob) {
+    if (b->tiles_valid) {  // the plan depends only on the batch and on (cp, has_hidden, subset)
+        if (b->tiles_cp == cp && b->tiles_hidden == has_hidden && b->tiles_wblob == wblob && b->tiles_subset == subset) {
             *ok = b->n_tiles > 0;
             return DG_OK;
         }
@@ -1080,8 +1086,8 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
     // A context that solves a stream of similar batches (dg_solve_host*) re-plans on every call: when the previous plan
     // was made for a batch of the same shape (graph count, largest graph), only its capacity and the two neighbouring
     // ones are simulated again.
-    const bool hinted = b->tiles_hint_n > 0 && b->tiles_hint_graphs == b->n_graphs && b->tiles_hint_min_n == min_n &&
-                        b->tiles_hint_cp == cp && b->tiles_hint_hidden == has_hidden;
+    const bool hinted = !subset && b->tiles_hint_n > 0 && b->tiles_hint_graphs == b->n_graphs &&
+                        b->tiles_hint_min_n == min_n && b->tiles_hint_cp == cp && b->tiles_hint_hidden == has_hidden;
     for (int cap_n = min_n; cap_n <= 1024; cap_n += 32) {
         if (forced_rows > 0 && cap_n != std::max(min_n, (forced_rows + 31) / 32 * 32)) continue;
         if (forced_rows <= 0 && hinted && (cap_n < b->tiles_hint_n - 32 || cap_n > b->tiles_hint_n + 32)) continue;
@@ -1092,7 +1098,7 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
         cap_nnz = std::min<long long>(cap_nnz, std::max<long long>(min_nnz, 48LL * cap_n));
         cap_nnz = cap_nnz / 64 * 64;
         if (cap_nnz < min_nnz) break;
-        pack_tiles(b, cap_n, (int)cap_nnz, &tiles);
+        pack_tiles(b, cap_n, (int)cap_nnz, subset, &tiles);
         const long long span = simulate_makespan(tiles, ctx->sm_count);
         if (best_span < 0 || span < best_span) {
             best_span = span;
@@ -1102,8 +1108,10 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
         }
     }
     if (best_span < 0) return DG_OK;
-    b->tiles_hint_n = best_n, b->tiles_hint_graphs = b->n_graphs, b->tiles_hint_min_n = min_n;
-    b->tiles_hint_cp = cp, b->tiles_hint_hidden = has_hidden;
+    if (!subset) {
+        b->tiles_hint_n = best_n, b->tiles_hint_graphs = b->n_graphs, b->tiles_hint_min_n = min_n;
+        b->tiles_hint_cp = cp, b->tiles_hint_hidden = has_hidden;
+    }
     std::vector<int> flat(best_tiles.size() * 8, 0);
     for (size_t t = 0; t < best_tiles.size(); ++t) {
         int *d = &flat[t * 8];
@@ -1130,6 +1138,7 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
     b->tiles_cp = cp;
     b->tiles_hidden = has_hidden;
     b->tiles_wblob = wblob;
+    b->tiles_subset = subset;
     b->tiles_valid = true;
     if (getenv("DG_FUSED_TIMING"))
         fprintf(stderr, "[fused tiles] %d tiles, cap_n %d, cap_nnz %d, simulated makespan %lld\n", b->n_tiles, best_n,
@@ -1144,6 +1153,9 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
                     int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
                     int32_t *steps, bool *handled, bool dit) {
     *handled = false;
+    // the tensor-core kernel has just solved this batch except the graphs beyond its limits: only those are left
+    const bool subset = b->tc_ran_partial && !dit;
+    b->tc_ran_partial = false;
     // member == nullptr: scores only (dg_gcn_forward); the greedy rounds are skipped
     if (member == nullptr && (d_wts == nullptr) && predict == DG_PREDICT_MWIS) return DG_OK;
     if (getenv("DG_DISABLE_FUSED")) return DG_OK;
@@ -1157,7 +1169,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     const size_t wblob = use_mma ? sizeof(float) * (size_t)(2 * 2 * 32 * 40 + 32)
                                  : sizeof(float) * (size_t)(2 * m->fused_cp * m->fused_cp + m->fused_cp);
     bool ok = false;
-    DG_TRY(build_tiles(ctx, b, m->fused_cp, has_hidden, wblob, &ok));
+    DG_TRY(build_tiles(ctx, b, m->fused_cp, has_hidden, wblob, subset, &ok));
     if (!ok) return DG_OK;
     FusedParams p{};
     p.tiles = b->tiles_dev;

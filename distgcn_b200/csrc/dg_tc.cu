@@ -1230,7 +1230,8 @@ inline long long tc_graph_cost(int nb, int Kp, int nnz) {
 bool tc_pack_lpt(const std::vector<TcGraph> &gs, int bins, size_t pool, std::vector<Open> *out) {
     std::vector<const TcGraph *> order;
     order.reserve(gs.size());
-    for (const TcGraph &t : gs) order.push_back(&t);
+    for (const TcGraph &t : gs)
+        if (t.nb > 0) order.push_back(&t);
     std::sort(order.begin(), order.end(), [](const TcGraph *a, const TcGraph *c) { return a->cost != c->cost ? a->cost > c->cost : a->g < c->g; });
     std::vector<Open> tiles((size_t)bins, Open{});
     typedef std::pair<long long, int> Key;  // (cost so far, tile)
@@ -1294,6 +1295,8 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     const auto &gp = b->h_graph_ptr;
     const auto &ge = b->h_graph_e;
     std::vector<TcGraph> gs((size_t)b->n_graphs);
+    b->tc_skip.assign((size_t)b->n_graphs, 0);
+    b->tc_n_skipped = 0;
     for (int g = 0; g < b->n_graphs; ++g) {
         TcGraph t;
         t.g = g;
@@ -1301,8 +1304,16 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         t.nb = std::max(1, (t.nv + 127) / 128);
         const size_t R = (size_t)((t.nv + 7) & ~7), Kp = (size_t)((t.nv + 31) & ~31);
         t.bytes = R * Kp + 128 * Kp;
+        if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + kTcOverread > pool) {
+            // beyond this kernel's limits (or empty): the graph is left to the CUDA-core kernel, the rest of the batch stays here
+            t.nb = 0;
+            t.cost = 0;
+            b->tc_skip[(size_t)g] = 1;
+            b->tc_n_skipped++;
+            gs[(size_t)g] = t;
+            continue;
+        }
         t.cost = tc_graph_cost(t.nb, (int)Kp, ge[g + 1] - ge[g]);
-        if (t.nv <= 0 || t.nb > kTcBlocks || t.bytes + kTcOverread > pool) return DG_OK;  // not eligible: the caller falls back
         gs[(size_t)g] = t;
     }
     // Largest graph first; every tile is then topped up with the largest remaining graphs that still fit (blocks, bytes
@@ -1313,7 +1324,9 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     // runs on the host for every streamed batch, 16 k graphs at a time in the large configurations.
     const int max_size = kTcBlocks * 128;
     std::vector<int> head((size_t)max_size + 1, -1), next_same((size_t)b->n_graphs, -1), prev_size((size_t)max_size + 1);
+    if (b->tc_n_skipped == b->n_graphs) return DG_OK;  // nothing for this kernel
     for (const TcGraph &t : gs) {
+        if (t.nb == 0) continue;
         next_same[(size_t)t.g] = head[(size_t)t.nv];
         head[(size_t)t.nv] = t.g;
     }
@@ -1329,7 +1342,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         }
         return r;
     };
-    int remaining = b->n_graphs;
+    int remaining = b->n_graphs - b->tc_n_skipped;
     while (remaining > 0) {
         Open o{};
         while (o.ng < kTcMaxG && o.blocks < kTcBlocks) {
@@ -1357,7 +1370,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
         const int k = ((int)tiles.size() + sms - 1) / sms;
         int want = k * sms;
         if (const char *e = getenv("DG_TC_TILES")) want = atoi(e);  // (experiments)
-        if (k <= 8 && want > (int)tiles.size() && want <= b->n_graphs) {
+        if (k <= 8 && want > (int)tiles.size() && want <= b->n_graphs - b->tc_n_skipped) {
             std::vector<Open> lpt;
             if (tc_pack_lpt(gs, want, pool, &lpt)) {
                 std::stable_sort(lpt.begin(), lpt.end(), [](const Open &a, const Open &c) { return a.cost > c.cost; });
@@ -1523,7 +1536,9 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
             }
         }
     }
-    *handled = true;
+    // graphs beyond this kernel's limits are solved next by the CUDA-core kernel (fused_try_solve reads the flag)
+    b->tc_ran_partial = b->tc_n_skipped > 0;
+    *handled = b->tc_n_skipped == 0;
     return DG_OK;
 }
 

@@ -655,16 +655,32 @@ def test_tensor_core_kernel_edge_cases(gpu_ctx, monkeypatch):
     assert _rel_err(out[:, 0], ref) <= SCORE_RTOL
     batch.set_x0(None)
     batch.close()
-    # one graph above the size limit (~352 vertices): the whole batch takes the CUDA-core kernel, same answers
+    # graphs above the size limit (~376 vertices) in the middle and at the end of the batch: the tensor-core kernel keeps the
+    # rest, the CUDA-core kernel (launched after it) solves those two - same answers as each kernel alone
     up = np.triu(rng.random((400, 400)) < 0.05, k=1)
-    big = pack_graphs(adjs + [sp.csr_matrix((up | up.T).astype(np.float64))])
-    wb = np.concatenate([w, rng.random(400)])
+    up2 = np.triu(rng.random((450, 450)) < 0.02, k=1)
+    k_mid = len(adjs) // 2
+    mixed = adjs[:k_mid] + [sp.csr_matrix((up2 | up2.T).astype(np.float64))] + adjs[k_mid:] + \
+        [sp.csr_matrix((up | up.T).astype(np.float64))]
+    big = pack_graphs(mixed)
+    v_mid = int(pb.graph_ptr[k_mid])
+    wb = np.concatenate([w[:v_mid], rng.random(450), w[v_mid:], rng.random(400)])
+    small_idx = np.concatenate([np.arange(v_mid), np.arange(v_mid + 450, n + 450)])
     bbatch = E.DeviceBatch(gpu_ctx, big)
-    rb = E.solve(gpu_ctx, model, bbatch, wb, remove_zero_weight=True, want_score=True)
-    assert gpu_ctx.last_kernel == "fused_solve_kernel"
+    launches0 = gpu_ctx.launch_count
+    rb = E.solve(gpu_ctx, model, bbatch, wb, remove_zero_weight=True, want_score=True, want_util=True, want_steps=True)
+    assert gpu_ctx.last_kernel == "fused_solve_kernel" and gpu_ctx.launch_count - launches0 == 2
     rs = E.solve(gpu_ctx, model, E.DeviceBatch(gpu_ctx, pb), w, remove_zero_weight=True, want_score=True)
     assert gpu_ctx.last_kernel == "tc_solve_kernel"
-    assert _rel_err(rb.score[:n, 0], rs.score[:, 0]) <= 2 * SCORE_RTOL
+    assert np.array_equal(rb.score[small_idx, 0], rs.score[:, 0])          # those graphs took the same kernel
+    assert _rel_err(rb.score[:, 0], util.exact_scores(big, wb, layers, "gcn2_dqn")) <= SCORE_RTOL
+    o = L.run_batch(big.graph_ptr, big.row_ptr, big.col_idx, rb.util, init_remain=(wb > 0).astype(np.uint8))
+    assert np.array_equal(o.member, rb.member) and np.array_equal(o.steps, rb.steps)
+    monkeypatch.setenv("DG_DISABLE_TC", "1")
+    rf = E.solve(gpu_ctx, model, bbatch, wb, remove_zero_weight=True, want_score=True)
+    monkeypatch.delenv("DG_DISABLE_TC")
+    big_idx = np.setdiff1d(np.arange(big.n_nodes), small_idx)
+    assert np.array_equal(rf.score[big_idx, 0], rb.score[big_idx, 0])      # ... and the two large ones the other
     bbatch.close()
     model.close()
 

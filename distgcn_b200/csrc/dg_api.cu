@@ -90,6 +90,17 @@ int copy_out(dg_context *ctx, T *host, const T *dev, size_t count) {
     return DG_OK;
 }
 
+// message for a status code a kernel left in the context's sticky status word
+static void set_kernel_status_error(int code) {
+    if (code == DG_ERR_NOT_CONVERGED)
+        set_error("greedy search hit the round cap (NaN utilities or self-loops?)");
+    else if (code == DG_ERR_CUDA)
+        set_error("a device-side wait gave up: the peer barrier of a row-partitioned solve timed out (a rank missing "
+                  "or its arena not mapped?)");
+    else
+        set_error("a kernel reported status %d", code);
+}
+
 // synchronise and surface sticky kernel-side errors
 int finish(dg_context *ctx) {
     // the kernels' sticky status word travels with the synchronisation, not with every launch
@@ -99,7 +110,7 @@ int finish(dg_context *ctx) {
         int code = ctx->h_flag[2];
         ctx->h_flag[2] = 0;
         cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
-        set_error("local greedy search hit the round cap (NaN utilities or self-loops?)");
+        set_kernel_status_error(code);
         return code;
     }
     return DG_OK;
@@ -932,15 +943,38 @@ static int solve_device(dg_context *ctx, const dg_model *m, dg_batch *b, const d
     DG_TRY(fused_try_solve(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, d_score, d_util, d_total, d_steps,
                            &handled));
     if (handled) return DG_OK;
-    if (remove_zero_weight) DG_TRY(set_keep_from_weights_device(b, d_wts));
-    const int d_out = m->layers.back().c_out;
-    if (!d_score) DG_TRY(scratch_as(ctx, kSlotScore, n * d_out, &d_score));
-    if (!d_util) DG_TRY(scratch_as(ctx, kSlotUtil, n, &d_util));
-    // with several output columns the utility uses column 0, as act_vals.flatten() does for diver_num == 1
-    DG_TRY(gcn_forward_device(ctx, m, b, d_score, d_wts, predict, d_util));
-    DG_TRY(lgs_device(ctx, b, d_util, -1, d_member, nullptr, d_steps, nullptr, nullptr, nullptr));
-    if (d_total) DG_TRY(member_weight_device(ctx, b, d_member, d_wts, d_total));
-    return DG_OK;
+    b->tc_ran_partial = false;
+    // Per-layer path.  Zero-weight removal (mwis_dqn_call.py:202-207) is a keep mask for THIS solve only: like the
+    // graph-resident kernels it replaces the caller's mask for the duration of the call and leaves the batch (mask and
+    // degrees) as it was found, so a later dg_lgs / dg_gcn_forward on the same batch sees the caller's graph.
+    uint8_t *const caller_keep = b->keep;
+    if (remove_zero_weight) {
+        uint8_t *tmp = nullptr;
+        DG_TRY(scratch_as(ctx, kSlotSolveKeep, std::max<size_t>(n, 1), &tmp));
+        DG_TRY(keep_from_weights_device(ctx, b->n_nodes, d_wts, tmp));
+        b->keep = tmp;
+        const int st0 = batch_compute_dinv(b);
+        if (st0 != DG_OK) {
+            b->keep = caller_keep;
+            return st0;
+        }
+    }
+    int st = DG_OK;
+    do {
+        const int d_out = m->layers.back().c_out;
+        if (!d_score && (st = scratch_as(ctx, kSlotScore, n * d_out, &d_score)) != DG_OK) break;
+        if (!d_util && (st = scratch_as(ctx, kSlotUtil, n, &d_util)) != DG_OK) break;
+        // with several output columns the utility uses column 0, as act_vals.flatten() does for diver_num == 1
+        if ((st = gcn_forward_device(ctx, m, b, d_score, d_wts, predict, d_util, /*try_resident=*/false)) != DG_OK) break;
+        if ((st = lgs_device(ctx, b, d_util, -1, d_member, nullptr, d_steps, nullptr, nullptr, nullptr)) != DG_OK) break;
+        if (d_total) st = member_weight_device(ctx, b, d_member, d_wts, d_total);
+    } while (false);
+    if (remove_zero_weight) {
+        b->keep = caller_keep;
+        const int st2 = batch_compute_dinv(b);
+        if (st == DG_OK) st = st2;
+    }
+    return st;
 }
 
 // GCN embedded into the greedy iteration (mwis_gdpg_call.py:278-318), device-space body

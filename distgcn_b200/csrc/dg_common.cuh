@@ -133,6 +133,7 @@ enum Slot : int {
     kSlotHostRowPtr,
     kSlotHostColIdx,
     kSlotPartial,     // per-slice partial sums of member_weight
+    kSlotSolveKeep,   // dg_solve's zero-weight keep mask on the per-layer path (the caller's mask is left alone)
     kSlotCount
 };
 
@@ -317,6 +318,9 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
                     int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
                     int32_t *steps, bool *handled, bool dit = false);
 
+// true when fused_try_solve would take this model and every graph of the batch fits one of its tiles (no launch)
+bool fused_fits(dg_context *ctx, const dg_model *m, const dg_batch *b);
+
 // ---- tensor-core solve kernel (dg_tc.cu) ---------------------------------------------------------
 // hidden-layer operand blobs from the layers' weights ([c_in, c_out] row-major, widths <= 32)
 void tc_build_weights(int n_hidden, const float *const *w0, const float *const *w1, const float *const *bias, const int *c_in,
@@ -327,8 +331,10 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
 
 // ---- kernels / drivers implemented in dg_gcn.cu ---------------------------------------------
 int batch_compute_dinv(dg_batch *b);
+// try_resident = false: go straight to the per-layer kernels (the caller has already tried the graph-resident ones)
 int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *out /*device*/,
-                       const double *wts /*device or null*/, int predict, double *util /*device or null*/);
+                       const double *wts /*device or null*/, int predict, double *util /*device or null*/,
+                       bool try_resident = true);
 int graph_convolution_device(dg_context *ctx, dg_batch *b, const dg_layer_dev &L, float alpha,
                              const float *x, int ldx, float *y, int ldy);
 int utility_device(dg_context *ctx, int n, const float *score, int stride, const double *wts, int predict,

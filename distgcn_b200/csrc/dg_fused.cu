@@ -1149,6 +1149,23 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
 
 }  // namespace
 
+bool fused_fits(dg_context *ctx, const dg_model *m, const dg_batch *b) {
+    if (getenv("DG_DISABLE_FUSED")) return false;
+    if (m->fused_cp == 0 || b->n_graphs == 0 || b->n_nodes == 0) return false;
+    if ((int)b->h_graph_e.size() != b->n_graphs + 1) return false;
+    const bool has_hidden = m->n_layers >= 3;
+    const bool use_mma = m->fused_cp == 32 && has_hidden && m->fused_wall_mma && getenv("DG_FUSED_MMA");
+    const size_t wblob = use_mma ? sizeof(float) * (size_t)(2 * 2 * 32 * 40 + 32)
+                                 : sizeof(float) * (size_t)(2 * m->fused_cp * m->fused_cp + m->fused_cp);
+    // the same feasibility test build_tiles starts with: the largest graph of the batch must fit a tile
+    const size_t budget = (size_t)ctx->max_smem_optin - 1024;
+    const int min_n = ((std::max(b->max_graph_nodes, 32) + 31) / 32) * 32;
+    const long long need_nnz = (long long)b->max_graph_nnz + 3LL * b->max_graph_nodes;
+    const int min_nnz = (int)((std::max<long long>(need_nnz, 64) + 63) / 64 * 64);
+    if (min_n > 1024) return false;
+    return fused_smem_bytes(m->fused_cp, min_n, min_nnz, has_hidden, wblob) <= budget;
+}
+
 int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
                     int remove_zero_weight, uint8_t *member, float *score, double *util, double *total,
                     int32_t *steps, bool *handled, bool dit) {

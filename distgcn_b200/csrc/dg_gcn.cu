@@ -757,10 +757,10 @@ int graph_convolution_device(dg_context *ctx, dg_batch *b, const dg_layer_dev &L
 }
 
 int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *out, const double *wts,
-                       int predict, double *util) {
+                       int predict, double *util, bool try_resident) {
     const int n = b->n_nodes;
     if (n == 0) return DG_OK;
-    {   // small graphs with a one-column linear head: the graph-resident kernel, stopped after the scores
+    if (try_resident) {   // small graphs with a one-column linear head: the graph-resident kernel, stopped after the scores
         bool handled = false;
         if (wts != nullptr || predict == DG_PREDICT_MIS) {
             DG_TRY(tc_try_solve(ctx, m, b, wts, predict, 0, nullptr, out, util, nullptr, nullptr, &handled));

@@ -1420,6 +1420,9 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     bool ok = false;
     DG_TRY(tc_build_tiles(ctx, b, &ok));
     if (!ok) return DG_OK;
+    // Graphs beyond this kernel's limits go to the CUDA-core graph-resident kernel in a second launch.  If that kernel
+    // cannot take them either, the whole batch belongs to the per-layer path: decline BEFORE launching anything.
+    if (b->tc_n_skipped > 0 && !fused_fits(ctx, m, b)) return DG_OK;
     TcParams p{};
     p.tiles = b->tc_tiles_dev;
     p.n_tiles = b->tc_n_tiles;

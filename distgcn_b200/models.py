@@ -116,7 +116,11 @@ class GCN_DQN(Model):
         _LAYER_UIDS["graphconvolution"] = 0
         common = dict(placeholders=self.placeholders, dropout=True, logging=self.logging, flags=fl)
         if fl.num_layer == 1:
-            self.layers.append(GraphConvolution(input_dim=self.input_dim, output_dim=fl.diver_num, act=L.identity,
+            last_act = getattr(fl, "last_act", "identity")
+            if last_act not in ("identity", "leaky_relu"):
+                raise ValueError("last_act must be 'identity' (source at HEAD) or 'leaky_relu' (as trained), got %r" % (last_act,))
+            self.layers.append(GraphConvolution(input_dim=self.input_dim, output_dim=fl.diver_num,
+                                                act=L.identity if last_act == "identity" else L.leaky_relu,
                                                 sparse_inputs=True, **common))
         else:
             self.layers.append(GraphConvolution(input_dim=self.input_dim, output_dim=fl.hidden1, act=L.leaky_relu,

@@ -37,6 +37,11 @@ class _Flags:
         self.epsilon_min = 0.001
         self.epsilon_decay = 0.985
         self.gamma = 1.0
+        # not a reference flag: activation of the ONLY layer of a 1-layer GCN_DQN.  'identity' is the source at HEAD
+        # (gcn/models.py:539-548); 'leaky_relu' is what the shipped *_l1_* checkpoints were trained with (their
+        # model.ckpt.meta ends graphconvolution_1/LeakyRelu -> ArgMax; tests/test_meta_pin.py).  Scores differ only
+        # where they are negative (by the factor 0.2).
+        self.last_act = "identity"
 
     def update(self, **kwargs):
         for k, v in kwargs.items():

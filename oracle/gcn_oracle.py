@@ -11,14 +11,19 @@ repository root).
 Parity status:
 * support / feature construction (``normalized_adjacency``, ``laplacian_supports``,
   ``row_normalised_features``): PINNED - checked against the reference's own ``gcn/utils.py``
-  (importable without TensorFlow) in ``tests/test_oracle_vs_reference.py`` and through the golden
+  (importable without TensorFlow) in ``tests/test_oracle_golden.py::test_supports_and_features_match_reference`` through the golden
   vectors made by ``tests/golden/make_golden.py``.
-* the layer / model forward (``graph_convolution``, ``gcn_forward``): PARITY UNPINNED.  The reference
-  runs it inside TensorFlow (``tf.compat.v1.sparse_tensor_dense_matmul``, ``tf.matmul``,
-  ``tf.add_n``, ``tf.nn.leaky_relu``; requirements.txt lists ``tensorflow`` unpinned, the shipped
-  ``.meta`` files say producer 1.15.0), TensorFlow is not installable here, and the reference ships
-  no stored activations.  The restatement follows the reference's operator order in fp32; the only
-  anchors are the 46 shipped checkpoints (weights) and the source.
+* the layer / model forward (``graph_convolution``, ``gcn_forward``): PINNED TO THE REFERENCE'S STORED GRAPHS.
+  The reference runs the forward inside TensorFlow, which is not installable here, and ships no stored
+  activations - but every checkpoint directory holds ``model.ckpt.meta``, the as-trained TensorFlow graph
+  (``SparseTensorDenseMatMul -> MatMul -> AddN -> LeakyRelu -> ArgMax``).  ``oracle/tf_meta.py`` evaluates
+  that stored graph op by op on inputs built and fed by the reference's own ``gcn/utils.py``;
+  ``tests/test_meta_pin.py`` checks this restatement against those activations (<= 1e-6 of the score scale
+  on 10 checkpoints x 10 graphs x 2 weight variants; bit-identical on most) and the wiring signature
+  against gcn/layers.py:198-216.  What stays unpinned is TensorFlow's own kernel arithmetic (summation
+  order / FMA contraction inside its CPU ops), i.e. the last ~1e-6.
+  One disagreement between the stored graphs and the source at HEAD is kept visible: 1-layer checkpoints
+  were trained with ``LeakyRelu`` on their only layer, gcn/models.py:539-548 says identity (``acts=``).
 """
 from __future__ import annotations
 

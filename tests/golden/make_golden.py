@@ -184,15 +184,106 @@ def make_dgs(ref_h):
     print("dgs_ref.npz: %d instances" % len(inst))
 
 
+META_CKPTS = ("is4sat_l1", "is4sat_l2_c64", "is4sat_l20_c32", "dqnba_l20_c32", "dqnmed_l1_bias", "is4sat_ld32_l3_c32",
+              "is4sat_l3_c16", "is4sat_l2_c8", "is4sat_l2_c1_cheb2", "is4sat_l1_c1_cheb2")
+META_EXTRA = {  # checkpoints whose weights are not among the CKPTS data fixtures (cheb2: three supports [I, L, L^2])
+    "is4sat_l2_c1_cheb2": "result_IS4SAT_deep_ld1_c1_l2_cheb2_diver1_mwis_dqn",
+    "is4sat_l1_c1_cheb2": "result_IS4SAT_deep_ld1_c1_l1_cheb2_diver1_mwis_dqn",
+}
+META_COPY = ("is4sat_l1", "is4sat_l2_c64", "dqnmed_l1_bias", "is4sat_l3_c16")  # small .meta files kept as data fixtures
+META_GRAPHS = (0, 6, 12, 18, 24, 25, 31, 37, 43, 49)
+
+
+def make_meta(ref_u, ref_root):
+    """meta_activations.npz: outputs of the reference's AS-TRAINED TensorFlow graphs (model/result_*/model.ckpt.meta),
+    evaluated op by op with numpy by oracle/tf_meta.py - TensorFlow itself is not installable here.  Inputs are built
+    exactly as DQNAgent.makestate does (mwis_dqn_call.py:129-138) with the reference's own preprocess_features /
+    simple_polynomials, and fed through the reference's own construct_feed_dict4pred (gcn/utils.py:157-168).
+    Per checkpoint and graph: model.outputs ([N, 1] float32), model.pred, the first layer's activation, and the
+    wiring signature (compute ops in execution order).  Two weight variants per graph: the file's weights and the
+    same with ~20 % zeros (empty feature rows, as makestate produces for zero weights)."""
+    from distgcn_b200 import ckpt as ckpt_reader
+    from oracle import tf_meta
+
+    z = np.load(os.path.join(HERE, "graphs_small.npz"))
+    gp, rp, ci, w_all = z["graph_ptr"], z["row_ptr"], z["col_idx"], z["weights"]
+    rng = np.random.default_rng(4242)
+    graphs = []
+    for g in META_GRAPHS:
+        v0, v1 = int(gp[g]), int(gp[g + 1])
+        e0, e1 = int(rp[v0]), int(rp[v1])
+        n = v1 - v0
+        adj = sp.csr_matrix((np.ones(e1 - e0), ci[e0:e1].astype(np.int64) - v0, rp[v0:v1 + 1].astype(np.int64) - e0),
+                            shape=(n, n))
+        w = w_all[v0:v1].copy()
+        wz = w.copy()
+        wz[rng.random(n) < 0.2] = 0.0
+        graphs.append((g, adj, w, wz))
+    out = {"graphs": np.asarray(META_GRAPHS)}
+    out["wz"] = np.concatenate([wz for _, _, _, wz in graphs])
+    meta_dir = os.path.join(HERE, "meta")
+    os.makedirs(meta_dir, exist_ok=True)
+    for short in META_CKPTS:
+        d = CKPTS.get(short) or META_EXTRA[short]
+        src = os.path.join(ref_root, "model", d)
+        sg = tf_meta.load_stored_graph(src, ckpt_reader.read_tensors)
+        roles = sg.roles()
+        n_sup = len(roles["support"])
+        sig = sg.signature()
+        first_act = [n.name for n in sg.forward_nodes() if n.op == "LeakyRelu"]
+        first_act = first_act[0] if first_act else sg.outputs
+        F = int(sg.variables[[k for k in sg.variables if k.endswith("graphconvolution_1_vars/weights_0")][0]].shape[0])
+        outs, outs_z, preds, h1 = [], [], [], []
+        for g, adj, w, wz in graphs:
+            for which, wts_nn in (("w", w), ("wz", wz)):
+                n = wts_nn.shape[0]
+                # ---- DQNAgent.makestate, mwis_dqn_call.py:129-138 (reference utilities, unmodified)
+                norm_wts = np.linalg.norm(wts_nn)
+                features = np.multiply(np.ones([n, F]), wts_nn.reshape(n, 1) / norm_wts)
+                features = sp.lil_matrix(features)
+                features = ref_u.preprocess_features(features)
+                support = ref_u.simple_polynomials(sp.csr_matrix(adj), n_sup - 1)
+                # ---- DQNAgent.predict, mwis_dqn_call.py:140-143
+                feed = ref_u.construct_feed_dict4pred(features, support, roles)
+                o, p, h = sg.run([sg.outputs, sg.pred, first_act], tf_meta.expand_feed(feed))
+                assert o.dtype == np.float32 and o.shape == (n, 1)
+                # the dropout sub-graph is live in the stored graph; at rate 0 it must not depend on the draws
+                o2, = sg.run([sg.outputs], tf_meta.expand_feed(feed), rng=np.random.default_rng(g + 1))
+                assert np.array_equal(o, o2)
+                if which == "w":
+                    outs.append(o[:, 0]), preds.append(int(p[0])), h1.append(np.asarray(h, dtype=np.float32).reshape(n, -1))
+                else:
+                    outs_z.append(o[:, 0])
+        out["%s_outputs" % short] = np.concatenate(outs)
+        out["%s_outputs_wz" % short] = np.concatenate(outs_z)
+        out["%s_pred" % short] = np.asarray(preds)
+        out["%s_h1" % short] = np.concatenate(h1)
+        out["%s_signature" % short] = np.asarray(sig)
+        out["%s_alphas" % short] = np.asarray(sg.leaky_alphas())
+        out["%s_dir" % short] = np.asarray(d)
+        if short in META_EXTRA:
+            for name, arr in sg.variables.items():
+                if "/Adam" not in name and "graphconvolution" in name:
+                    out["%s_var|%s" % (short, name)] = arr
+        if short in META_COPY:
+            shutil.copyfile(os.path.join(src, "model.ckpt.meta"), os.path.join(meta_dir, d + ".meta"))
+        print("meta %-22s %3d ops  last: %s" % (short, len(sig), sig[-2:]))
+    np.savez_compressed(os.path.join(HERE, "meta_activations.npz"), **out)
+    print("meta_activations.npz written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--full", action="store_true", help="also write the full 500-graph ER/BA test2 fixtures")
-    ap.add_argument("--only", default=None, choices=["dgs"], help="regenerate just one fixture family")
+    ap.add_argument("--only", default=None, choices=["dgs", "meta"], help="regenerate just one fixture family")
     args = ap.parse_args()
     ref_h, ref_u = import_reference(args.reference)
     if args.only == "dgs":
         make_dgs(ref_h)
+        return
+    if args.only == "meta":
+        make_meta(ref_u, args.reference)
         return
     from distgcn_b200 import ckpt as ckpt_reader
     from oracle import gcn_oracle as G
@@ -386,6 +477,7 @@ def main():
                                 oracle_act=np.concatenate(acts),
                                 member_gcn_lgs=np.packbits(np.concatenate(members)),
                                 member_raw_lgs=np.packbits(np.concatenate(lgs_raw)))
+    make_meta(ref_u, args.reference)
     print("golden fixtures written to", HERE)
 
 

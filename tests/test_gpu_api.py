@@ -249,9 +249,9 @@ def test_mwis_dqn_test_harness_ratios():
     assert np.allclose(greedy_util, z["greedy_utility"], rtol=1e-12, atol=1e-12)
     ref_member = np.unpackbits(z["member_gcn_lgs"])[:pb.n_nodes]
     ref_total = np.add.reduceat(np.where(ref_member == 1, w, 0.0), pb.graph_ptr[:-1])
-    agree = np.isclose(total, ref_total, rtol=1e-12)
-    assert agree.mean() > 0.995           # a near-tie flipped by fp32 rounding may change a graph or two
-    assert np.allclose(p[agree], (ref_total / z["greedy_utility"])[agree], rtol=1e-12)
+    assert np.array_equal(member, ref_member)   # every graph, as test_full_config_sets asserts on the same set
+    assert np.allclose(total, ref_total, rtol=1e-12)
+    assert np.allclose(p, ref_total / z["greedy_utility"], rtol=1e-12)
     assert 1.0 < np.nanmean(p) < 1.12     # survey-time restatement: 1.041; Gurobi optimum of the set: 1.1197
     p2, total2, _, _ = evaluate(agent, pb, w, search="greedy")
-    assert np.isclose(total2, total, rtol=1e-12).mean() > 0.99   # the weights of this set have no zeros
+    assert np.allclose(total2, total, rtol=1e-12)   # the weights of this set have no zeros: both searches solve the same graph

@@ -297,6 +297,112 @@ def test_gcn_forward_matches_oracle(gpu_ctx, short, path, monkeypatch):
     model.close()
 
 
+def _set_path(monkeypatch, path):
+    monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    monkeypatch.delenv("DG_DISABLE_TC", raising=False)
+    monkeypatch.delenv("DG_FUSED_MMA", raising=False)
+    if path == "layer_kernels":
+        monkeypatch.setenv("DG_DISABLE_FUSED", "1")
+    elif path == "fused":
+        monkeypatch.setenv("DG_DISABLE_TC", "1")
+
+
+def _elementwise_report(tag, out, ref):
+    """Element-wise relative error |out - ref| / |ref| (elements with |ref| >= 1e-3 of the scale), as a distribution."""
+    out = np.asarray(out, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    big = np.abs(ref) >= 1e-3 * scale
+    rel = np.abs(out[big] - ref[big]) / np.abs(ref[big])
+    q = np.quantile(rel, [0.5, 0.99, 1.0]) if rel.size else np.zeros(3)
+    print("%s: element-wise relative error median %.2g  p99 %.2g  max %.2g  (%d of %d elements above 1e-3 of the scale);"
+          " norm-wise %.2g" % (tag, q[0], q[1], q[2], int(big.sum()), ref.size, float(np.abs(out - ref).max()) / scale))
+    return q, float(np.abs(out - ref).max()) / scale
+
+
+META_SHORTS = ["is4sat_l1", "is4sat_l2_c64", "is4sat_l20_c32", "dqnba_l20_c32", "dqnmed_l1_bias", "is4sat_ld32_l3_c32",
+               "is4sat_l3_c16", "is4sat_l2_c8"]
+
+
+@pytest.mark.parametrize("path", ["tensor_core", "fused", "layer_kernels"])
+@pytest.mark.parametrize("short", META_SHORTS)
+def test_scores_match_stored_graph(gpu_ctx, short, path, monkeypatch):
+    """CUDA scores against activations of the reference's AS-TRAINED TensorFlow graph (model.ckpt.meta evaluated op
+    by op, tests/golden/make_golden.py::make_meta) - the reference-held pin of the forward.  1-layer checkpoints are
+    checked with both last activations: 'leaky_relu' reproduces the stored graph, 'identity' (source at HEAD,
+    gcn/models.py:539-548) reproduces it on the non-negative scores and is 1/0.2 times it on the negative ones.
+    The weight variant with zeros exercises empty feature rows (x0 = 0) without vertex removal, as makestate does."""
+    E = _engine()
+    from distgcn_b200.batch import pack_graphs
+    _set_path(monkeypatch, path)
+    z = util.load_npz("meta_activations.npz")
+    pb_all, w_all = util.small_graphs()
+    picks = [int(g) for g in z["graphs"]]
+    pb = pack_graphs([pb_all.graph_adj(g) for g in picks])
+    layers = util.load_layers(short)
+    F = layers[0].c_in
+    one_layer = len(layers) == 1
+    acts = E.gcn_dqn_acts(len(layers))
+    if one_layer:
+        acts = [E.ACT_LEAKY_RELU]
+    model = E.Model(gpu_ctx, layers, acts)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    ref = z["%s_outputs" % short]
+    out = E.gcn_forward(gpu_ctx, model, batch)[:, 0]
+    tol = SCORE_RTOL_VS_FP32_ORACLE if len(layers) >= 20 else SCORE_RTOL
+    _, nw = _elementwise_report("%s stored graph (%s)" % (short, path), out, ref)
+    for i in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[i]), int(pb.graph_ptr[i + 1])
+        assert _rel_err(out[v0:v1], ref[v0:v1]) <= tol, "graph %d" % picks[i]
+        a, p_ref = int(np.argmax(out[v0:v1])), int(z["%s_pred" % short][i])  # model.pred; equal unless a near-tie
+        assert a == p_ref or abs(float(ref[v0 + a]) - float(ref[v0 + p_ref])) <= tol * float(np.abs(ref[v0:v1]).max())
+    # zero weights: rows of the feature matrix are empty, vertices stay in the graph (makestate, mwis_dqn_call.py:129-135)
+    wz = z["wz"]
+    batch.set_x0(np.where(wz != 0, np.float32(1.0 / F), np.float32(0)).astype(np.float32))
+    out_z = E.gcn_forward(gpu_ctx, model, batch)[:, 0]
+    ref_z = z["%s_outputs_wz" % short]
+    for i in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[i]), int(pb.graph_ptr[i + 1])
+        assert _rel_err(out_z[v0:v1], ref_z[v0:v1]) <= tol, "graph %d (zero weights)" % picks[i]
+    model.close()
+    if one_layer:
+        batch.set_x0(None)
+        model = E.Model(gpu_ctx, layers, [E.ACT_IDENTITY])
+        ident = E.gcn_forward(gpu_ctx, model, batch)[:, 0]
+        scale = float(np.abs(ref).max())
+        pos = ref >= 0
+        assert np.abs(ident[pos] - ref[pos]).max() <= tol * scale
+        if (~pos).any():
+            assert np.abs(np.float32(0.2) * ident[~pos] - ref[~pos]).max() <= tol * scale
+        model.close()
+    batch.close()
+
+
+@pytest.mark.parametrize("path", ["tensor_core", "fused", "layer_kernels"])
+@pytest.mark.parametrize("short", ["is4sat_l20_c32", "dqnba_l20_c32", "is4sat_l2_c64"])
+def test_dense_graph_scores_against_float64(gpu_ctx, short, path, monkeypatch):
+    """Dense graphs (G(n, 0.3): average degree 30-90) are where summation order matters most.  Every path is compared
+    with the float64 evaluation of the network (oracle.gcn_forward_fp64), norm-wise per graph against the 1e-5 bar
+    and element-wise as a printed distribution."""
+    E = _engine()
+    _set_path(monkeypatch, path)
+    rng = np.random.default_rng(303)
+    pb, _ = util.random_graph_batch(rng, 24, 100, 300, p_lo=0.3, p_hi=0.3)
+    w = rng.random(pb.n_nodes)
+    layers = util.load_layers(short)
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    out = E.gcn_forward(gpu_ctx, model, batch)[:, 0]
+    exact = util.exact_scores(pb, w, layers, remove_zero_weight=False)
+    q, nw = _elementwise_report("%s dense p=0.3 (%s)" % (short, path), out, exact)
+    for g in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        assert _rel_err(out[v0:v1], exact[v0:v1]) <= SCORE_RTOL, "graph %d: %.3g" % (g, _rel_err(out[v0:v1], exact[v0:v1]))
+    assert q[1] <= 1e-4, "99 %% of the elements must be within 1e-4 of their own magnitude"
+    batch.close()
+    model.close()
+
+
 @pytest.mark.parametrize("path", ["tensor_core", "fused", "layer_kernels", "fused_mma"])
 @pytest.mark.parametrize("short", ["is4sat_l1", "is4sat_l20_c32", "is4sat_l2_c64", "dqnba_l20_c32"])
 def test_solve_membership_matches_reference_lgs(gpu_ctx, short, path, monkeypatch):
@@ -682,6 +788,57 @@ def test_tensor_core_kernel_edge_cases(gpu_ctx, monkeypatch):
     big_idx = np.setdiff1d(np.arange(big.n_nodes), small_idx)
     assert np.array_equal(rf.score[big_idx, 0], rb.score[big_idx, 0])      # ... and the two large ones the other
     bbatch.close()
+    model.close()
+
+
+def test_solve_leaves_the_batch_as_found_and_oversize_graphs(gpu_ctx):
+    """(1) dg_solve with remove_zero_weight on the per-layer path (a graph above 1024 vertices) must not leave its
+    zero-weight mask on the batch: a later dg_lgs on the same DeviceBatch sees the caller's graph, zero-weight vertices
+    included, as the reference's local_greedy_search does; a caller-installed keep mask survives too.
+    (2) a batch the tensor-core kernel would take except for one graph that not even the CUDA-core graph-resident
+    kernel can hold goes to the per-layer kernels as a whole, without a discarded tensor-core launch."""
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    rng = np.random.default_rng(99)
+
+    def er(n, p):
+        up = np.triu(rng.random((n, n)) < p, k=1)
+        return sp.csr_matrix((up | up.T).astype(np.float64))
+    layers = util.load_layers("is4sat_l20_c32")
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    adjs = [er(150, 0.05), er(1500, 0.004), er(220, 0.04), er(120, 0.1)]
+    pb = pack_graphs(adjs)
+    w = rng.random(pb.n_nodes)
+    w[rng.random(pb.n_nodes) < 0.2] = 0.0
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    launches0 = gpu_ctx.launch_count
+    r = E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True, want_score=True, want_util=True, want_steps=True)
+    assert gpu_ctx.last_kernel not in ("tc_solve_kernel", "fused_solve_kernel")  # per-layer path for the whole batch
+    n_launch = gpu_ctx.launch_count - launches0
+    exact = util.exact_scores(pb, w, layers)
+    assert _rel_err(r.score[:, 0], exact) <= SCORE_RTOL
+    o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, r.util, init_remain=(w > 0).astype(np.uint8))
+    assert np.array_equal(o.member, r.member) and np.array_equal(o.steps, r.steps)
+    # a second identical solve launches the same number of kernels (no extra resident-kernel attempts)
+    launches1 = gpu_ctx.launch_count
+    r_again = E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True)
+    assert gpu_ctx.launch_count - launches1 == n_launch and np.array_equal(r_again.member, r.member)
+    # (1) the batch is as it was found: plain LGS keeps the zero-weight vertices in the graph
+    util_all = rng.random(pb.n_nodes)
+    rl = E.lgs(gpu_ctx, batch, util_all)
+    ol = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, util_all)
+    assert np.array_equal(rl.member, ol.member) and np.array_equal(rl.steps, ol.steps)
+    out_all = E.gcn_forward(gpu_ctx, model, batch)[:, 0]
+    assert _rel_err(out_all, util.exact_scores(pb, np.ones(pb.n_nodes), layers)) <= SCORE_RTOL
+    # ... and a caller-installed mask survives a solve that removes zero weights
+    keep = (rng.random(pb.n_nodes) < 0.8).astype(np.uint8)
+    batch.set_keep(keep)
+    E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True)
+    rk = E.lgs(gpu_ctx, batch, util_all)
+    ok = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, util_all, init_remain=keep)
+    assert np.array_equal(rk.member, ok.member) and np.array_equal(rk.steps, ok.steps)
+    batch.close()
     model.close()
 
 

@@ -94,3 +94,26 @@ def exact_scores(pb, w, layers, kind: str = "gcn_dqn", remove_zero_weight: bool 
         sup = G.laplacian_supports(a, len(layers[0].weights) - 1)
         out[v0 + keep] = G.gcn_forward_fp64(feats, sup, layers, kind)[:, 0]
     return out
+
+
+def layers_from_meta_fixture(z, short: str):
+    """LayerWeights of a checkpoint whose variables travel inside meta_activations.npz (the cheb2 checkpoints, which
+    are not among the tests/golden/ckpt data fixtures)."""
+    import re
+    by_layer = {}
+    prefix = "%s_var|" % short
+    for key in z.files:
+        if not key.startswith(prefix):
+            continue
+        m = re.match(r"^[^/]+/graphconvolution_(\d+)_vars/(weights_(\d+)|bias)$", key[len(prefix):])
+        if m:
+            by_layer.setdefault(int(m.group(1)), {})[m.group(2)] = z[key]
+    layers = []
+    for lid in sorted(by_layer):
+        v = by_layer[lid]
+        ks = sorted(int(k.split("_")[1]) for k in v if k.startswith("weights_"))
+        lw = ckpt.LayerWeights(weights=[np.ascontiguousarray(v["weights_%d" % k], dtype=np.float32) for k in ks])
+        if "bias" in v:
+            lw.bias = np.ascontiguousarray(v["bias"], dtype=np.float32).reshape(-1)
+        layers.append(lw)
+    return layers

@@ -1,5 +1,6 @@
-"""torchrun --nproc-per-node 2 tests/run_partition_2gpu.py : row-partitioned solve on 2 GPUs (NCCL) against
-the CPU oracle for a 2-layer model and against the single-GPU result for a deep one."""
+"""torchrun --nproc-per-node 2 tests/run_partition_2gpu.py : row-partitioned solve on 2 (or more) GPUs, both exchange
+modes, against the CPU oracle (float64 scores, oracle.lgs membership on the path's own utilities).  Collected by
+pytest through tests/test_gpu_partition.py::test_partitioned_multi_rank."""
 import os
 import sys
 import time
@@ -11,7 +12,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import util  # noqa: E402
-from tests.test_gpu_partition import _big_graph, _ModelSpec  # noqa: E402
+from tests.test_gpu_partition import _big_graph, _ModelSpec, oracle_check  # noqa: E402
 from distgcn_b200 import engine as E  # noqa: E402
 from distgcn_b200.batch import pack_graphs  # noqa: E402
 from distgcn_b200.shard import RowPartitionedSolver, row_slices, slice_csr  # noqa: E402
@@ -51,23 +52,10 @@ def main():
         if rank == 0:
             full_m = np.concatenate([g[0] for g in gathered])[:n]
             full_s = np.concatenate([g[1] for g in gathered])[:n]
-            ctx = E.Context(torch.cuda.current_device())
-            model = E.Model(ctx, layers, acts)
-            batch = E.DeviceBatch(ctx, pack_graphs([a]))
-            ref = E.solve(ctx, model, batch, w, want_score=True)
-            same = bool(np.array_equal(full_m, ref.member))
-            err = float(np.abs(full_s - ref.score[:, 0]).max() / max(np.abs(ref.score).max(), 1e-30))
-            print("PART %s %s n=%d world=%d rounds=%d ms=%.2f exchanged_MB=%.1f membership_equal=%s score_err=%.2e"
-                  % (short, exchange, n, world, rounds, ms, solver.exchanged_bytes / 1e6, same, err))
-            tol = 2e-6 if len(layers) < 20 else 2e-5
-            if not same:   # only near-ties flipped by fp32 summation order may differ (see test_gpu_partition.py)
-                from oracle import lgs as OL
-                keep = (w != 0).astype(np.uint8)
-                o = OL.run(a.indptr, a.indices, full_s.astype(np.float64) * w, init_remain=keep)
-                same = bool(np.array_equal(o.member, full_m)) and int((full_m != ref.member).sum()) <= 8
-                print("   exact on its own utilities: %s" % same)
-            ok = ok and same and err < tol
-            batch.close(); model.close(); ctx.close()
+            err, same, steps = oracle_check(a, w, layers, full_m, full_s, n)
+            print("PART %s %s n=%d world=%d rounds=%d ms=%.2f exchanged_MB=%.1f membership_equals_oracle=%s "
+                  "score_err_vs_fp64=%.2e" % (short, exchange, n, world, rounds, ms, solver.exchanged_bytes / 1e6, same, err))
+            ok = ok and same and err <= 1e-5 and rounds == steps
         solver.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -102,8 +102,69 @@ class PackedBatch:
             raise ValueError("adjacency pattern is not symmetric")
 
 
-def pack_graphs(adjs: Iterable) -> PackedBatch:
-    """Pack scipy / dense adjacency matrices into one PackedBatch."""
+def _as_csr32(adj):
+    """A matrix the native packer can read: CSR / CSC with int32 C-contiguous indptr / indices and float64 data.
+    (The adjacency is symmetric, so the CSC arrays the .mat files load as are the CSR arrays as well.)"""
+    if sp.issparse(adj) and adj.format in ("csr", "csc"):
+        a = adj
+    elif sp.issparse(adj):
+        a = adj.tocsr()
+    else:
+        a = sp.csr_matrix(np.asarray(adj))
+    if a.shape[0] != a.shape[1]:
+        raise ValueError("adjacency matrix must be square, got %s" % (a.shape,))
+    if a.indptr.dtype != np.int32 or a.indices.dtype != np.int32 or a.data.dtype != np.float64 or \
+            not (a.indptr.flags.c_contiguous and a.indices.flags.c_contiguous and a.data.flags.c_contiguous):
+        a = type(a)((np.ascontiguousarray(a.data, dtype=np.float64), np.ascontiguousarray(a.indices, dtype=np.int32),
+                     np.ascontiguousarray(a.indptr, dtype=np.int32)), shape=a.shape)
+    return a
+
+
+class GraphTables:
+    """Pointer tables of a list of per-graph matrices for the native ingest entry points (dg_pack_graphs_host,
+    dg_solve_graphs_host): built by the C helper ``_pyingest.collect`` without a Python loop.  Holds the matrices'
+    arrays alive.  ``check_values``: also pass the stored values so that stored zeros are not taken for edges."""
+
+    def __init__(self, adjs, check_values: bool = True):
+        from . import _pyingest
+        adjs = adjs if isinstance(adjs, (list, tuple)) else list(adjs)
+        try:
+            tabs = _pyingest.collect(adjs, check_values)
+        except TypeError:
+            adjs = [_as_csr32(a) for a in adjs]     # other formats / index types: normalise once, in Python
+            tabs = _pyingest.collect(adjs, check_values)
+        self.indptr, self.indices, self.data, self.n_rows_raw, self._keep, self.n_nodes = tabs
+        self._adjs = adjs
+        self.n_graphs = len(adjs)
+        self.n_rows = np.frombuffer(self.n_rows_raw, dtype=np.int32)
+        for a in adjs[:1] + adjs[-1:]:
+            shp = getattr(a, "shape", None)
+            if shp is not None and len(shp) == 2 and shp[0] != shp[1]:
+                raise ValueError("adjacency matrix must be square, got %s" % (shp,))
+
+
+def pack_graphs(adjs: Iterable, check_values: bool = True, n_threads: int = 0) -> PackedBatch:
+    """Pack scipy / dense adjacency matrices into one PackedBatch - natively: the per-graph arrays are handed to
+    dg_pack_graphs_host as pointer tables and packed by the library's host threads (no per-graph Python work).
+    Replaces the per-call networkx conversions of mwis_dqn_call.py:202-207."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    t = adjs if isinstance(adjs, GraphTables) else GraphTables(adjs, check_values)
+    n_nodes, nnz = C.c_int64(), C.c_int64()
+    _lib.check(lib.dg_pack_graphs_sizes(t.n_graphs, t.indptr, t.data, t.n_rows_raw, C.byref(n_nodes), C.byref(nnz), None))
+    gp = np.empty(t.n_graphs + 1, dtype=np.int32)
+    rp = np.empty(n_nodes.value + 1, dtype=np.int32)
+    ci = np.empty(nnz.value, dtype=np.int32)
+    _lib.check(lib.dg_pack_graphs_host(t.n_graphs, t.indptr, t.indices, t.data, t.n_rows_raw, gp.ctypes.data, rp.ctypes.data,
+                                       ci.ctypes.data if nnz.value else np.empty(1, np.int32).ctypes.data, None,
+                                       int(n_threads)))
+    return PackedBatch(graph_ptr=gp, row_ptr=rp, col_idx=ci)
+
+
+def pack_graphs_python(adjs: Iterable) -> PackedBatch:
+    """The pure numpy/scipy packer (one conversion per graph): kept as the independent check of the native one."""
     gp: List[int] = [0]
     rps: List[np.ndarray] = [np.zeros(1, dtype=np.int64)]
     cis: List[np.ndarray] = []

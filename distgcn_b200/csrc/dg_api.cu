@@ -220,6 +220,7 @@ void dg_context_destroy(dg_context *ctx) {
         dg_batch_destroy(ctx->host_batch);
         ctx->host_batch = nullptr;
     }
+    ingest_staging_free(ctx);
     for (auto &b : ctx->slots)
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
@@ -1102,7 +1103,7 @@ int dg_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *wts,
 static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
                            const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
                            const double *wts, int predict, int remove_zero_weight, uint8_t *member, double *total,
-                           bool wait, const uint16_t *col_local16 = nullptr) {
+                           bool wait, const uint16_t *col_local16 = nullptr, cudaEvent_t copied = nullptr) {
     clear_error();
     DG_TRY(check_ctx(ctx));
     DG_REQUIRE(m && wts && member, DG_ERR_INVALID, "null argument");
@@ -1129,6 +1130,7 @@ static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs,
     double *d_wts = nullptr, *d_total = nullptr;
     uint8_t *d_member = nullptr;
     DG_TRY(stage_in(ctx, kSlotWts, wts, n, &d_wts));
+    if (copied) DG_CUDA_CHECK(cudaEventRecord(copied, ctx->stream));
     DG_TRY(scratch_as(ctx, kSlotMember, n, &d_member));
     if (total) DG_TRY(scratch_as(ctx, kSlotTotal, G, &d_total));
     DG_TRY(solve_device(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, nullptr, nullptr, d_total, nullptr));
@@ -1136,6 +1138,18 @@ static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs,
     DG_TRY(copy_out(ctx, total, d_total, G));
     return wait ? finish(ctx) : DG_OK;
 }
+
+extern "C++" {
+namespace dg {
+int solve_host_staged(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                      const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
+                      int predict, int remove_zero_weight, uint8_t *member, double *total, bool wait,
+                      const uint16_t *col_local16, cudaEvent_t copied) {
+    return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, wts, predict, remove_zero_weight,
+                           member, total, wait, col_local16, copied);
+}
+}  // namespace dg
+}  // extern "C++"
 
 int dg_solve_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
                   const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,

@@ -101,6 +101,7 @@ struct dg_context {
     size_t prof_used = 0;                  // events recorded since the last collect
     double prof_bytes = 0.0;               // algorithmic bytes of the recorded launches
     const char *last_kernel = "";          // dominant kernel of the most recent solve (dg_context_last_kernel)
+    void *ingest_staging = nullptr;        // pinned staging of dg_solve_graphs_host (dg_ingest.cu)
 };
 
 namespace dg {
@@ -350,6 +351,14 @@ int member_weight_device(dg_context *ctx, const dg_batch *b, const uint8_t *memb
                          double *total);
 
 inline int pad_width(int c) { return c <= 32 ? 32 : 64; }
+
+// host-CSR solve on the context's reusable batch (dg_api.cu); `copied` (optional) is recorded on the stream once the
+// H2D copies of the inputs have been enqueued, so a caller may recycle its staging as soon as it has fired
+int solve_host_staged(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
+                      const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
+                      int predict, int remove_zero_weight, uint8_t *member, double *total, bool wait,
+                      const uint16_t *col_local16, cudaEvent_t copied);
+void ingest_staging_free(dg_context *ctx);  // dg_ingest.cu
 
 // profiling helpers (dg_api.cu)
 void prof_begin(dg_context *ctx);

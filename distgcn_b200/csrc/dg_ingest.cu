@@ -1,0 +1,378 @@
+// Native ingest: the reference's per-graph inputs -> one packed batch, without a Python loop.
+//
+// The reference hands every graph to the solver as its own scipy sparse matrix (mwis_dqn_call.py:198; the .mat files
+// of Data_Generation.py:214-219 load as float64 CSC with int32 indptr / indices) and converts it per call through
+// networkx (mwis_dqn_call.py:202-207).  Here the caller passes the per-graph arrays as they are - tables of pointers
+// to each matrix's indptr / indices (and optionally data: stored zeros are not edges, np.nonzero(adj[v]) at
+// heuristics.py:94) - and a small pool of host threads writes the packed form (graph_ptr, row_ptr, 16-bit graph-local
+// or 32-bit batch-global column ids) straight into pinned staging, from where the usual H2D copies and kernels run.
+// Host code only; compiled into the same library as the kernels.
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+#include "dg_common.cuh"
+
+namespace dg {
+namespace {
+
+// A persistent pool: parallel_for(n, fn) runs fn(task) for task = 0..n-1 on the workers and the calling thread.
+class Pool {
+  public:
+    static Pool &get() {
+        static Pool p;
+        return p;
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    void parallel_for(int n_tasks, int max_threads, const std::function<void(int)> &fn) {
+        if (n_tasks <= 0) return;
+        const int helpers = std::min({(int)workers_.size(), std::max(0, max_threads - 1), n_tasks - 1});
+        if (helpers == 0) {
+            for (int t = 0; t < n_tasks; ++t) fn(t);
+            return;
+        }
+        std::unique_lock<std::mutex> run(run_mu_);  // one parallel_for at a time
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            n_tasks_ = n_tasks;
+            next_.store(0);
+            pending_ = helpers;
+            wanted_ = helpers;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        for (int t; (t = next_.fetch_add(1)) < n_tasks;) fn(t);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    Pool() {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = (int)std::min<unsigned>(hc ? hc : 4, 16) - 1;
+        if (const char *e = getenv("DG_INGEST_THREADS")) n = std::max(0, atoi(e) - 1);
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+    }
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+                if (id >= wanted_) continue;
+                fn = fn_;
+                n = n_tasks_;
+            }
+            for (int t; (t = next_.fetch_add(1)) < n;) (*fn)(t);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                --pending_;
+            }
+            done_cv_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_tasks_ = 0, pending_ = 0, wanted_ = 0;
+    std::atomic<int> next_{0};
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
+struct PackPlan {
+    std::vector<int64_t> v0, e0;  // vertex / edge offset of every graph, n_graphs + 1
+    bool has_zeros = false;       // some stored value is zero: edge counts come from a counting pass
+};
+
+// sizes: vertex and edge offsets of every graph.  With `data`, stored zeros do not count.
+int plan_sizes(int32_t n_graphs, const int32_t *const *indptr, const double *const *data, const int32_t *n_rows,
+               int threads, PackPlan *plan) {
+    plan->v0.assign((size_t)n_graphs + 1, 0);
+    plan->e0.assign((size_t)n_graphs + 1, 0);
+    std::vector<int64_t> nnz((size_t)n_graphs, 0);
+    std::atomic<int> bad{-1};
+    std::atomic<bool> zeros{false};
+    const int chunk = 64;
+    const int n_tasks = (n_graphs + chunk - 1) / chunk;
+    Pool::get().parallel_for(n_tasks, data ? threads : 1, [&](int t) {
+        for (int g = t * chunk; g < std::min(n_graphs, (t + 1) * chunk); ++g) {
+            const int n = n_rows[g];
+            if (n < 0 || (n > 0 && (!indptr[g] || indptr[g][0] != 0 || indptr[g][n] < 0))) {
+                bad.store(g);
+                continue;
+            }
+            int64_t e = n > 0 ? indptr[g][n] : 0;
+            if (data && data[g] && e > 0) {
+                int64_t nz = 0;
+                const double *d = data[g];
+                for (int64_t k = 0; k < e; ++k) nz += d[k] != 0.0;
+                if (nz != e) zeros.store(true);
+                e = nz;
+            }
+            nnz[(size_t)g] = e;
+        }
+    });
+    DG_REQUIRE(bad.load() < 0, DG_ERR_INVALID, "graph %d: indptr must start at 0 and have n_rows + 1 entries", bad.load());
+    for (int g = 0; g < n_graphs; ++g) {
+        plan->v0[(size_t)g + 1] = plan->v0[(size_t)g] + n_rows[g];
+        plan->e0[(size_t)g + 1] = plan->e0[(size_t)g] + nnz[(size_t)g];
+    }
+    plan->has_zeros = zeros.load();
+    DG_REQUIRE(plan->v0.back() < (1LL << 31) && plan->e0.back() < (1LL << 31), DG_ERR_INVALID,
+               "batch too large for int32 indexing: %lld vertices, %lld edges", (long long)plan->v0.back(),
+               (long long)plan->e0.back());
+    return DG_OK;
+}
+
+// the parallel pack; exactly one of col_idx / col16 is written
+int pack_into(int32_t n_graphs, const int32_t *const *indptr, const int32_t *const *indices, const double *const *data,
+              const int32_t *n_rows, const PackPlan &plan, int threads, int32_t *graph_ptr, int32_t *row_ptr,
+              int32_t *col_idx, uint16_t *col16) {
+    for (int g = 0; g <= n_graphs; ++g) graph_ptr[g] = (int32_t)plan.v0[(size_t)g];
+    row_ptr[0] = 0;
+    std::atomic<int> bad{-1};
+    // tasks of roughly equal edge count: contiguous graph ranges
+    const int64_t total_e = plan.e0.back() + plan.v0.back();
+    const int want = std::max(1, std::min<int>(n_graphs, threads * 4));
+    std::vector<int> cut{0};
+    for (int k = 1; k < want; ++k) {
+        const int64_t target = total_e * k / want;
+        int lo = cut.back(), hi = n_graphs;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (plan.e0[(size_t)mid] + plan.v0[(size_t)mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo > cut.back() && lo < n_graphs) cut.push_back(lo);
+    }
+    cut.push_back(n_graphs);
+    Pool::get().parallel_for((int)cut.size() - 1, threads, [&](int t) {
+        for (int g = cut[(size_t)t]; g < cut[(size_t)t + 1]; ++g) {
+            const int n = n_rows[g];
+            if (n == 0) continue;
+            const int32_t *ip = indptr[g], *ix = indices[g];
+            const double *d = (data && plan.has_zeros) ? data[g] : nullptr;
+            const int64_t v0 = plan.v0[(size_t)g], e0 = plan.e0[(size_t)g];
+            int32_t *rp = row_ptr + v0 + 1;
+            bool ok = true;
+            if (!d) {
+                for (int r = 0; r < n; ++r) {
+                    ok &= ip[r + 1] >= ip[r];
+                    rp[r] = (int32_t)(e0 + ip[r + 1]);
+                }
+                const int64_t e = ip[n];
+                if (!ok || (e > 0 && !ix)) {
+                    bad.store(g);
+                    continue;
+                }
+                unsigned acc = 0;  // any id outside [0, n) sets a bit at or above position 31 or compares >= n
+                if (col16) {
+                    uint16_t *out = col16 + e0;
+                    for (int64_t k = 0; k < e; ++k) {
+                        const uint32_t c = (uint32_t)ix[k];
+                        acc |= (c >= (uint32_t)n);
+                        out[k] = (uint16_t)c;
+                    }
+                } else {
+                    int32_t *out = col_idx + e0;
+                    for (int64_t k = 0; k < e; ++k) {
+                        const uint32_t c = (uint32_t)ix[k];
+                        acc |= (c >= (uint32_t)n);
+                        out[k] = (int32_t)(c + (uint32_t)v0);
+                    }
+                }
+                if (acc) bad.store(g);
+            } else {  // stored zeros are dropped
+                int64_t w = e0;
+                for (int r = 0; r < n; ++r) {
+                    if (ip[r + 1] < ip[r]) {
+                        ok = false;
+                        break;
+                    }
+                    for (int k = ip[r]; k < ip[r + 1]; ++k) {
+                        if (d[k] == 0.0) continue;
+                        const uint32_t c = (uint32_t)ix[k];
+                        if (c >= (uint32_t)n) ok = false;
+                        if (col16) col16[w] = (uint16_t)c;
+                        else col_idx[w] = (int32_t)(c + (uint32_t)v0);
+                        ++w;
+                    }
+                    rp[r] = (int32_t)w;
+                }
+                if (!ok || w != plan.e0[(size_t)g + 1]) bad.store(g);
+            }
+        }
+    });
+    DG_REQUIRE(bad.load() < 0, DG_ERR_INVALID,
+               "graph %d: malformed pattern (indptr not non-decreasing, or a column id outside [0, n_rows))", bad.load());
+    return DG_OK;
+}
+
+int default_threads(int32_t n_threads, int64_t work) {
+    int t = n_threads > 0 ? n_threads : Pool::get().size();
+    if (work < (1 << 16)) t = 1;  // a handful of graphs: the hand-off costs more than the copy
+    return std::max(1, std::min(t, Pool::get().size()));
+}
+
+struct Staging {  // pinned, grow-only, one per context
+    int32_t *gp = nullptr, *rp = nullptr, *c32 = nullptr;
+    uint16_t *c16 = nullptr;
+    double *w = nullptr;
+    size_t cap_g = 0, cap_n = 0, cap_e16 = 0, cap_e32 = 0, cap_w = 0;
+    cudaEvent_t copied = nullptr;  // the H2D copies of the previous call have read the staging
+    bool in_flight = false;
+};
+
+template <typename T>
+int grow_pinned(T **p, size_t *cap, size_t need) {
+    if (*cap >= need && *p) return DG_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    const size_t c = need + need / 4 + 64;
+    DG_CUDA_CHECK(cudaHostAlloc((void **)p, sizeof(T) * c, cudaHostAllocDefault));
+    *cap = c;
+    return DG_OK;
+}
+
+}  // namespace
+
+void ingest_staging_free(dg_context *ctx) {
+    Staging *s = static_cast<Staging *>(ctx->ingest_staging);
+    if (!s) return;
+    if (s->gp) cudaFreeHost(s->gp);
+    if (s->rp) cudaFreeHost(s->rp);
+    if (s->c32) cudaFreeHost(s->c32);
+    if (s->c16) cudaFreeHost(s->c16);
+    if (s->w) cudaFreeHost(s->w);
+    if (s->copied) cudaEventDestroy(s->copied);
+    delete s;
+    ctx->ingest_staging = nullptr;
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" {
+
+int dg_pack_graphs_sizes(int32_t n_graphs, const int32_t *const *indptr, const double *const *data,
+                         const int32_t *n_rows, int64_t *n_nodes, int64_t *nnz, int32_t *max_rows) {
+    clear_error();
+    DG_REQUIRE(n_graphs >= 0 && (n_graphs == 0 || (indptr && n_rows)), DG_ERR_INVALID, "null argument");
+    PackPlan plan;
+    DG_TRY(plan_sizes(n_graphs, indptr, data, n_rows, default_threads(0, data ? (1 << 20) : 0), &plan));
+    if (n_nodes) *n_nodes = plan.v0.back();
+    if (nnz) *nnz = plan.e0.back();
+    if (max_rows) {
+        int32_t m = 0;
+        for (int g = 0; g < n_graphs; ++g) m = std::max(m, n_rows[g]);
+        *max_rows = m;
+    }
+    return DG_OK;
+}
+
+int dg_pack_graphs_host(int32_t n_graphs, const int32_t *const *indptr, const int32_t *const *indices,
+                        const double *const *data, const int32_t *n_rows, int32_t *graph_ptr, int32_t *row_ptr,
+                        int32_t *col_idx, uint16_t *col_local16, int32_t n_threads) {
+    clear_error();
+    DG_REQUIRE(n_graphs >= 0 && graph_ptr && row_ptr, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(n_graphs == 0 || (indptr && indices && n_rows), DG_ERR_INVALID, "null argument");
+    DG_REQUIRE((col_idx != nullptr) != (col_local16 != nullptr), DG_ERR_INVALID,
+               "pass exactly one of col_idx (32-bit batch-global ids) and col_local16 (16-bit graph-local ids)");
+    PackPlan plan;
+    const int threads0 = default_threads(n_threads, 1 << 20);
+    DG_TRY(plan_sizes(n_graphs, indptr, data, n_rows, threads0, &plan));
+    if (col_local16)
+        for (int g = 0; g < n_graphs; ++g)
+            DG_REQUIRE(n_rows[g] <= 65536, DG_ERR_INVALID, "graph %d has %d vertices: 16-bit column ids need <= 65536", g,
+                       n_rows[g]);
+    const int threads = default_threads(n_threads, plan.e0.back() + plan.v0.back());
+    return pack_into(n_graphs, indptr, indices, data, n_rows, plan, threads, graph_ptr, row_ptr, col_idx, col_local16);
+}
+
+int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, const int32_t *const *indptr,
+                         const int32_t *const *indices, const double *const *data, const int32_t *n_rows,
+                         const double *const *wts_per_graph, const double *wts_packed, int predict,
+                         int remove_zero_weight, uint8_t *member, double *total, int wait) {
+    clear_error();
+    DG_REQUIRE(ctx && m && member, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(n_graphs >= 0 && (n_graphs == 0 || (indptr && indices && n_rows)), DG_ERR_INVALID, "null argument");
+    DG_REQUIRE((wts_per_graph != nullptr) != (wts_packed != nullptr) || n_graphs == 0, DG_ERR_INVALID,
+               "pass exactly one of wts_per_graph and wts_packed");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != ctx->device) cudaSetDevice(ctx->device);
+    struct Restore {
+        int prev, dev;
+        ~Restore() {
+            if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+        }
+    } restore{prev, ctx->device};
+    if (!ctx->ingest_staging) {
+        Staging *s = new (std::nothrow) Staging();
+        DG_REQUIRE(s != nullptr, DG_ERR_INVALID, "out of host memory");
+        if (cudaEventCreateWithFlags(&s->copied, cudaEventDisableTiming) != cudaSuccess) {
+            delete s;
+            set_error("cudaEventCreate failed");
+            return DG_ERR_CUDA;
+        }
+        ctx->ingest_staging = s;
+    }
+    Staging *s = static_cast<Staging *>(ctx->ingest_staging);
+    PackPlan plan;
+    DG_TRY(plan_sizes(n_graphs, indptr, data, n_rows, default_threads(0, 1 << 20), &plan));
+    const int64_t n = plan.v0.back(), e = plan.e0.back();
+    int32_t max_rows = 0;
+    for (int g = 0; g < n_graphs; ++g) max_rows = std::max(max_rows, n_rows[g]);
+    const bool narrow = max_rows <= 65536;
+    // the previous call's copies must have read the staging before it is overwritten (its kernels may still run)
+    if (s->in_flight) {
+        DG_CUDA_CHECK(cudaEventSynchronize(s->copied));
+        s->in_flight = false;
+    }
+    DG_TRY(grow_pinned(&s->gp, &s->cap_g, (size_t)n_graphs + 1));
+    DG_TRY(grow_pinned(&s->rp, &s->cap_n, (size_t)n + 1));
+    if (narrow) DG_TRY(grow_pinned(&s->c16, &s->cap_e16, (size_t)e + 1));
+    else DG_TRY(grow_pinned(&s->c32, &s->cap_e32, (size_t)e + 1));
+    const int threads = default_threads(0, e + n);
+    DG_TRY(pack_into(n_graphs, indptr, indices, data, n_rows, plan, threads, s->gp, s->rp, narrow ? nullptr : s->c32,
+                     narrow ? s->c16 : nullptr));
+    const double *w = wts_packed;
+    if (wts_per_graph) {
+        DG_TRY(grow_pinned(&s->w, &s->cap_w, (size_t)n + 1));
+        for (int g = 0; g < n_graphs; ++g) {
+            DG_REQUIRE(wts_per_graph[g] || n_rows[g] == 0, DG_ERR_INVALID, "graph %d: null weights", g);
+            if (n_rows[g]) memcpy(s->w + plan.v0[(size_t)g], wts_per_graph[g], sizeof(double) * (size_t)n_rows[g]);
+        }
+        w = s->w;
+    }
+    static const double kNoWeights = 0.0;
+    if (!w) w = &kNoWeights;  // empty batch
+    const int st = solve_host_staged(ctx, m, n_graphs, (int32_t)n, (int32_t)e, s->gp, s->rp, narrow ? nullptr : s->c32, w,
+                                     predict, remove_zero_weight, member, total, wait != 0, narrow ? s->c16 : nullptr,
+                                     s->copied);
+    s->in_flight = st == DG_OK && wait == 0;
+    return st;
+}
+
+}  // extern "C"

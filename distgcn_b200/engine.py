@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from ._lib import (ACT_IDENTITY, ACT_LEAKY_RELU, ACT_RELU, HEAD_LINEAR, HEAD_PAIR_SOFTMAX, MEM_DEVICE, MEM_HOST,
                    PREDICT_MIS, PREDICT_MWIS, check)
-from .batch import PackedBatch
+from .batch import GraphTables, PackedBatch
 
 LEAKY_ALPHA = 0.2  # tf.nn.leaky_relu default, the alpha of every shipped checkpoint
 
@@ -422,6 +422,43 @@ def solve_host(ctx: Context, model: Model, packed: PackedBatch, wts, predict="mw
     return member, total
 
 
+def solve_graphs_host(ctx: Context, model: Model, graphs, wts, predict="mwis", remove_zero_weight: bool = True,
+                      member: Optional[np.ndarray] = None, total: Optional[np.ndarray] = None, wait: bool = True,
+                      check_values: bool = False):
+    """``DQNAgent.solve_mwis`` for a LIST of per-graph matrices as the reference holds them (one scipy CSR/CSC matrix
+    per graph, mwis_dqn_call.py:198), in one native call (dg_solve_graphs_host): the per-graph arrays are packed by the
+    library's host threads into pinned staging, copied, solved and the membership (original vertex ids, graph after
+    graph) copied back.  ``graphs``: list of matrices or a ``GraphTables``; ``wts``: one float64 array over all
+    vertices, or a list of per-graph arrays.  ``check_values``: treat stored zeros as non-edges (costs a pass over the
+    values; adjacency matrices loaded from the reference's .mat files hold only ones)."""
+    t = graphs if isinstance(graphs, GraphTables) else GraphTables(graphs, check_values)
+    per_graph = None
+    keep = None
+    w = None
+    if isinstance(wts, (list, tuple)):
+        from . import _pyingest
+        arrs = [a if (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous) else
+                _np(a, np.float64).reshape(-1) for a in wts]
+        per_graph, lens, keep = _pyingest.pointers(arrs, 8)
+        if len(arrs) != t.n_graphs or not np.array_equal(np.frombuffer(lens, dtype=np.int32), t.n_rows):
+            raise ValueError("one weight per vertex of every graph is needed")
+    else:
+        w = wts if (isinstance(wts, np.ndarray) and wts.dtype == np.float64 and wts.flags.c_contiguous) else _np(wts, np.float64)
+        w = w.reshape(-1)
+        if w.shape[0] != t.n_nodes:
+            raise ValueError("weights have %d entries for %d vertices" % (w.shape[0], t.n_nodes))
+    if member is None:
+        member = np.empty(t.n_nodes, dtype=np.uint8)
+    if total is None:
+        total = np.empty(t.n_graphs, dtype=np.float64)
+    check(ctx._lib.dg_solve_graphs_host(ctx.handle, model.handle, t.n_graphs, t.indptr, t.indices, t.data, t.n_rows_raw,
+                                        per_graph, _ptr(w), predict_code(predict), 1 if remove_zero_weight else 0,
+                                        _ptr(member), _ptr(total), 1 if wait else 0))
+    if not wait:
+        return member, total, (t, w, keep)   # what must stay alive until ctx.synchronize()
+    return member, total
+
+
 class HostPipeline:
     """Streams of host batches through ``depth`` contexts used in turn (the ingest side
     becomes the bottleneck once the kernels are fast): while one context's kernels run, the next batch's CSR
@@ -448,9 +485,23 @@ class HostPipeline:
         slot = self._next
         self._next = (slot + 1) % len(self.ctxs)
         self.wait(slot)
+        if not (isinstance(wts, np.ndarray) and wts.dtype == np.float64 and wts.flags.c_contiguous):
+            wts = _np(wts, np.float64)   # the converted copy is what the copy engine reads: it must outlive the call
         solve_host(self.ctxs[slot], self.models[slot], packed, wts, predict, remove_zero_weight, member, total,
                    wait=False, col_local16=col_local16)
         self._busy[slot] = (packed, wts, member, total, col_local16)  # keep the arrays alive
+        return slot
+
+    def submit_graphs(self, graphs, wts, member: np.ndarray, total: Optional[np.ndarray] = None, predict="mwis",
+                      remove_zero_weight: bool = True, check_values: bool = False) -> int:
+        """The same for the reference's native input: a list of per-graph scipy matrices (or a GraphTables) and their
+        weights; packing happens inside the call, in the library (dg_solve_graphs_host)."""
+        slot = self._next
+        self._next = (slot + 1) % len(self.ctxs)
+        self.wait(slot)
+        _, _, alive = solve_graphs_host(self.ctxs[slot], self.models[slot], graphs, wts, predict, remove_zero_weight,
+                                        member, total, wait=False, check_values=check_values)
+        self._busy[slot] = (alive, member, total)
         return slot
 
     def wait(self, slot: Optional[int] = None) -> None:

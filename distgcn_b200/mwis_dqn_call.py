@@ -40,6 +40,9 @@ class DQNAgent:
         self.epsilon_decay = 0.985
         self.learning_rate = self.flags.learning_rate
         self.ctx = default_context(device)
+        # True: stored zeros in an adjacency matrix are not edges (np.nonzero semantics, heuristics.py:94) at the cost
+        # of one pass over the stored values per call; the reference's datasets store only ones
+        self.check_values = True
         self.placeholders = L.make_placeholders(1 + self.flags.max_degree, feature_size)
         self.model = self._build_model()
 
@@ -96,14 +99,24 @@ class DQNAgent:
         if (wts_0 < 0).any():
             raise ValueError("negative weights: the reference drops wts == 0 but keeps wts > 0 only "
                              "(mwis_dqn_call.py:203-204), so its behaviour is undefined here")
-        member, total = self._solve_packed(pack_graphs([adj_0]), wts_0)
+        # one native call: the matrix's own indptr / indices go to the library as they are (dg_solve_graphs_host)
+        member, total = self._solve_graphs([adj_0], wts_0)
         return set(np.flatnonzero(member).tolist()), float(total[0]), 1.0
 
     def solve_mwis_batch(self, graphs, wts):
-        """Many graphs in one launch.  `graphs`: PackedBatch or list of adjacency matrices; `wts`: one
-        weight per packed vertex.  Returns (member uint8 [n_nodes], total weight per graph)."""
-        packed = graphs if isinstance(graphs, PackedBatch) else pack_graphs(graphs)
-        return self._solve_packed(packed, np.asarray(wts, dtype=np.float64).reshape(-1))
+        """Many graphs in one launch.  `graphs`: PackedBatch, GraphTables or list of adjacency matrices (the
+        reference's native form - packed inside the library, no Python loop); `wts`: one weight per vertex (one array,
+        or a list of per-graph arrays).  Returns (member uint8 [n_nodes], total weight per graph)."""
+        if isinstance(graphs, PackedBatch):
+            return self._solve_packed(graphs, np.asarray(wts, dtype=np.float64).reshape(-1))
+        return self._solve_graphs(graphs, wts)
+
+    def _solve_graphs(self, graphs, wts):
+        model = self.model.compile(self.ctx)
+        if model.out_width != 1:
+            raise NotImplementedError("solve_mwis needs diver_num == 1 (act_vals.flatten() * wts, mwis_dqn_call.py:232)")
+        return engine.solve_graphs_host(self.ctx, model, graphs, wts, predict=self.flags.predict, remove_zero_weight=True,
+                                        check_values=self.check_values)
 
     def _solve_packed(self, packed, wts):
         model = self.model.compile(self.ctx)

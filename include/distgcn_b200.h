@@ -226,6 +226,37 @@ DG_API int dg_solve_host_compact(dg_context *ctx, const dg_model *model, int32_t
                           const int32_t *graph_ptr, const int32_t *row_ptr, const uint16_t *col_local, const double *wts,
                           int predict, int remove_zero_weight, uint8_t *member, double *total, int wait);
 
+/* ---- native ingest: the reference's per-graph inputs, as they are ----------------------------------------------
+ * The reference passes every graph as its own scipy sparse matrix (mwis_dqn_call.py:198; the .mat files written by
+ * Data_Generation.py:214-219 load as float64 CSC with int32 indptr / indices) and converts it on every call through
+ * networkx (mwis_dqn_call.py:202-207), then maps the solution back (:240-241).  These entry points take TABLES OF
+ * POINTERS to the per-graph arrays - indptr[g] (n_rows[g] + 1 entries starting at 0), indices[g] (column ids local to
+ * the graph; the adjacency is symmetric, so CSC and CSR coincide), optionally data[g] (float64 stored values: a stored
+ * zero is not an edge, np.nonzero(adj[v]) at heuristics.py:94; data or any data[g] may be NULL = all ones) - and pack
+ * them with a pool of host threads: no per-graph work in Python.  Malformed input (decreasing indptr, a column id
+ * outside [0, n_rows[g])) is DG_ERR_INVALID. */
+
+/* Sizes of the packed batch (to allocate the outputs of dg_pack_graphs_host). */
+DG_API int dg_pack_graphs_sizes(int32_t n_graphs, const int32_t *const *indptr, const double *const *data,
+                         const int32_t *n_rows, int64_t *n_nodes, int64_t *nnz, int32_t *max_rows);
+/* Pack into caller arrays: graph_ptr [n_graphs + 1], row_ptr [n_nodes + 1] and EXACTLY ONE of col_idx (int32,
+ * batch-global ids: the packed form of dg_batch_create / dg_solve_host) and col_local16 (uint16, graph-local ids: the
+ * compact form of dg_solve_host_compact; graphs of at most 65536 vertices).  n_threads <= 0: all pool threads.
+ * Host-only: needs no GPU. */
+DG_API int dg_pack_graphs_host(int32_t n_graphs, const int32_t *const *indptr, const int32_t *const *indices,
+                        const double *const *data, const int32_t *n_rows, int32_t *graph_ptr, int32_t *row_ptr,
+                        int32_t *col_idx, uint16_t *col_local16, int32_t n_threads);
+/* DQNAgent.solve_mwis for a list of graphs in one call (mwis_dqn_call.py:198-261 per graph): pack into the context's
+ * pinned staging, copy, solve (dg_solve semantics: zero-weight removal, GCN, utility, local greedy search), copy the
+ * results back.  Weights either per graph (wts_per_graph[g]: n_rows[g] doubles) or packed (wts_packed: one double per
+ * vertex in graph order); exactly one of the two.  member: sum(n_rows) bytes in ORIGINAL vertex ids of each graph;
+ * total (may be NULL): n_graphs doubles.  wait == 0: enqueue only - the per-graph arrays may be released on return
+ * (they have been packed), member / total / wts_packed must stay valid until dg_context_synchronize. */
+DG_API int dg_solve_graphs_host(dg_context *ctx, const dg_model *model, int32_t n_graphs, const int32_t *const *indptr,
+                         const int32_t *const *indices, const double *const *data, const int32_t *n_rows,
+                         const double *const *wts_per_graph, const double *wts_packed, int predict,
+                         int remove_zero_weight, uint8_t *member, double *total, int wait);
+
 /* ---- one giant graph, row-partitioned over several GPUs (no reference counterpart: the
  * reference handles one 100-300 vertex graph per call) ------------------------------------------------
  * A dg_part is one rank's slice: rows row0 .. row0+n_local-1 of a graph with n_global vertices (row0 and

@@ -255,3 +255,58 @@ def test_mwis_dqn_test_harness_ratios():
     assert 1.0 < np.nanmean(p) < 1.12     # survey-time restatement: 1.041; Gurobi optimum of the set: 1.1197
     p2, total2, _, _ = evaluate(agent, pb, w, search="greedy")
     assert np.allclose(total2, total, rtol=1e-12)   # the weights of this set have no zeros: both searches solve the same graph
+
+
+def test_native_ingest_list_of_scipy_matrices():
+    """solve_mwis_batch(list of scipy matrices, weights): the reference's native input goes through
+    dg_solve_graphs_host (packed by the library's host threads) and gives what the packed path gives - for one
+    weight array or per-graph weight arrays, CSC / CSR / other formats, with zero weights (original vertex ids) and
+    with stored zeros in a matrix; the streaming form (HostPipeline.submit_graphs) too."""
+    from distgcn_b200 import engine as E
+    from distgcn_b200.mwis_dqn_call import DQNAgent
+    gold = util.load_npz("gcn_oracle_small.npz")
+    pb, w = util.small_graphs()
+    agent = DQNAgent(1, 5000, flags=_flags())
+    agent.load(util.ckpt_dir("is4sat_l20_c32"))
+    adjs = [sp.csc_matrix(pb.graph_adj(g)) for g in range(pb.n_graphs)]
+    member, total = agent.solve_mwis_batch(adjs, w)
+    assert np.array_equal(member, gold["is4sat_l20_c32_member"])
+    ref_total = np.add.reduceat(np.where(member == 1, w, 0.0), pb.graph_ptr[:-1])
+    assert np.allclose(total, ref_total, rtol=1e-12)
+    # per-graph weight arrays, mixed matrix formats
+    w_list = [w[pb.graph_ptr[g]:pb.graph_ptr[g + 1]] for g in range(pb.n_graphs)]
+    mixed = [a.tocsr() if i % 3 == 0 else (a.tolil() if i % 3 == 1 else a) for i, a in enumerate(adjs)]
+    member2, total2 = agent.solve_mwis_batch(mixed, w_list)
+    assert np.array_equal(member2, member) and np.array_equal(total2, total)
+    # zero weights
+    wz = gold["wz"]
+    member_z, _ = agent.solve_mwis_batch(adjs, wz)
+    assert np.array_equal(member_z, gold["is4sat_l20_c32_wz_member"])
+    # a stored zero is not an edge: same result as the matrix without those entries
+    g = 7
+    x = adjs[g].tocsr().copy()
+    rows = np.repeat(np.arange(x.shape[0]), np.diff(x.indptr))
+    drop = ((rows + x.indices) % 5 == 0)                  # a symmetric set of pairs
+    x.data = np.where(drop, 0.0, x.data)
+    y = x.copy()
+    y.eliminate_zeros()
+    assert 0 < y.nnz < x.nnz
+    wg = w_list[g]
+    m_x, t_x, _ = agent.solve_mwis(x, wg)
+    m_y, t_y, _ = agent.solve_mwis(y, wg)
+    m_full, _, _ = agent.solve_mwis(adjs[g], wg)
+    assert m_x == m_y and t_x == t_y and m_x != m_full
+    # streaming form
+    pipe = E.HostPipeline(0, util.load_layers("is4sat_l20_c32"), E.gcn_dqn_acts(20), depth=2)
+    outs = [(E.pinned_empty(pb.n_nodes, np.uint8), E.pinned_empty(pb.n_graphs, np.float64)) for _ in range(4)]
+    for k in range(4):
+        pipe.submit_graphs(adjs, w if k % 2 == 0 else wz, outs[k][0], outs[k][1])
+    pipe.wait()
+    for k in range(4):
+        assert np.array_equal(np.asarray(outs[k][0]), member if k % 2 == 0 else member_z)
+    pipe.close()
+    # one graph per call, as the reference's scripts do (wireless_dqn_test_mc.py:289,323)
+    for g in (3, 28):
+        v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+        mw, tw, _ = agent.solve_mwis(adjs[g], w_list[g])
+        assert mw == set(np.flatnonzero(member[v0:v1]).tolist())

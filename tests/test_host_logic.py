@@ -256,3 +256,77 @@ def test_local_columns_compact_format():
     big = PackedBatch(np.array([0, 70000], np.int32), np.zeros(70001, np.int32), np.zeros(0, np.int32))
     with pytest.raises(ValueError):
         big.local_columns()
+
+
+# ---- native ingest (dg_pack_graphs_host; host code of the library, no GPU needed) ------------------------
+def _random_adjs(rng, count, n_lo=1, n_hi=120):
+    out = []
+    for _ in range(count):
+        n = int(rng.integers(n_lo, n_hi + 1))
+        up = np.triu(rng.random((n, n)) < rng.uniform(0.02, 0.3), k=1)
+        out.append(sp.csc_matrix((up | up.T).astype(np.float64)))     # the .mat files load as CSC
+    return out
+
+
+def test_native_packer_equals_python_packer():
+    rng = np.random.default_rng(8)
+    adjs = _random_adjs(rng, 300)
+    a, b = B.pack_graphs(adjs), B.pack_graphs_python(adjs)
+    for x, y in ((a.graph_ptr, b.graph_ptr), (a.row_ptr, b.row_ptr), (a.col_idx, b.col_idx)):
+        assert x.dtype == np.int32 and np.array_equal(x, y)
+    a.validate()
+    # single thread, all threads, and the value check switched off give the same arrays
+    for kw in (dict(n_threads=1), dict(n_threads=64), dict(check_values=False)):
+        c = B.pack_graphs(adjs, **kw)
+        assert np.array_equal(c.col_idx, b.col_idx) and np.array_equal(c.row_ptr, b.row_ptr)
+    # a large batch (threads engaged: > 64 k entries)
+    big = _random_adjs(rng, 60, 250, 300)
+    assert np.array_equal(B.pack_graphs(big).col_idx, B.pack_graphs_python(big).col_idx)
+
+
+def test_native_packer_input_forms_and_errors():
+    from distgcn_b200 import _lib
+    rng = np.random.default_rng(9)
+    adjs = _random_adjs(rng, 6, 5, 40)
+    mixed = [adjs[0].tolil(), adjs[1].toarray(), sp.csr_matrix((0, 0)), adjs[2].tocsr(), adjs[3].tocoo(),
+             sp.csr_matrix((adjs[4].data, adjs[4].indices.astype(np.int64), adjs[4].indptr.astype(np.int64)),
+                           shape=adjs[4].shape)]
+    a, b = B.pack_graphs(mixed), B.pack_graphs_python(mixed)
+    assert np.array_equal(a.graph_ptr, b.graph_ptr) and np.array_equal(a.row_ptr, b.row_ptr)
+    assert np.array_equal(a.col_idx, b.col_idx)
+    # stored zeros are not edges (np.nonzero(adj[v]), heuristics.py:94) ...
+    x = adjs[5].tocsr().copy()
+    x.data[::3] = 0.0
+    a, b = B.pack_graphs([adjs[0], x, adjs[1]]), B.pack_graphs_python([adjs[0], x, adjs[1]])
+    assert a.nnz == b.nnz < adjs[0].nnz + x.nnz + adjs[1].nnz and np.array_equal(a.col_idx, b.col_idx)
+    assert np.array_equal(a.row_ptr, b.row_ptr)
+    # ... unless the caller vouches for a pattern-only input
+    assert B.pack_graphs([x], check_values=False).nnz == x.nnz
+    # empty list, empty graphs
+    e = B.pack_graphs([])
+    assert e.n_graphs == 0 and e.n_nodes == 0 and e.nnz == 0
+    e = B.pack_graphs([sp.csr_matrix((3, 3)), sp.csr_matrix((0, 0))])
+    assert e.graph_ptr.tolist() == [0, 3, 3] and e.row_ptr.tolist() == [0, 0, 0, 0]
+    # malformed patterns are refused with the graph's index
+    bad = adjs[2].tocsr().copy()
+    bad.indices = bad.indices.copy()
+    bad.indices[0] = bad.shape[0] + 7
+    with pytest.raises(_lib.DistGCNError) as ei:
+        B.pack_graphs([adjs[0], bad])
+    assert ei.value.code == _lib.ERR_INVALID and "graph 1" in str(ei.value)
+    with pytest.raises(ValueError):
+        B.pack_graphs([np.zeros((2, 3))])
+    # the 16-bit compact form straight from the per-graph arrays equals PackedBatch.local_columns()
+    import ctypes as C
+    lib = _lib.load()
+    t = B.GraphTables(adjs, True)
+    pb = B.pack_graphs(adjs)
+    gp = np.empty(t.n_graphs + 1, np.int32)
+    rp = np.empty(pb.n_nodes + 1, np.int32)
+    c16 = np.empty(pb.nnz, np.uint16)
+    _lib.check(lib.dg_pack_graphs_host(t.n_graphs, t.indptr, t.indices, t.data, t.n_rows_raw, gp.ctypes.data, rp.ctypes.data,
+                                       None, c16.ctypes.data, 0))
+    assert np.array_equal(c16, pb.local_columns()) and np.array_equal(rp, pb.row_ptr) and np.array_equal(gp, pb.graph_ptr)
+    with pytest.raises(_lib.DistGCNError):   # exactly one column output
+        _lib.check(lib.dg_pack_graphs_host(t.n_graphs, t.indptr, t.indices, t.data, t.n_rows_raw, gp.ctypes.data,
+                                           rp.ctypes.data, None, None, 0))

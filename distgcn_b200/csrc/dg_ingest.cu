@@ -8,6 +8,8 @@
 // or 32-bit batch-global column ids) straight into pinned staging, from where the usual H2D copies and kernels run.
 // Host code only; compiled into the same library as the kernels.
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -16,8 +18,83 @@
 
 #include "dg_common.cuh"
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 namespace dg {
 namespace {
+
+// ---- the two inner loops of the packer: column ids of one graph, narrowed to 16 bits or re-based to batch ids.
+// Return non-zero when some id lies outside [0, n).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) unsigned narrow16_avx2(const int32_t *ix, int64_t e, uint32_t n, uint16_t *out) {
+    const __m256i lim = _mm256_set1_epi32((int)(n - 1));
+    __m256i bad = _mm256_setzero_si256();
+    int64_t k = 0;
+    for (; k + 16 <= e; k += 16) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(ix + k));
+        const __m256i b = _mm256_loadu_si256((const __m256i *)(ix + k + 8));
+        // unsigned c > n - 1  <=>  max_u(c, n - 1) != n - 1 ... use min: min_u(c, lim) != c
+        bad = _mm256_or_si256(bad, _mm256_xor_si256(_mm256_min_epu32(a, lim), a));
+        bad = _mm256_or_si256(bad, _mm256_xor_si256(_mm256_min_epu32(b, lim), b));
+        const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi32(a, b), 0xD8);
+        _mm256_storeu_si256((__m256i *)(out + k), p);
+    }
+    unsigned acc = _mm256_testz_si256(bad, bad) ? 0u : 1u;
+    for (; k < e; ++k) {
+        const uint32_t c = (uint32_t)ix[k];
+        acc |= (c >= n);
+        out[k] = (uint16_t)c;
+    }
+    return acc;
+}
+__attribute__((target("avx2"))) unsigned rebase32_avx2(const int32_t *ix, int64_t e, uint32_t n, uint32_t v0, int32_t *out) {
+    const __m256i lim = _mm256_set1_epi32((int)(n - 1)), off = _mm256_set1_epi32((int)v0);
+    __m256i bad = _mm256_setzero_si256();
+    int64_t k = 0;
+    for (; k + 8 <= e; k += 8) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(ix + k));
+        bad = _mm256_or_si256(bad, _mm256_xor_si256(_mm256_min_epu32(a, lim), a));
+        _mm256_storeu_si256((__m256i *)(out + k), _mm256_add_epi32(a, off));
+    }
+    unsigned acc = _mm256_testz_si256(bad, bad) ? 0u : 1u;
+    for (; k < e; ++k) {
+        const uint32_t c = (uint32_t)ix[k];
+        acc |= (c >= n);
+        out[k] = (int32_t)(c + v0);
+    }
+    return acc;
+}
+const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+#else
+const bool kHaveAvx2 = false;
+#endif
+
+unsigned narrow16(const int32_t *ix, int64_t e, uint32_t n, uint16_t *out) {
+#if defined(__x86_64__)
+    if (kHaveAvx2 && n > 0) return narrow16_avx2(ix, e, n, out);
+#endif
+    unsigned acc = 0;
+    for (int64_t k = 0; k < e; ++k) {
+        const uint32_t c = (uint32_t)ix[k];
+        acc |= (c >= n);
+        out[k] = (uint16_t)c;
+    }
+    return acc;
+}
+unsigned rebase32(const int32_t *ix, int64_t e, uint32_t n, uint32_t v0, int32_t *out) {
+#if defined(__x86_64__)
+    if (kHaveAvx2 && n > 0) return rebase32_avx2(ix, e, n, v0, out);
+#endif
+    unsigned acc = 0;
+    for (int64_t k = 0; k < e; ++k) {
+        const uint32_t c = (uint32_t)ix[k];
+        acc |= (c >= n);
+        out[k] = (int32_t)(c + v0);
+    }
+    return acc;
+}
 
 // A persistent pool: parallel_for(n, fn) runs fn(task) for task = 0..n-1 on the workers and the calling thread.
 class Pool {
@@ -185,22 +262,8 @@ int pack_into(int32_t n_graphs, const int32_t *const *indptr, const int32_t *con
                     bad.store(g);
                     continue;
                 }
-                unsigned acc = 0;  // any id outside [0, n) sets a bit at or above position 31 or compares >= n
-                if (col16) {
-                    uint16_t *out = col16 + e0;
-                    for (int64_t k = 0; k < e; ++k) {
-                        const uint32_t c = (uint32_t)ix[k];
-                        acc |= (c >= (uint32_t)n);
-                        out[k] = (uint16_t)c;
-                    }
-                } else {
-                    int32_t *out = col_idx + e0;
-                    for (int64_t k = 0; k < e; ++k) {
-                        const uint32_t c = (uint32_t)ix[k];
-                        acc |= (c >= (uint32_t)n);
-                        out[k] = (int32_t)(c + (uint32_t)v0);
-                    }
-                }
+                const unsigned acc = col16 ? narrow16(ix, e, (uint32_t)n, col16 + e0)
+                                           : rebase32(ix, e, (uint32_t)n, (uint32_t)v0, col_idx + e0);
                 if (acc) bad.store(g);
             } else {  // stored zeros are dropped
                 int64_t w = e0;
@@ -339,6 +402,8 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
         ctx->ingest_staging = s;
     }
     Staging *s = static_cast<Staging *>(ctx->ingest_staging);
+    static const bool timing = getenv("DG_INGEST_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
     PackPlan plan;
     DG_TRY(plan_sizes(n_graphs, indptr, data, n_rows, default_threads(0, 1 << 20), &plan));
     const int64_t n = plan.v0.back(), e = plan.e0.back();
@@ -346,10 +411,12 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
     for (int g = 0; g < n_graphs; ++g) max_rows = std::max(max_rows, n_rows[g]);
     const bool narrow = max_rows <= 65536;
     // the previous call's copies must have read the staging before it is overwritten (its kernels may still run)
+    const auto t_plan = std::chrono::steady_clock::now();
     if (s->in_flight) {
         DG_CUDA_CHECK(cudaEventSynchronize(s->copied));
         s->in_flight = false;
     }
+    const auto t_wait = std::chrono::steady_clock::now();
     DG_TRY(grow_pinned(&s->gp, &s->cap_g, (size_t)n_graphs + 1));
     DG_TRY(grow_pinned(&s->rp, &s->cap_n, (size_t)n + 1));
     if (narrow) DG_TRY(grow_pinned(&s->c16, &s->cap_e16, (size_t)e + 1));
@@ -368,10 +435,19 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
     }
     static const double kNoWeights = 0.0;
     if (!w) w = &kNoWeights;  // empty batch
+    const auto t_pack = std::chrono::steady_clock::now();
     const int st = solve_host_staged(ctx, m, n_graphs, (int32_t)n, (int32_t)e, s->gp, s->rp, narrow ? nullptr : s->c32, w,
                                      predict, remove_zero_weight, member, total, wait != 0, narrow ? s->c16 : nullptr,
                                      s->copied);
     s->in_flight = st == DG_OK && wait == 0;
+    if (timing) {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::micro>(b - a).count();
+        };
+        fprintf(stderr, "[ingest] %d graphs %lld nnz, %d threads: plan %.0f us, wait staging %.0f us, pack %.0f us, enqueue %.0f us\n",
+                n_graphs, (long long)e, threads, us(t_begin, t_plan), us(t_plan, t_wait), us(t_wait, t_pack), us(t_pack, t_end));
+    }
     return st;
 }
 

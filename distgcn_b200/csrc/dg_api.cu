@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <new>
 
+#include <chrono>
+
 #include "dg_common.cuh"
 
 namespace dg {
@@ -581,10 +583,15 @@ static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nn
     DG_REQUIRE(n_graphs >= 0 && n_nodes >= 0 && nnz >= 0, DG_ERR_INVALID, "negative size");
     DG_REQUIRE(graph_ptr && row_ptr && (col_idx || col_local16 || nnz == 0), DG_ERR_INVALID, "null CSR pointer");
     DG_REQUIRE(!col_local16 || mem == DG_MEM_HOST, DG_ERR_INVALID, "the compact column format is a host format");
+    b->cols_pending = false;
+    const bool meta_ready = b->meta_ready && mem == DG_MEM_HOST && b->n_graphs == n_graphs && b->n_nodes == n_nodes &&
+                            b->nnz == nnz;
+    b->meta_ready = false;
     b->n_graphs = n_graphs;
     b->n_nodes = n_nodes;
     b->nnz = nnz;
-    b->cols_pending = false;
+    if (meta_ready) goto upload;  // host_batch_set_meta has described this very batch (and a tile plan may be waiting)
+    b->tc_plan_ready = false;
     b->h_graph_ptr.resize((size_t)n_graphs + 1);
     if (mem == DG_MEM_HOST) {
         std::copy(graph_ptr, graph_ptr + n_graphs + 1, b->h_graph_ptr.begin());
@@ -614,6 +621,7 @@ static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nn
         DG_REQUIRE(b->h_graph_e[g + 1] >= b->h_graph_e[g], DG_ERR_INVALID, "row_ptr decreases at graph %d", g);
         b->max_graph_nnz = std::max(b->max_graph_nnz, b->h_graph_e[g + 1] - b->h_graph_e[g]);
     }
+upload:
     if (mem == DG_MEM_HOST) {
         if (b->cap_graphs < (size_t)n_graphs + 1 || !b->graph_ptr) {
             if (b->graph_ptr) cudaFree(b->graph_ptr);
@@ -1125,22 +1133,64 @@ static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs,
         b->keep = nullptr;
     }
     // with zero-weight removal the degrees are computed once the keep mask is known (solve_device)
+    static const bool timing = getenv("DG_INGEST_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     DG_TRY(batch_fill(b, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, DG_MEM_HOST, !remove_zero_weight, col_local16));
     const size_t n = (size_t)n_nodes, G = (size_t)n_graphs;
     double *d_wts = nullptr, *d_total = nullptr;
     uint8_t *d_member = nullptr;
     DG_TRY(stage_in(ctx, kSlotWts, wts, n, &d_wts));
     if (copied) DG_CUDA_CHECK(cudaEventRecord(copied, ctx->stream));
+    const auto t1 = std::chrono::steady_clock::now();
     DG_TRY(scratch_as(ctx, kSlotMember, n, &d_member));
     if (total) DG_TRY(scratch_as(ctx, kSlotTotal, G, &d_total));
     DG_TRY(solve_device(ctx, m, b, d_wts, predict, remove_zero_weight, d_member, nullptr, nullptr, d_total, nullptr));
+    const auto t2 = std::chrono::steady_clock::now();
     DG_TRY(copy_out(ctx, member, d_member, n));
     DG_TRY(copy_out(ctx, total, d_total, G));
+    if (timing) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) {
+            return std::chrono::duration<double, std::micro>(c - a).count();
+        };
+        fprintf(stderr, "[solve_host] batch_fill + weights %.0f us, plan + launch %.0f us, copy-out enqueue %.0f us\n", us(t0, t1),
+                us(t1, t2), us(t2, t3));
+    }
     return wait ? finish(ctx) : DG_OK;
 }
 
 extern "C++" {
 namespace dg {
+int host_batch_set_meta(dg_context *ctx, int32_t n_graphs, const int64_t *v0, const int64_t *e0, dg_batch **out) {
+    if (!ctx->host_batch) {
+        ctx->host_batch = new (std::nothrow) dg_batch();
+        DG_REQUIRE(ctx->host_batch != nullptr, DG_ERR_INVALID, "out of host memory");
+        ctx->host_batch->ctx = ctx;
+    }
+    dg_batch *b = ctx->host_batch;
+    b->n_graphs = n_graphs;
+    b->n_nodes = (int)v0[n_graphs];
+    b->nnz = (int)e0[n_graphs];
+    b->h_graph_ptr.resize((size_t)n_graphs + 1);
+    b->h_graph_e.resize((size_t)n_graphs + 1);
+    b->max_graph_nodes = 0;
+    b->max_graph_nnz = 0;
+    for (int g = 0; g <= n_graphs; ++g) {
+        b->h_graph_ptr[(size_t)g] = (int32_t)v0[g];
+        b->h_graph_e[(size_t)g] = (int32_t)e0[g];
+        if (g) {
+            b->max_graph_nodes = std::max(b->max_graph_nodes, (int)(v0[g] - v0[g - 1]));
+            b->max_graph_nnz = std::max(b->max_graph_nnz, (int)(e0[g] - e0[g - 1]));
+        }
+    }
+    b->tiles_valid = false;
+    b->tc_tiles_valid = false;
+    b->tc_plan_ready = false;
+    b->meta_ready = true;
+    *out = b;
+    return DG_OK;
+}
+
 int solve_host_staged(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
                       const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
                       int predict, int remove_zero_weight, uint8_t *member, double *total, bool wait,

@@ -214,6 +214,8 @@ struct dg_batch {
     size_t tc_tiles_cap = 0;
     int tc_n_tiles = 0;
     bool tc_tiles_valid = false;
+    bool tc_plan_ready = false;      // tc_tiles_host already holds the plan of the current batch (made ahead, on a pool thread)
+    bool meta_ready = false;         // host metadata (h_graph_ptr, h_graph_e, maxima) already describe the batch being filled
     std::vector<int> tc_tiles_host;  // host copy of the table (scheduling diagnostics)
     std::vector<uint8_t> tc_skip;    // per graph: 1 = beyond the tensor-core kernel's limits (left to the CUDA-core kernel)
     int tc_n_skipped = 0;
@@ -326,6 +328,8 @@ bool fused_fits(dg_context *ctx, const dg_model *m, const dg_batch *b);
 // hidden-layer operand blobs from the layers' weights ([c_in, c_out] row-major, widths <= 32)
 void tc_build_weights(int n_hidden, const float *const *w0, const float *const *w1, const float *const *bias, const int *c_in,
                       const int *c_out, std::vector<unsigned char> *blob);
+// host-only: plan the tensor-core kernel's tiles for the batch described by b's host metadata, ahead of the solve
+void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b);
 int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
                  int remove_zero_weight, uint8_t *member, float *score, double *util, double *total, int32_t *steps,
                  bool *handled);
@@ -359,6 +363,9 @@ int solve_host_staged(dg_context *ctx, const dg_model *m, int32_t n_graphs, int3
                       int predict, int remove_zero_weight, uint8_t *member, double *total, bool wait,
                       const uint16_t *col_local16, cudaEvent_t copied);
 void ingest_staging_free(dg_context *ctx);  // dg_ingest.cu
+// set the host metadata of the context's reusable batch from per-graph vertex / edge offsets (n_graphs + 1 each) before
+// its arrays exist; the following solve_host_staged(..) call then skips recomputing them
+int host_batch_set_meta(dg_context *ctx, int32_t n_graphs, const int64_t *v0, const int64_t *e0, dg_batch **out);
 
 // profiling helpers (dg_api.cu)
 void prof_begin(dg_context *ctx);

@@ -1283,14 +1283,11 @@ long long tc_makespan(const std::vector<Open> &tiles, int workers) {
     return *std::max_element(load.begin(), load.end());
 }
 
-int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
-    *ok = false;
-    if (b->tc_tiles_valid) {
-        *ok = b->tc_n_tiles > 0;
-        return DG_OK;
-    }
-    b->tc_tiles_valid = true;
+// host half of the tile plan: fills b->tc_tiles_host / tc_skip / tc_n_tiles from the batch's host metadata
+// (h_graph_ptr, h_graph_e).  No CUDA calls: dg_solve_graphs_host runs it on a pool thread while the others pack.
+void tc_plan_tiles_host(dg_context *ctx, dg_batch *b) {
     b->tc_n_tiles = 0;
+    b->tc_tiles_host.clear();
     const size_t pool = tc_smem_bytes(ctx) - kTcOffPool;
     const auto &gp = b->h_graph_ptr;
     const auto &ge = b->h_graph_e;
@@ -1324,7 +1321,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     // runs on the host for every streamed batch, 16 k graphs at a time in the large configurations.
     const int max_size = kTcBlocks * 128;
     std::vector<int> head((size_t)max_size + 1, -1), next_same((size_t)b->n_graphs, -1), prev_size((size_t)max_size + 1);
-    if (b->tc_n_skipped == b->n_graphs) return DG_OK;  // nothing for this kernel
+    if (b->tc_n_skipped == b->n_graphs) return;  // nothing for this kernel
     for (const TcGraph &t : gs) {
         if (t.nb == 0) continue;
         next_same[(size_t)t.g] = head[(size_t)t.nv];
@@ -1387,6 +1384,20 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
             d[0] = g, d[1] = gp[g], d[2] = gp[g + 1] - gp[g], d[3] = ge[g], d[4] = ge[g + 1] - ge[g];
         }
     }
+    b->tc_n_tiles = (int)tiles.size();
+    b->tc_tiles_host.swap(flat);
+}
+
+int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
+    *ok = false;
+    if (b->tc_tiles_valid) {
+        *ok = b->tc_n_tiles > 0;
+        return DG_OK;
+    }
+    if (!b->tc_plan_ready) tc_plan_tiles_host(ctx, b);
+    b->tc_plan_ready = false;
+    b->tc_tiles_valid = true;
+    const std::vector<int> &flat = b->tc_tiles_host;
     if (b->tc_tiles_cap < flat.size() || !b->tc_tiles_dev) {
         if (b->tc_tiles_dev) {
             DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1399,14 +1410,22 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
     if (!flat.empty())
         DG_CUDA_CHECK(cudaMemcpyAsync(b->tc_tiles_dev, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice,
                                       ctx->stream));
-    b->tc_n_tiles = (int)tiles.size();
-    b->tc_tiles_host = flat;
     if (getenv("DG_FUSED_TIMING")) fprintf(stderr, "[tc tiles] %d tiles for %d graphs\n", b->tc_n_tiles, b->n_graphs);
     *ok = b->tc_n_tiles > 0;
     return DG_OK;
 }
 
 }  // namespace
+
+bool tc_model_eligible(const dg_model *m) {
+    return !(getenv("DG_DISABLE_TC") || getenv("DG_DISABLE_FUSED")) && m->tc_wall && m->n_layers >= 3;
+}
+
+void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b) {
+    if (!tc_model_eligible(m) || b->n_graphs == 0 || b->n_nodes == 0) return;
+    tc_plan_tiles_host(ctx, b);
+    b->tc_plan_ready = true;
+}
 
 static int *g_wide_buf = nullptr;  // DG_TC_DEBUG: pinned table the stuck threads log their wait sites into
 

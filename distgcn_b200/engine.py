@@ -437,10 +437,12 @@ def solve_graphs_host(ctx: Context, model: Model, graphs, wts, predict="mwis", r
     w = None
     if isinstance(wts, (list, tuple)):
         from . import _pyingest
-        arrs = [a if (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous) else
-                _np(a, np.float64).reshape(-1) for a in wts]
-        per_graph, lens, keep = _pyingest.pointers(arrs, 8)
-        if len(arrs) != t.n_graphs or not np.array_equal(np.frombuffer(lens, dtype=np.int32), t.n_rows):
+        try:     # float64 C-contiguous arrays (what the reference passes): pointer table built in C, no Python loop
+            per_graph, lens, keep = _pyingest.pointers(wts, 8)
+        except (TypeError, BufferError, ValueError):
+            arrs = [_np(a, np.float64).reshape(-1) for a in wts]
+            per_graph, lens, keep = _pyingest.pointers(arrs, 8)
+        if lens != t.n_rows_raw:   # bytes compare: one int32 length per graph
             raise ValueError("one weight per vertex of every graph is needed")
     else:
         w = wts if (isinstance(wts, np.ndarray) and wts.dtype == np.float64 and wts.flags.c_contiguous) else _np(wts, np.float64)

@@ -607,6 +607,7 @@ static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nn
     // row_ptr at the graph boundaries (host copy): per-graph nnz for the fused kernel's tile table
     b->tiles_valid = false;
     b->tc_tiles_valid = false;
+    b->gs_valid = false;
     b->h_graph_e.resize((size_t)n_graphs + 1);
     if (mem == DG_MEM_HOST) {
         for (int g = 0; g <= n_graphs; ++g) b->h_graph_e[g] = row_ptr[b->h_graph_ptr[g]];
@@ -706,6 +707,7 @@ void dg_batch_destroy(dg_batch *b) {
     if (b->x0) cudaFree(b->x0);
     if (b->tiles_dev) cudaFree(b->tiles_dev);
     if (b->tc_tiles_dev) cudaFree(b->tc_tiles_dev);
+    if (b->gs_tiles_dev) cudaFree(b->gs_tiles_dev);
     delete b;
 }
 
@@ -1185,6 +1187,7 @@ int host_batch_set_meta(dg_context *ctx, int32_t n_graphs, const int64_t *v0, co
     }
     b->tiles_valid = false;
     b->tc_tiles_valid = false;
+    b->gs_valid = false;
     b->tc_plan_ready = false;
     b->meta_ready = true;
     *out = b;

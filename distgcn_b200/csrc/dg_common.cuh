@@ -214,6 +214,11 @@ struct dg_batch {
     size_t tc_tiles_cap = 0;
     int tc_n_tiles = 0;
     bool tc_tiles_valid = false;
+    // tile table of the graph-staged streaming layer kernel (dg_stream.cu): row ranges aligned to graph boundaries
+    int *gs_tiles_dev = nullptr;
+    size_t gs_tiles_cap = 0;
+    int gs_n_tiles = 0, gs_grid = 0;
+    bool gs_valid = false;
     bool tc_plan_ready = false;      // tc_tiles_host already holds the plan of the current batch (made ahead, on a pool thread)
     bool meta_ready = false;         // host metadata (h_graph_ptr, h_graph_e, maxima) already describe the batch being filled
     std::vector<int> tc_tiles_host;  // host copy of the table (scheduling diagnostics)
@@ -332,6 +337,32 @@ void tc_build_weights(int n_hidden, const float *const *w0, const float *const *
 void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b);
 int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
                  int remove_zero_weight, uint8_t *member, float *score, double *util, double *total, int32_t *steps,
+                 bool *handled);
+
+// arguments of one fused hidden GraphConvolution layer (gc_layer_kernel in dg_gcn.cu, gs_layer_kernel in dg_stream.cu)
+struct LayerArgs {
+    int n;
+    int nnz;
+    int row0;  // row-slice form: rows row0 .. row0+n-1 of a larger graph, per-vertex arrays global
+    const int *row_ptr;
+    const int *col_idx;
+    const float *dinv;
+    const float *hin;       // [n, CPI] (dense input)
+    const float2 *pair_in;  // (x0, s)   (implicit input)
+    const float *in_a0, *in_a1, *in_b;  // first layer's column sums / bias, [CPI]
+    int in_act;
+    const float *wcat;      // [2*CPI, CPO]
+    const float *bias;      // [CPO]
+    int act;
+    float alpha;
+    float *hout;            // [n, CPO]
+    const float *tail_w0, *tail_w1;  // [CPO]
+    float *tail_q, *tail_zs;  // (q, zs) planes
+    PeerMap pm;             // row-partitioned runs: output rows / zs are also stored to the peers' arenas
+};
+
+// ---- graph-staged streaming layer kernel (dg_stream.cu): batches of small graphs, 32-wide layers ----
+int gs_try_layer(dg_context *ctx, dg_batch *b, int cpi, int cpo, bool implicit_in, bool tail, const LayerArgs &a,
                  bool *handled);
 
 // ---- kernels / drivers implemented in dg_gcn.cu ---------------------------------------------

@@ -248,26 +248,6 @@ __global__ void utility_kernel(int n, const float *__restrict__ score, int strid
 // warp shuffles.  Projection: the warp's rows sit in shared memory, lane c owns output column c
 // (and c+32), weights are read from shared memory once per 8 rows.
 // ---------------------------------------------------------------------------------------------
-struct LayerArgs {
-    int n;
-    int nnz;
-    int row0;  // row-slice form: rows row0 .. row0+n-1 of a larger graph, per-vertex arrays global
-    const int *row_ptr;
-    const int *col_idx;
-    const float *dinv;
-    const float *hin;       // [n, CPI] (dense input)
-    const float2 *pair_in;  // (x0, s)   (implicit input)
-    const float *in_a0, *in_a1, *in_b;  // first layer's column sums / bias, [CPI]
-    int in_act;
-    const float *wcat;      // [2*CPI, CPO]
-    const float *bias;      // [CPO]
-    int act;
-    float alpha;
-    float *hout;            // [n, CPO]
-    const float *tail_w0, *tail_w1;  // [CPO]
-    float *tail_q, *tail_zs;  // (q, zs) planes
-    PeerMap pm;             // row-partitioned runs: output rows / zs are also stored to the peers' arenas
-};
 
 template <int CPI, int CPO, bool IMPLICIT_IN, bool TAIL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -848,7 +828,9 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
         } else {
             a.hout = nxt;
         }
-        DG_TRY(launch_layer(ctx, ly.cpi, ly.cpo, implicit_in, tail, a));
+        bool staged = false;  // batches of small graphs: the graph-staged kernel (dg_stream.cu), else warp per row
+        DG_TRY(gs_try_layer(ctx, b, ly.cpi, ly.cpo, implicit_in, tail, a, &staged));
+        if (!staged) DG_TRY(launch_layer(ctx, ly.cpi, ly.cpo, implicit_in, tail, a));
         cur = nxt;
         nxt = (nxt == fa) ? fb : fa;
     }

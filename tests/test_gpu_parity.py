@@ -843,6 +843,67 @@ def test_solve_leaves_the_batch_as_found_and_oversize_graphs(gpu_ctx):
     model.close()
 
 
+def test_graph_staged_streaming_layer_kernel(gpu_ctx, monkeypatch):
+    """The per-layer path on a batch of small graphs runs gs_layer_kernel (dg_stream.cu: tiles of whole graphs staged
+    in shared memory).  Scores against the float64 oracle for a 20-layer and a 3-layer 32-wide model (implicit-input
+    first hidden layer, plain hidden layers, tail-fused last hidden layer all occur), with zero weights, empty and
+    single-vertex graphs in the batch, tiles of several small graphs, and equality of the membership with the
+    warp-per-row kernel's (DG_DISABLE_STAGED=1) on the same utilities."""
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    from distgcn_b200.ckpt import LayerWeights
+    rng = np.random.default_rng(77)
+    monkeypatch.setenv("DG_DISABLE_FUSED", "1")     # per-layer path
+    monkeypatch.delenv("DG_DISABLE_STAGED", raising=False)
+
+    def er(n, p):
+        up = np.triu(rng.random((n, n)) < p, k=1)
+        return sp.csr_matrix((up | up.T).astype(np.float64))
+    adjs = [er(int(rng.integers(100, 301)), 0.1) for _ in range(40)]
+    adjs += [er(int(rng.integers(5, 60)), 0.2) for _ in range(30)]           # several per tile
+    adjs += [sp.csr_matrix((0, 0)), sp.csr_matrix((1, 1)), er(304, 0.05), sp.csr_matrix((7, 7))]
+    order = rng.permutation(len(adjs))
+    adjs = [adjs[i] for i in order]
+    pb = pack_graphs(adjs)
+    w = rng.random(pb.n_nodes)
+    w[rng.random(pb.n_nodes) < 0.1] = 0.0
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    for short in ("is4sat_l20_c32", "is4sat_ld32_l3_c32"):
+        layers = util.load_layers(short)
+        model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+        r = E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True, want_score=True, want_util=True, want_steps=True)
+        assert gpu_ctx.last_kernel == "gs_layer_kernel"
+        exact = util.exact_scores(pb, w, layers)
+        q, nw = _elementwise_report("%s graph-staged layer kernel" % short, r.score[:, 0], exact)
+        assert nw <= SCORE_RTOL and q[1] <= SCORE_RTOL
+        for g in range(pb.n_graphs):
+            v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+            if v1 > v0 and np.abs(exact[v0:v1]).max() > 0:
+                assert _rel_err(r.score[v0:v1, 0], exact[v0:v1]) <= 2 * SCORE_RTOL, "graph %d" % g
+        o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, r.util, init_remain=(w > 0).astype(np.uint8))
+        assert np.array_equal(o.member, r.member) and np.array_equal(o.steps, r.steps)
+        # the warp-per-row kernel on the same batch: same scores to fp32 rounding
+        monkeypatch.setenv("DG_DISABLE_STAGED", "1")
+        r2 = E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True, want_score=True)
+        assert gpu_ctx.last_kernel == "gc_layer_kernel"
+        monkeypatch.delenv("DG_DISABLE_STAGED")
+        assert _rel_err(r2.score[:, 0], r.score[:, 0]) <= 2 * SCORE_RTOL
+        model.close()
+    # a batch with a graph too large for a tile falls back to the warp-per-row kernel as a whole
+    big = pack_graphs(adjs[:10] + [er(400, 0.05)])
+    bbatch = E.DeviceBatch(gpu_ctx, big)
+    layers = util.load_layers("is4sat_ld32_l3_c32")
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    wb = rng.random(big.n_nodes)
+    rb = E.solve(gpu_ctx, model, bbatch, wb, want_score=True)
+    assert gpu_ctx.last_kernel == "gc_layer_kernel"
+    assert _rel_err(rb.score[:, 0], util.exact_scores(big, wb, layers)) <= SCORE_RTOL
+    model.close()
+    bbatch.close()
+    batch.close()
+
+
 def test_error_reporting(gpu_ctx):
     E = _engine()
     from distgcn_b200 import _lib

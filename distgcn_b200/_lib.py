@@ -91,6 +91,16 @@ SIGNATURES = {
     "dg_pack_graphs_sizes": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "dg_pack_graphs_host": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32]),
     "dg_solve_graphs_host": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_int]),
+    "dg_wireless_create": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, C.POINTER(_p)]),
+    "dg_wireless_destroy": (None, [_p]),
+    "dg_wireless_buffers": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "dg_wireless_begin_slot": (C.c_int, [_p, _i32]),
+    "dg_wireless_joint_weights": (C.c_int, [_p, _i32]),
+    "dg_wireless_joint_serve": (C.c_int, [_p, _i32]),
+    "dg_wireless_seq_weights": (C.c_int, [_p, _i32, _i32]),
+    "dg_wireless_seq_serve": (C.c_int, [_p, _i32, _i32]),
+    "dg_wireless_end_slot": (C.c_int, [_p, _i32]),
+    "dg_wireless_read_history": (C.c_int, [_p, _p]),
 }
 
 _lib = None

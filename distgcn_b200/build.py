@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_NAME = "libdistgcn_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["dg_api.cu", "dg_gcn.cu", "dg_lgs.cu", "dg_fused.cu", "dg_tc.cu", "dg_ingest.cu", "dg_stream.cu"]
+SOURCES = ["dg_api.cu", "dg_gcn.cu", "dg_lgs.cu", "dg_fused.cu", "dg_tc.cu", "dg_ingest.cu", "dg_stream.cu", "dg_wireless.cu"]
 HEADERS = ["dg_common.cuh", os.path.join("..", "..", "include", "distgcn_b200.h")]
 PYINGEST_SRC = os.path.join(CSRC, "pyingest.c")
 PYINGEST_PATH = os.path.join(HERE, "_pyingest" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))

@@ -27,8 +27,9 @@ synthetic stand-in with the constants of wireless_dqn_test_mc.py:91-94 (100 node
 node pairs within ``r_c``, two links conflict when they share a node or any two of their end points are within
 ``r_i``); everything downstream of the conflict graph follows the reference.
 
-The schedules come from the CUDA library (dg_solve / dg_lgs on a resident packed batch); the queue
-bookkeeping is a handful of vectorised numpy operations over all instances.  Where the sequential variants
+The schedules come from the CUDA library (dg_solve / dg_lgs on a resident packed batch).  ``run`` keeps the queue
+bookkeeping on the device as well (dg_wireless_*: a sweep is a stream of kernel launches with one synchronisation at
+the end); ``step`` / ``run_host`` do it in vectorised numpy with one synchronous solver call per slot.  Where the sequential variants
 schedule one link on several channels the reference's ``capacity[schedule] = rates`` keeps whichever entry numpy
 assigns last, in Python-set iteration order; here the highest channel wins (ascending vertex id, which is what
 that iteration order is for small integers).
@@ -168,7 +169,16 @@ class BatchedScheduler:
     """All instances of a sweep advanced slot by slot; graphs stay resident on the device."""
 
     def __init__(self, ctx: engine.Context, instances: Sequence[Instance], algo: str = "DGCN-LGS",
-                 model: Optional[engine.Model] = None, predict: str = "mwis"):
+                 model: Optional[engine.Model] = None, predict: str = "mwis", agent_generation: int = 1):
+        """`agent_generation`: the agent "DGCN-LGS" stands for on the joint graph.  1 (default) =
+        mwis_dqn_call.DQNAgent.solve_mwis, which drops zero-weight vertices before scoring (mwis_dqn_call.py:202-207) -
+        the agent the shipped checkpoints belong to; 2 = mwis_gdpg_call.MWISSolver.solve_mwis(adj, wts, train, grd)
+        (mwis_gdpg_call.py:200-235, the signature wireless_dqn_test_mc.py:289 calls at HEAD), which keeps them in the
+        graph.  With empty queues the two see different graphs.  "DGCN-LGS-it" is generation 2 by definition; the
+        sequential variants slice the non-zero sub-graph themselves (:299-301), so the generations coincide there."""
+        if agent_generation not in (1, 2):
+            raise ValueError("agent_generation must be 1 or 2")
+        self.agent_generation = agent_generation
         if algo not in ALGOS:
             raise ValueError("algo must be one of %s" % (ALGOS,))
         if algo.startswith("DGCN") and model is None:
@@ -182,6 +192,7 @@ class BatchedScheduler:
         self.n_links = int(self.lp[-1])
         self.q = np.zeros(self.n_links)                            # queue lengths, all instances
         self.seq = algo.endswith("-Seq")
+        self._remove_zero = self.seq or agent_generation == 1
         if self.seq:
             # one packed batch per channel; vertex = link
             self.packed = [pack_graphs([i.adj_list[k] for i in self.inst]) for k in range(self.n_ch)]
@@ -195,6 +206,8 @@ class BatchedScheduler:
             self.v_link = (np.repeat(self.lp[:-1], np.diff(gp)) + vloc % nf_v).astype(np.int64)
         self.batches = [engine.DeviceBatch(ctx, p) for p in self.packed]
         self.t = 0
+        self._t_device = 0     # slots advanced by the device-resident loop
+        self._ws = None        # (dg_wireless handle, weights buffer, membership buffer)
         self.solver_calls = 0
         self.last_weights = None   # what the solver saw in the last slot (for parity tests)
         self.last_member = None
@@ -215,7 +228,7 @@ class BatchedScheduler:
             return engine.dist_greedy(self.ctx, self.batches[k], w, epsilon=GREEDY_TH_EPSILON, want_steps=False).member
         if self.algo.startswith("DGCN"):
             return engine.solve(self.ctx, self.model, self.batches[k], w, predict=self.predict,
-                                remove_zero_weight=True, want_total=False).member
+                                remove_zero_weight=self._remove_zero, want_total=False).member
         if self.seq:   # LGS on the sub-graph of non-zero weights (wireless_dqn_test_mc.py:300-303)
             self.batches[k].set_keep_from_weights(w)
         return engine.lgs(self.ctx, self.batches[k], w, want_steps=False).member
@@ -252,8 +265,8 @@ class BatchedScheduler:
         self.q -= dep                                                          # :365
         return dep
 
-    def run(self, n_slots: Optional[int] = None):
-        """Run the remaining slots; returns the queue-length matrix [slots, n_links]."""
+    def run_host(self, n_slots: Optional[int] = None):
+        """The slot loop with the queue bookkeeping in numpy and one synchronous solver call per slot (`step`)."""
         n = (self.T - 1 - self.t) if n_slots is None else min(n_slots, self.T - 1 - self.t)
         qs = np.zeros((n, self.n_links))
         for s in range(n):
@@ -261,6 +274,85 @@ class BatchedScheduler:
             qs[s] = self.q
         return qs
 
+    # ---- device-resident loop: queues, weights, capacities and the history stay on the GPU ------------------------
+    def _device_state(self):
+        if self._ws is not None:
+            return self._ws
+        import ctypes as C
+        lib = self.ctx._lib
+        arrivals = np.ascontiguousarray(np.concatenate([i.arrivals[:self.T] for i in self.inst], axis=1), dtype=np.float64)
+        rates = np.ascontiguousarray(np.concatenate([i.rates[:self.T] for i in self.inst], axis=1), dtype=np.int32)
+        if self.seq:
+            v0 = nf = None
+            n_vertices = self.n_links
+        else:
+            gp = self.packed[0].graph_ptr.astype(np.int64)
+            nfl = np.diff(self.lp)
+            v0 = np.ascontiguousarray(np.repeat(gp[:-1], nfl) + (np.arange(self.n_links) - np.repeat(self.lp[:-1], nfl)),
+                                      dtype=np.int32)
+            nf = np.ascontiguousarray(np.repeat(nfl, nfl), dtype=np.int32)
+            n_vertices = int(gp[-1])
+        h = C.c_void_p()
+        engine.check(lib.dg_wireless_create(self.ctx.handle, self.n_links, self.n_ch, self.T, arrivals.ctypes.data,
+                                            rates.ctypes.data, None if v0 is None else v0.ctypes.data,
+                                            None if nf is None else nf.ctypes.data, n_vertices, C.byref(h)))
+        w, member, q = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        engine.check(lib.dg_wireless_buffers(h, C.byref(w), C.byref(member), C.byref(q)))
+        self._ws = (h, w, member)
+        return self._ws
+
+    def _solve_device(self, k: int, w, member) -> None:
+        """The slot's scheduler on device buffers (DG_MEM_DEVICE: enqueue only)."""
+        lib, ctx, b = self.ctx._lib, self.ctx, self.batches[k]
+        self.solver_calls += 1
+        pc = engine.predict_code(self.predict)
+        if self.algo == "DGCN-LGS-it":
+            engine.check(lib.dg_solve_dit(ctx.handle, self.model.handle, b.handle, w, pc, member, None, None, engine.MEM_DEVICE))
+        elif self.algo == "Greedy-Th":
+            import ctypes as C
+            engine.check(lib.dg_dist_greedy(ctx.handle, b.handle, w, C.c_double(GREEDY_TH_EPSILON), member, None,
+                                            engine.MEM_DEVICE))
+        elif self.algo.startswith("DGCN"):
+            engine.check(lib.dg_solve(ctx.handle, self.model.handle, b.handle, w, pc, 1 if self._remove_zero else 0, member,
+                                      None, None, None, None, engine.MEM_DEVICE))
+        else:
+            if self.seq:
+                engine.check(lib.dg_batch_set_keep_from_weights(b.handle, w, engine.MEM_DEVICE))
+            engine.check(lib.dg_lgs(ctx.handle, b.handle, w, -1, member, None, None, None, None, None, engine.MEM_DEVICE))
+
+    def run(self, n_slots: Optional[int] = None):
+        """Run the remaining slots on the device - q += arrivals, weights, schedule, capacities, departures are all
+        kernels on resident arrays, enqueued slot after slot without a host synchronisation - and return the
+        queue-length matrix [slots, n_links] (one copy at the end).  Not to be mixed with `step` / `run_host`."""
+        if self.t != self._t_device:
+            raise RuntimeError("run() continues the device-resident loop; this scheduler has been stepped on the host")
+        n = (self.T - 1 - self.t) if n_slots is None else min(n_slots, self.T - 1 - self.t)
+        lib = self.ctx._lib
+        h, w, member = self._device_state()
+        t0 = self.t
+        for s in range(n):
+            t = self.t + 1
+            engine.check(lib.dg_wireless_begin_slot(h, t))
+            if not self.seq:
+                engine.check(lib.dg_wireless_joint_weights(h, t))
+                self._solve_device(0, w, member)
+                engine.check(lib.dg_wireless_joint_serve(h, t))
+            else:
+                for ic in range(self.n_ch):
+                    engine.check(lib.dg_wireless_seq_weights(h, t, ic))
+                    self._solve_device(ic, w, member)
+                    engine.check(lib.dg_wireless_seq_serve(h, t, ic))
+            engine.check(lib.dg_wireless_end_slot(h, t))
+            self.t = t
+        self._t_device = self.t
+        hist = np.empty((self.T, self.n_links), dtype=np.float64)
+        engine.check(lib.dg_wireless_read_history(h, hist.ctypes.data))
+        self.q = hist[self.t].copy()
+        return hist[t0 + 1:self.t + 1]
+
     def close(self) -> None:
+        if self._ws is not None:
+            self.ctx._lib.dg_wireless_destroy(self._ws[0])
+            self._ws = None
         for b in self.batches:
             b.close()

@@ -257,6 +257,37 @@ DG_API int dg_solve_graphs_host(dg_context *ctx, const dg_model *model, int32_t 
                          const double *const *wts_per_graph, const double *wts_packed, int predict,
                          int remove_zero_weight, uint8_t *member, double *total, int wait);
 
+/* ---- multi-channel wireless scheduling: the queue bookkeeping of the slot loop, resident on the device ----------
+ * wireless_dqn_test_mc.py:225-366 advances one network one time slot at a time in numpy around one solver call.  A
+ * dg_wireless holds the state of MANY (network, load) instances advanced together - queues, arrivals [T][n_links]
+ * (float64), link rates [T][n_links][n_ch] (int32), the queue history - on the device, and its calls only ENQUEUE
+ * kernels on the context's stream; with the solvers called in DG_MEM_DEVICE mode on the buffers of
+ * dg_wireless_buffers a whole sweep runs without a host synchronisation until dg_wireless_read_history.
+ * Joint-graph algorithms (Greedy, Greedy-Th, DGCN-LGS, DGCN-LGS-it; vertex link_v0[l] + k * link_nf[l] = link l on
+ * channel k, wireless_rollout_test_flood.py:98-133), per slot t = 1 .. T-1:
+ *     begin_slot(t): q += arrivals[t] (:227);  joint_weights(t): w[v] = q[link] * rate[t][link][channel] (:228-240);
+ *     <solver on w -> member>;  joint_serve(t): capacity[link] = rate of its scheduled vertex (:358-363);
+ *     end_slot(t): q -= min(q, capacity), history[t] = q (:364-365).
+ * Sequential variants (LGS-Seq, DGCN-LGS-Seq; vertex = link, one graph batch per channel), per slot:
+ *     begin_slot(t); for every channel: seq_weights(t, ic): w = queue estimate * rate[:, ic] (:298);  <solver>;
+ *     seq_serve(t, ic): capacity of the scheduled links, estimate -= min(estimate, rate) on them (:306-309);  end_slot(t). */
+typedef struct dg_wireless dg_wireless;
+DG_API int dg_wireless_create(dg_context *ctx, int32_t n_links, int32_t n_ch, int32_t n_slots, const double *arrivals,
+                       const int32_t *rates, const int32_t *link_v0, const int32_t *link_nf, int32_t n_vertices,
+                       dg_wireless **out);
+DG_API void dg_wireless_destroy(dg_wireless *s);
+/* device buffers: w (weights for the solver, max(n_vertices, n_links) doubles), member (the solver writes its answer
+ * here), q (current queue lengths, n_links doubles); any of the outputs may be NULL */
+DG_API int dg_wireless_buffers(dg_wireless *s, double **w, uint8_t **member, double **q);
+DG_API int dg_wireless_begin_slot(dg_wireless *s, int32_t t);
+DG_API int dg_wireless_joint_weights(dg_wireless *s, int32_t t);
+DG_API int dg_wireless_joint_serve(dg_wireless *s, int32_t t);
+DG_API int dg_wireless_seq_weights(dg_wireless *s, int32_t t, int32_t channel);
+DG_API int dg_wireless_seq_serve(dg_wireless *s, int32_t t, int32_t channel);
+DG_API int dg_wireless_end_slot(dg_wireless *s, int32_t t);
+/* synchronise and copy the queue history [n_slots][n_links] (row t = queues after slot t; row 0 zeros) to the host */
+DG_API int dg_wireless_read_history(dg_wireless *s, double *history);
+
 /* ---- one giant graph, row-partitioned over several GPUs (no reference counterpart: the
  * reference handles one 100-300 vertex graph per call) ------------------------------------------------
  * A dg_part is one rank's slice: rows row0 .. row0+n_local-1 of a graph with n_global vertices (row0 and

@@ -20,11 +20,15 @@ from . import gcn_oracle as G
 from . import lgs as L
 
 
-def solve_graph(adj, w, layers, predict: str = "mwis", kind: str = "gcn_dqn", remove_zero_weight: bool = True):
+def solve_graph(adj, w, layers, predict: str = "mwis", kind: str = "gcn_dqn", remove_zero_weight: bool = True,
+                generation: int = 1):
     """One graph.  Returns (score[N] fp32, util[N] fp64, member[N] uint8) indexed by ORIGINAL vertex
-    ids; removed vertices carry zeros."""
+    ids; removed vertices carry zeros.  generation 2 = MWISSolver.solve_mwis (mwis_gdpg_call.py:200-235): no
+    zero-weight removal, all-ones features (:82-96)."""
     w = np.asarray(w, dtype=np.float64).reshape(-1)
     n = w.shape[0]
+    if generation == 2:
+        remove_zero_weight = False
     if remove_zero_weight:
         keep = np.where(w > 0)[0]  # kp_nodes, mwis_dqn_call.py:204
     else:
@@ -38,7 +42,7 @@ def solve_graph(adj, w, layers, predict: str = "mwis", kind: str = "gcn_dqn", re
     if keep.shape[0] != n:
         a = a[keep][:, keep].tocsr()
     wk = w[keep]
-    feats = G.features_gen1(wk, layers[0].c_in)
+    feats = G.features_gen2(wk, layers[0].c_in, predict) if generation == 2 else G.features_gen1(wk, layers[0].c_in)
     sup = G.laplacian_supports(a, len(layers[0].weights) - 1)
     act = G.gcn_forward(feats, sup, layers, kind)
     u = G.utility(act[:, 0], wk, predict)

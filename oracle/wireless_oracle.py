@@ -20,13 +20,15 @@ def _lgs_set(adj, w):
     return np.flatnonzero(L.run(a.indptr, a.indices, w).member)
 
 
-def _dgcn_set(adj, w, layers, predict):
-    _, _, member = pipeline.solve_graph(adj, w, layers, predict)
+def _dgcn_set(adj, w, layers, predict, generation=1):
+    _, _, member = pipeline.solve_graph(adj, w, layers, predict, generation=generation)
     return np.flatnonzero(member)
 
 
-def run_instance(adj_list, adj_gK, arrivals, rates, algo, layers=None, predict="mwis", n_slots=None):
-    """Returns (queue matrix [T, nflows], list of per-slot schedules as sorted vertex arrays)."""
+def run_instance(adj_list, adj_gK, arrivals, rates, algo, layers=None, predict="mwis", n_slots=None, agent_generation=1):
+    """Returns (queue matrix [T, nflows], list of per-slot schedules as sorted vertex arrays).  `agent_generation`: which
+    agent DGCN-LGS calls on the joint graph - 1 = mwis_dqn_call.DQNAgent.solve_mwis (drops zero-weight vertices first),
+    2 = mwis_gdpg_call.MWISSolver.solve_mwis (keeps them, all-ones features)."""
     T, nflows = arrivals.shape
     n_ch = len(adj_list)
     if n_slots is not None:
@@ -44,7 +46,7 @@ def run_instance(adj_list, adj_gK, arrivals, rates, algo, layers=None, predict="
             a = sp.csr_matrix(adj_gK)
             mwis = np.flatnonzero(L.dist_greedy(a.indptr, a.indices, wts1, 0.1)[0])      # :252 (ascending-id scan, lgs_oracle.c)
         elif algo == "DGCN-LGS":
-            mwis = _dgcn_set(adj_gK, wts1, layers, predict)                              # :289
+            mwis = _dgcn_set(adj_gK, wts1, layers, predict, agent_generation)            # :289
         elif algo == "DGCN-LGS-it":
             mwis = np.flatnonzero(pipeline.solve_graph_dit(adj_gK, wts1, layers, predict)[0])   # :264
         elif algo in ("LGS-Seq", "DGCN-LGS-Seq"):

@@ -72,7 +72,7 @@ def test_batched_slot_loop_matches_per_instance_restatement(algo, ck):
     ctx = E.Context(0)
     model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
     sim = W.BatchedScheduler(ctx, insts, algo, model)
-    qs = sim.run()
+    qs = sim.run()                       # device-resident loop: one synchronisation at the end of the sweep
     assert qs.shape == (n_slots, sim.n_links) and sim.solver_calls == n_slots * (3 if sim.seq else 1)
     for k, inst in enumerate(insts):
         q_ref, _ = WO.run_instance(inst.adj_list, inst.adj_gK, inst.arrivals, inst.rates, algo, layers, n_slots=n_slots)
@@ -80,6 +80,49 @@ def test_batched_slot_loop_matches_per_instance_restatement(algo, ck):
         assert np.array_equal(qs[:, l0:l1], q_ref[1:]), "instance %d: queue trajectories differ" % k
     assert qs.sum() > 0
     sim.close()
+    # the host-side loop (numpy bookkeeping, one synchronous solve per slot) walks the same trajectory; run() in two
+    # pieces continues where it stopped
+    sim_h = W.BatchedScheduler(ctx, insts, algo, model)
+    assert np.array_equal(sim_h.run_host(), qs)
+    sim_h.close()
+    sim_2 = W.BatchedScheduler(ctx, insts, algo, model)
+    first = sim_2.run(5)
+    rest = sim_2.run()
+    assert np.array_equal(np.concatenate([first, rest]), qs)
+    with pytest.raises(RuntimeError):
+        sim_2.t -= 1
+        sim_2.run(1)
+    sim_2.close()
+    model.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_agent_generation_is_an_explicit_choice():
+    """DGCN-LGS on the joint graph with the generation-2 agent (no zero-weight removal, all-ones features): trajectories
+    equal the restatement's for that generation, and differ from generation 1 once queues run empty."""
+    from distgcn_b200 import engine as E
+    from distgcn_b200 import wireless as W
+    from oracle import wireless_oracle as WO
+    n_slots = 12
+    insts = W.make_instances(n_networks=2, loads=[0.05, 0.3], n_ch=3, timeslots=n_slots + 1, seed=3, n_nodes=60, area=150.0)
+    layers = util.load_layers("is4sat_l20_c32")
+    ctx = E.Context(0)
+    model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
+    out = {}
+    for gen in (1, 2):
+        sim = W.BatchedScheduler(ctx, insts, "DGCN-LGS", model, agent_generation=gen)
+        qs = sim.run()
+        for k, inst in enumerate(insts):
+            q_ref, _ = WO.run_instance(inst.adj_list, inst.adj_gK, inst.arrivals, inst.rates, "DGCN-LGS", layers,
+                                       n_slots=n_slots, agent_generation=gen)
+            l0, l1 = int(sim.lp[k]), int(sim.lp[k + 1])
+            assert np.array_equal(qs[:, l0:l1], q_ref[1:]), "generation %d, instance %d" % (gen, k)
+        out[gen] = qs
+        sim.close()
+    assert not np.array_equal(out[1], out[2])
+    with pytest.raises(ValueError):
+        W.BatchedScheduler(ctx, insts, "DGCN-LGS", model, agent_generation=3)
     model.close()
     ctx.close()
 

@@ -18,8 +18,9 @@ with no collective): weak scaling.
     configs       the other BASELINE configs, each measured the same way in the same run:
                   er500 (config 1), synth-er-<G> (a config-4 batch; carries roofline_streaming: the per-layer
                   streaming kernel on an input larger than L2 against the HBM roofline), per_graph_call (one graph per
-                  call, the reference's call pattern), partitioned (N >= 2: one large graph row-partitioned over the
-                  ranks, both exchange modes - the path with real communication)
+                  call, the reference's call pattern), wireless (config 3: slots/s of the batched multi-channel slot
+                  loop), partitioned (N >= 2: one large graph row-partitioned over the ranks, both exchange modes -
+                  the path with real communication)
 
 `--impl reference` times the CPU port of the reference path on the host cores with the same `config`.
 """
@@ -695,6 +696,37 @@ def bench_single_calls(env, n_calls=200):
     return out
 
 
+def bench_wireless(env, n_networks=20, timeslots=100):
+    """BASELINE config 3: the multi-channel wireless slot loop (wireless_dqn_test_mc.py:225-366) on synthetic networks
+    with the reference's constants, every (network, load) instance advanced together, queue bookkeeping resident on the
+    device (distgcn_b200.wireless.BatchedScheduler.run).  Slots/s of the whole sweep, host wall clock."""
+    from distgcn_b200 import engine as E
+    from distgcn_b200 import wireless as W
+    from tests import util
+    loads = np.round(np.arange(0.1, 1.25, 0.1), 2)   # bash/twc_major_wireless_mc_test.sh
+    insts = W.make_instances(n_networks, loads, n_ch=3, timeslots=timeslots, seed=0)
+    out = {"workload": "synthetic stand-in for data/wireless_test: %d networks x %d loads = %d instances, 3 channels, %d slots, "
+                       "joint conflict graphs of %.0f vertices on average"
+                       % (n_networks, len(loads), len(insts), timeslots - 1, float(np.mean([i.adj_gK.shape[0] for i in insts]))),
+           "instances": len(insts)}
+    ctx = E.Context(env.local_rank)
+    for ck in ("is4sat_l1", "is4sat_l20_c32"):
+        layers = util.load_layers(ck)
+        model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
+        for algo in ("DGCN-LGS", "DGCN-LGS-Seq") + (("Greedy",) if ck == "is4sat_l1" else ()):
+            sim = W.BatchedScheduler(ctx, insts, algo, model)
+            sim.run(5)
+            t0 = time.perf_counter()
+            qs = sim.run()
+            dt = time.perf_counter() - t0
+            out["%s/%s" % (ck, algo)] = {"slots_per_s": qs.shape[0] / dt, "instance_slots_per_s": qs.shape[0] * len(insts) / dt,
+                                         "solver_graphs_per_s": qs.shape[0] * sim.graphs_per_slot / dt}
+            sim.close()
+        model.close()
+    ctx.close()
+    return out
+
+
 def bench_partitioned(env, n, deg, reps=3):
     """ONE G(n, m = n*deg/2) graph row-partitioned over the ranks (SURVEY.md 8e, config 5 shape; c64 l2 checkpoint): both
     exchange modes, device-timed (max over ranks), membership compared with the single-GPU solve of the same graph."""
@@ -805,6 +837,7 @@ def run_ours(args):
             configs[name] = rec
         if rank == 0:
             configs["per_graph_call"] = bench_single_calls(env)
+            configs["wireless"] = bench_wireless(env)
         if env.use_dist:
             env.dist.barrier()
             configs["partitioned"] = bench_partitioned(env, args.part_nodes, 16)

@@ -330,10 +330,48 @@ int dg_model_create(dg_context *ctx, int n_layers, int n_supports, const int32_t
     DG_REQUIRE(out != nullptr, DG_ERR_INVALID, "null out pointer");
     *out = nullptr;
     DG_REQUIRE(n_layers >= 1 && n_layers <= kMaxLayers, DG_ERR_INVALID, "n_layers %d out of range", n_layers);
-    DG_REQUIRE(n_supports == 2, DG_ERR_UNSUPPORTED,
-               "n_supports %d: only the cheb1 supports [I, L] are implemented", n_supports);
     DG_REQUIRE(c_in && c_out && weights && act, DG_ERR_INVALID, "null model argument");
     DG_REQUIRE(head == DG_HEAD_LINEAR || head == DG_HEAD_PAIR_SOFTMAX, DG_ERR_INVALID, "unknown head %d", head);
+    if (n_supports != 2) {
+        // Higher polynomial orders ([I, L, L^2, ..], simple_polynomials with max_degree >= 2): implemented for networks
+        // whose layers all have ONE output column - the shape of the shipped cheb2 checkpoints (1 -> 1 -> 1 and 32 -> 1).
+        bool scalar = n_supports >= 1 && n_supports <= 8 && head == DG_HEAD_LINEAR;
+        for (int l = 0; l < n_layers && scalar; ++l) scalar = c_out[l] == 1 && c_in[l] >= 1 && (l == 0 || c_in[l] == 1);
+        DG_REQUIRE(scalar, DG_ERR_UNSUPPORTED,
+                   "n_supports %d: beyond the cheb1 supports [I, L] only networks whose layers all have one output column are "
+                   "implemented", n_supports);
+        DeviceGuard guard(ctx->device);
+        dg_model *m = new (std::nothrow) dg_model();
+        DG_REQUIRE(m != nullptr, DG_ERR_INVALID, "out of host memory");
+        m->ctx = ctx;
+        m->n_layers = n_layers;
+        m->n_supports = n_supports;
+        m->alpha = leaky_alpha;
+        m->head = head;
+        m->scalar_net = true;
+        m->layers.resize(n_layers);
+        for (int l = 0; l < n_layers; ++l) {
+            DG_REQUIRE(act[l] >= DG_ACT_IDENTITY && act[l] <= DG_ACT_RELU, DG_ERR_INVALID, "layer %d: activation", l);
+            m->layers[l].c_in = c_in[l];
+            m->layers[l].c_out = 1;
+            m->layers[l].cpo = pad_width(1);
+            m->layers[l].act = act[l];
+            for (int k = 0; k < n_supports; ++k) {
+                const float *w = weights[(size_t)n_supports * l + k];
+                if (!w) {
+                    delete m;
+                    set_error("layer %d: null weights", l);
+                    return DG_ERR_INVALID;
+                }
+                float sum = 0.f;  // sequential fp32 sum over the constant input features (TF's sparse x dense order)
+                for (int f = 0; f < c_in[l]; ++f) sum += w[f];
+                m->scalar_w.push_back(sum);
+            }
+            m->scalar_b.push_back((bias && bias[l]) ? bias[l][0] : 0.f);
+        }
+        *out = m;
+        return DG_OK;
+    }
     for (int l = 0; l < n_layers; ++l) {
         DG_REQUIRE(c_in[l] >= 1 && c_out[l] >= 1, DG_ERR_INVALID, "layer %d: empty shape", l);
         DG_REQUIRE(c_out[l] <= kMaxWidth && (l == 0 || c_in[l] <= kMaxWidth), DG_ERR_UNSUPPORTED,

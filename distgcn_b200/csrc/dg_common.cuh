@@ -183,6 +183,12 @@ struct dg_model {
     // operands of the tensor-core solve kernel (dg_tc.cu); null when the model is not eligible
     unsigned char *tc_wall = nullptr;  // hidden layers: bf16 terms of [W_0 | W_1 r], bias, 1/r, bound factor
     float tc_tail_norm = 0.f;          // sum |W_1[:,0]| of the last layer (fixed-point bound of its scalar aggregation)
+    // Scalar network: every layer has ONE output column, any number of supports [I, L, L^2, ...] (the shipped cheb2
+    // checkpoints: gcn/utils.py:258-274 with max_degree = 2).  Layer l is out = act(sum_k L^k (z * w[l][k]) + b[l]) on a
+    // per-vertex scalar z; scalar_w[l * n_supports + k] is W_k[0,0], or for the first layer the column sum of W_k over the
+    // (constant) input features.  Host copies: the values travel as kernel arguments.
+    bool scalar_net = false;
+    std::vector<float> scalar_w, scalar_b;
 };
 
 struct dg_batch {

@@ -22,6 +22,8 @@
 //     fused with the fp64 utility product of mwis_dqn_call.py:232.
 #include <math.h>
 
+#include <utility>
+
 #include "dg_common.cuh"
 
 namespace dg {
@@ -673,6 +675,44 @@ int part_last(dg_context *ctx, const PartView &pv, const dg_model *m, const floa
     return DG_OK;
 }
 
+// ---- scalar networks with any number of supports (the cheb2 checkpoints) ----------------------------------------
+// first-layer input: z_i = x0_i on kept vertices (the row-normalised constant features, gcn/utils.py:98-106), else 0
+__global__ void scalar_input_kernel(int n, const uint8_t *__restrict__ keep, const float *__restrict__ x0, float x0val,
+                                    float *__restrict__ z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool k = keep ? keep[i] != 0 : true;
+    z[i] = k ? (x0 ? x0[i] : x0val) : 0.f;
+}
+__global__ void scalar_scale_kernel(int n, const float *__restrict__ z, float w, float *__restrict__ t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] = z[i] * w;   // pre_sup = dot(x, W_k), gcn/layers.py:202
+}
+// t_out = L t_in, (L t)_i = t_i - dinv_i * sum_j dinv_j t_j; one thread per row, neighbours in ascending order
+__global__ void scalar_lap_kernel(int n, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                  const float *__restrict__ dinv, const float *__restrict__ t_in, float *__restrict__ t_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+        const int j = __ldg(col_idx + e);
+        acc = fmaf(__ldg(dinv + j), __ldg(t_in + j), acc);
+    }
+    t_out[i] = fmaf(-dinv[i], acc, t_in[i]);
+}
+__global__ void scalar_add_kernel(int n, const float *__restrict__ t, float *__restrict__ acc, int first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] = first ? t[i] : acc[i] + t[i];   // tf.add_n over the supports, in order (gcn/layers.py:208)
+}
+__global__ void scalar_act_kernel(int n, const float *__restrict__ acc, float bias, int act, float alpha,
+                                  const uint8_t *__restrict__ keep, int zero_removed, float *__restrict__ z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = act_apply(acc[i] + bias, act, alpha);
+    if (zero_removed && keep && !keep[i]) v = 0.f;
+    z[i] = v;
+}
+
 // =================================================================================================
 // drivers
 // =================================================================================================
@@ -748,6 +788,39 @@ int gcn_forward_device(dg_context *ctx, const dg_model *m, dg_batch *b, float *o
                 DG_TRY(fused_try_solve(ctx, m, b, wts, predict, 0, nullptr, out, util, nullptr, nullptr, &handled));
         }
         if (handled) return DG_OK;
+    }
+    if (m->scalar_net) {
+        // every layer: acc = sum_k L^k (z * w_k) + b, z' = act(acc) - K (K - 1) / 2 scalar passes over the graph per layer
+        cudaStream_t st = ctx->stream;
+        const int K = m->n_supports, grid = grid_for(n, 256);
+        float *z = nullptr, *acc = nullptr, *ta = nullptr, *tb = nullptr;
+        DG_TRY(scratch_as(ctx, kSlotY, (size_t)n, &z));
+        DG_TRY(scratch_as(ctx, kSlotFeatA, (size_t)n * kMaxWidth, &acc));
+        ta = acc + n;
+        tb = ta + n;
+        scalar_input_kernel<<<grid, 256, 0, st>>>(n, b->keep, b->x0, 1.0f / (float)m->layers[0].c_in, z);
+        ctx->launches++;
+        for (int l = 0; l < m->n_layers; ++l) {
+            for (int k = 0; k < K; ++k) {
+                float *t = ta, *u = tb;
+                scalar_scale_kernel<<<grid, 256, 0, st>>>(n, z, m->scalar_w[(size_t)l * K + k], t);
+                for (int p = 0; p < k; ++p) {   // L^k as k applications of L (the reference multiplies by a materialised L^k)
+                    scalar_lap_kernel<<<grid, 256, 0, st>>>(n, b->row_ptr, b->col_idx, b->dinv, t, u);
+                    std::swap(t, u);
+                    ctx->launches++;
+                }
+                scalar_add_kernel<<<grid, 256, 0, st>>>(n, t, acc, k == 0 ? 1 : 0);
+                ctx->launches += 2;
+            }
+            const bool last_layer = l + 1 == m->n_layers;
+            scalar_act_kernel<<<grid, 256, 0, st>>>(n, acc, m->scalar_b[(size_t)l], m->layers[l].act, m->alpha, b->keep,
+                                                    last_layer ? 1 : 0, last_layer ? out : z);
+            ctx->launches++;
+        }
+        DG_CUDA_CHECK(cudaGetLastError());
+        ctx->last_kernel = "scalar_lap_kernel";
+        if (util) DG_TRY(utility_device(ctx, n, out, 1, wts, predict, util));
+        return DG_OK;
     }
     const int L = m->n_layers;
     const dg_layer_dev &first = m->layers[0];

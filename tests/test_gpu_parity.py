@@ -904,6 +904,58 @@ def test_graph_staged_streaming_layer_kernel(gpu_ctx, monkeypatch):
     batch.close()
 
 
+@pytest.mark.parametrize("short", ["is4sat_l2_c1_cheb2", "is4sat_l1_c1_cheb2"])
+def test_cheb2_checkpoints(gpu_ctx, short):
+    """The two shipped cheb2 checkpoints (three supports [I, L, L^2], gcn/utils.py:258-274 with max_degree = 2; both are
+    networks of one-column layers): scores against the activations of their as-trained TensorFlow graphs
+    (meta_activations.npz), with and without empty feature rows, and the whole solve against the oracle pipeline."""
+    E = _engine()
+    from oracle import lgs as L
+    from oracle import pipeline
+    from distgcn_b200.batch import pack_graphs
+    z = util.load_npz("meta_activations.npz")
+    layers = util.layers_from_meta_fixture(z, short)
+    assert all(len(lw.weights) == 3 for lw in layers)
+    pb_all, w_all = util.small_graphs()
+    picks = [int(g) for g in z["graphs"]]
+    pb = pack_graphs([pb_all.graph_adj(g) for g in picks])
+    acts = [E.ACT_LEAKY_RELU] * (len(layers) - 1) + [E.ACT_LEAKY_RELU if len(layers) == 1 else E.ACT_IDENTITY]  # as trained
+    model = E.Model(gpu_ctx, layers, acts)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    out = E.gcn_forward(gpu_ctx, model, batch)[:, 0]
+    ref = z["%s_outputs" % short]
+    q, nw = _elementwise_report("%s stored graph" % short, out, ref)
+    assert nw <= SCORE_RTOL and q[1] <= SCORE_RTOL
+    wz = z["wz"]
+    F = layers[0].c_in
+    batch.set_x0(np.where(wz != 0, np.float32(1.0 / F), np.float32(0)).astype(np.float32))
+    out_z = E.gcn_forward(gpu_ctx, model, batch)[:, 0]
+    assert _rel_err(out_z, z["%s_outputs_wz" % short]) <= SCORE_RTOL
+    batch.set_x0(None)
+    # end to end with zero-weight removal, source-at-HEAD activations, against the oracle
+    model.close()
+    model = E.Model(gpu_ctx, layers, E.gcn_dqn_acts(len(layers)))
+    w = np.concatenate([w_all[pb_all.graph_ptr[g]:pb_all.graph_ptr[g + 1]] for g in picks])
+    w[::9] = 0.0
+    r = E.solve(gpu_ctx, model, batch, w, remove_zero_weight=True, want_score=True, want_util=True, want_steps=True)
+    for i in range(pb.n_graphs):
+        v0, v1 = int(pb.graph_ptr[i]), int(pb.graph_ptr[i + 1])
+        score, _, _ = pipeline.solve_graph(pb.graph_adj(i), w[v0:v1], layers, "mwis")
+        assert _rel_err(r.score[v0:v1, 0], score) <= SCORE_RTOL, "graph %d" % picks[i]
+    o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, r.util, init_remain=(w > 0).astype(np.uint8))
+    assert np.array_equal(o.member, r.member) and np.array_equal(o.steps, r.steps)
+    assert np.array_equal(r.util, r.score[:, 0].astype(np.float64) * w)
+    batch.close()
+    model.close()
+    # wide layers with three supports stay unsupported, and say so
+    from distgcn_b200 import _lib
+    from distgcn_b200.ckpt import LayerWeights
+    wide = [LayerWeights(weights=[np.zeros((1, 8), np.float32)] * 3), LayerWeights(weights=[np.zeros((8, 1), np.float32)] * 3)]
+    with pytest.raises(_lib.DistGCNError) as ei:
+        E.Model(gpu_ctx, wide, E.gcn_dqn_acts(2))
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
 def test_error_reporting(gpu_ctx):
     E = _engine()
     from distgcn_b200 import _lib
@@ -913,9 +965,9 @@ def test_error_reporting(gpu_ctx):
     with pytest.raises(_lib.DistGCNError) as ei:
         E.Model(gpu_ctx, too_wide, [1, 0])
     assert ei.value.code == _lib.ERR_UNSUPPORTED
-    cheb2 = [LayerWeights(weights=[np.zeros((1, 1), np.float32)] * 3)]
-    with pytest.raises(_lib.DistGCNError) as ei:
-        E.Model(gpu_ctx, cheb2, [0])
+    cheb2_wide = [LayerWeights(weights=[np.zeros((1, 4), np.float32)] * 3), LayerWeights(weights=[np.zeros((4, 1), np.float32)] * 3)]
+    with pytest.raises(_lib.DistGCNError) as ei:    # three supports: only networks of one-column layers (test_cheb2_checkpoints)
+        E.Model(gpu_ctx, cheb2_wide, [1, 0])
     assert ei.value.code == _lib.ERR_UNSUPPORTED
     from distgcn_b200.batch import PackedBatch
     bad = PackedBatch(np.array([0, 5], np.int32), np.array([0, 1, 2], np.int32), np.array([1, 0], np.int32))

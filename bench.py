@@ -665,6 +665,41 @@ def bench_streaming(env, name, rec):
             "peak_source": env.peaks["source"]}
 
 
+def bench_spmm(env, name, rec):
+    """The stand-alone SpMM Y = L.Z (the reference's sparse_tensor_dense_matmul(support[1], pre_sup), 32 columns) on the
+    config-4 batch: B_spmm of SURVEY.md 8d / kernel time, CUDA events around every launch."""
+    from distgcn_b200 import engine as E
+    torch = env.torch
+    copies, ctxs, layers, sets = rec["_keep"]
+    ctx = ctxs[0]
+    lib = ctx._lib
+    c = copies[0]
+    pb = c["pb"]
+    z = torch.randn(pb.n_nodes, 32, dtype=torch.float32, device=env.dev)
+    y = torch.empty_like(z)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        E.spmm_laplacian(ctx, c["dev"], z, y)
+    ctx.synchronize()
+    tot_ms, n_launch, alg_bytes = C.c_double(), C.c_uint64(), C.c_double()
+    lib.dg_profile_enable(ctx.handle, 1)
+    for _ in range(20):
+        E.spmm_laplacian(ctx, c["dev"], z, y)
+    ctx.synchronize()
+    E.check(lib.dg_profile_collect(ctx.handle, C.byref(tot_ms), C.byref(n_launch), C.byref(alg_bytes)))
+    lib.dg_profile_enable(ctx.handle, 0)
+    kernel = ctx.last_kernel
+    n_l = max(int(n_launch.value), 1)
+    achieved = (alg_bytes.value / 1e9) / (tot_ms.value / 1e3) if tot_ms.value > 0 else 0.0
+    row = ncu_row(name, kernel)
+    return {"bound": "hbm", "kernel": "%s (Y = L.Z alone, rows staged in shared memory and pre-scaled by dinv)" % kernel,
+            "achieved": achieved, "peak": env.peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / env.peaks["hbm_gbs"],
+            "traffic": (float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])) if row else None,
+            "ncu_source": row["source"] if row else None, "algorithmic_bytes_per_launch": alg_bytes.value / n_l,
+            "avg_launch_us": 1e3 * tot_ms.value / n_l, "launches_timed": int(n_launch.value),
+            "peak_source": env.peaks["source"]}
+
+
 def bench_single_calls(env, n_calls=200):
     """The reference's real call pattern: ONE graph per call (wireless_dqn_test_mc.py:289,323 call
     dqn_agent.solve_mwis(adj, wts) per time slot).  Host wall clock per call, scipy CSC matrix in, Python set out."""
@@ -827,6 +862,7 @@ def run_ours(args):
                                        args.warmup, detail=False)
             if name.startswith("synth"):
                 rec["roofline_streaming"] = bench_streaming(env, name, rec)
+                rec["roofline_spmm"] = bench_spmm(env, name, rec)
             keep = rec.pop("_keep")
             if name == "er500" and world == 1 and not args.no_cpu_baseline and rank == 0:
                 pb0, w0 = keep[3][0]
@@ -863,6 +899,7 @@ def run_ours(args):
         synth = configs.get("synth-er-%d" % args.synth_graphs)
         if synth and "roofline_streaming" in synth:
             line["roofline_streaming"] = synth["roofline_streaming"]
+            line["roofline_spmm"] = synth.get("roofline_spmm")
         if not args.no_cpu_baseline and world == 1:
             pb0, w0 = main_sets[0]
             sample = min(pb0.n_graphs, 500)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "dg_batch_set_x0": (C.c_int, [_p, _p, C.c_int]),
     "dg_graph_convolution": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, C.c_int, C.c_float, _p, _p, C.c_int]),
     "dg_gcn_forward": (C.c_int, [_p, _p, _p, _p, C.c_int]),
+    "dg_spmm_laplacian": (C.c_int, [_p, _p, _i32, _p, _p, C.c_int]),
     "dg_utility": (C.c_int, [_p, _p, _p, _i32, _p, C.c_int, _p, C.c_int]),
     "dg_lgs": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, C.c_int]),
     "dg_dist_greedy": (C.c_int, [_p, _p, _p, C.c_double, _p, _p, C.c_int]),

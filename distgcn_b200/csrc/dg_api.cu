@@ -861,6 +861,23 @@ int dg_graph_convolution(dg_context *ctx, dg_batch *b, int32_t c_in, int32_t c_o
     return DG_OK;
 }
 
+int dg_spmm_laplacian(dg_context *ctx, dg_batch *b, int32_t width, const float *z, float *y, int mem) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    DG_REQUIRE(b && z && y, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(width >= 1 && width <= 1024, DG_ERR_INVALID, "bad width %d", width);
+    DeviceGuard guard(ctx->device);
+    DG_TRY(batch_ensure_cols(b));
+    const size_t count = (size_t)b->n_nodes * width;
+    if (mem == DG_MEM_DEVICE) return spmm_laplacian_device(ctx, b, width, z, y);
+    float *dz = nullptr, *dy = nullptr;
+    DG_TRY(stage_in(ctx, kSlotStageIn0, z, count, &dz));
+    DG_TRY(scratch_as(ctx, kSlotStageOut0, count, &dy));
+    DG_TRY(spmm_laplacian_device(ctx, b, width, dz, dy));
+    DG_TRY(copy_out(ctx, y, dy, count));
+    return finish(ctx);
+}
+
 int dg_gcn_forward(dg_context *ctx, const dg_model *m, dg_batch *b, float *out, int mem) {
     clear_error();
     DG_TRY(check_ctx(ctx));

@@ -371,6 +371,9 @@ struct LayerArgs {
 int gs_try_layer(dg_context *ctx, dg_batch *b, int cpi, int cpo, bool implicit_in, bool tail, const LayerArgs &a,
                  bool *handled);
 
+// Y = L.Z for 32-wide rows on a batch of small graphs through the graph-staged kernel
+int gs_try_spmm(dg_context *ctx, dg_batch *b, int width, const float *z, float *y, bool *handled);
+
 // ---- kernels / drivers implemented in dg_gcn.cu ---------------------------------------------
 int batch_compute_dinv(dg_batch *b);
 // try_resident = false: go straight to the per-layer kernels (the caller has already tried the graph-resident ones)
@@ -381,6 +384,7 @@ int graph_convolution_device(dg_context *ctx, dg_batch *b, const dg_layer_dev &L
                              const float *x, int ldx, float *y, int ldy);
 int utility_device(dg_context *ctx, int n, const float *score, int stride, const double *wts, int predict,
                    double *util);
+int spmm_laplacian_device(dg_context *ctx, dg_batch *b, int width, const float *z, float *y);
 int keep_from_weights_device(dg_context *ctx, int n, const double *wts, uint8_t *keep);
 
 // ---- implemented in dg_lgs.cu ------------------------------------------------------------------

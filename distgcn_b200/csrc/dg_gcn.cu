@@ -713,6 +713,24 @@ __global__ void scalar_act_kernel(int n, const float *__restrict__ acc, float bi
     z[i] = v;
 }
 
+// Y = L.Z, Z [n, width] row-major: the generic form (one warp per row, lanes over the feature columns, neighbours in
+// ascending order); batches of small graphs with 32-wide rows take the graph-staged kernel of dg_stream.cu instead
+__global__ void spmm_laplacian_kernel(int n, int width, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                      const float *__restrict__ dinv, const float *__restrict__ z, float *__restrict__ y) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float di = dinv[row];
+    for (int c = lane; c < width; c += 32) {
+        float acc = 0.f;
+        for (int e = row_ptr[row]; e < row_ptr[row + 1]; ++e) {
+            const int j = __ldg(col_idx + e);
+            acc = fmaf(__ldg(dinv + j), __ldg(z + (size_t)j * width + c), acc);
+        }
+        y[(size_t)row * width + c] = fmaf(-di, acc, z[(size_t)row * width + c]);
+    }
+}
+
 // =================================================================================================
 // drivers
 // =================================================================================================
@@ -741,6 +759,22 @@ int utility_device(dg_context *ctx, int n, const float *score, int stride, const
                    double *util) {
     if (n == 0) return DG_OK;
     utility_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, score, stride, wts, predict, util);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+int spmm_laplacian_device(dg_context *ctx, dg_batch *b, int width, const float *z, float *y) {
+    const int n = b->n_nodes;
+    if (n == 0) return DG_OK;
+    bool staged = false;
+    DG_TRY(gs_try_spmm(ctx, b, width, z, y, &staged));
+    if (staged) return DG_OK;
+    const double bytes = 4.0 * (n + 1.0) + 4.0 * b->nnz + 4.0 * n + 8.0 * (double)n * width;
+    ctx->last_kernel = "spmm_laplacian_kernel";
+    prof_begin(ctx);
+    spmm_laplacian_kernel<<<grid_for((size_t)n * 32, 256), 256, 0, ctx->stream>>>(n, width, b->row_ptr, b->col_idx, b->dinv, z, y);
+    prof_end(ctx, bytes);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
     return DG_OK;

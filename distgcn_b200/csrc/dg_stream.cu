@@ -9,7 +9,8 @@
 // a trip to L2, and the output rows stream out with 128-bit stores.  HBM traffic per layer = the algorithmic
 // B_layer of SURVEY.md 8d: CSR pattern + dinv + H in + H' out.
 //
-// One CTA = 8 warps, two CTAs per SM: while one CTA waits for its tile's rows the other computes.  A warp owns
+// One CTA = 8 warps, two CTAs per SM: while one CTA waits for its tile's rows the other computes (kGsBufs = 2 instead
+// prefetches the next tile inside one 16-warp CTA; measured slower, see the constant).  A warp owns
 // 16-row units: it gathers the unit (a lane group of 8 lanes per row, float4 per lane, four rows in flight, four
 // partial sums per row combined pairwise - the summation tree of gc_layer_kernel), parks (L H)_i in its private
 // scratch and projects the unit with a 4 x 4 register tile per lane (operands: 4 row chunks + 4 weight rows per 64
@@ -53,35 +54,43 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// one staged tile: feature rows, dinv, column ids, row_ptr
+constexpr int kGsBufWords = kGsMaxRows * kGsStride + kGsMaxRows + (kGsMaxNnz + 8) + (kGsMaxRows + 8);
+constexpr int kGsBufs = 1;   // 2 = prefetch the next tile inside the CTA (one 16-warp CTA per SM): measured SLOWER than two
+                             // single-buffered 8-warp CTAs per SM (1290 vs 1106 us per layer on the config-4 batch): with one CTA
+                             // the per-tile barrier idles the SM, with two the other CTA fills the gap
 constexpr size_t gs_smem_bytes() {
-    return sizeof(float) * ((size_t)kGsMaxRows * kGsStride            // staged rows
+    return sizeof(float) * ((size_t)kGsBufs * kGsBufWords
                             + (size_t)kGsWarps * kGsUnit * kGsStride  // per-warp (L H) scratch
-                            + 2 * kGsC * kGsC + kGsC                  // [W_0 ; W_1], bias
-                            + kGsMaxRows)                             // dinv
-           + sizeof(int) * ((size_t)kGsMaxNnz + 8 + kGsMaxRows + 8);  // column ids, row_ptr
+                            + 2 * kGsC * kGsC + kGsC);                // [W_0 ; W_1], bias
 }
 
-template <bool IMPLICIT_IN, bool TAIL>
-__global__ void __launch_bounds__(kGsThreads, 2) gs_layer_kernel(const GsArgs P) {
+// SPMM_ONLY: Y = L.Z alone (the reference's sparse_tensor_dense_matmul(support[1], pre_sup), gcn/layers.py:206) - no
+// projection; the staged rows are pre-scaled by dinv once (G_j = dinv_j Z_j, two roundings per term like the unfused
+// multiply-then-add of the reference's CPU kernel), so the gather is a plain sum of shared-memory rows, and the row's
+// own value comes from global memory again (an L2 hit: the tile has just been read).
+template <bool IMPLICIT_IN, bool TAIL, bool SPMM_ONLY = false>
+__global__ void __launch_bounds__(kGsThreads, kGsBufs == 1 ? 2 : 1) gs_layer_kernel(const GsArgs P) {
     extern __shared__ __align__(16) unsigned char gs_smem[];
-    float *hs = reinterpret_cast<float *>(gs_smem);                       // [kGsMaxRows][36]
-    float *us_all = hs + kGsMaxRows * kGsStride;                          // [warps][16][36]
+    float *buf0 = reinterpret_cast<float *>(gs_smem);                     // two staged tiles
+    float *us_all = buf0 + kGsBufs * kGsBufWords;                         // [warps][16][36]
     float *ws = us_all + kGsWarps * kGsUnit * kGsStride;                  // [64][32]
     float *bs = ws + 2 * kGsC * kGsC;                                     // [32]
-    float *dinv_s = bs + kGsC;                                            // [kGsMaxRows]
-    int *cols = reinterpret_cast<int *>(dinv_s + kGsMaxRows);             // [kGsMaxNnz + 8]
-    int *rp = cols + kGsMaxNnz + 8;                                       // [kGsMaxRows + 8]
 
     const LayerArgs &a = P.a;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 3, q = lane & 7;   // lane group (row in flight) / 16-byte chunk of a row
     float *us = us_all + warp * (kGsUnit * kGsStride);
 
-    for (int k = tid * 4; k < 2 * kGsC * kGsC; k += kGsThreads * 4)
-        *reinterpret_cast<float4 *>(ws + k) = __ldg(reinterpret_cast<const float4 *>(a.wcat + k));
-    if (tid < kGsC) bs[tid] = a.bias[tid];
+    if (!SPMM_ONLY) {
+        for (int k = tid * 4; k < 2 * kGsC * kGsC; k += kGsThreads * 4)
+            *reinterpret_cast<float4 *>(ws + k) = __ldg(reinterpret_cast<const float4 *>(a.wcat + k));
+        if (tid < kGsC) bs[tid] = a.bias[tid];
+    }
 
     // per-thread constants of the optional forms
     float4 ia0, ia1, ib;
@@ -97,10 +106,14 @@ __global__ void __launch_bounds__(kGsThreads, 2) gs_layer_kernel(const GsArgs P)
     }
 
     const int t_begin = P.cta_first[blockIdx.x], t_end = P.cta_first[blockIdx.x + 1];
-    for (int t = t_begin; t < t_end; ++t) {
+    // stage tile t into buffer `which` (asynchronous copies; one commit group per tile)
+    auto stage = [&](int t, int which) {
+        float *hs = buf0 + which * kGsBufWords;
+        float *dinv_s = hs + kGsMaxRows * kGsStride;
+        int *cols = reinterpret_cast<int *>(dinv_s + kGsMaxRows);
+        int *rp = cols + kGsMaxNnz + 8;
         const int4 tile = __ldg(P.tiles + t);
         const int v0 = tile.x, n = tile.y, e0 = tile.z, nnz = tile.w;
-        // ---- stage: feature rows, column ids (16-byte aligned window around [e0, e0 + nnz)), row_ptr, dinv ----------
         if (IMPLICIT_IN) {
             for (int item = tid; item < n * 8; item += kGsThreads) {   // item & 7 == q for every item of this thread
                 const int r = item >> 3;
@@ -117,17 +130,43 @@ __global__ void __launch_bounds__(kGsThreads, 2) gs_layer_kernel(const GsArgs P)
             for (int item = tid; item < n * 8; item += kGsThreads)
                 cp_async16(hs + (item >> 3) * kGsStride + 4 * (item & 7), src + (size_t)item * 4);
         }
-        const int ea = e0 & ~3;            // aligned start of the column window
-        const int eoff = e0 - ea;          // the tile's first edge inside the window
-        {
-            const int chunks = (nnz + eoff + 3) >> 2;
-            const int *src = a.col_idx + ea;
-            for (int c = tid; c < chunks; c += kGsThreads) cp_async16(cols + 4 * c, src + 4 * c);
-        }
+        const int ea = e0 & ~3;            // 16-byte aligned start of the column window around [e0, e0 + nnz)
+        const int chunks = (nnz + (e0 - ea) + 3) >> 2;
+        const int *csrc = a.col_idx + ea;
+        for (int c = tid; c < chunks; c += kGsThreads) cp_async16(cols + 4 * c, csrc + 4 * c);
         for (int r = tid; r <= n; r += kGsThreads) cp_async4(rp + r, a.row_ptr + v0 + r);
         for (int r = tid; r < n; r += kGsThreads) cp_async4(dinv_s + r, a.dinv + v0 + r);
-        cp_async_wait_all();
+        cp_async_commit();
+    };
+    if (kGsBufs == 2 && t_begin < t_end) stage(t_begin, 0);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int which = kGsBufs == 2 ? ((t - t_begin) & 1) : 0;
+        if (kGsBufs == 2 && t + 1 < t_end) {
+            stage(t + 1, which ^ 1);       // the other buffer was released by the barrier that ended the previous tile
+            cp_async_wait_group<1>();      // everything but the group just committed has landed: tile t is here
+        } else {
+            if (kGsBufs == 1) stage(t, 0);
+            cp_async_wait_group<0>();
+        }
         __syncthreads();
+        float *hs = buf0 + which * kGsBufWords;
+        float *dinv_s = hs + kGsMaxRows * kGsStride;
+        int *cols = reinterpret_cast<int *>(dinv_s + kGsMaxRows);
+        int *rp = cols + kGsMaxNnz + 8;
+        const int4 tile = __ldg(P.tiles + t);
+        const int v0 = tile.x, n = tile.y, e0 = tile.z;
+        const int ea = e0 & ~3;
+        if (SPMM_ONLY) {   // G_j = dinv_j Z_j in place
+            for (int item = tid; item < n * 8; item += kGsThreads) {
+                const int r = item >> 3;
+                float4 *p = reinterpret_cast<float4 *>(hs + r * kGsStride + 4 * (item & 7));
+                const float d = dinv_s[r];
+                float4 v = *p;
+                v.x *= d, v.y *= d, v.z *= d, v.w *= d;
+                *p = v;
+            }
+            __syncthreads();
+        }
 
         // ---- units of 16 rows: gather, then project ---------------------------------------------------------------
         const int n_units = (n + kGsUnit - 1) / kGsUnit;
@@ -146,26 +185,39 @@ __global__ void __launch_bounds__(kGsThreads, 2) gs_layer_kernel(const GsArgs P)
                 float4 acc[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // the ids (and dinv) of the NEXT eight edges are fetched while the current eight rows are being summed
+                int jl = 0;
+                float d = 0.f;
+                if (beg + q < end) {
+                    jl = cols[beg + q] - v0;      // neighbour's row inside the tile
+                    if (!SPMM_ONLY) d = dinv_s[jl];
+                }
                 for (int e = beg; __any_sync(0xffffffffu, e < end); e += 8) {
-                    const bool in = e + q < end;
-                    int jl = 0;
-                    float d = 0.f;
-                    if (in) {
-                        jl = cols[e + q] - v0;    // neighbour's row inside the tile
-                        d = dinv_s[jl];
+                    int jl_next = 0;
+                    float d_next = 0.f;
+                    if (e + 8 + q < end) {
+                        jl_next = cols[e + 8 + q] - v0;
+                        if (!SPMM_ONLY) d_next = dinv_s[jl_next];
                     }
 #pragma unroll
                     for (int tt = 0; tt < 8; ++tt) {
                         const int jj = __shfl_sync(0xffffffffu, jl, tt, 8);
-                        const float dj = __shfl_sync(0xffffffffu, d, tt, 8);
+                        float dj = 1.f;
+                        if (!SPMM_ONLY) dj = __shfl_sync(0xffffffffu, d, tt, 8);
                         if (e + tt < end) {       // uniform inside a lane group
                             const float4 v = *reinterpret_cast<const float4 *>(hs + jj * kGsStride + 4 * q);
-                            acc[tt & 3].x = fmaf(dj, v.x, acc[tt & 3].x);
-                            acc[tt & 3].y = fmaf(dj, v.y, acc[tt & 3].y);
-                            acc[tt & 3].z = fmaf(dj, v.z, acc[tt & 3].z);
-                            acc[tt & 3].w = fmaf(dj, v.w, acc[tt & 3].w);
+                            if (SPMM_ONLY) {
+                                acc[tt & 3].x += v.x, acc[tt & 3].y += v.y, acc[tt & 3].z += v.z, acc[tt & 3].w += v.w;
+                            } else {
+                                acc[tt & 3].x = fmaf(dj, v.x, acc[tt & 3].x);
+                                acc[tt & 3].y = fmaf(dj, v.y, acc[tt & 3].y);
+                                acc[tt & 3].z = fmaf(dj, v.z, acc[tt & 3].z);
+                                acc[tt & 3].w = fmaf(dj, v.w, acc[tt & 3].w);
+                            }
                         }
                     }
+                    jl = jl_next;
+                    d = d_next;
                 }
                 acc[0].x += acc[1].x, acc[0].y += acc[1].y, acc[0].z += acc[1].z, acc[0].w += acc[1].w;
                 acc[2].x += acc[3].x, acc[2].y += acc[3].y, acc[2].z += acc[3].z, acc[2].w += acc[3].w;
@@ -173,12 +225,15 @@ __global__ void __launch_bounds__(kGsThreads, 2) gs_layer_kernel(const GsArgs P)
                 float4 lh = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
                     const float di = dinv_s[r];
-                    const float4 hi = *reinterpret_cast<const float4 *>(hs + r * kGsStride + 4 * q);
+                    const float4 hi = SPMM_ONLY ? __ldcg(reinterpret_cast<const float4 *>(a.hin + (size_t)(v0 + r) * kGsC) + q)
+                                                : *reinterpret_cast<const float4 *>(hs + r * kGsStride + 4 * q);
                     lh = make_float4(fmaf(-di, acc[0].x, hi.x), fmaf(-di, acc[0].y, hi.y), fmaf(-di, acc[0].z, hi.z),
                                      fmaf(-di, acc[0].w, hi.w));
+                    if (SPMM_ONLY) *reinterpret_cast<float4 *>(a.hout + (size_t)(v0 + r) * kGsC + 4 * q) = lh;
                 }
-                *reinterpret_cast<float4 *>(us + lr * kGsStride + 4 * q) = lh;
+                if (!SPMM_ONLY) *reinterpret_cast<float4 *>(us + lr * kGsStride + 4 * q) = lh;
             }
+            if (SPMM_ONLY) continue;
             __syncwarp();
             // projection: lane (g, q) owns rows 4 j + g (j = 0..3) of the unit and columns 4 q .. 4 q + 3
             float4 out[4];
@@ -264,7 +319,7 @@ int gs_build_plan(dg_context *ctx, dg_batch *b, bool *ok) {
         if (n > 0) {
             flat.push_back(v0), flat.push_back(n), flat.push_back(e0), flat.push_back(nnz);
             const int units = (n + kGsUnit - 1) / kGsUnit;
-            // a warp round costs about a unit's gather + projection; 8 warps work in rounds
+            // a warp round costs about a unit's gather + projection; the CTA's warps work in rounds
             cost.push_back((long long)nnz + 14LL * kGsUnit * ((units + kGsWarps - 1) / kGsWarps) * kGsWarps + 600);
         }
         n = 0, nnz = 0;
@@ -279,7 +334,7 @@ int gs_build_plan(dg_context *ctx, dg_batch *b, bool *ok) {
     flush();
     const int n_tiles = (int)cost.size();
     if (n_tiles == 0) return DG_OK;
-    const int grid = std::min(n_tiles, ctx->sm_count * 2);
+    const int grid = std::min(n_tiles, ctx->sm_count * (kGsBufs == 1 ? 2 : 1));
     // contiguous runs of tiles with balanced cost: CTA c starts at the first tile whose cost prefix reaches c / grid
     std::vector<int> first((size_t)grid + 1, n_tiles);
     std::vector<long long> prefix((size_t)n_tiles + 1, 0);
@@ -315,9 +370,9 @@ int gs_build_plan(dg_context *ctx, dg_batch *b, bool *ok) {
     return DG_OK;
 }
 
-template <bool IMPLICIT_IN, bool TAIL>
+template <bool IMPLICIT_IN, bool TAIL, bool SPMM_ONLY = false>
 int gs_launch(dg_context *ctx, dg_batch *b, const LayerArgs &a) {
-    auto kern = gs_layer_kernel<IMPLICIT_IN, TAIL>;
+    auto kern = gs_layer_kernel<IMPLICIT_IN, TAIL, SPMM_ONLY>;
     constexpr size_t smem = gs_smem_bytes();
     static bool attr_set = false;
     if (!attr_set) {
@@ -329,9 +384,10 @@ int gs_launch(dg_context *ctx, dg_batch *b, const LayerArgs &a) {
     P.cta_first = b->gs_tiles_dev + (size_t)b->gs_n_tiles * 4;
     P.a = a;
     const double n = (double)a.n, nnz = (double)a.nnz;
+    // B_layer / B_spmm of SURVEY.md 8d
     const double bytes = 4.0 * (n + 1) + 4.0 * nnz + 4.0 * n + 4.0 * n * (IMPLICIT_IN ? 2 : kGsC) +
-                         4.0 * n * (TAIL ? 2 : kGsC) + 4.0 * (2 * kGsC * kGsC + kGsC);
-    ctx->last_kernel = "gs_layer_kernel";
+                         4.0 * n * (TAIL ? 2 : kGsC) + (SPMM_ONLY ? 0.0 : 4.0 * (2 * kGsC * kGsC + kGsC));
+    ctx->last_kernel = SPMM_ONLY ? "gs_spmm_kernel" : "gs_layer_kernel";
     prof_begin(ctx);
     kern<<<b->gs_grid, kGsThreads, smem, ctx->stream>>>(P);
     prof_end(ctx, bytes);
@@ -341,6 +397,25 @@ int gs_launch(dg_context *ctx, dg_batch *b, const LayerArgs &a) {
 }
 
 }  // namespace
+
+int gs_try_spmm(dg_context *ctx, dg_batch *b, int width, const float *z, float *y, bool *handled) {
+    *handled = false;
+    if (width != kGsC || getenv("DG_DISABLE_STAGED") || b->n_graphs < 8) return DG_OK;
+    bool ok = false;
+    DG_TRY(gs_build_plan(ctx, b, &ok));
+    if (!ok) return DG_OK;
+    LayerArgs a{};
+    a.n = b->n_nodes;
+    a.nnz = b->nnz;
+    a.row_ptr = b->row_ptr;
+    a.col_idx = b->col_idx;
+    a.dinv = b->dinv;
+    a.hin = z;
+    a.hout = y;
+    DG_TRY((gs_launch<false, false, true>(ctx, b, a)));
+    *handled = true;
+    return DG_OK;
+}
 
 int gs_try_layer(dg_context *ctx, dg_batch *b, int cpi, int cpo, bool implicit_in, bool tail, const LayerArgs &a,
                  bool *handled) {

@@ -381,6 +381,23 @@ def solve_dit(ctx: Context, model: Model, batch: DeviceBatch, wts, predict="mwis
     return res
 
 
+def spmm_laplacian(ctx: Context, batch: DeviceBatch, z, out=None):
+    """``L . z`` with ``L = I - D^-1/2 A D^-1/2`` of the batch: the stand-alone form of the reference's
+    ``tf.sparse_tensor_dense_matmul(support[1], pre_sup)`` (gcn/layers.py:206).  ``z``: [n_nodes, width] float32, numpy
+    (copied) or a CUDA tensor (zero-copy; ``out`` must then be a CUDA tensor of the same shape)."""
+    if _is_device_tensor(z):
+        if out is None or not _is_device_tensor(out):
+            raise TypeError("device input needs a device output tensor")
+        check(ctx._lib.dg_spmm_laplacian(ctx.handle, batch.handle, int(z.shape[1]), _ptr(z), _ptr(out), MEM_DEVICE))
+        return out
+    zz = _np(z, np.float32)
+    if zz.ndim != 2 or zz.shape[0] != batch.n_nodes:
+        raise ValueError("z must be [n_nodes, width]")
+    y = np.empty_like(zz)
+    check(ctx._lib.dg_spmm_laplacian(ctx.handle, batch.handle, int(zz.shape[1]), _ptr(zz), _ptr(y), MEM_HOST))
+    return y
+
+
 def solve_device(ctx: Context, model: Model, batch: DeviceBatch, wts, member, predict="mwis",
                  remove_zero_weight: bool = True, score=None, util=None, total=None, steps=None) -> None:
     """Zero-copy form: every array is a CUDA tensor on the context's device; work is only enqueued."""

@@ -139,6 +139,11 @@ DG_API int dg_batch_set_keep_from_weights(dg_batch *batch, const double *wts, in
 DG_API int dg_batch_set_x0(dg_batch *batch, const float *x0, int mem);
 
 /* ---- operators ------------------------------------------------------------------------------ */
+/* y = L.z with L = I - D^-1/2 A D^-1/2 of the batch (values never stored: applied from dinv), z and y [n_nodes, width]
+ * row-major float32.  Replaces tf.sparse_tensor_dense_matmul(support[1], pre_sup) of GraphConvolution._call
+ * (gcn/layers.py:206) as a stand-alone operator.  Batches of small graphs with width 32 stage whole graphs in shared
+ * memory (gs_spmm_kernel); everything else runs one warp per row. */
+DG_API int dg_spmm_laplacian(dg_context *ctx, dg_batch *batch, int32_t width, const float *z, float *y, int mem);
 /* One GraphConvolution layer on dense inputs: y = act(x.W_0 + L.(x.W_1) + b).
  * Replaces GraphConvolution.__call__ (gcn/layers.py:189-216).  x is [n_nodes, c_in] row-major,
  * y is [n_nodes, c_out]; W_k are host pointers ([c_in, c_out]); bias may be NULL. */

@@ -956,6 +956,47 @@ def test_cheb2_checkpoints(gpu_ctx, short):
     assert ei.value.code == _lib.ERR_UNSUPPORTED
 
 
+def test_spmm_laplacian_operator(gpu_ctx, monkeypatch):
+    """dg_spmm_laplacian = the reference's tf.sparse_tensor_dense_matmul(support[1], pre_sup) (gcn/layers.py:206) alone:
+    against L built by the oracle's (reference-pinned) laplacian_supports in float64, for the graph-staged kernel (batch
+    of small graphs, 32 columns), the generic warp-per-row kernel (other widths, one large graph) and with a keep mask."""
+    E = _engine()
+    from oracle import gcn_oracle as G
+    monkeypatch.delenv("DG_DISABLE_STAGED", raising=False)
+    rng = np.random.default_rng(21)
+    pb, adjs = util.random_graph_batch(rng, 40, 20, 300, p_lo=0.03, p_hi=0.15)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+
+    def reference(z, keep=None):
+        out = np.zeros_like(z, dtype=np.float64)
+        for g, a in enumerate(adjs):
+            v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+            if keep is None:
+                lap = G.to_fp32_csr(G.laplacian_supports(a, 1)[1]).astype(np.float64)
+                out[v0:v1] = lap @ z[v0:v1].astype(np.float64)
+            else:
+                k = np.flatnonzero(keep[v0:v1])
+                sub = a[k][:, k]
+                lap = G.to_fp32_csr(G.laplacian_supports(sub, 1)[1]).astype(np.float64)
+                zz = z[v0:v1].astype(np.float64)
+                out[v0:v1] = zz                                  # removed rows: dinv = 0, the row passes through
+                out[v0 + k] = lap @ zz[k]
+        return out
+    for width, kernel in ((32, "gs_spmm_kernel"), (16, "spmm_laplacian_kernel"), (64, "spmm_laplacian_kernel")):
+        z = rng.standard_normal((pb.n_nodes, width)).astype(np.float32)
+        y = E.spmm_laplacian(gpu_ctx, batch, z)
+        assert gpu_ctx.last_kernel == kernel, (width, gpu_ctx.last_kernel)
+        ref = reference(z)
+        assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
+    keep = (rng.random(pb.n_nodes) < 0.7).astype(np.uint8)
+    batch.set_keep(keep)
+    z = rng.standard_normal((pb.n_nodes, 32)).astype(np.float32)
+    y = E.spmm_laplacian(gpu_ctx, batch, z)
+    ref = reference(z, keep)
+    assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
+    batch.close()
+
+
 def test_error_reporting(gpu_ctx):
     E = _engine()
     from distgcn_b200 import _lib

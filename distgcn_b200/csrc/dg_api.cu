@@ -1049,6 +1049,10 @@ static int solve_dit_device(dg_context *ctx, const dg_model *m, dg_batch *b, con
     const size_t n = (size_t)b->n_nodes, G = (size_t)b->n_graphs;
     if (n == 0 || G == 0) return DG_OK;
     bool handled = false;
+    // small graphs: the whole iteration inside one graph-resident launch, on the tensor cores when the model allows
+    DG_TRY(tc_try_solve(ctx, m, b, d_wts, predict, 0, d_member, nullptr, nullptr, d_total, d_steps, &handled, true));
+    if (handled) return DG_OK;
+    DG_TRY(batch_ensure_cols(b));
     DG_TRY(fused_try_solve(ctx, m, b, d_wts, predict, 0, d_member, nullptr, nullptr, d_total, d_steps, &handled, true));
     if (handled) return DG_OK;
     // generic path: a handful of launches per iteration over the per-layer kernels

@@ -343,7 +343,7 @@ void tc_build_weights(int n_hidden, const float *const *w0, const float *const *
 void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b);
 int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict,
                  int remove_zero_weight, uint8_t *member, float *score, double *util, double *total, int32_t *steps,
-                 bool *handled);
+                 bool *handled, bool dit = false);
 
 // arguments of one fused hidden GraphConvolution layer (gc_layer_kernel in dg_gcn.cu, gs_layer_kernel in dg_stream.cu)
 struct LayerArgs {

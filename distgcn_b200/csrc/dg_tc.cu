@@ -404,6 +404,13 @@ __device__ __forceinline__ void tc_split8(const float *h, uint4 *hi, uint4 *mid,
 // 4 adjacency bytes (0/1 each) -> 4 bits (byte k -> bit k)
 __device__ __forceinline__ uint32_t tc_bits4(uint32_t w) { return (w * 0x01020408u) >> 24; }
 
+// DIT: the GCN embedded into the greedy iteration (MWISSolver.solve_mwis_dit, mwis_gdpg_call.py:278-318): the layers and ONE
+// greedy round repeat on the residual graph (vertices neither taken nor excluded yet) until no graph of the tile has a
+// residual vertex of positive weight.  The adjacency bytes are built once; a residual graph is the same bytes seen through
+// the current keep mask (degrees count kept columns only, removed vertices have dinv = 0 and so contribute zero digits).
+// All graphs of a tile iterate together (they share the weight ring); a finished graph idles through the layers with an
+// empty mask.
+template <bool DIT>
 __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *wring = smem + kTcOffRing;
@@ -412,6 +419,8 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
     uint32_t *remain = keepw + 16, *joined = keepw + 32, *memb = keepw + 48;
     uint32_t *gmax = reinterpret_cast<uint32_t *>(smem + kTcOffGmax);  // [4][2]
     uint32_t *gmax0 = gmax + 8;                                         // [4]
+    unsigned char *kb = smem + kTcOffDinv;                              // [512] DIT: current keep mask as bytes, by tile slot
+    uint32_t *gpos = reinterpret_cast<uint32_t *>(smem + kTcOffDinv + 512);  // [4] DIT: the graph still has positive residual weight
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + kTcOffBar);  // [2]  weight ring
     uint32_t *cnt_p = reinterpret_cast<uint32_t *>(bar_full + 22);     // [4] per block: warps whose H terms are in place
     uint32_t *cnt_a = cnt_p + 4;                                        // [4] per graph: warps whose Y digits are in place
@@ -628,6 +637,38 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             tk = now;
         }
 
+        int dit_steps = 0;
+        uint32_t ea = 0, ep = 0, em = 0;  // aggregation / projection / max events consumed -> barrier parities (per tile)
+        for (int dit_iter = 0;; ++dit_iter) {
+        if (DIT) {
+            // residual bookkeeping of this iteration (whole CTA): a graph goes on while a residual vertex has positive weight
+            if (tid < 4) gpos[tid] = 0u;
+            if (tid < 8) gmax[tid] = 0u;     // the layer maxima (the previous iteration's last layer left one slot set)
+            __syncthreads();
+            if (gi >= 0 && valid && keep && wt_v > 0.0) gpos[gi] = 1u;
+            __syncthreads();
+            if (gi >= 0) keep = keep && gpos[gi] != 0u;
+            kb[tid] = keep ? 1 : 0;
+            const uint32_t kw = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) keepw[warp] = kw;
+            if (!__syncthreads_or(keep ? 1 : 0)) {
+                if (dit_iter == 0) {   // nothing to solve in this tile: consume the weight fills issued at its top
+                    const uint32_t issued = (uint32_t)min(n_hidden, 2);
+                    if (tid == 0)
+                        for (uint32_t h = 0; h < issued; ++h) mbar_wait(&bar_full[(wseq + h) & 1u], ((wseq + h) >> 1) & 1u, 11);
+                    wseq += issued;
+                }
+                break;
+            }
+            if (gi >= 0 && gpos[gi]) ++dit_steps;
+            if (dit_iter > 0 && tid == 0) {   // this iteration's first two weight fills (the previous iteration has drained)
+                for (int h = 0; h < n_hidden && h < 2; ++h) {
+                    const uint32_t buf = (wseq + h) & 1u;
+                    mbar_expect_tx(&bar_full[buf], kTcWBlob);
+                    bulk_g2s(wring + buf * kTcWBlob, P.wall + (size_t)h * kTcWBlob, kTcWBlob, &bar_full[buf]);
+                }
+            }
+        }
         if (gi >= 0) {
             // ================= vertex threads =========================================================================
             const int b = tid >> 7;
@@ -637,7 +678,6 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             const uint32_t taddr = tmem + (uint32_t)b * 128u + ((uint32_t)((warp & 3) * 32) << 16);
             unsigned char *adj = pool + G.adj;
             unsigned char *yrow = pool + G.yoff + (r >> 3) * 128 + (r & 7) * 16;  // ... and in the Y digit runs
-            uint32_t ea = 0, ep = 0, em = 0;  // aggregation / projection / max events consumed -> barrier parities
 
             // ---- hand-off to the tensor cores: the warp that completes an operand issues the MMAs that consume it ----
             const uint32_t pool_addr = s32(pool);
@@ -730,14 +770,16 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
 
             // degree on the kept sub-graph, dinv, x0, and the scalar operand of the rank-1 first layer
             unsigned deg = 0;
-            if (valid) {
+            if (valid && (!DIT || keep)) {
                 const int nch = G.Kp >> 4;
                 for (int c = 0; c < nch; ++c) {
                     const uint4 w = *reinterpret_cast<const uint4 *>(adj + (size_t)c * G.R * 16 + r * 16);
-                    deg = __dp4a(w.x, 0x01010101u, deg);
-                    deg = __dp4a(w.y, 0x01010101u, deg);
-                    deg = __dp4a(w.z, 0x01010101u, deg);
-                    deg = __dp4a(w.w, 0x01010101u, deg);
+                    uint4 km = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+                    if (DIT) km = *reinterpret_cast<const uint4 *>(kb + G.fb * 128 + c * 16);  // kept columns only
+                    deg = __dp4a(w.x, km.x, deg);
+                    deg = __dp4a(w.y, km.y, deg);
+                    deg = __dp4a(w.z, km.z, deg);
+                    deg = __dp4a(w.w, km.w, deg);
                 }
             }
             const float di = deg > 0 ? (float)(1.0 / sqrt((double)deg)) : 0.f;  // gcn/utils.py:122-125
@@ -1046,6 +1088,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 // nbr := all kept neighbours (for the removal of a joined vertex's neighbourhood)
                 int rounds = 0, steps = 0;
                 for (;;) {
+                    if (DIT && rounds >= 1) break;   // one greedy round per re-scoring
                     uint32_t any = 0u;
 #pragma unroll
                     for (int w = 0; w < 12; ++w)
@@ -1079,8 +1122,12 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                     ++rounds;
                     bar_sync(dom_bar, dom_cnt);
                 }
-                if (r == 0 && P.steps) P.steps[G.g] = steps;
-                if (P.total) {  // member weights through shared memory, summed in the order dg_fused.cu uses
+                if (DIT) {
+                    keep = valid && ((remain[warp] >> lane) & 1u);   // the residual graph of the next iteration
+                    bar_sync(dom_bar, dom_cnt);                      // (every thread of the graph has read `remain`)
+                }
+                if (!DIT && r == 0 && P.steps) P.steps[G.g] = steps;
+                if (!DIT && P.total) {  // member weights through shared memory, summed in the order dg_fused.cu uses
                     util_sm[tid] = (valid && ((memb[warp] >> lane) & 1u)) ? wt_v : 0.0;  // mwis_dqn_call.py:241
                     bar_sync(dom_bar, dom_cnt);
                     if (jb == 0 && (warp & 3) == 0) {
@@ -1099,6 +1146,27 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             tk = now;
         }
         wseq += (uint32_t)n_hidden;
+        if (!DIT) break;
+        tc_fence_before();
+        __syncthreads();  // the next iteration reuses tensor memory, the Y regions and the weight ring
+        tc_fence_after();
+        }  // dit_iter
+        if (DIT && gi >= 0) {   // per-graph outputs of the iterative solve
+            const TcMeta G2 = meta[gi];
+            const int b2 = tid >> 7;
+            if (r == 0 && P.steps) P.steps[G2.g] = dit_steps;
+            if (P.total) {
+                util_sm[tid] = (valid && ((memb[warp] >> lane) & 1u)) ? wt_v : 0.0;  // mwis_gdpg_call.py:313
+                bar_sync(1 + G2.fb, 128 * G2.nb);
+                if (b2 == G2.fb && (warp & 3) == 0) {
+                    double acc = 0.0;
+                    for (int i = lane; i < G2.nv; i += 32) acc += util_sm[G2.fb * 128 + i];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                    if (lane == 0) P.total[G2.g] = acc;
+                }
+            }
+        }
         tc_fence_before();
         __syncthreads();  // shared memory, tensor memory and the barriers are recycled by the next tile
         tc_fence_after();
@@ -1430,8 +1498,9 @@ void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b) {
 static int *g_wide_buf = nullptr;  // DG_TC_DEBUG: pinned table the stuck threads log their wait sites into
 
 int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *d_wts, int predict, int remove_zero_weight,
-                 uint8_t *member, float *score, double *util, double *total, int32_t *steps, bool *handled) {
+                 uint8_t *member, float *score, double *util, double *total, int32_t *steps, bool *handled, bool dit) {
     *handled = false;
+    if (dit && (member == nullptr || d_wts == nullptr)) return DG_OK;
     if (getenv("DG_DISABLE_TC") || getenv("DG_DISABLE_FUSED")) return DG_OK;
     if (!m->tc_wall || m->n_layers < 3 || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
     if ((int)b->h_graph_e.size() != b->n_graphs + 1) return DG_OK;
@@ -1441,7 +1510,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     if (!ok) return DG_OK;
     // Graphs beyond this kernel's limits go to the CUDA-core graph-resident kernel in a second launch.  If that kernel
     // cannot take them either, the whole batch belongs to the per-layer path: decline BEFORE launching anything.
-    if (b->tc_n_skipped > 0 && !fused_fits(ctx, m, b)) return DG_OK;
+    if (b->tc_n_skipped > 0 && (dit || !fused_fits(ctx, m, b))) return DG_OK;
     TcParams p{};
     p.tiles = b->tc_tiles_dev;
     p.n_tiles = b->tc_n_tiles;
@@ -1483,7 +1552,8 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         p.dbg = dbg;
     }
     if (!ctx->tc_attr_set) {  // once per context (the attribute is per device)
-        DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->tc_attr_set = true;
     }
     const int grid = std::min(ctx->sm_count * kTcCtasPerSm, p.n_tiles);
@@ -1508,7 +1578,8 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         const double lgs = csr + 9.0 * n;
         ctx->last_kernel = "tc_solve_kernel";
         prof_begin(ctx);
-        tc_solve_kernel<<<grid, kTcThreads, smem, ctx->stream>>>(p);
+        if (dit) tc_solve_kernel<true><<<grid, kTcThreads, smem, ctx->stream>>>(p);
+        else tc_solve_kernel<false><<<grid, kTcThreads, smem, ctx->stream>>>(p);
         ctx->launches++;
         prof_end(ctx, hidden + scalar_passes + lgs);
         DG_CUDA_CHECK(cudaGetLastError());

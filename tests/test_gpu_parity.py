@@ -552,17 +552,21 @@ def test_full_config_sets(gpu_ctx, fam, short):
     model.close()
 
 
-@pytest.mark.parametrize("path", ["fused", "layer_kernels"])
+@pytest.mark.parametrize("path", ["tensor_core", "fused", "layer_kernels"])
 @pytest.mark.parametrize("short,kind", [("is4sat_l1", "gcn_dqn"), ("is4sat_l20_c32", "gcn_dqn"),
-                                        ("is4sat_l2_c64", "gcn_dqn"), ("is4sat_l3_c16", "gcn2_dqn")])
+                                        ("is4sat_l2_c64", "gcn_dqn"), ("is4sat_l3_c16", "gcn2_dqn"),
+                                        ("dqnba_l20_c32", "gcn_dqn")])
 def test_solve_dit_matches_restatement(gpu_ctx, short, kind, path, monkeypatch):
     """GCN embedded into the greedy iteration (MWISSolver.solve_mwis_dit, mwis_gdpg_call.py:278-318): the
     device-side loop against the per-graph CPU restatement - same sets, same weights, same iteration counts."""
     E = _engine()
     from oracle import pipeline
     monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    monkeypatch.delenv("DG_DISABLE_TC", raising=False)
     if path == "layer_kernels":
         monkeypatch.setenv("DG_DISABLE_FUSED", "1")
+    elif path == "fused":
+        monkeypatch.setenv("DG_DISABLE_TC", "1")
     pb, w = util.small_graphs()
     sub = pb.slice(0, 24)
     n = sub.n_nodes
@@ -576,6 +580,10 @@ def test_solve_dit_matches_restatement(gpu_ctx, short, kind, path, monkeypatch):
     model = E.Model(gpu_ctx, layers, acts)
     batch = E.DeviceBatch(gpu_ctx, sub)
     r = E.solve_dit(gpu_ctx, model, batch, ws, want_steps=True)
+    if path == "tensor_core" and "l20" in short:
+        assert gpu_ctx.last_kernel == "tc_solve_kernel"       # the iteration runs inside the tcgen05 kernel
+    elif path == "fused" and "l20" in short:
+        assert gpu_ctx.last_kernel == "fused_solve_kernel"
     plain = E.solve(gpu_ctx, model, batch, ws, remove_zero_weight=False)   # the batch is left as it was found
     differs_from_plain = 0
     for g in range(sub.n_graphs):

@@ -220,6 +220,7 @@ struct dg_batch {
     size_t tc_tiles_cap = 0;
     int tc_n_tiles = 0;
     bool tc_tiles_valid = false;
+    int tc_plan_hidden = -1;         // hidden-layer count the cached tile plan was made for (its cost model scales with depth)
     // tile table of the graph-staged streaming layer kernel (dg_stream.cu): row ranges aligned to graph boundaries
     int *gs_tiles_dev = nullptr;
     size_t gs_tiles_cap = 0;

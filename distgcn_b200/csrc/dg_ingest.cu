@@ -310,6 +310,10 @@ int pack_into(int32_t n_graphs, const int32_t *const *indptr, const int32_t *con
         if (lo > cut.back() && lo < n_graphs) cut.push_back(lo);
     }
     cut.push_back(n_graphs);
+    if (side_task && threads <= 1) {   // a handful of graphs: waking a pool thread costs more than the plan itself
+        (*side_task)();
+        side_task = nullptr;
+    }
     const int first = side_task ? 1 : 0;  // task 0 = the side task (the tile plan of the batch being packed)
     Pool::get().parallel_for((int)cut.size() - 1 + first, std::max(threads, first + 1), [&](int t_all) {
         if (t_all < first) {

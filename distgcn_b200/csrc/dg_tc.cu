@@ -1286,13 +1286,23 @@ struct Open {  // a tile being filled
     long long cost;
 };
 
-// Fitted cost model of a tile in cycles (profiles/r01_notes.md r01-j: 1610 tiles of the BA set in five packings, rms error
-// 2.2 %): 92.9 k per tile - the dependent hand-offs of the 20 layers, whatever the tile holds - plus, per graph,
-// 8.6 k per 128-row block + 43.6 per block and adjacency column + 2.3 per edge.
-constexpr long long kTcTileFixedCost = 92900;
-inline long long tc_graph_cost(int nb, int Kp, int nnz) {
-    return 8574LL * nb + (436LL * nb * Kp) / 10 + (23LL * nnz) / 10;
-}
+// Cost model of a tile in cycles.  Fitted on the 20-layer model (profiles/r01_notes.md r01-j: 1610 tiles of the BA set in five
+// packings, rms error 2.2 %): 92.9 k per tile - the dependent hand-offs of the layers, whatever the tile holds - plus, per
+// graph, 8.6 k per 128-row block + 43.6 per block and adjacency column + 2.3 per edge.  Everything but the per-edge term
+// (staging, greedy rounds) and ~7 k of set-up is work per LAYER, so for a model with `layers` = n_hidden + 2 layers the
+// constants scale: 7.0 k + 4.3 k per layer and tile, 429 per layer and block, 2.18 per layer, block and adjacency column.
+struct TcCost {
+    long long fixed, per_block, per_block_col_x100;
+    explicit TcCost(int n_hidden) {
+        const long long layers = n_hidden + 2;
+        fixed = 7000 + 4295 * layers;
+        per_block = 429 * layers;
+        per_block_col_x100 = 218 * layers;
+    }
+    long long graph(int nb, int Kp, int nnz) const {
+        return per_block * nb + (per_block_col_x100 * nb * Kp) / 100 + (23LL * nnz) / 10;
+    }
+};
 
 // `bins` tiles filled longest-processing-time first: every graph, heaviest first, goes to the lightest tile that can take it
 bool tc_pack_lpt(const std::vector<TcGraph> &gs, int bins, size_t pool, std::vector<Open> *out) {
@@ -1341,11 +1351,11 @@ bool tc_pack_lpt(const std::vector<TcGraph> &gs, int bins, size_t pool, std::vec
 }
 
 // makespan of heaviest-first list scheduling on `workers` CTAs (what the kernel's atomic tile counter does); `tiles` sorted
-long long tc_makespan(const std::vector<Open> &tiles, int workers) {
+long long tc_makespan(const std::vector<Open> &tiles, int workers, long long tile_fixed) {
     std::vector<long long> load((size_t)workers, 0);
     for (const Open &t : tiles) {
         std::pop_heap(load.begin(), load.end(), std::greater<long long>());
-        load.back() += t.cost + kTcTileFixedCost;
+        load.back() += t.cost + tile_fixed;
         std::push_heap(load.begin(), load.end(), std::greater<long long>());
     }
     return *std::max_element(load.begin(), load.end());
@@ -1353,7 +1363,9 @@ long long tc_makespan(const std::vector<Open> &tiles, int workers) {
 
 // host half of the tile plan: fills b->tc_tiles_host / tc_skip / tc_n_tiles from the batch's host metadata
 // (h_graph_ptr, h_graph_e).  No CUDA calls: dg_solve_graphs_host runs it on a pool thread while the others pack.
-void tc_plan_tiles_host(dg_context *ctx, dg_batch *b) {
+void tc_plan_tiles_host(dg_context *ctx, dg_batch *b, int n_hidden) {
+    const TcCost cost_model(n_hidden);
+    b->tc_plan_hidden = n_hidden;
     b->tc_n_tiles = 0;
     b->tc_tiles_host.clear();
     const size_t pool = tc_smem_bytes(ctx) - kTcOffPool;
@@ -1378,7 +1390,7 @@ void tc_plan_tiles_host(dg_context *ctx, dg_batch *b) {
             gs[(size_t)g] = t;
             continue;
         }
-        t.cost = tc_graph_cost(t.nb, (int)Kp, ge[g + 1] - ge[g]);
+        t.cost = cost_model.graph(t.nb, (int)Kp, ge[g + 1] - ge[g]);
         gs[(size_t)g] = t;
     }
     // Largest graph first; every tile is then topped up with the largest remaining graphs that still fit (blocks, bytes
@@ -1439,7 +1451,7 @@ void tc_plan_tiles_host(dg_context *ctx, dg_batch *b) {
             std::vector<Open> lpt;
             if (tc_pack_lpt(gs, want, pool, &lpt)) {
                 std::stable_sort(lpt.begin(), lpt.end(), [](const Open &a, const Open &c) { return a.cost > c.cost; });
-                if (tc_makespan(lpt, sms) < tc_makespan(tiles, sms)) tiles.swap(lpt);
+                if (tc_makespan(lpt, sms, cost_model.fixed) < tc_makespan(tiles, sms, cost_model.fixed)) tiles.swap(lpt);
             }
         }
     }
@@ -1456,13 +1468,13 @@ void tc_plan_tiles_host(dg_context *ctx, dg_batch *b) {
     b->tc_tiles_host.swap(flat);
 }
 
-int tc_build_tiles(dg_context *ctx, dg_batch *b, bool *ok) {
+int tc_build_tiles(dg_context *ctx, dg_batch *b, int n_hidden, bool *ok) {
     *ok = false;
-    if (b->tc_tiles_valid) {
+    if (b->tc_tiles_valid && b->tc_plan_hidden == n_hidden) {   // the plan depends on the batch and on the model's depth
         *ok = b->tc_n_tiles > 0;
         return DG_OK;
     }
-    if (!b->tc_plan_ready) tc_plan_tiles_host(ctx, b);
+    if (!b->tc_plan_ready || b->tc_plan_hidden != n_hidden) tc_plan_tiles_host(ctx, b, n_hidden);
     b->tc_plan_ready = false;
     b->tc_tiles_valid = true;
     const std::vector<int> &flat = b->tc_tiles_host;
@@ -1491,7 +1503,7 @@ bool tc_model_eligible(const dg_model *m) {
 
 void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b) {
     if (!tc_model_eligible(m) || b->n_graphs == 0 || b->n_nodes == 0) return;
-    tc_plan_tiles_host(ctx, b);
+    tc_plan_tiles_host(ctx, b, m->n_layers - 2);
     b->tc_plan_ready = true;
 }
 
@@ -1506,7 +1518,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     if ((int)b->h_graph_e.size() != b->n_graphs + 1) return DG_OK;
     if (member == nullptr && d_wts == nullptr && predict == DG_PREDICT_MWIS) return DG_OK;
     bool ok = false;
-    DG_TRY(tc_build_tiles(ctx, b, &ok));
+    DG_TRY(tc_build_tiles(ctx, b, m->n_layers - 2, &ok));
     if (!ok) return DG_OK;
     // Graphs beyond this kernel's limits go to the CUDA-core graph-resident kernel in a second launch.  If that kernel
     // cannot take them either, the whole batch belongs to the per-layer path: decline BEFORE launching anything.

@@ -876,7 +876,7 @@ def run_ours(args):
             configs["wireless"] = bench_wireless(env)
         if env.use_dist:
             env.dist.barrier()
-            configs["partitioned"] = bench_partitioned(env, args.part_nodes, 16)
+            configs["partitioned"] = bench_partitioned(env, args.part_nodes or 6000000 * world, 16)
     if rank == 0:
         roof = main_rec.pop("roofline")
         line = {
@@ -965,7 +965,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--main-only", action="store_true", help="skip the `configs` block (other workloads)")
     ap.add_argument("--synth-graphs", type=int, default=16384, help="graphs in the config-4 batch of `configs`")
-    ap.add_argument("--part-nodes", type=int, default=8000000, help="vertices of the row-partitioned graph (N >= 2)")
+    ap.add_argument("--part-nodes", type=int, default=0,
+                    help="vertices of the row-partitioned graph (N >= 2); 0 = 6 M per GPU (48 M at N = 8: BASELINE config 5 is 50 M)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

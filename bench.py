@@ -629,6 +629,7 @@ def bench_streaming(env, name, rec):
     model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
     c = copies[0]
     os.environ["DG_DISABLE_FUSED"] = "1"
+    E.reload_env()   # the library reads its options once per context, not on the solve path
     try:
         for _ in range(2):
             E.solve_device(ctx, model, c["dev"], c["d_w"], c["d_member"], predict="mwis", remove_zero_weight=True,
@@ -648,6 +649,7 @@ def bench_streaming(env, name, rec):
         kernel = ctx.last_kernel
     finally:
         del os.environ["DG_DISABLE_FUSED"]
+        E.reload_env()
     model.close()
     pb = c["pb"]
     n_l = max(int(n_launch.value), 1)

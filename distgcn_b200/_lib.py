@@ -41,6 +41,7 @@ SIGNATURES = {
     "dg_context_create": (C.c_int, [C.c_int, _p, C.POINTER(_p)]),
     "dg_context_destroy": (None, [_p]),
     "dg_context_synchronize": (C.c_int, [_p]),
+    "dg_context_reload_env": (C.c_int, [_p]),
     "dg_host_alloc": (_p, [C.c_uint64]),
     "dg_host_free": (None, [_p]),
     "dg_context_launch_count": (C.c_uint64, [_p]),

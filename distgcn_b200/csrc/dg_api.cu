@@ -43,6 +43,28 @@ int scratch(dg_context *ctx, int slot, size_t bytes, void **out) {
     return DG_OK;
 }
 
+void env_read(dg_env *env) {
+    auto on = [](const char *name) { return getenv(name) != nullptr; };
+    auto num = [](const char *name) {
+        const char *v = getenv(name);
+        return v ? atoi(v) : 0;
+    };
+    auto str = [](const char *name) {
+        const char *v = getenv(name);
+        return std::string(v ? v : "");
+    };
+    env->disable_tc = on("DG_DISABLE_TC");
+    env->disable_fused = on("DG_DISABLE_FUSED");
+    env->disable_staged = on("DG_DISABLE_STAGED");
+    env->fused_mma = on("DG_FUSED_MMA");
+    env->fused_timing = on("DG_FUSED_TIMING");
+    env->tc_debug = on("DG_TC_DEBUG");
+    env->tile_rows = num("DG_TILE_ROWS");
+    env->tc_tiles = num("DG_TC_TILES");
+    env->fused_tile_dump = str("DG_FUSED_TILE_DUMP");
+    env->tc_tile_dump = str("DG_TC_TILE_DUMP");
+}
+
 constexpr size_t kProfMaxPairs = 8192;
 
 void prof_begin(dg_context *ctx) {
@@ -187,6 +209,7 @@ int dg_context_create(int device, void *stream, dg_context **out) {
     dg_context *ctx = new (std::nothrow) dg_context();
     DG_REQUIRE(ctx != nullptr, DG_ERR_INVALID, "out of host memory");
     ctx->device = device;
+    env_read(&ctx->env);
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->slots.resize(kSlotCount);
@@ -233,6 +256,13 @@ void dg_context_destroy(dg_context *ctx) {
     if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int dg_context_reload_env(dg_context *ctx) {
+    clear_error();
+    DG_TRY(check_ctx(ctx));
+    env_read(&ctx->env);
+    return DG_OK;
 }
 
 int dg_context_synchronize(dg_context *ctx) {

@@ -81,7 +81,19 @@ struct Buffer {
 
 }  // namespace dg
 
+// Options read from the environment ONCE per context (dg_context_create) and on dg_context_reload_env: the solve path
+// never calls getenv.  DG_DISABLE_TC / DG_DISABLE_FUSED / DG_DISABLE_STAGED force the next kernel family down the
+// list (tensor-core -> CUDA-core graph-resident -> per-layer; graph-staged -> warp-per-row), DG_FUSED_MMA selects the
+// mma.sync projection of the fused kernel, the rest are measurement aids.
+struct dg_env {
+    bool disable_tc = false, disable_fused = false, disable_staged = false, fused_mma = false;
+    bool fused_timing = false, tc_debug = false;
+    int tile_rows = 0, tc_tiles = 0;
+    std::string fused_tile_dump, tc_tile_dump;
+};
+
 struct dg_context {
+    dg_env env;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -405,6 +417,7 @@ int solve_host_staged(dg_context *ctx, const dg_model *m, int32_t n_graphs, int3
                       int predict, int remove_zero_weight, uint8_t *member, double *total, bool wait,
                       const uint16_t *col_local16, cudaEvent_t copied);
 void ingest_staging_free(dg_context *ctx);  // dg_ingest.cu
+void env_read(dg_env *env);                 // dg_api.cu
 // set the host metadata of the context's reusable batch from per-graph vertex / edge offsets (n_graphs + 1 each) before
 // its arrays exist; the following solve_host_staged(..) call then skips recomputing them
 int host_batch_set_meta(dg_context *ctx, int32_t n_graphs, const int64_t *v0, const int64_t *e0, dg_batch **out);

@@ -1078,7 +1078,7 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
     if (min_n > 65535 - 1) return DG_OK;
     if (fused_smem_bytes(cp, min_n, min_nnz, has_hidden, wblob) > budget) return DG_OK;  // largest graph does not fit
     int forced_rows = 0;
-    if (const char *env = getenv("DG_TILE_ROWS")) forced_rows = atoi(env);
+    forced_rows = ctx->env.tile_rows;
     // candidate row capacities: multiples of 32 from the largest graph up to what shared memory allows
     std::vector<Tile> best_tiles, tiles;
     int best_n = 0, best_nnz = 0;
@@ -1140,7 +1140,7 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
     b->tiles_wblob = wblob;
     b->tiles_subset = subset;
     b->tiles_valid = true;
-    if (getenv("DG_FUSED_TIMING"))
+    if (ctx->env.fused_timing)
         fprintf(stderr, "[fused tiles] %d tiles, cap_n %d, cap_nnz %d, simulated makespan %lld\n", b->n_tiles, best_n,
                 best_nnz, best_span);
     *ok = b->n_tiles > 0;
@@ -1150,11 +1150,11 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
 }  // namespace
 
 bool fused_fits(dg_context *ctx, const dg_model *m, const dg_batch *b) {
-    if (getenv("DG_DISABLE_FUSED")) return false;
+    if (ctx->env.disable_fused) return false;
     if (m->fused_cp == 0 || b->n_graphs == 0 || b->n_nodes == 0) return false;
     if ((int)b->h_graph_e.size() != b->n_graphs + 1) return false;
     const bool has_hidden = m->n_layers >= 3;
-    const bool use_mma = m->fused_cp == 32 && has_hidden && m->fused_wall_mma && getenv("DG_FUSED_MMA");
+    const bool use_mma = m->fused_cp == 32 && has_hidden && m->fused_wall_mma && ctx->env.fused_mma;
     const size_t wblob = use_mma ? sizeof(float) * (size_t)(2 * 2 * 32 * 40 + 32)
                                  : sizeof(float) * (size_t)(2 * m->fused_cp * m->fused_cp + m->fused_cp);
     // the same feasibility test build_tiles starts with: the largest graph of the batch must fit a tile
@@ -1175,14 +1175,14 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     b->tc_ran_partial = false;
     // member == nullptr: scores only (dg_gcn_forward); the greedy rounds are skipped
     if (member == nullptr && (d_wts == nullptr) && predict == DG_PREDICT_MWIS) return DG_OK;
-    if (getenv("DG_DISABLE_FUSED")) return DG_OK;
+    if (ctx->env.disable_fused) return DG_OK;
     if (m->fused_cp == 0 || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
     if ((int)b->h_graph_e.size() != b->n_graphs + 1) return DG_OK;
     const bool has_hidden = m->n_layers >= 3;
     // The split-TF32 mma.sync projection is kept as an option (DG_FUSED_MMA=1): it is ~2x more accurate
     // than the FFMA chain but not faster on B200 - legacy mma.sync TF32 issues at about the FFMA rate
     // and the 3-term split triples the work (profiles/r01_notes.md).
-    const bool use_mma = m->fused_cp == 32 && has_hidden && m->fused_wall_mma && getenv("DG_FUSED_MMA");
+    const bool use_mma = m->fused_cp == 32 && has_hidden && m->fused_wall_mma && ctx->env.fused_mma;
     const size_t wblob = use_mma ? sizeof(float) * (size_t)(2 * 2 * 32 * 40 + 32)
                                  : sizeof(float) * (size_t)(2 * m->fused_cp * m->fused_cp + m->fused_cp);
     bool ok = false;
@@ -1224,7 +1224,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     p.do_lgs = member != nullptr ? 1 : 0;
     p.dit = (dit && member != nullptr) ? 1 : 0;
     p.dbg = nullptr;
-    if (getenv("DG_FUSED_TIMING")) {
+    if (ctx->env.fused_timing) {
         long long *dbg = nullptr;
         DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * 4 * 16 + (size_t)p.n_tiles * 4, &dbg));
         DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * 4 * 16 + (size_t)p.n_tiles * 4),
@@ -1276,7 +1276,7 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
             fprintf(stderr, "[fused timing] %-8s min %10lld avg %12.0f max %10lld (%d CTAs)\n", names[k], mn,
                     cnt ? sum / cnt : 0.0, mx, cnt);
         }
-        if (const char *path = getenv("DG_FUSED_TILE_DUMP")) {  // per-tile (cycles, rows, padded nnz, graphs)
+        if (const char *path = ctx->env.fused_tile_dump.empty() ? nullptr : ctx->env.fused_tile_dump.c_str()) {  // per-tile (cycles, rows, padded nnz, graphs)
             if (FILE *f = fopen(path, "w")) {
                 const int grid = std::min(p.n_tiles, ctx->sm_count * 4);
                 (void)grid;

@@ -400,7 +400,7 @@ int gs_launch(dg_context *ctx, dg_batch *b, const LayerArgs &a) {
 
 int gs_try_spmm(dg_context *ctx, dg_batch *b, int width, const float *z, float *y, bool *handled) {
     *handled = false;
-    if (width != kGsC || getenv("DG_DISABLE_STAGED") || b->n_graphs < 8) return DG_OK;
+    if (width != kGsC || ctx->env.disable_staged || b->n_graphs < 8) return DG_OK;
     bool ok = false;
     DG_TRY(gs_build_plan(ctx, b, &ok));
     if (!ok) return DG_OK;
@@ -421,7 +421,7 @@ int gs_try_layer(dg_context *ctx, dg_batch *b, int cpi, int cpo, bool implicit_i
                  bool *handled) {
     *handled = false;
     if (cpi != kGsC || cpo != kGsC || a.row0 != 0 || a.pm.world > 1) return DG_OK;
-    if (getenv("DG_DISABLE_STAGED")) return DG_OK;
+    if (ctx->env.disable_staged) return DG_OK;
     if (a.n != b->n_nodes || a.row_ptr != b->row_ptr) return DG_OK;
     // a handful of large graphs gain nothing from staging; the plan needs every graph to fit a tile
     if (b->n_graphs < 8) return DG_OK;

@@ -1446,7 +1446,7 @@ void tc_plan_tiles_host(dg_context *ctx, dg_batch *b, int n_hidden) {
         const int sms = ctx->sm_count * kTcCtasPerSm;
         const int k = ((int)tiles.size() + sms - 1) / sms;
         int want = k * sms;
-        if (const char *e = getenv("DG_TC_TILES")) want = atoi(e);  // (experiments)
+        if (ctx->env.tc_tiles > 0) want = ctx->env.tc_tiles;  // (experiments)
         if (k <= 8 && want > (int)tiles.size() && want <= b->n_graphs - b->tc_n_skipped) {
             std::vector<Open> lpt;
             if (tc_pack_lpt(gs, want, pool, &lpt)) {
@@ -1490,19 +1490,19 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, int n_hidden, bool *ok) {
     if (!flat.empty())
         DG_CUDA_CHECK(cudaMemcpyAsync(b->tc_tiles_dev, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice,
                                       ctx->stream));
-    if (getenv("DG_FUSED_TIMING")) fprintf(stderr, "[tc tiles] %d tiles for %d graphs\n", b->tc_n_tiles, b->n_graphs);
+    if (ctx->env.fused_timing) fprintf(stderr, "[tc tiles] %d tiles for %d graphs\n", b->tc_n_tiles, b->n_graphs);
     *ok = b->tc_n_tiles > 0;
     return DG_OK;
 }
 
 }  // namespace
 
-bool tc_model_eligible(const dg_model *m) {
-    return !(getenv("DG_DISABLE_TC") || getenv("DG_DISABLE_FUSED")) && m->tc_wall && m->n_layers >= 3;
+bool tc_model_eligible(const dg_context *ctx, const dg_model *m) {
+    return !(ctx->env.disable_tc || ctx->env.disable_fused) && m->tc_wall && m->n_layers >= 3;
 }
 
 void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b) {
-    if (!tc_model_eligible(m) || b->n_graphs == 0 || b->n_nodes == 0) return;
+    if (!tc_model_eligible(ctx, m) || b->n_graphs == 0 || b->n_nodes == 0) return;
     tc_plan_tiles_host(ctx, b, m->n_layers - 2);
     b->tc_plan_ready = true;
 }
@@ -1513,7 +1513,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
                  uint8_t *member, float *score, double *util, double *total, int32_t *steps, bool *handled, bool dit) {
     *handled = false;
     if (dit && (member == nullptr || d_wts == nullptr)) return DG_OK;
-    if (getenv("DG_DISABLE_TC") || getenv("DG_DISABLE_FUSED")) return DG_OK;
+    if (ctx->env.disable_tc || ctx->env.disable_fused) return DG_OK;
     if (!m->tc_wall || m->n_layers < 3 || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
     if ((int)b->h_graph_e.size() != b->n_graphs + 1) return DG_OK;
     if (member == nullptr && d_wts == nullptr && predict == DG_PREDICT_MWIS) return DG_OK;
@@ -1557,7 +1557,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     p.do_lgs = member != nullptr ? 1 : 0;
     p.dbg = nullptr;
     const size_t smem = tc_smem_bytes(ctx);
-    if (getenv("DG_FUSED_TIMING")) {
+    if (ctx->env.fused_timing) {
         long long *dbg = nullptr;
         DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2, &dbg));
         DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2), ctx->stream));
@@ -1572,7 +1572,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     {
         int *wd = ctx->h_flag + 3;  // pinned host memory: readable after a device-side trap
         int wide = 0;
-        if (getenv("DG_TC_DEBUG")) {
+        if (ctx->env.tc_debug) {
             if (!g_wide_buf) DG_CUDA_CHECK(cudaHostAlloc((void **)&g_wide_buf, sizeof(int) * (1 + 148 * 512), cudaHostAllocDefault));
             memset(g_wide_buf, 0, sizeof(int) * (1 + 148 * 512));
             wd = g_wide_buf;
@@ -1596,7 +1596,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         prof_end(ctx, hidden + scalar_passes + lgs);
         DG_CUDA_CHECK(cudaGetLastError());
     }
-    if (getenv("DG_TC_DEBUG")) {
+    if (ctx->env.tc_debug) {
         const cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess && g_wide_buf) {
             const int w = g_wide_buf[0];
@@ -1629,7 +1629,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
             fprintf(stderr, "[tc timing] %-6s min %10lld avg %12.0f max %10lld (%d CTAs)\n", names[k], mn, cnt ? sum / cnt : 0.0,
                     mx, cnt);
         }
-        if (const char *path = getenv("DG_TC_TILE_DUMP")) {  // per tile: cycles, then the vertex counts of its graphs
+        if (const char *path = ctx->env.tc_tile_dump.empty() ? nullptr : ctx->env.tc_tile_dump.c_str()) {  // per tile: cycles, then the vertex counts of its graphs
             if (FILE *f = fopen(path, "w")) {
                 for (int t = 0; t < p.n_tiles; ++t) {
                     const int *td = &b->tc_tiles_host[(size_t)t * 32];

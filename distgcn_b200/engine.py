@@ -43,16 +43,35 @@ def predict_code(predict) -> int:
     raise ValueError("predict must be 'mwis' or 'mis', got %r" % (predict,))
 
 
+_LIVE_CONTEXTS = None   # weak set of live contexts (reload_env)
+
+
+def reload_env() -> None:
+    """Make every live context re-read the library's DG_* environment options (they are read once, when a context is
+    created; tests and bench.py call this after changing os.environ)."""
+    for ctx in list(_LIVE_CONTEXTS or ()):
+        ctx.reload_env()
+
+
 class Context:
     """One device + one stream + reusable scratch.  Replaces the reference's module-level
     ``tf.compat.v1.Session`` (mwis_dqn_call.py:336-344)."""
 
     def __init__(self, device: int = 0, stream: Optional[int] = None):
+        global _LIVE_CONTEXTS
         self._lib = _lib.load()
         h = C.c_void_p()
         check(self._lib.dg_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = int(device)
+        if _LIVE_CONTEXTS is None:
+            import weakref
+            _LIVE_CONTEXTS = weakref.WeakSet()
+        _LIVE_CONTEXTS.add(self)
+
+    def reload_env(self) -> None:
+        if self._h is not None:
+            check(self._lib.dg_context_reload_env(self._h))
 
     @property
     def handle(self):

@@ -85,6 +85,10 @@ DG_API int dg_device_count(void);
 DG_API int dg_context_create(int device, void *stream, dg_context **out);
 DG_API void dg_context_destroy(dg_context *ctx);
 DG_API int dg_context_synchronize(dg_context *ctx);
+/* The library's options (DG_DISABLE_TC, DG_DISABLE_FUSED, DG_DISABLE_STAGED, DG_FUSED_MMA and the DG_*_TIMING / DG_*_DUMP
+ * measurement aids) are read from the environment when a context is created - never on the solve path.  Call this after
+ * changing them for a live context. */
+DG_API int dg_context_reload_env(dg_context *ctx);
 /* Pinned host memory for staging HOST-space calls at full PCIe speed. */
 DG_API void *dg_host_alloc(uint64_t bytes);
 DG_API void dg_host_free(void *p);

@@ -24,3 +24,29 @@ def gpu_ctx():
     ctx = engine.Context(0)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(autouse=True)
+def _library_env_follows_monkeypatch(monkeypatch):
+    """The library reads its DG_* options once per context (never on the solve path): every setenv / delenv of a test, and
+    the start of every test (the previous test's changes have been undone by then), is followed by a reload on the live
+    contexts."""
+    import sys
+    eng = sys.modules.get("distgcn_b200.engine")
+    if eng is not None:
+        eng.reload_env()
+    orig_set, orig_del = monkeypatch.setenv, monkeypatch.delenv
+
+    def setenv(name, value, prepend=None):
+        orig_set(name, value, prepend)
+        e = sys.modules.get("distgcn_b200.engine")
+        if e is not None and name.startswith("DG_"):
+            e.reload_env()
+
+    def delenv(name, raising=True):
+        orig_del(name, raising)
+        e = sys.modules.get("distgcn_b200.engine")
+        if e is not None and name.startswith("DG_"):
+            e.reload_env()
+    monkeypatch.setenv, monkeypatch.delenv = setenv, delenv
+    yield

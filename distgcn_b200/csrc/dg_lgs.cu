@@ -651,10 +651,19 @@ int dist_greedy_device(dg_context *ctx, const dg_batch *b, const double *wts, do
                        int32_t *steps) {
     const int G = b->n_graphs;
     if (G == 0) return DG_OK;
-    DG_REQUIRE(b->max_graph_nodes <= kLgsCtaMaxNodes, DG_ERR_UNSUPPORTED,
-               "dist_greedy_search runs one CTA per graph: graphs above %d vertices are not supported", kLgsCtaMaxNodes);
+    // One CTA per graph with its four bitmaps in shared memory: 4 n / 8 bytes, so the opt-in limit of an SM (227 KB) holds
+    // graphs of up to ~460 k vertices - far above the one-CTA limit of the local greedy search, whose per-round state is
+    // larger.  (A graph that size runs on ONE SM: the ascending-id scan of a round's candidates is inherently a chain.)
     const int words_cap = (b->max_graph_nodes + 31) / 32 + 1;
     const size_t smem = sizeof(uint32_t) * 4 * (size_t)words_cap;
+    DG_REQUIRE(smem <= (size_t)ctx->max_smem_optin, DG_ERR_UNSUPPORTED,
+               "dist_greedy_search runs one CTA per graph: a graph of %d vertices needs %zu bytes of shared memory (limit %d, "
+               "about %d vertices)", b->max_graph_nodes, smem, ctx->max_smem_optin, ctx->max_smem_optin * 2 - 64);
+    static size_t smem_set = 0;   // the attribute only ever grows (per device kind)
+    if (smem > 48 * 1024 && smem > smem_set) {
+        DG_CUDA_CHECK(cudaFuncSetAttribute(dgs_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_smem_optin));
+        smem_set = (size_t)ctx->max_smem_optin;
+    }
     dgs_cta_kernel<<<G, kLgsCtaThreads, smem, ctx->stream>>>(b->graph_ptr, b->row_ptr, b->col_idx, wts, b->keep, alpha,
                                                              kLgsRoundCap, words_cap, member, steps, ctx->d_status);
     ctx->launches++;

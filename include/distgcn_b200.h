@@ -184,8 +184,9 @@ DG_API int dg_lgs(dg_context *ctx, const dg_batch *batch, const double *util, in
  *            or wts[v] >= max(remaining neighbours' wts) / (1 + epsilon / 3)
  *   member   out, n_nodes bytes;  steps  out or NULL, n_graphs int32, rounds executed
  * Each round's candidates are scanned in ascending vertex id (the reference scans them in Python-set
- * iteration order; identical whenever no two candidates of a round are adjacent).  Graphs above 8192
- * vertices: DG_ERR_UNSUPPORTED.  Vertices removed by dg_batch_set_keep start outside `remain`. */
+ * iteration order; identical whenever no two candidates of a round are adjacent).  One CTA per graph with the
+ * round's four bitmaps in shared memory: graphs of up to ~460 000 vertices (DG_ERR_UNSUPPORTED beyond).  Vertices
+ * removed by dg_batch_set_keep start outside `remain`. */
 DG_API int dg_dist_greedy(dg_context *ctx, const dg_batch *batch, const double *wts, double epsilon, uint8_t *member,
                    int32_t *steps, int mem);
 

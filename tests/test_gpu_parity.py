@@ -166,6 +166,31 @@ def test_dist_greedy_matches_oracle_and_reference(gpu_ctx, eps, tag):
     batch.close()
 
 
+def test_dist_greedy_large_graph(gpu_ctx):
+    """dist_greedy_search above the 8192-vertex one-CTA limit of the local greedy search: a 30 000-vertex graph (its four
+    bitmaps still fit one SM's shared memory) against the restatement, with tie-heavy integer weights as well."""
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    rng = np.random.default_rng(12)
+    n, m = 30000, 90000
+    u, v = rng.integers(0, n, m), rng.integers(0, n, m)
+    ok = u != v
+    a = sp.coo_matrix((np.ones(ok.sum()), (u[ok], v[ok])), shape=(n, n))
+    a = ((a + a.T) > 0).astype(np.float64).tocsr()
+    small = sp.csr_matrix(np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]], dtype=float))
+    pb = pack_graphs([small, a])
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    for w in (rng.random(pb.n_nodes), rng.integers(0, 4, pb.n_nodes).astype(np.float64)):
+        r = E.dist_greedy(gpu_ctx, batch, w, epsilon=0.1)
+        for g in range(pb.n_graphs):
+            v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
+            sub = pb.slice(g, g + 1)
+            member, rounds, _ = L.dist_greedy(sub.row_ptr, sub.col_idx, w[v0:v1], 0.1)
+            assert np.array_equal(r.member[v0:v1], member) and int(r.steps[g]) == rounds
+    batch.close()
+
+
 def test_dist_greedy_keep_mask_edge_cases_and_full_sets(gpu_ctx):
     E = _engine()
     from oracle import lgs as L
@@ -201,12 +226,19 @@ def test_dist_greedy_keep_mask_edge_cases_and_full_sets(gpu_ctx):
     r = E.dist_greedy(gpu_ctx, batch, np.ones(n))
     assert np.array_equal(r.member, (np.arange(n) % 2 == 0).astype(np.uint8)) and r.steps.tolist() == [1]
     batch.close()
-    # one CTA per graph: graphs above 8192 vertices are refused, not mis-solved
+    # one CTA per graph, four bitmaps in shared memory: a 9000-vertex path is solved (the local greedy search's one-CTA limit
+    # is 8192), a graph whose bitmaps exceed an SM's shared memory (~460 k vertices) is refused, not mis-solved
     nbig = 9000
     big = sp.diags([np.ones(nbig - 1), np.ones(nbig - 1)], [-1, 1], format="csr")
     batch = E.DeviceBatch(gpu_ctx, pack_graphs([big]))
+    r = E.dist_greedy(gpu_ctx, batch, np.ones(nbig))
+    assert np.array_equal(r.member, (np.arange(nbig) % 2 == 0).astype(np.uint8)) and r.steps.tolist() == [1]
+    batch.close()
+    nhuge = 600000
+    huge = sp.diags([np.ones(nhuge - 1), np.ones(nhuge - 1)], [-1, 1], format="csr")
+    batch = E.DeviceBatch(gpu_ctx, pack_graphs([huge]))
     with pytest.raises(_lib.DistGCNError) as ei:
-        E.dist_greedy(gpu_ctx, batch, np.ones(nbig))
+        E.dist_greedy(gpu_ctx, batch, np.ones(nhuge))
     assert ei.value.code == _lib.ERR_UNSUPPORTED
     batch.close()
     # negative weights leave the candidate set empty for ever (the reference never returns): reported

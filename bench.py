@@ -428,17 +428,18 @@ def bench_batch_workload(env, name, steps, warmup, detail):
         d_w = torch.from_numpy(w).to(env.dev)
         d_member = torch.empty(pb.n_nodes, dtype=torch.uint8, device=env.dev)
         d_total = torch.empty(pb.n_graphs, dtype=torch.float64, device=env.dev)
-        c16 = pb.local_columns()  # the compact host format: 16-bit graph-local column ids (dg_solve_host_compact)
+        # the upper host format: 16-bit graph-local column ids of the entries above the diagonal (dg_solve_host_upper)
+        rp_u, c16 = pb.upper_compact()
         h = {k: E.pinned_empty(a.shape, a.dtype) for k, a in
-             (("gp", pb.graph_ptr), ("rp", pb.row_ptr), ("w", w), ("c16", c16))}
-        h["gp"][:], h["rp"][:], h["w"][:], h["c16"][:] = pb.graph_ptr, pb.row_ptr, w, c16
+             (("gp", pb.graph_ptr), ("rp", pb.row_ptr), ("w", w), ("c16", c16), ("rpu", rp_u))}
+        h["gp"][:], h["rp"][:], h["w"][:], h["c16"][:], h["rpu"][:] = pb.graph_ptr, pb.row_ptr, w, c16, rp_u
         h["ci"] = pb.col_idx
         if detail:   # the packed int32 form, for the one-call-at-a-time figure
             h["ci"] = E.pinned_empty(pb.col_idx.shape, pb.col_idx.dtype)
             h["ci"][:] = pb.col_idx
         adjs, w_list = per_graph_inputs(pb, np.asarray(h["w"]), scipy_objects=not synth)
         copies.append(dict(pb=pb, w=w, dev=dev_batch, d_w=d_w, d_member=d_member, d_total=d_total,
-                           h_pb=PackedBatch(h["gp"], h["rp"], h["ci"]), h_w=h["w"], h_c16=h["c16"],
+                           h_pb=PackedBatch(h["gp"], h["rp"], h["ci"]), h_w=h["w"], h_upper=(h["rpu"], h["c16"]),
                            h_member=E.pinned_empty(pb.n_nodes, np.uint8), h_total=E.pinned_empty(pb.n_graphs, np.float64),
                            adjs=adjs, w_list=w_list))
         input_bytes += 4 * (pb.n_graphs + 1) + 4 * (pb.n_nodes + 1) + 4 * pb.nnz + 8 * pb.n_nodes
@@ -527,7 +528,7 @@ def bench_batch_workload(env, name, steps, warmup, detail):
     def pipe_step(i):
         c = copies[i % R]
         pipe.submit(c["h_pb"], c["h_w"], c["h_member"], c["h_total"], predict="mwis", remove_zero_weight=True,
-                    col_local16=c["h_c16"])
+                    upper=c["h_upper"])
 
     def graphs_step(i):   # the reference's native input: a list of per-graph matrices + per-graph weight vectors
         c = copies[i % R]
@@ -564,7 +565,7 @@ def bench_batch_workload(env, name, steps, warmup, detail):
     same = env.all_true(same)
 
     world = env.world
-    h2d = 4 * (c0.n_graphs + 1) + 4 * (c0.n_nodes + 1) + 2 * c0.nnz + 8 * c0.n_nodes  # compact: 16-bit column ids
+    h2d = 4 * (c0.n_graphs + 1) + 4 * (c0.n_nodes + 1) + c0.nnz + 8 * c0.n_nodes  # upper format: nnz / 2 16-bit column ids
     d2h = c0.n_nodes + 8 * c0.n_graphs
     kern_launches = int(n_launch.value)
     avg_us = 1e3 * tot_ms.value / max(kern_launches, 1)
@@ -577,8 +578,9 @@ def bench_batch_workload(env, name, steps, warmup, detail):
         "e2e": {"value": world * n_graphs * steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / steps,
                 "h2d_gbs_per_rank": h2d / (e2e_ms / steps) / 1e6,
-                "api": "engine.HostPipeline.submit (dg_solve_host_compact, 2 contexts in turn): pinned host CSR with 16-bit "
-                       "graph-local column ids + weights in, membership + totals out, every step; wall clock over the K steps",
+                "api": "engine.HostPipeline.submit (dg_solve_host_upper, 2 contexts in turn): pinned host arrays - row offsets and "
+                       "16-bit graph-local column ids of the entries above the diagonal, weights - in, membership + totals out, "
+                       "every step; wall clock over the K steps",
                 "gpu_launches": int(pipe_launches),
                 "from_reference_inputs": {
                     "value": world * n_graphs * steps / (ref_ms / 1e3), "unit": UNIT, "ms_per_step": ref_ms / steps,

@@ -92,6 +92,8 @@ SIGNATURES = {
     "dg_solve_host_compact": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_int]),
     "dg_pack_graphs_sizes": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "dg_pack_graphs_host": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32]),
+    "dg_pack_graphs_upper_host": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32]),
+    "dg_solve_host_upper": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_int]),
     "dg_solve_graphs_host": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_int]),
     "dg_wireless_create": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, C.POINTER(_p)]),
     "dg_wireless_destroy": (None, [_p]),

@@ -63,6 +63,23 @@ class PackedBatch:
         base = np.repeat(self.graph_ptr[:-1].astype(np.int64), self.graph_nnz())
         return (self.col_idx.astype(np.int64) - base).astype(np.uint16)
 
+    def upper_compact(self):
+        """(row_ptr_upper int32 [n_nodes + 1], col_local_upper uint16 [nnz / 2]): only the entries with column > row,
+        graph-local ids - the UPPER host format of ``engine.solve_host(..., upper=...)`` / dg_solve_host_upper, a third of
+        the host->device bytes of ``col_idx``.  The adjacency must be symmetric with a zero diagonal; graphs of at most
+        8192 vertices."""
+        if self.n_graphs and int(self.graph_sizes().max()) > 8192:
+            raise ValueError("the upper host format takes graphs of at most 8192 vertices")
+        rows = np.repeat(np.arange(self.n_nodes, dtype=np.int64), np.diff(self.row_ptr))
+        cols = self.col_idx.astype(np.int64)
+        keep = cols > rows
+        if int(keep.sum()) * 2 != self.nnz:
+            raise ValueError("adjacency pattern is not symmetric with a zero diagonal")
+        base = np.repeat(self.graph_ptr[:-1].astype(np.int64), self.graph_sizes())[rows[keep]]
+        rp_u = np.zeros(self.n_nodes + 1, dtype=np.int64)
+        np.add.at(rp_u, rows[keep] + 1, 1)
+        return np.cumsum(rp_u).astype(np.int32), (cols[keep] - base).astype(np.uint16)
+
     def slice(self, g0: int, g1: int) -> "PackedBatch":
         """Graphs g0 .. g1-1 as their own batch (vertex ids re-based)."""
         v0, v1 = int(self.graph_ptr[g0]), int(self.graph_ptr[g1])

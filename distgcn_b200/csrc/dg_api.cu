@@ -59,6 +59,8 @@ void env_read(dg_env *env) {
     env->fused_mma = on("DG_FUSED_MMA");
     env->fused_timing = on("DG_FUSED_TIMING");
     env->tc_debug = on("DG_TC_DEBUG");
+    env->ingest_upper = on("DG_INGEST_UPPER");
+    env->ingest_timing = on("DG_INGEST_TIMING");
     env->tile_rows = num("DG_TILE_ROWS");
     env->tc_tiles = num("DG_TC_TILES");
     env->fused_tile_dump = str("DG_FUSED_TILE_DUMP");
@@ -632,9 +634,130 @@ expand_cols16_kernel(const int32_t *__restrict__ graph_ptr, const int32_t *__res
     for (int e = row_ptr[v0] + (int)threadIdx.x; e < e1; e += (int)blockDim.x) col_idx[e] = (int32_t)col16[e] + v0;
 }
 
-// batch-global int32 column ids of a batch that arrived in the compact format (no-op otherwise)
+// Upper-triangle lists (column > row, graph-local 16-bit ids) -> the full symmetric CSR with batch-global ids, one CTA per
+// graph: per-vertex counts with shared-memory atomics, an exclusive scan for the row offsets, the upper entries copied in
+// place behind each row's lower part, the lower parts filled through per-row cursors and then sorted (rows come out in
+// ascending column order whatever the order of the atomics: the result is deterministic).
+constexpr int kSymMaxNodes = 8192;
+__global__ void __launch_bounds__(256)
+symmetrize_upper_kernel(const int32_t *__restrict__ graph_ptr, const int32_t *__restrict__ row_ptr_u,
+                        const uint16_t *__restrict__ col_u, int32_t *__restrict__ row_ptr, int32_t *__restrict__ col_idx,
+                        int n_graphs) {
+    extern __shared__ int sym_sm[];
+    const int g = blockIdx.x;
+    const int v0 = graph_ptr[g], n = graph_ptr[g + 1] - v0;
+    int *cnt = sym_sm;          // [n] degree, then exclusive offsets
+    int *low = sym_sm + n;      // [n] entries below the diagonal (cursor while filling)
+    __shared__ int part[256];
+    const int tid = threadIdx.x;
+    const int eu0 = row_ptr_u[v0];
+    const int base = 2 * eu0;   // full offsets: every earlier graph holds twice its upper count
+    for (int i = tid; i < n; i += 256) cnt[i] = 0, low[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int b0 = row_ptr_u[v0 + i], b1 = row_ptr_u[v0 + i + 1];
+        atomicAdd(&cnt[i], b1 - b0);
+        for (int e = b0; e < b1; ++e) {
+            const int j = col_u[e];
+            atomicAdd(&cnt[j], 1);
+            atomicAdd(&low[j], 1);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of cnt: contiguous chunks per thread
+    const int chunk = (n + 255) / 256;
+    const int c0 = min(tid * chunk, n), c1 = min(c0 + chunk, n);
+    int sum = 0;
+    for (int i = c0; i < c1; ++i) sum += cnt[i];
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t < 256; ++t) {
+            const int v = part[t];
+            part[t] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    int run = part[tid];
+    for (int i = c0; i < c1; ++i) {
+        const int v = cnt[i];
+        cnt[i] = run;
+        row_ptr[v0 + i] = base + run;
+        run += v;
+    }
+    if (g == n_graphs - 1 && tid == 255) row_ptr[v0 + n] = 2 * row_ptr_u[v0 + n];
+    __syncthreads();
+    // upper parts in place (ascending as given), lower parts through the cursors
+    for (int i = tid; i < n; i += 256) {
+        const int b0 = row_ptr_u[v0 + i], b1 = row_ptr_u[v0 + i + 1];
+        int *dst = col_idx + base + cnt[i] + low[i];
+        for (int e = b0; e < b1; ++e) dst[e - b0] = v0 + (int)col_u[e];
+    }
+    __syncthreads();   // `low` becomes the fill cursor counting down
+    for (int i = tid; i < n; i += 256) {
+        const int b0 = row_ptr_u[v0 + i], b1 = row_ptr_u[v0 + i + 1];
+        for (int e = b0; e < b1; ++e) {
+            const int j = col_u[e];
+            const int pos = atomicSub(&low[j], 1) - 1;
+            col_idx[base + cnt[j] + pos] = v0 + i;
+        }
+    }
+    __syncthreads();
+    __threadfence_block();
+    // sort every row's lower part (short lists: insertion sort, one thread per row)
+    for (int i = tid; i < n; i += 256) {
+        const int b0 = row_ptr_u[v0 + i], b1 = row_ptr_u[v0 + i + 1];
+        const int end_i = (i + 1 < n) ? cnt[i + 1] : -1;
+        const int deg = (end_i >= 0 ? end_i : (2 * (row_ptr_u[v0 + n] - eu0))) - cnt[i];
+        const int nl = deg - (b1 - b0);
+        int *a = col_idx + base + cnt[i];
+        for (int x = 1; x < nl; ++x) {
+            const int key = a[x];
+            int y = x - 1;
+            while (y >= 0 && a[y] > key) {
+                a[y + 1] = a[y];
+                --y;
+            }
+            a[y + 1] = key;
+        }
+    }
+}
+
+// batch-global int32 column ids (and, for the upper format, the full symmetric CSR) of a batch that arrived in a compact
+// host format (no-op otherwise)
 static int batch_ensure_cols(dg_batch *b) {
     if (!b->cols_pending) return DG_OK;
+    dg_context *ctx = b->ctx;
+    if (b->upper_pending) {
+        if (b->n_graphs > 0 && b->n_nodes > 0) {
+            const size_t smem = sizeof(int) * 2 * (size_t)std::max(b->max_graph_nodes, 1);
+            static bool attr_set = false;
+            if (!attr_set) {
+                DG_CUDA_CHECK(cudaFuncSetAttribute(symmetrize_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(sizeof(int) * 2 * kSymMaxNodes)));
+                attr_set = true;
+            }
+            symmetrize_upper_kernel<<<b->n_graphs, 256, smem, ctx->stream>>>(b->graph_ptr, b->row_ptr_u, b->col16, b->row_ptr,
+                                                                            b->col_idx, b->n_graphs);
+            ctx->launches++;
+            DG_CUDA_CHECK(cudaGetLastError());
+        }
+        b->upper_pending = false;
+        b->cols_pending = false;
+        b->nnz *= 2;
+        for (auto &e : b->h_graph_e) e *= 2;
+        b->max_graph_nnz *= 2;
+        b->tiles_valid = false;
+        b->tc_tiles_valid = false;
+        b->gs_valid = false;
+        if (b->dinv_deferred) {
+            b->dinv_deferred = false;
+            DG_TRY(batch_compute_dinv(b));
+        }
+        return DG_OK;
+    }
     if (b->n_graphs > 0 && b->nnz > 0) {
         expand_cols16_kernel<<<b->n_graphs, 256, 0, b->ctx->stream>>>(b->graph_ptr, b->row_ptr, b->col16, b->col_idx);
         b->ctx->launches++;
@@ -646,8 +769,11 @@ static int batch_ensure_cols(dg_batch *b) {
 
 static int batch_fill(dg_batch *b, int32_t n_graphs, int32_t n_nodes, int32_t nnz, const int32_t *graph_ptr,
                       const int32_t *row_ptr, const int32_t *col_idx, int mem, bool compute_dinv = true,
-                      const uint16_t *col_local16 = nullptr) {
+                      const uint16_t *col_local16 = nullptr, bool upper = false) {
     dg_context *ctx = b->ctx;
+    DG_REQUIRE(!upper || col_local16, DG_ERR_INVALID, "the upper-triangle format is a compact (16-bit) host format");
+    b->upper_pending = false;
+    b->dinv_deferred = false;
     DG_REQUIRE(n_graphs >= 0 && n_nodes >= 0 && nnz >= 0, DG_ERR_INVALID, "negative size");
     DG_REQUIRE(graph_ptr && row_ptr && (col_idx || col_local16 || nnz == 0), DG_ERR_INVALID, "null CSR pointer");
     DG_REQUIRE(!col_local16 || mem == DG_MEM_HOST, DG_ERR_INVALID, "the compact column format is a host format");
@@ -706,20 +832,35 @@ upload:
             DG_CUDA_CHECK(cudaMalloc((void **)&b->row_ptr, sizeof(int32_t) * (cap + 1)));
             DG_TRY(batch_alloc_aux(b, cap));  // sets cap_nodes
         }
-        if (b->cap_nnz < (size_t)nnz || !b->col_idx) {
+        const size_t need_nnz = upper ? 2 * (size_t)nnz : (size_t)nnz;  // the expansion of the upper format doubles it
+        if (b->cap_nnz < need_nnz || !b->col_idx) {
             if (b->col_idx) cudaFree(b->col_idx);
             if (b->col16) cudaFree(b->col16);
             b->col_idx = nullptr;
             b->col16 = nullptr;
-            b->cap_nnz = (size_t)nnz + (size_t)nnz / 4 + 1;
+            b->cap_nnz = need_nnz + need_nnz / 4 + 1;
             DG_CUDA_CHECK(cudaMalloc((void **)&b->col_idx, sizeof(int32_t) * b->cap_nnz));
         }
         if (col_local16 && !b->col16) DG_CUDA_CHECK(cudaMalloc((void **)&b->col16, sizeof(uint16_t) * b->cap_nnz));
+        if (upper && (!b->row_ptr_u || b->cap_row_ptr_u < b->cap_nodes + 1)) {
+            if (b->row_ptr_u) cudaFree(b->row_ptr_u);
+            b->row_ptr_u = nullptr;
+            b->cap_row_ptr_u = 0;
+            DG_CUDA_CHECK(cudaMalloc((void **)&b->row_ptr_u, sizeof(int32_t) * (b->cap_nodes + 1)));
+            b->cap_row_ptr_u = b->cap_nodes + 1;
+        }
         b->owns_csr = true;
         DG_CUDA_CHECK(cudaMemcpyAsync(b->graph_ptr, graph_ptr, sizeof(int32_t) * ((size_t)n_graphs + 1),
                                       cudaMemcpyHostToDevice, ctx->stream));
-        DG_CUDA_CHECK(cudaMemcpyAsync(b->row_ptr, row_ptr, sizeof(int32_t) * ((size_t)n_nodes + 1),
+        DG_CUDA_CHECK(cudaMemcpyAsync(upper ? b->row_ptr_u : b->row_ptr, row_ptr, sizeof(int32_t) * ((size_t)n_nodes + 1),
                                       cudaMemcpyHostToDevice, ctx->stream));
+        if (upper) {
+            DG_REQUIRE(b->max_graph_nodes <= kSymMaxNodes, DG_ERR_UNSUPPORTED,
+                       "the upper-triangle host format takes graphs of at most %d vertices", kSymMaxNodes);
+            b->upper_pending = true;
+            b->dinv_deferred = compute_dinv;
+            compute_dinv = false;   // the degrees need the full rows: computed when (and if) they are expanded
+        }
         if (nnz && col_local16) {
             DG_REQUIRE(b->max_graph_nodes <= 65536, DG_ERR_INVALID, "16-bit column ids need graphs of at most 65536 vertices");
             DG_CUDA_CHECK(cudaMemcpyAsync(b->col16, col_local16, sizeof(uint16_t) * (size_t)nnz, cudaMemcpyHostToDevice,
@@ -776,6 +917,7 @@ void dg_batch_destroy(dg_batch *b) {
     if (b->tiles_dev) cudaFree(b->tiles_dev);
     if (b->tc_tiles_dev) cudaFree(b->tc_tiles_dev);
     if (b->gs_tiles_dev) cudaFree(b->gs_tiles_dev);
+    if (b->row_ptr_u) cudaFree(b->row_ptr_u);
     delete b;
 }
 
@@ -1202,7 +1344,8 @@ int dg_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *wts,
 static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
                            const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx,
                            const double *wts, int predict, int remove_zero_weight, uint8_t *member, double *total,
-                           bool wait, const uint16_t *col_local16 = nullptr, cudaEvent_t copied = nullptr) {
+                           bool wait, const uint16_t *col_local16 = nullptr, cudaEvent_t copied = nullptr,
+                           bool upper = false) {
     clear_error();
     DG_TRY(check_ctx(ctx));
     DG_REQUIRE(m && wts && member, DG_ERR_INVALID, "null argument");
@@ -1224,9 +1367,10 @@ static int solve_host_impl(dg_context *ctx, const dg_model *m, int32_t n_graphs,
         b->keep = nullptr;
     }
     // with zero-weight removal the degrees are computed once the keep mask is known (solve_device)
-    static const bool timing = getenv("DG_INGEST_TIMING") != nullptr;
+    const bool timing = ctx->env.ingest_timing;
     const auto t0 = std::chrono::steady_clock::now();
-    DG_TRY(batch_fill(b, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, DG_MEM_HOST, !remove_zero_weight, col_local16));
+    DG_TRY(batch_fill(b, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, DG_MEM_HOST, !remove_zero_weight, col_local16,
+                      upper));
     const size_t n = (size_t)n_nodes, G = (size_t)n_graphs;
     double *d_wts = nullptr, *d_total = nullptr;
     uint8_t *d_member = nullptr;
@@ -1286,9 +1430,9 @@ int host_batch_set_meta(dg_context *ctx, int32_t n_graphs, const int64_t *v0, co
 int solve_host_staged(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
                       const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
                       int predict, int remove_zero_weight, uint8_t *member, double *total, bool wait,
-                      const uint16_t *col_local16, cudaEvent_t copied) {
+                      const uint16_t *col_local16, cudaEvent_t copied, bool upper) {
     return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, col_idx, wts, predict, remove_zero_weight,
-                           member, total, wait, col_local16, copied);
+                           member, total, wait, col_local16, copied, upper);
 }
 }  // namespace dg
 }  // extern "C++"
@@ -1313,6 +1457,14 @@ int dg_solve_host_compact(dg_context *ctx, const dg_model *m, int32_t n_graphs, 
     DG_REQUIRE(col_local || nnz == 0, DG_ERR_INVALID, "null column array");
     return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz, graph_ptr, row_ptr, nullptr, wts, predict, remove_zero_weight,
                            member, total, wait != 0, col_local);
+}
+
+int dg_solve_host_upper(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz_upper,
+                        const int32_t *graph_ptr, const int32_t *row_ptr_upper, const uint16_t *col_local_upper,
+                        const double *wts, int predict, int remove_zero_weight, uint8_t *member, double *total, int wait) {
+    DG_REQUIRE(col_local_upper || nnz_upper == 0, DG_ERR_INVALID, "null column array");
+    return solve_host_impl(ctx, m, n_graphs, n_nodes, nnz_upper, graph_ptr, row_ptr_upper, nullptr, wts, predict,
+                           remove_zero_weight, member, total, wait != 0, col_local_upper, nullptr, true);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -87,7 +87,7 @@ struct Buffer {
 // mma.sync projection of the fused kernel, the rest are measurement aids.
 struct dg_env {
     bool disable_tc = false, disable_fused = false, disable_staged = false, fused_mma = false;
-    bool fused_timing = false, tc_debug = false;
+    bool fused_timing = false, tc_debug = false, ingest_upper = false, ingest_timing = false;
     int tile_rows = 0, tc_tiles = 0;
     std::string fused_tile_dump, tc_tile_dump;
 };
@@ -211,6 +211,13 @@ struct dg_batch {
     int32_t *graph_ptr = nullptr, *row_ptr = nullptr, *col_idx = nullptr;  // device
     uint16_t *col16 = nullptr;  // device copy of graph-local 16-bit column ids (compact host format), cap_nnz entries
     bool cols_pending = false;  // col16 holds the batch's columns and col_idx has not been expanded from it yet
+    // "upper" host format: col16 / row_ptr_u hold only the entries with column > row (the adjacency is symmetric, so half
+    // of it says everything).  The tensor-core kernel builds its dense adjacency bytes from them directly; every other
+    // path first expands them into the full row_ptr / col_idx on the device (batch_ensure_cols).
+    int32_t *row_ptr_u = nullptr;
+    size_t cap_row_ptr_u = 0;
+    bool upper_pending = false;
+    bool dinv_deferred = false;  // the degrees wait for that expansion
     std::vector<int32_t> h_graph_ptr;  // host copy (small) for launch planning
     float *dinv = nullptr;     // [n_nodes] fp32(deg^-1/2) on the kept sub-graph, 0 for isolated/removed
     uint8_t *keep = nullptr;   // [n_nodes] or nullptr = all kept
@@ -415,7 +422,7 @@ inline int pad_width(int c) { return c <= 32 ? 32 : 64; }
 int solve_host_staged(dg_context *ctx, const dg_model *m, int32_t n_graphs, int32_t n_nodes, int32_t nnz,
                       const int32_t *graph_ptr, const int32_t *row_ptr, const int32_t *col_idx, const double *wts,
                       int predict, int remove_zero_weight, uint8_t *member, double *total, bool wait,
-                      const uint16_t *col_local16, cudaEvent_t copied);
+                      const uint16_t *col_local16, cudaEvent_t copied, bool upper = false);
 void ingest_staging_free(dg_context *ctx);  // dg_ingest.cu
 void env_read(dg_env *env);                 // dg_api.cu
 // set the host metadata of the context's reusable batch from per-graph vertex / edge offsets (n_graphs + 1 each) before

@@ -1160,7 +1160,7 @@ bool fused_fits(dg_context *ctx, const dg_model *m, const dg_batch *b) {
     // the same feasibility test build_tiles starts with: the largest graph of the batch must fit a tile
     const size_t budget = (size_t)ctx->max_smem_optin - 1024;
     const int min_n = ((std::max(b->max_graph_nodes, 32) + 31) / 32) * 32;
-    const long long need_nnz = (long long)b->max_graph_nnz + 3LL * b->max_graph_nodes;
+    const long long need_nnz = (long long)b->max_graph_nnz * (b->upper_pending ? 2 : 1) + 3LL * b->max_graph_nodes;
     const int min_nnz = (int)((std::max<long long>(need_nnz, 64) + 63) / 64 * 64);
     if (min_n > 1024) return false;
     return fused_smem_bytes(m->fused_cp, min_n, min_nnz, has_hidden, wblob) <= budget;

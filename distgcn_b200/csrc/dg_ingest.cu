@@ -243,6 +243,9 @@ class Pool {
     bool stop_ = false;
 };
 
+bool pack_graph_upper(const int32_t *ip, const int32_t *ix, const double *d, int n, int64_t eu0, int64_t expect_u,
+                      int32_t *rp_u, uint16_t *out);
+
 struct PackPlan {
     std::vector<int64_t> v0, e0;  // vertex / edge offset of every graph, n_graphs + 1
     bool has_zeros = false;       // some stored value is zero: edge counts come from a counting pass
@@ -250,7 +253,7 @@ struct PackPlan {
 
 // sizes: vertex and edge offsets of every graph.  With `data`, stored zeros do not count.
 int plan_sizes(int32_t n_graphs, const int32_t *const *indptr, const double *const *data, const int32_t *n_rows,
-               int threads, PackPlan *plan) {
+               int threads, PackPlan *plan, bool upper = false) {
     plan->v0.assign((size_t)n_graphs + 1, 0);
     plan->e0.assign((size_t)n_graphs + 1, 0);
     std::vector<int64_t> nnz((size_t)n_graphs, 0);
@@ -282,6 +285,13 @@ int plan_sizes(int32_t n_graphs, const int32_t *const *indptr, const double *con
         plan->e0[(size_t)g + 1] = plan->e0[(size_t)g] + nnz[(size_t)g];
     }
     plan->has_zeros = zeros.load();
+    if (upper) {   // symmetric, zero diagonal: exactly half of every graph's non-zeros lie above the diagonal
+        for (int g = 0; g < n_graphs; ++g)
+            DG_REQUIRE((nnz[(size_t)g] & 1) == 0, DG_ERR_INVALID,
+                       "graph %d: %lld stored non-zeros - an adjacency matrix is symmetric with a zero diagonal", g,
+                       (long long)nnz[(size_t)g]);
+        for (int g = 0; g <= n_graphs; ++g) plan->e0[(size_t)g] /= 2;
+    }
     DG_REQUIRE(plan->v0.back() < (1LL << 31) && plan->e0.back() < (1LL << 31), DG_ERR_INVALID,
                "batch too large for int32 indexing: %lld vertices, %lld edges", (long long)plan->v0.back(),
                (long long)plan->e0.back());
@@ -291,7 +301,7 @@ int plan_sizes(int32_t n_graphs, const int32_t *const *indptr, const double *con
 // the parallel pack; exactly one of col_idx / col16 is written
 int pack_into(int32_t n_graphs, const int32_t *const *indptr, const int32_t *const *indices, const double *const *data,
               const int32_t *n_rows, const PackPlan &plan, int threads, int32_t *graph_ptr, int32_t *row_ptr,
-              int32_t *col_idx, uint16_t *col16, const std::function<void()> *side_task = nullptr) {
+              int32_t *col_idx, uint16_t *col16, const std::function<void()> *side_task = nullptr, bool upper = false) {
     for (int g = 0; g <= n_graphs; ++g) graph_ptr[g] = (int32_t)plan.v0[(size_t)g];
     row_ptr[0] = 0;
     std::atomic<int> bad{-1};
@@ -329,6 +339,12 @@ int pack_into(int32_t n_graphs, const int32_t *const *indptr, const int32_t *con
             const int64_t v0 = plan.v0[(size_t)g], e0 = plan.e0[(size_t)g];
             int32_t *rp = row_ptr + v0 + 1;
             bool ok = true;
+            if (upper) {   // plan.e0 already counts upper entries (half of the stored non-zeros)
+                if (!pack_graph_upper(ip, ix, (data && plan.has_zeros) ? data[g] : nullptr, n, e0,
+                                      plan.e0[(size_t)g + 1] - e0, rp, col16 + e0))
+                    bad.store(g);
+                continue;
+            }
             if (!d) {
                 ok = rowptr(ip, n, (int32_t)e0, rp) == 0;
                 const int64_t e = ip[n];
@@ -370,6 +386,84 @@ int default_threads(int32_t n_threads, int64_t work) {
     int t = n_threads > 0 ? n_threads : Pool::get().size();
     if (work < (1 << 16)) t = 1;  // a handful of graphs: the hand-off costs more than the copy
     return std::max(1, std::min(t, Pool::get().size()));
+}
+
+// ordinary memory -> pinned staging with non-temporal stores (head / tail up to the 32-byte boundaries with plain ones)
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_nt_bytes_avx2(const void *src_v, size_t bytes, void *dst_v) {
+    const char *src = (const char *)src_v;
+    char *dst = (char *)dst_v;
+    size_t k = 0;
+    const size_t head = std::min(bytes, (size_t)((32 - ((uintptr_t)dst & 31)) & 31));
+    if (head) memcpy(dst, src, head);
+    for (k = head; k + 32 <= bytes; k += 32)
+        _mm256_stream_si256((__m256i *)(dst + k), _mm256_loadu_si256((const __m256i *)(src + k)));
+    if (k < bytes) memcpy(dst + k, src + k, bytes - k);
+}
+#endif
+void copy_to_staging(const void *src, size_t bytes, void *dst) {
+#if defined(__x86_64__)
+    if (kHaveAvx2) return copy_nt_bytes_avx2(src, bytes, dst);
+#endif
+    memcpy(dst, src, bytes);
+}
+
+// Upper-triangle pack of one graph: entries with column > row, graph-local 16-bit ids; row_ptr_u[r + 1] = running count.
+// Returns false when the pattern is malformed or not half above the diagonal (asymmetric, or with diagonal entries).
+// The rows are filtered branch-free into a thread-local scratch (every stored entry is written, the cursor only advances
+// past the ones that stay) and the result goes to the pinned staging in one non-temporal copy.
+bool pack_graph_upper(const int32_t *ip, const int32_t *ix, const double *d, int n, int64_t eu0, int64_t expect_u,
+                      int32_t *rp_u /* this graph's rows: n entries following row_ptr_u[v0] */, uint16_t *out /* at eu0 */) {
+    static thread_local std::vector<uint16_t> cols;
+    static thread_local std::vector<int32_t> rows;
+    const int64_t stored = ip[n];
+    if (stored < 0) return false;
+    if (cols.size() < (size_t)stored + 1) cols.resize((size_t)stored + 1 + (size_t)stored / 4);
+    if (rows.size() < (size_t)n) rows.resize((size_t)n + (size_t)n / 4);
+    uint16_t *tmp = cols.data();
+    int32_t *rt = rows.data();
+    int64_t w = 0;
+    unsigned bad = 0;
+    // symmetry: every pair {i, j} must be stored once above and once below the diagonal - a signed sum of a hash of the
+    // pair over all stored entries (+ above, - below) is zero for a symmetric pattern
+    uint64_t balance = 0;
+    auto pair_hash = [](uint32_t a, uint32_t b) {
+        uint64_t h = ((uint64_t)std::min(a, b) << 32 | std::max(a, b)) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+        return h * 0xBF58476D1CE4E5B9ull;
+    };
+    for (int r = 0; r < n; ++r) {
+        const int b0 = ip[r], b1 = ip[r + 1];
+        if (b1 < b0 || b1 > stored) return false;
+        if (!d) {
+            for (int k = b0; k < b1; ++k) {
+                const uint32_t c = (uint32_t)ix[k];
+                bad |= (c >= (uint32_t)n) | (c == (uint32_t)r);
+                tmp[w] = (uint16_t)c;
+                const bool up = c > (uint32_t)r;
+                w += up;
+                const uint64_t h = pair_hash(c, (uint32_t)r);
+                balance += up ? h : (uint64_t)0 - h;
+            }
+        } else {
+            for (int k = b0; k < b1; ++k) {
+                const uint32_t c = (uint32_t)ix[k];
+                const bool nz = d[k] != 0.0;
+                bad |= (c >= (uint32_t)n) | ((c == (uint32_t)r) & nz);
+                tmp[w] = (uint16_t)c;
+                const bool up = c > (uint32_t)r;
+                w += up & nz;
+                const uint64_t h = nz ? pair_hash(c, (uint32_t)r) : 0;
+                balance += up ? h : (uint64_t)0 - h;
+            }
+        }
+        rt[r] = (int32_t)(eu0 + w);
+    }
+    bad |= balance != 0;
+    if (bad || w != expect_u) return false;
+    copy_to_staging(tmp, sizeof(uint16_t) * (size_t)w, out);
+    copy_to_staging(rt, sizeof(int32_t) * (size_t)n, rp_u);
+    return true;
 }
 
 struct Staging {  // pinned, grow-only, one per context
@@ -448,6 +542,22 @@ int dg_pack_graphs_host(int32_t n_graphs, const int32_t *const *indptr, const in
     return pack_into(n_graphs, indptr, indices, data, n_rows, plan, threads, graph_ptr, row_ptr, col_idx, col_local16);
 }
 
+int dg_pack_graphs_upper_host(int32_t n_graphs, const int32_t *const *indptr, const int32_t *const *indices,
+                              const double *const *data, const int32_t *n_rows, int32_t *graph_ptr, int32_t *row_ptr_upper,
+                              uint16_t *col_local_upper, int32_t n_threads) {
+    clear_error();
+    DG_REQUIRE(n_graphs >= 0 && graph_ptr && row_ptr_upper && col_local_upper, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(n_graphs == 0 || (indptr && indices && n_rows), DG_ERR_INVALID, "null argument");
+    for (int g = 0; g < n_graphs; ++g)
+        DG_REQUIRE(n_rows[g] <= 65536, DG_ERR_INVALID, "graph %d has %d vertices: 16-bit column ids need <= 65536", g, n_rows[g]);
+    PackPlan plan;
+    DG_TRY(plan_sizes(n_graphs, indptr, data, n_rows, default_threads(n_threads, 1 << 20), &plan, true));
+    const int threads = default_threads(n_threads, 2 * plan.e0.back() + plan.v0.back());
+    DG_TRY(pack_into(n_graphs, indptr, indices, data, n_rows, plan, threads, graph_ptr, row_ptr_upper, nullptr, col_local_upper,
+                     nullptr, true));
+    return DG_OK;
+}
+
 int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, const int32_t *const *indptr,
                          const int32_t *const *indices, const double *const *data, const int32_t *n_rows,
                          const double *const *wts_per_graph, const double *wts_packed, int predict,
@@ -469,7 +579,7 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
     if (!ctx->ingest_staging) {
         Staging *s = new (std::nothrow) Staging();
         DG_REQUIRE(s != nullptr, DG_ERR_INVALID, "out of host memory");
-        if (cudaEventCreateWithFlags(&s->copied, getenv("DG_INGEST_TIMING") ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
+        if (cudaEventCreateWithFlags(&s->copied, ctx->env.ingest_timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
             delete s;
             set_error("cudaEventCreate failed");
             return DG_ERR_CUDA;
@@ -477,14 +587,18 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
         ctx->ingest_staging = s;
     }
     Staging *s = static_cast<Staging *>(ctx->ingest_staging);
-    static const bool timing = getenv("DG_INGEST_TIMING") != nullptr;
+    const bool timing = ctx->env.ingest_timing;
     const auto t_begin = std::chrono::steady_clock::now();
-    PackPlan plan;
-    DG_TRY(plan_sizes(n_graphs, indptr, data, n_rows, default_threads(0, 1 << 20), &plan));
-    const int64_t n = plan.v0.back(), e = plan.e0.back();
     int32_t max_rows = 0;
     for (int g = 0; g < n_graphs; ++g) max_rows = std::max(max_rows, n_rows[g]);
     const bool narrow = max_rows <= 65536;
+    // DG_INGEST_UPPER=1: small graphs travel as their upper triangle - half the column ids over PCIe, but the filtering
+    // pack costs ~8x the straight narrowing one (2.9 vs 0.36 ns per stored entry and thread), so it only pays where the
+    // link, not the host, is the limit.  Pre-packed callers use dg_pack_graphs_upper_host once + dg_solve_host_upper.
+    const bool upper = narrow && max_rows <= 8192 && ctx->env.ingest_upper;
+    PackPlan plan;
+    DG_TRY(plan_sizes(n_graphs, indptr, data, n_rows, default_threads(0, 1 << 20), &plan, upper));
+    const int64_t n = plan.v0.back(), e = plan.e0.back();
     // the previous call's copies must have read the staging before it is overwritten (its kernels may still run)
     const auto t_plan = std::chrono::steady_clock::now();
     if (s->in_flight) {
@@ -494,7 +608,7 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
     const auto t_wait = std::chrono::steady_clock::now();
     DG_TRY(grow_pinned(&s->gp, &s->cap_g, (size_t)n_graphs + 1));
     DG_TRY(grow_pinned(&s->rp, &s->cap_n, (size_t)n + 1));
-    if (narrow) DG_TRY(grow_pinned(&s->c16, &s->cap_e16, (size_t)e + 1));
+    if (narrow) DG_TRY(grow_pinned(&s->c16, &s->cap_e16, (size_t)e + (size_t)max_rows + 16));  // (+ the filter's slack)
     else DG_TRY(grow_pinned(&s->c32, &s->cap_e32, (size_t)e + 1));
     const int threads = default_threads(0, e + n);
     // the tensor-core kernel's tile plan needs only the graphs' sizes: one pool thread makes it while the others pack
@@ -502,7 +616,7 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
     DG_TRY(host_batch_set_meta(ctx, n_graphs, plan.v0.data(), plan.e0.data(), &hb));
     const std::function<void()> plan_tiles = [&] { tc_plan_ahead(ctx, m, hb); };
     DG_TRY(pack_into(n_graphs, indptr, indices, data, n_rows, plan, threads, s->gp, s->rp, narrow ? nullptr : s->c32,
-                     narrow ? s->c16 : nullptr, &plan_tiles));
+                     narrow ? s->c16 : nullptr, &plan_tiles, upper));
     const double *w = wts_packed;
     if (wts_per_graph) {
         DG_TRY(grow_pinned(&s->w, &s->cap_w, (size_t)n + 1));
@@ -524,7 +638,7 @@ int dg_solve_graphs_host(dg_context *ctx, const dg_model *m, int32_t n_graphs, c
     }
     const int st = solve_host_staged(ctx, m, n_graphs, (int32_t)n, (int32_t)e, s->gp, s->rp, narrow ? nullptr : s->c32, w,
                                      predict, remove_zero_weight, member, total, wait != 0, narrow ? s->c16 : nullptr,
-                                     s->copied);
+                                     s->copied, upper);
     s->in_flight = st == DG_OK && wait == 0;
     if (timing) {
         const auto t_end = std::chrono::steady_clock::now();

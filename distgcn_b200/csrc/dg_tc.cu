@@ -108,6 +108,7 @@ struct TcParams {
     int *tile_counter;
     const int *graph_ptr, *row_ptr, *col_idx;
     const uint16_t *col16;  // graph-local column ids (compact host format) or nullptr: then col_idx, batch-global
+    int upper;              // the lists hold only the entries with column > row: every edge sets both adjacency bytes
     const double *wts;
     const uint8_t *keep_in;
     const float *x0;
@@ -623,7 +624,10 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         if (j >= 0) {
                             const uint32_t ki = (keepw[m.fb * 4 + (lo >> 5)] >> (lo & 31)) & 1u;
                             const uint32_t kj = (keepw[m.fb * 4 + (j >> 5)] >> (j & 31)) & 1u;
-                            if (ki & kj) adj[(size_t)(j >> 4) * m.R * 16 + lo * 16 + (j & 15)] = 1;
+                            if (ki & kj) {
+                                adj[(size_t)(j >> 4) * m.R * 16 + lo * 16 + (j & 15)] = 1;
+                                if (P.upper) adj[(size_t)(lo >> 4) * m.R * 16 + j * 16 + (lo & 15)] = 1;
+                            }
                         }
                     }
                 }
@@ -1528,9 +1532,10 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     p.n_tiles = b->tc_n_tiles;
     p.tile_counter = ctx->d_status + 1;
     p.graph_ptr = b->graph_ptr;
-    p.row_ptr = b->row_ptr;
+    p.row_ptr = b->upper_pending ? b->row_ptr_u : b->row_ptr;
     p.col_idx = b->col_idx;
     p.col16 = b->cols_pending ? b->col16 : nullptr;
+    p.upper = b->upper_pending ? 1 : 0;
     p.wts = d_wts;
     p.keep_in = remove_zero_weight ? nullptr : b->keep;
     p.x0 = b->x0;
@@ -1583,7 +1588,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     }
     {
         // work-equivalent algorithmic bytes, the same figure dg_fused.cu reports (SURVEY.md 8d / DESIGN.md)
-        const double n = (double)b->n_nodes, nnz = (double)b->nnz, cp = 32.0;
+        const double n = (double)b->n_nodes, nnz = (double)b->nnz * (b->upper_pending ? 2.0 : 1.0), cp = 32.0;
         const double csr = 4.0 * (n + 1) + 4.0 * nnz;
         const double hidden = (double)p.n_hidden * (csr + 4.0 * n + 8.0 * n * cp + 8.0 * cp * cp);
         const double scalar_passes = 2.0 * (csr + 12.0 * n);

@@ -430,12 +430,29 @@ def solve_device(ctx: Context, model: Model, batch: DeviceBatch, wts, member, pr
 
 def solve_host(ctx: Context, model: Model, packed: PackedBatch, wts, predict="mwis", remove_zero_weight: bool = True,
                member: Optional[np.ndarray] = None, total: Optional[np.ndarray] = None, wait: bool = True,
-               col_local16: Optional[np.ndarray] = None):
+               col_local16: Optional[np.ndarray] = None, upper=None):
     """One-shot host CSR in / host membership out (dg_solve_host): H2D, kernels and D2H in one call.
     ``wait=False`` only enqueues (dg_solve_host_async): the arrays must stay alive (and should be pinned,
     see ``pinned_empty``) until ``ctx.synchronize()``.  ``col_local16`` (``PackedBatch.local_columns()``, uint16):
-    the compact host format - it crosses PCIe instead of ``packed.col_idx`` (dg_solve_host_compact)."""
+    the compact host format - it crosses PCIe instead of ``packed.col_idx`` (dg_solve_host_compact).  ``upper``
+    (``PackedBatch.upper_compact()``: (row_ptr_upper, col_local_upper)): the upper-triangle format - half of that again
+    (dg_solve_host_upper)."""
     gp, rp, ci = packed.graph_ptr, packed.row_ptr, packed.col_idx
+    if upper is not None:
+        rp_u, c_u = upper
+        if rp_u.dtype != np.int32 or c_u.dtype != np.uint16 or not (rp_u.flags.c_contiguous and c_u.flags.c_contiguous) \
+                or rp_u.shape[0] != packed.n_nodes + 1 or gp.dtype != np.int32:
+            raise TypeError("upper = (row_ptr_upper int32 [n_nodes + 1], col_local_upper uint16), both contiguous")
+        w = wts if (isinstance(wts, np.ndarray) and wts.dtype == np.float64 and wts.flags.c_contiguous) else _np(wts, np.float64)
+        n, g = packed.n_nodes, packed.n_graphs
+        if member is None:
+            member = np.empty(n, dtype=np.uint8)
+        if total is None:
+            total = np.empty(g, dtype=np.float64)
+        check(ctx._lib.dg_solve_host_upper(ctx.handle, model.handle, g, n, int(c_u.shape[0]), _ptr(gp), _ptr(rp_u), _ptr(c_u), _ptr(w),
+                                           predict_code(predict), 1 if remove_zero_weight else 0, _ptr(member), _ptr(total),
+                                           1 if wait else 0))
+        return member, total
     for a in (gp, rp) + (() if col_local16 is not None else (ci,)):
         if a.dtype != np.int32 or not a.flags.c_contiguous:
             raise TypeError("PackedBatch arrays must be contiguous int32")
@@ -519,15 +536,15 @@ class HostPipeline:
         return sum(c.launch_count for c in self.ctxs)
 
     def submit(self, packed: PackedBatch, wts, member: np.ndarray, total: Optional[np.ndarray] = None,
-               predict="mwis", remove_zero_weight: bool = True, col_local16: Optional[np.ndarray] = None) -> int:
+               predict="mwis", remove_zero_weight: bool = True, col_local16: Optional[np.ndarray] = None, upper=None) -> int:
         slot = self._next
         self._next = (slot + 1) % len(self.ctxs)
         self.wait(slot)
         if not (isinstance(wts, np.ndarray) and wts.dtype == np.float64 and wts.flags.c_contiguous):
             wts = _np(wts, np.float64)   # the converted copy is what the copy engine reads: it must outlive the call
         solve_host(self.ctxs[slot], self.models[slot], packed, wts, predict, remove_zero_weight, member, total,
-                   wait=False, col_local16=col_local16)
-        self._busy[slot] = (packed, wts, member, total, col_local16)  # keep the arrays alive
+                   wait=False, col_local16=col_local16, upper=upper)
+        self._busy[slot] = (packed, wts, member, total, col_local16, upper)  # keep the arrays alive
         return slot
 
     def submit_graphs(self, graphs, wts, member: np.ndarray, total: Optional[np.ndarray] = None, predict="mwis",

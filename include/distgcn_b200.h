@@ -256,6 +256,13 @@ DG_API int dg_pack_graphs_sizes(int32_t n_graphs, const int32_t *const *indptr, 
 DG_API int dg_pack_graphs_host(int32_t n_graphs, const int32_t *const *indptr, const int32_t *const *indices,
                         const double *const *data, const int32_t *n_rows, int32_t *graph_ptr, int32_t *row_ptr,
                         int32_t *col_idx, uint16_t *col_local16, int32_t n_threads);
+/* The same in the UPPER format: only the entries with column > row (an adjacency matrix is symmetric with a zero
+ * diagonal - self-loops make the reference's greedy search loop for ever - so half of it says everything): graph_ptr
+ * [n_graphs + 1], row_ptr_upper [n_nodes + 1], col_local_upper (uint16, graph-local, sum(nnz) / 2 entries).  A graph
+ * whose stored non-zeros are not exactly half above the diagonal is DG_ERR_INVALID. */
+DG_API int dg_pack_graphs_upper_host(int32_t n_graphs, const int32_t *const *indptr, const int32_t *const *indices,
+                              const double *const *data, const int32_t *n_rows, int32_t *graph_ptr, int32_t *row_ptr_upper,
+                              uint16_t *col_local_upper, int32_t n_threads);
 /* DQNAgent.solve_mwis for a list of graphs in one call (mwis_dqn_call.py:198-261 per graph): pack into the context's
  * pinned staging, copy, solve (dg_solve semantics: zero-weight removal, GCN, utility, local greedy search), copy the
  * results back.  Weights either per graph (wts_per_graph[g]: n_rows[g] doubles) or packed (wts_packed: one double per
@@ -297,6 +304,14 @@ DG_API int dg_wireless_seq_serve(dg_wireless *s, int32_t t, int32_t channel);
 DG_API int dg_wireless_end_slot(dg_wireless *s, int32_t t);
 /* synchronise and copy the queue history [n_slots][n_links] (row t = queues after slot t; row 0 zeros) to the host */
 DG_API int dg_wireless_read_history(dg_wireless *s, double *history);
+
+/* dg_solve_host_compact with the UPPER format (column > row only; see dg_pack_graphs_upper_host): a third of the
+ * host->device bytes of the packed int32 form.  The tensor-core kernel builds its dense adjacency from the half lists
+ * directly; other paths expand them to the full CSR on the device first (deterministically: rows in ascending column
+ * order).  Graphs of at most 8192 vertices. */
+DG_API int dg_solve_host_upper(dg_context *ctx, const dg_model *model, int32_t n_graphs, int32_t n_nodes, int32_t nnz_upper,
+                        const int32_t *graph_ptr, const int32_t *row_ptr_upper, const uint16_t *col_local_upper,
+                        const double *wts, int predict, int remove_zero_weight, uint8_t *member, double *total, int wait);
 
 /* ---- one giant graph, row-partitioned over several GPUs (no reference counterpart: the
  * reference handles one 100-300 vertex graph per call) ------------------------------------------------

@@ -310,3 +310,77 @@ def test_native_ingest_list_of_scipy_matrices():
         v0, v1 = int(pb.graph_ptr[g]), int(pb.graph_ptr[g + 1])
         mw, tw, _ = agent.solve_mwis(adjs[g], w_list[g])
         assert mw == set(np.flatnonzero(member[v0:v1]).tolist())
+
+
+@pytest.mark.parametrize("short,nl", [("is4sat_l20_c32", 20), ("is4sat_l1", 1), ("is4sat_l2_c64", 2)])
+def test_upper_host_format_matches_the_packed_one(short, nl, monkeypatch):
+    """dg_solve_host_upper (column > row only) gives the memberships of dg_solve_host: through the tensor-core kernel
+    (which builds its dense adjacency from the half lists) and through the device-side expansion to the full CSR (other
+    models; DG_DISABLE_TC), with zero weights, empty graphs, a graph beyond the tensor-core kernel's limits, pipelined."""
+    from distgcn_b200 import engine as E
+    from distgcn_b200.batch import pack_graphs
+    rng = np.random.default_rng(17)
+    pb0, w0 = util.small_graphs()
+    extra = []
+    up = np.triu(rng.random((420, 420)) < 0.03, k=1)
+    extra.append(sp.csr_matrix((up | up.T).astype(np.float64)))
+    adjs = [pb0.graph_adj(g) for g in range(0, 50, 2)] + [sp.csr_matrix((0, 0)), sp.csr_matrix((4, 4))] + extra
+    pb = pack_graphs(adjs)
+    w = rng.random(pb.n_nodes)
+    w[rng.random(pb.n_nodes) < 0.15] = 0.0
+    upper = pb.upper_compact()
+    layers = util.load_layers(short)
+    ctx = E.Context(0)
+    model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
+    ref_m, ref_t = E.solve_host(ctx, model, pb, w)
+    kernel_full = ctx.last_kernel
+    m1, t1 = E.solve_host(ctx, model, pb, w, upper=upper)
+    assert np.array_equal(m1, ref_m) and np.allclose(t1, ref_t, rtol=1e-12)
+    assert ctx.last_kernel == kernel_full
+    monkeypatch.setenv("DG_DISABLE_TC", "1")       # every graph through the expansion + the CUDA-core kernel
+    m2, _ = E.solve_host(ctx, model, pb, w, upper=upper)
+    m2f, _ = E.solve_host(ctx, model, pb, w)
+    assert np.array_equal(m2, m2f)
+    monkeypatch.setenv("DG_DISABLE_FUSED", "1")    # ... and through the per-layer kernels
+    m3, _ = E.solve_host(ctx, model, pb, w, upper=upper)
+    m3f, _ = E.solve_host(ctx, model, pb, w)
+    assert np.array_equal(m3, m3f)
+    monkeypatch.delenv("DG_DISABLE_FUSED")
+    monkeypatch.delenv("DG_DISABLE_TC")
+    pipe = E.HostPipeline(0, layers, E.gcn_dqn_acts(len(layers)), depth=2)
+    outs = [(E.pinned_empty(pb.n_nodes, np.uint8), E.pinned_empty(pb.n_graphs, np.float64)) for _ in range(4)]
+    for k in range(4):
+        pipe.submit(pb, w, outs[k][0], outs[k][1], upper=upper)
+    pipe.wait()
+    for k in range(4):
+        assert np.array_equal(np.asarray(outs[k][0]), ref_m)
+    pipe.close()
+    model.close()
+    ctx.close()
+
+
+def test_native_ingest_upper_option(monkeypatch):
+    """DG_INGEST_UPPER=1: dg_solve_graphs_host packs only the entries above the diagonal (filtered from the scipy arrays,
+    stored zeros dropped) and gives the same memberships; an asymmetric matrix is refused instead of being mis-read."""
+    from distgcn_b200 import _lib
+    from distgcn_b200.mwis_dqn_call import DQNAgent
+    pb, w = util.small_graphs()
+    adjs = [sp.csc_matrix(pb.graph_adj(g)) for g in range(pb.n_graphs)]
+    x = adjs[7].tocsr().copy()
+    rows = np.repeat(np.arange(x.shape[0]), np.diff(x.indptr))
+    x.data = np.where((rows + x.indices) % 5 == 0, 0.0, x.data)
+    adjs[7] = x
+    wz = w.copy()
+    wz[::7] = 0.0
+    for short in ("is4sat_l20_c32", "is4sat_l1"):
+        agent = DQNAgent(1, 5000, flags=_flags(num_layer=20 if "l20" in short else 1))
+        agent.load(util.ckpt_dir(short))
+        ref = [agent.solve_mwis_batch(adjs, ww) for ww in (w, wz)]
+        monkeypatch.setenv("DG_INGEST_UPPER", "1")
+        for (m0, t0), ww in zip(ref, (w, wz)):
+            m1, t1 = agent.solve_mwis_batch(adjs, ww)
+            assert np.array_equal(m0, m1) and np.array_equal(t0, t1)
+        skew = sp.csr_matrix(np.array([[0, 1, 1], [1, 0, 0], [0, 1, 0]], dtype=float))
+        with pytest.raises(_lib.DistGCNError):
+            agent.solve_mwis_batch([skew], np.ones(3))
+        monkeypatch.delenv("DG_INGEST_UPPER")

@@ -330,3 +330,55 @@ def test_native_packer_input_forms_and_errors():
     with pytest.raises(_lib.DistGCNError):   # exactly one column output
         _lib.check(lib.dg_pack_graphs_host(t.n_graphs, t.indptr, t.indices, t.data, t.n_rows_raw, gp.ctypes.data,
                                            rp.ctypes.data, None, None, 0))
+
+
+def test_upper_format_packer_and_python_form_agree():
+    """dg_pack_graphs_upper_host (native, from the per-graph matrices) == PackedBatch.upper_compact() (numpy, from the packed
+    batch); stored zeros dropped; asymmetric or diagonal-carrying input refused."""
+    import ctypes as C
+    from distgcn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(31)
+    adjs = _random_adjs(rng, 80, 1, 200) + [sp.csr_matrix((0, 0)), sp.csr_matrix((3, 3))]
+    pb = B.pack_graphs(adjs)
+    rp_ref, c_ref = pb.upper_compact()
+    assert c_ref.shape[0] * 2 == pb.nnz
+    t = B.GraphTables(adjs, True)
+    gp = np.empty(t.n_graphs + 1, np.int32)
+    rp = np.empty(pb.n_nodes + 1, np.int32)
+    cu = np.empty(pb.nnz // 2, np.uint16)
+    for threads in (1, 0):
+        _lib.check(lib.dg_pack_graphs_upper_host(t.n_graphs, t.indptr, t.indices, t.data, t.n_rows_raw, gp.ctypes.data,
+                                                 rp.ctypes.data, cu.ctypes.data, threads))
+        assert np.array_equal(gp, pb.graph_ptr) and np.array_equal(rp, rp_ref) and np.array_equal(cu, c_ref)
+    # stored zeros (a symmetric set of pairs) are not edges
+    x = adjs[5].tocsr().copy()
+    rows = np.repeat(np.arange(x.shape[0]), np.diff(x.indptr))
+    x.data = np.where((rows + x.indices) % 3 == 0, 0.0, x.data)
+    y = x.copy()
+    y.eliminate_zeros()
+    tx = B.GraphTables([x], True)
+    rp1, cu1 = np.empty(x.shape[0] + 1, np.int32), np.empty(y.nnz // 2, np.uint16)
+    gp1 = np.empty(2, np.int32)
+    _lib.check(lib.dg_pack_graphs_upper_host(1, tx.indptr, tx.indices, tx.data, tx.n_rows_raw, gp1.ctypes.data, rp1.ctypes.data,
+                                             cu1.ctypes.data, 1))
+    rp_y, c_y = B.pack_graphs([y]).upper_compact()
+    assert np.array_equal(rp1, rp_y) and np.array_equal(cu1, c_y)
+    # not symmetric / diagonal entries: refused
+    bad = sp.csr_matrix(np.array([[0, 1, 1], [0, 0, 0], [0, 0, 0]], dtype=float))    # two entries, both above the diagonal
+    tb = B.GraphTables([bad], False)
+    with pytest.raises(_lib.DistGCNError):
+        _lib.check(lib.dg_pack_graphs_upper_host(1, tb.indptr, tb.indices, None, tb.n_rows_raw, gp1.ctypes.data,
+                                                 np.empty(4, np.int32).ctypes.data, np.empty(4, np.uint16).ctypes.data, 1))
+    skew = sp.csr_matrix(np.array([[0, 1, 1], [1, 0, 0], [0, 1, 0]], dtype=float))   # half above, half below, not symmetric
+    ts = B.GraphTables([skew], False)
+    with pytest.raises(_lib.DistGCNError):
+        _lib.check(lib.dg_pack_graphs_upper_host(1, ts.indptr, ts.indices, None, ts.n_rows_raw, gp1.ctypes.data,
+                                                 np.empty(4, np.int32).ctypes.data, np.empty(4, np.uint16).ctypes.data, 1))
+    diag = sp.csr_matrix(np.array([[1, 1], [1, 0]], dtype=float))                     # odd count
+    td = B.GraphTables([diag], False)
+    with pytest.raises(_lib.DistGCNError):
+        _lib.check(lib.dg_pack_graphs_upper_host(1, td.indptr, td.indices, None, td.n_rows_raw, gp1.ctypes.data,
+                                                 np.empty(3, np.int32).ctypes.data, np.empty(4, np.uint16).ctypes.data, 1))
+    with pytest.raises(ValueError):
+        B.pack_graphs([bad]).upper_compact()

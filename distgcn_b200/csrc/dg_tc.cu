@@ -133,6 +133,8 @@ struct TcParams {
     int round_cap;
     int do_lgs;
     long long *dbg;
+    long long *trace;   // DG_TC_TRACE builds: per-warp event clocks of one tile [16 warps][24 layers][8 events]
+    int trace_tile;
     int *watchdog;      // pinned host memory the wait site of a protocol error is left in
     int watchdog_wide;
 };
@@ -312,7 +314,8 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
 }
 
 // Every activation of the path is v >= 0 ? v : slope * v with slope = alpha (leaky ReLU), 0 (ReLU) or 1 (none); as
-// max(v, slope v) for slope <= 1 and min(v, slope v) otherwise it is branch-free and bit-identical to the select form.
+// max(v, slope v) it is branch-free and bit-identical to the select form for slope <= 1 (models with alpha > 1 are not
+// taken by this kernel: tc_model_eligible).
 // one lane of a converged warp (the lane that issues tcgen05.mma / commit for it)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -326,10 +329,7 @@ __device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xf
 __device__ __forceinline__ float tc_slope(int act, float alpha) {
     return act == DG_ACT_LEAKY_RELU ? alpha : act == DG_ACT_RELU ? 0.f : 1.f;
 }
-__device__ __forceinline__ float tc_act(float v, float slope, bool use_max) {
-    const float t = v * slope;
-    return use_max ? fmaxf(v, t) : fminf(v, t);
-}
+__device__ __forceinline__ float tc_act(float v, float slope) { return fmaxf(v, v * slope); }
 
 // fixed-point scale for values bounded by `bound` (>= 0): q = 2^k with |v| * q < 2^30, and its inverse
 __device__ __forceinline__ void tc_scale(float bound, float *q, float *inv_q) {
@@ -411,6 +411,15 @@ __device__ __forceinline__ uint32_t tc_bits4(uint32_t w) { return (w * 0x0102040
 // the current keep mask (degrees count kept columns only, removed vertices have dinv = 0 and so contribute zero digits).
 // All graphs of a tile iterate together (they share the weight ring); a finished graph idles through the layers with an
 // empty mask.
+#ifdef DG_TC_TRACE
+#define TC_TRACE(h, e)                                                                                       \
+    do {                                                                                                     \
+        if (P.trace && t == P.trace_tile && lane == 0 && (h) < 24)                                           \
+            P.trace[((size_t)warp * 24 + (h)) * 8 + (e)] = clock64();                                        \
+    } while (0)
+#else
+#define TC_TRACE(h, e) do { } while (0)
+#endif
 template <bool DIT>
 __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -505,7 +514,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 fb += m.nb;
                 mbar_inval(&bar_mx[gi]);
                 mbar_inval(&bar_ra[gi]);
-                mbar_init(&bar_mx[gi], 128 * m.nb);
+                mbar_init(&bar_mx[gi], 4 * m.nb);
                 mbar_init(&bar_ra[gi], 4 * m.nb);
             }
             for (int b = 0; b < fb; ++b) {
@@ -679,7 +688,12 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             const int jb = b - G.fb;
             const int lastb = G.fb + G.nb - 1;
             const int dom_bar = 1 + G.fb, dom_cnt = 128 * G.nb;
-            const uint32_t taddr = tmem + (uint32_t)b * 128u + ((uint32_t)((warp & 3) * 32) << 16);
+            // (the same for every lane of the warp: handed over as warp-uniform so that it lives in a uniform register
+            // instead of being recomputed from the thread id in front of every tensor-memory access)
+            const uint32_t taddr = uniform(tmem + (uint32_t)b * 128u + ((uint32_t)((warp & 3) * 32) << 16));
+            // a warp none of whose lanes is a vertex (the tail of a graph's last block) keeps every hand-off and barrier of
+            // the protocol but skips the arithmetic and the tensor-memory traffic of the epilogues
+            const bool live = __any_sync(0xffffffffu, valid);
             unsigned char *adj = pool + G.adj;
             unsigned char *yrow = pool + G.yoff + (r >> 3) * 128 + (r & 7) * 16;  // ... and in the Y digit runs
 
@@ -823,9 +837,11 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             auto publish_max = [&](int slot) {
                 const uint32_t mine = (valid && keep) ? __float_as_uint(hmax) : 0u;
                 const uint32_t wmax = __reduce_max_sync(0xffffffffu, mine);
-                if (lane == 0) atomicMax(&gmax[gi * 2 + slot], wmax);
+                if (lane == 0) {
+                    atomicMax(&gmax[gi * 2 + slot], wmax);
+                    mbar_arrive(&bar_mx[gi]);   // one arrival per warp (release: the maximum above is visible to the waiters)
+                }
                 hmax = 0.f;
-                mbar_arrive(&bar_mx[gi]);
             };
             // the graph's max |H|, once every vertex of the graph has published
             auto graph_max = [&](int slot) -> float {
@@ -845,7 +861,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             mbar_wait(&bar_da[b], ea & 1u, 6);
             ++ea;
             tc_fence_after();
-            {
+            if (live) {
                 uint32_t d4[4];
                 tmem_ld4(taddr, d4);
                 const float s_i = xi - di * (tc_combine(d4) * iq0);
@@ -858,10 +874,10 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         const float4 a0 = __ldg(reinterpret_cast<const float4 *>(P.first) + 2 * q + half);
                         const float4 a1 = __ldg(reinterpret_cast<const float4 *>(P.first + 32) + 2 * q + half);
                         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(P.first + 64) + 2 * q + half);
-                        hv[4 * half + 0] = tc_act(fmaf(s_i, a1.x, fmaf(xi, a0.x, b0.x)), sl0, sl0 <= 1.f);
-                        hv[4 * half + 1] = tc_act(fmaf(s_i, a1.y, fmaf(xi, a0.y, b0.y)), sl0, sl0 <= 1.f);
-                        hv[4 * half + 2] = tc_act(fmaf(s_i, a1.z, fmaf(xi, a0.z, b0.z)), sl0, sl0 <= 1.f);
-                        hv[4 * half + 3] = tc_act(fmaf(s_i, a1.w, fmaf(xi, a0.w, b0.w)), sl0, sl0 <= 1.f);
+                        hv[4 * half + 0] = tc_act(fmaf(s_i, a1.x, fmaf(xi, a0.x, b0.x)), sl0);
+                        hv[4 * half + 1] = tc_act(fmaf(s_i, a1.y, fmaf(xi, a0.y, b0.y)), sl0);
+                        hv[4 * half + 2] = tc_act(fmaf(s_i, a1.z, fmaf(xi, a0.z, b0.z)), sl0);
+                        hv[4 * half + 3] = tc_act(fmaf(s_i, a1.w, fmaf(xi, a0.w, b0.w)), sl0);
                     }
                     emit(q, hv, n_hidden > 0);
                 }
@@ -876,9 +892,11 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             for (int h = 0; h < n_hidden; ++h) {
                 // this block's H terms are in place (tensor memory): its projection may start
                 tmem_st_wait();
+                TC_TRACE(h, 0);
                 tc_fence_before();
                 if (last_warp(&cnt_p[b], 4u)) issue_proj(h);
                 publish_max(h & 1);
+                TC_TRACE(h, 1);
                 const uint32_t seq = wseq + h;
                 const unsigned char *wb = wring + (seq & 1u) * kTcWBlob;
                 const float *bias = reinterpret_cast<const float *>(wb + 12288);
@@ -887,6 +905,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 mbar_wait(&bar_dp[b], ep & 1u, 7);
                 ++ep;
                 tc_fence_after();
+                TC_TRACE(h, 2);
                 if (timing) {
                     const long long now = clock64();
                     tm[3] += now - tq;
@@ -895,6 +914,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 mbar_wait(&bar_full[seq & 1u], (seq >> 1) & 1u, 8);  // (already complete: the projection has read it)
                 float qs, iqs;
                 tc_scale(graph_max(h & 1) * bias[64], &qs, &iqs);
+                TC_TRACE(h, 3);
                 const float dq = di * qs, ndq = -di * iqs;
                 float c[32];
                 uint32_t pa[16], pb[16];
@@ -921,6 +941,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         if (valid) *reinterpret_cast<uint4 *>(yrow + (size_t)(f >> 2) * G.Kp * 16) = dg4;
                     }
                 };
+                if (live) {
                 tmem_ld16_issue(taddr + 32, pa);
                 tmem_ld16_wait(pa);
                 tmem_ld16_issue(taddr + 48, pb);
@@ -941,11 +962,13 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                     const uint64_t t2 = add2(pk(c[16 + f], c[17 + f]), (uint64_t)pb[f] | ((uint64_t)pb[f + 1] << 32));
                     c[16 + f] = pk_lo(t2), c[17 + f] = pk_hi(t2);
                 }
+                }
                 fence_async_smem();
                 tc_fence_before();
+                TC_TRACE(h, 4);
                 hand_off_agg(false);
+                TC_TRACE(h, 5);
                 const float slope = tc_slope(__ldg(P.acts + h + 1), P.alpha);
-                const bool act_max = slope <= 1.f;
                 const bool more = h + 1 < n_hidden;
                 if (timing) {
                     const long long now = clock64();
@@ -955,6 +978,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 mbar_wait(&bar_da[b], ea & 1u, 9);
                 ++ea;
                 tc_fence_after();
+                TC_TRACE(h, 6);
                 if (timing) {
                     const long long now = clock64();
                     tm[5] += now - tq;
@@ -973,8 +997,8 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         const uint64_t comb = fma2(pk((float)hi0, (float)hi1), pk(65536.f, 65536.f), pk((float)lo0, (float)lo1));
                         const uint64_t v2 = fma2(comb, mul2(ndq2, rv2[k >> 1]), pk(c[f0 + k], c[f0 + k + 1]));
                         const uint64_t t2 = mul2(v2, slope2);
-                        hv[k] = act_max ? fmaxf(pk_lo(v2), pk_lo(t2)) : fminf(pk_lo(v2), pk_lo(t2));
-                        hv[k + 1] = act_max ? fmaxf(pk_hi(v2), pk_hi(t2)) : fminf(pk_hi(v2), pk_hi(t2));
+                        hv[k] = fmaxf(pk_lo(v2), pk_lo(t2));
+                        hv[k + 1] = fmaxf(pk_hi(v2), pk_hi(t2));
                     }
                 };
                 // feature groups in the order 2, 3, 0, 1 when H terms follow (see the column map); 0..3 for the last hidden
@@ -995,8 +1019,11 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         emit(q, hv, qx != 0);
                     }
                 };
-                if (more) run_c(std::integral_constant<int, 2>{}); else run_c(std::integral_constant<int, 0>{});
+                if (live) {
+                    if (more) run_c(std::integral_constant<int, 2>{}); else run_c(std::integral_constant<int, 0>{});
+                }
                 if (timing) tm[6] += clock64() - tq;
+                TC_TRACE(h, 7);
             }
 
             // -- last layer, projected first: q = H.w_0 + z, z = H.w_1, score = act(q - dinv_i sum_j A_ij dinv_j z_j + b)
@@ -1018,7 +1045,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 tmem_ld4(taddr, d4);
                 tc_fence_before();
                 const float sll = tc_slope(P.last_act, P.alpha);
-                score = tc_act((t0 + t1) - di * (tc_combine(d4) * iqs) + P.tail_bias, sll, sll <= 1.f);
+                score = tc_act((t0 + t1) - di * (tc_combine(d4) * iqs) + P.tail_bias, sll);
                 if (!keep) score = 0.f;
             }
             // -- utility (mwis_dqn_call.py:230-235) ------------------------------------------------------------------
@@ -1502,7 +1529,7 @@ int tc_build_tiles(dg_context *ctx, dg_batch *b, int n_hidden, bool *ok) {
 }  // namespace
 
 bool tc_model_eligible(const dg_context *ctx, const dg_model *m) {
-    return !(ctx->env.disable_tc || ctx->env.disable_fused) && m->tc_wall && m->n_layers >= 3;
+    return !(ctx->env.disable_tc || ctx->env.disable_fused) && m->tc_wall && m->n_layers >= 3 && m->alpha <= 1.0f;
 }
 
 void tc_plan_ahead(dg_context *ctx, const dg_model *m, dg_batch *b) {
@@ -1518,7 +1545,7 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
     *handled = false;
     if (dit && (member == nullptr || d_wts == nullptr)) return DG_OK;
     if (ctx->env.disable_tc || ctx->env.disable_fused) return DG_OK;
-    if (!m->tc_wall || m->n_layers < 3 || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
+    if (!m->tc_wall || m->n_layers < 3 || !(m->alpha <= 1.0f) || b->n_graphs == 0 || b->n_nodes == 0) return DG_OK;
     if ((int)b->h_graph_e.size() != b->n_graphs + 1) return DG_OK;
     if (member == nullptr && d_wts == nullptr && predict == DG_PREDICT_MWIS) return DG_OK;
     bool ok = false;
@@ -1567,6 +1594,13 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
         DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2, &dbg));
         DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2), ctx->stream));
         p.dbg = dbg;
+#ifdef DG_TC_TRACE
+        DG_TRY(scratch_as(ctx, kSlotLgsWords, (size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2 + 16 * 24 * 8, &dbg));
+        DG_CUDA_CHECK(cudaMemsetAsync(dbg, 0, sizeof(long long) * ((size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2 + 16 * 24 * 8), ctx->stream));
+        p.dbg = dbg;
+        p.trace = dbg + (size_t)ctx->sm_count * kTcCtasPerSm * 12 + (size_t)p.n_tiles * 2;
+        p.trace_tile = getenv("DG_TC_TRACE_TILE") ? atoi(getenv("DG_TC_TRACE_TILE")) : 0;
+#endif
     }
     if (!ctx->tc_attr_set) {  // once per context (the attribute is per device)
         DG_CUDA_CHECK(cudaFuncSetAttribute(tc_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1634,6 +1668,26 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
             fprintf(stderr, "[tc timing] %-6s min %10lld avg %12.0f max %10lld (%d CTAs)\n", names[k], mn, cnt ? sum / cnt : 0.0,
                     mx, cnt);
         }
+#ifdef DG_TC_TRACE
+        {
+            std::vector<long long> tr(16 * 24 * 8);
+            DG_CUDA_CHECK(cudaMemcpy(tr.data(), p.trace, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost));
+            const int *td = &b->tc_tiles_host[(size_t)p.trace_tile * 32];
+            fprintf(stderr, "[tc trace] tile %d:", p.trace_tile);
+            for (int k = 0; k < td[0]; ++k) fprintf(stderr, " nv=%d nnz=%d", td[1 + 6 * k + 2], td[1 + 6 * k + 4]);
+            fprintf(stderr, "\n");
+            long long t0 = 0;
+            for (int w = 0; w < 16; ++w) if (tr[(size_t)w * 24 * 8] && (!t0 || tr[(size_t)w * 24 * 8] < t0)) t0 = tr[(size_t)w * 24 * 8];
+            for (int h = 0; h < std::min(p.n_hidden, 24); ++h)
+                for (int w = 0; w < 16; ++w) {
+                    const long long *e = &tr[((size_t)w * 24 + h) * 8];
+                    if (!e[0]) continue;
+                    fprintf(stderr, "[tc trace] h %2d warp %2d:", h, w);
+                    for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", e[k] ? e[k] - t0 : -1);
+                    fprintf(stderr, "\n");
+                }
+        }
+#endif
         if (const char *path = ctx->env.tc_tile_dump.empty() ? nullptr : ctx->env.tc_tile_dump.c_str()) {  // per tile: cycles, then the vertex counts of its graphs
             if (FILE *f = fopen(path, "w")) {
                 for (int t = 0; t < p.n_tiles; ++t) {

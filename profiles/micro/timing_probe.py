@@ -8,6 +8,7 @@ layers = util.load_layers('is4sat_l20_c32')
 ctx = E.Context(0); model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers))); batch = E.DeviceBatch(ctx, pb)
 for i in range(3): E.solve(ctx, model, batch, w)
 os.environ['DG_FUSED_TIMING'] = '1'
+E.reload_env()
 E.solve(ctx, model, batch, w)
 import os
 if os.environ.get('DG_FUSED_TILE_DUMP'):

@@ -79,6 +79,7 @@ SIGNATURES = {
     "dg_part_lgs_init": (C.c_int, [_p, _p, _p, _p, _p]),
     "dg_part_lgs_decide": (C.c_int, [_p, _p, _p, _p, _p]),
     "dg_part_lgs_remove": (C.c_int, [_p, _p, _p, _p]),
+    "dg_part_lgs_run": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int32, _p]),
     "dg_peer_alloc": (C.c_int, [_p, C.c_uint64, _p, _p]),
     "dg_peer_open": (C.c_int, [_p, _p, _p]),
     "dg_peer_close": (C.c_int, [_p, _p]),

@@ -1521,6 +1521,8 @@ void dg_part_destroy(dg_part *p) {
         if (p->row_ptr) cudaFree(p->row_ptr);
         if (p->col_idx) cudaFree(p->col_idx);
     }
+    if (p->h_counts) cudaFreeHost(p->h_counts);
+    if (p->d_rounds) cudaFree(p->d_rounds);
     delete p;
 }
 
@@ -1704,6 +1706,48 @@ int dg_part_barrier(dg_part *p, const int64_t *count) {
     p->epoch += 1;
     DG_TRY(part_barrier(p->ctx, p->peers, p->flags_off, p->epoch, reinterpret_cast<const long long *>(count),
                         p->counts_off));
+    return DG_OK;
+}
+
+// The greedy rounds of the row-partitioned solve, driven from here instead of from Python: `check_every` rounds are enqueued
+// back to back (decide, barrier, remove, barrier with the ranks' remaining counts) before the counts are read once; rounds
+// past the end find nothing left and change nothing, and a one-thread kernel counts only the rounds that started with a vertex
+// left, so *rounds_out is what one-round-at-a-time gives.  Every rank sees the same counts, so every rank stops at the same check.
+int dg_part_lgs_run(dg_part *p, const double *util, uint32_t *remain, uint32_t *joined, uint8_t *member, int64_t *count,
+                    int32_t check_every, int32_t *rounds_out) {
+    clear_error();
+    DG_REQUIRE(p && util && remain && joined && member && count && rounds_out, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(p->peers.world >= 2, DG_ERR_INVALID, "dg_part_lgs_run needs the peer arenas (dg_part_set_peers)");
+    DG_REQUIRE(check_every >= 1 && check_every <= 64, DG_ERR_INVALID, "check_every must be in 1 .. 64");
+    dg_context *ctx = p->ctx;
+    DeviceGuard guard(ctx->device);
+    const int world = p->peers.world;
+    if (!p->h_counts) DG_CUDA_CHECK(cudaHostAlloc((void **)&p->h_counts, sizeof(long long) * (kMaxPeers + 1), cudaHostAllocDefault));
+    if (!p->d_rounds) DG_CUDA_CHECK(cudaMalloc((void **)&p->d_rounds, sizeof(int)));
+    DG_CUDA_CHECK(cudaMemsetAsync(p->d_rounds, 0, sizeof(int), ctx->stream));
+    const long long *counts = reinterpret_cast<const long long *>(p->peers.base[p->peers.rank] + p->counts_off);
+    long long *cnt = reinterpret_cast<long long *>(count);
+    const PartView pv = part_view(p);
+    for (int checks = 0;; ++checks) {
+        for (int i = 0; i < check_every; ++i) {
+            DG_TRY(part_tally(ctx, counts, world, cnt, p->d_rounds));
+            DG_TRY(part_lgs_decide(ctx, pv, util, remain, joined, member));
+            p->epoch += 1;
+            DG_TRY(part_barrier(ctx, p->peers, p->flags_off, p->epoch, nullptr, p->counts_off));
+            DG_TRY(part_lgs_remove(ctx, pv, joined, remain, cnt));
+            p->epoch += 1;
+            DG_TRY(part_barrier(ctx, p->peers, p->flags_off, p->epoch, cnt, p->counts_off));
+        }
+        DG_CUDA_CHECK(cudaMemcpyAsync(p->h_counts, counts, sizeof(long long) * world, cudaMemcpyDeviceToHost, ctx->stream));
+        DG_CUDA_CHECK(cudaMemcpyAsync(p->h_counts + kMaxPeers, p->d_rounds, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DG_TRY(finish(ctx));
+        long long left = 0;
+        for (int r = 0; r < world; ++r) left += p->h_counts[r];
+        if (left == 0) break;
+        DG_REQUIRE((checks + 1) * check_every < kLgsRoundCap, DG_ERR_NOT_CONVERGED,
+                   "local greedy search hit the round cap (NaN utilities or self-loops?)");
+    }
+    *rounds_out = *reinterpret_cast<const int *>(p->h_counts + kMaxPeers);
     return DG_OK;
 }
 

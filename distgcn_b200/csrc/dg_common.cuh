@@ -262,6 +262,8 @@ struct dg_part {  // one rank's row slice of a single large graph (device CSR, g
     dg::PeerMap peers;          // world == 1 until dg_part_set_peers
     unsigned long long flags_off = 0, counts_off = 0;  // arena offsets of the barrier flags / per-rank counts
     unsigned epoch = 0;         // barrier generation
+    long long *h_counts = nullptr;  // pinned: the ranks' remaining-vertex counts + the round counter (dg_part_lgs_run)
+    int *d_rounds = nullptr;        // device: rounds in which some rank still had a vertex left
 };
 
 namespace dg {
@@ -301,6 +303,7 @@ int part_lgs_init(dg_context *ctx, const PartView &pv, const uint8_t *keep, uint
 int part_lgs_decide(dg_context *ctx, const PartView &pv, const double *util, const uint32_t *remain, uint32_t *joined,
                     uint8_t *member);
 int part_lgs_remove(dg_context *ctx, const PartView &pv, const uint32_t *joined, uint32_t *remain, long long *cnt);
+int part_tally(dg_context *ctx, const long long *counts, int world, long long *own_count, int *rounds);
 
 // ---- graph-resident fused kernel (dg_fused.cu) -------------------------------------------------
 constexpr int kFusedMaxTileGraphs = 64;

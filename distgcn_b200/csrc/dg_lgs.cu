@@ -764,6 +764,22 @@ int dit_update_device(dg_context *ctx, int n, const uint8_t *joined, const uint8
     return DG_OK;
 }
 
+// one thread: a round is counted when some rank still had a vertex left at the last barrier; this rank's count restarts
+__global__ void part_tally_kernel(const long long *__restrict__ counts, int world, long long *__restrict__ own_count,
+                                  int *__restrict__ rounds) {
+    long long left = 0;
+    for (int r = 0; r < world; ++r) left += counts[r];
+    if (left > 0) *rounds += 1;
+    *own_count = 0;
+}
+
+int part_tally(dg_context *ctx, const long long *counts, int world, long long *own_count, int *rounds) {
+    part_tally_kernel<<<1, 1, 0, ctx->stream>>>(counts, world, own_count, rounds);
+    ctx->launches++;
+    DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
 int part_barrier(dg_context *ctx, const PeerMap &pm, unsigned long long flags_off, unsigned epoch,
                  const long long *count_src, unsigned long long counts_off) {
     if (pm.world <= 1) return DG_OK;

@@ -163,6 +163,7 @@ class RowPartitionedSolver:
         self.part = h
         self.exchanged_bytes = 0
         self.keep_on_device = False   # True: solve() returns CUDA tensors instead of numpy arrays
+        self.check_every = 4          # p2p exchange: greedy rounds enqueued per read of the ranks' remaining counts
         if exchange not in ("nccl", "p2p"):
             raise ValueError("exchange must be 'nccl' or 'p2p'")
         self.exchange = exchange if self.world > 1 else "nccl"
@@ -277,22 +278,14 @@ class RowPartitionedSolver:
         barrier()   # utilities
         member = torch.zeros(n_pad, dtype=torch.uint8, device=dev)
         count = torch.zeros(1, dtype=torch.int64, device=dev)
-        counts_view = _device_view(self.arena + self.lay["counts"], (self.world,), "<i8", dev)
         self.check(lib.dg_part_lgs_init(part, self._a("keep"), self._a("remain"), self._p(member), self._p(count)))
         barrier(self._p(count))
-        rounds = 0
-        while True:
-            if int(counts_view.sum().item()) == 0:
-                break
-            if rounds >= (1 << 20):
-                raise RuntimeError("local greedy search did not converge (NaN utilities or self-loops?)")
-            self.check(lib.dg_part_lgs_decide(part, self._a("util"), self._a("remain"), self._a("joined"),
-                                              self._p(member)))
-            barrier()
-            count.zero_()
-            self.check(lib.dg_part_lgs_remove(part, self._a("joined"), self._a("remain"), self._p(count)))
-            barrier(self._p(count))
-            rounds += 1
+        # the rounds are driven natively: `check_every` rounds enqueued back to back per read of the ranks' remaining counts
+        # (no Python, no torch kernel and no host synchronisation per round)
+        r_out = C.c_int32(0)
+        self.check(lib.dg_part_lgs_run(part, self._a("util"), self._a("remain"), self._a("joined"), self._p(member),
+                                       self._p(count), int(self.check_every), C.byref(r_out)))
+        rounds = int(r_out.value)
         self.ctx.synchronize()   # also surfaces a barrier time-out
         # bytes this rank stored into its peers' arenas (what an all-gather would have moved)
         per_solve = per * (1 + 4 + 4 + 8) + (rounds * 2 + 1) * (per // 8)

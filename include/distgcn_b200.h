@@ -353,6 +353,12 @@ DG_API int dg_part_lgs_init(dg_part *part, const uint8_t *keep, uint32_t *remain
 DG_API int dg_part_lgs_decide(dg_part *part, const double *util, const uint32_t *remain, uint32_t *joined,
                               uint8_t *member);
 DG_API int dg_part_lgs_remove(dg_part *part, const uint32_t *joined, uint32_t *remain, int64_t *count);
+/* All greedy rounds after dg_part_lgs_init + dg_part_barrier(count), driven natively (peer arenas required): `check_every`
+ * rounds are enqueued back to back before the ranks' remaining counts are read once (rounds past the end change nothing);
+ * *rounds_out = the rounds that started with a vertex left, i.e. what the reference's loop counts (heuristics.py:92-116).
+ * No reference counterpart (the reference never partitions a graph). */
+DG_API int dg_part_lgs_run(dg_part *part, const double *util, uint32_t *remain, uint32_t *joined, uint8_t *member,
+                           int64_t *count, int32_t check_every, int32_t *rounds_out);
 
 /* ---- exchange fused into the kernels: peer arenas over NVLink / NVSwitch (one process per GPU) ------------
  * Instead of all-gathering after every dg_part_* call, the ranks can share one "arena" each: a device

@@ -39,6 +39,15 @@ def main():
         solver = RowPartitionedSolver(_ModelSpec(layers, acts), n, rp, ci, rank=rank, world_size=world,
                                       exchange=exchange)
         w_local = w[rank * per:min(n, (rank + 1) * per)]
+        if exchange == "p2p":   # greedy rounds enqueued per count read: one at a time and speculatively give the same answer
+            solver.check_every = 1
+            m1, _, r1 = solver.solve(w_local)
+            solver.check_every = 5
+            m5, _, r5 = solver.solve(w_local)
+            if not (np.array_equal(m1, m5) and r1 == r5):
+                print("PART rank %d: check_every 1 / 5 disagree (rounds %d / %d)" % (rank, r1, r5))
+                ok = False
+            solver.check_every = 4
         solver.solve(w_local)   # warm-up (allocations, NCCL channels)
         solver.exchanged_bytes = 0
         torch.cuda.synchronize()
@@ -58,11 +67,11 @@ def main():
             ok = ok and same and err <= 1e-5 and rounds == steps
         solver.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # any rank's failure fails the run
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print("PARTITION_2GPU_OK" if ok else "PARTITION_2GPU_FAILED")
+        print("PARTITION_2GPU_OK" if int(flag.item()) else "PARTITION_2GPU_FAILED")
     sys.exit(0 if int(flag.item()) else 1)
 
 

@@ -548,11 +548,15 @@ class HostPipeline:
         return slot
 
     def submit_graphs(self, graphs, wts, member: np.ndarray, total: Optional[np.ndarray] = None, predict="mwis",
-                      remove_zero_weight: bool = True, check_values: bool = False) -> int:
+                      remove_zero_weight: bool = True, check_values: bool = False, slot: Optional[int] = None) -> int:
         """The same for the reference's native input: a list of per-graph scipy matrices (or a GraphTables) and their
-        weights; packing happens inside the call, in the library (dg_solve_graphs_host)."""
-        slot = self._next
-        self._next = (slot + 1) % len(self.ctxs)
+        weights; packing happens inside the call, in the library (dg_solve_graphs_host).  ``slot``: use this context
+        instead of the next one in turn - one producer THREAD per slot may then submit concurrently (a context belongs to
+        one host thread at a time; the native call releases the GIL, so one thread's pointer-table walk overlaps the
+        other's packing)."""
+        if slot is None:
+            slot = self._next
+            self._next = (slot + 1) % len(self.ctxs)
         self.wait(slot)
         _, _, alive = solve_graphs_host(self.ctxs[slot], self.models[slot], graphs, wts, predict, remove_zero_weight,
                                         member, total, wait=False, check_values=check_values)

@@ -304,6 +304,21 @@ def test_native_ingest_list_of_scipy_matrices():
     pipe.wait()
     for k in range(4):
         assert np.array_equal(np.asarray(outs[k][0]), member if k % 2 == 0 else member_z)
+    # two producer threads, one per context of the pipeline (submit_graphs(slot = k))
+    import threading
+    outs2 = [(E.pinned_empty(pb.n_nodes, np.uint8), E.pinned_empty(pb.n_graphs, np.float64)) for _ in range(6)]
+
+    def producer(k):
+        for i in range(k, 6, 2):
+            pipe.submit_graphs(adjs, w if i % 2 == 0 else wz, outs2[i][0], outs2[i][1], slot=k)
+    threads = [threading.Thread(target=producer, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    pipe.wait()
+    for i in range(6):
+        assert np.array_equal(np.asarray(outs2[i][0]), member if i % 2 == 0 else member_z)
     pipe.close()
     # one graph per call, as the reference's scripts do (wireless_dqn_test_mc.py:289,323)
     for g in (3, 28):

@@ -523,7 +523,7 @@ def bench_batch_workload(env, name, steps, warmup, detail):
     # the streaming form of the same API (engine.HostPipeline over dg_solve_host_compact): every step still copies its
     # own CSR + weights from pinned host memory and its membership + totals back, two contexts take turns so that one
     # batch's copies overlap the other's kernels.  This is the headline e2e number.
-    pipe = E.HostPipeline(env.local_rank, layers, E.gcn_dqn_acts(len(layers)), depth=2)
+    pipe = E.HostPipeline(env.local_rank, layers, E.gcn_dqn_acts(len(layers)), depth=args.pipe_depth)
 
     def pipe_step(i):
         c = copies[i % R]
@@ -535,7 +535,7 @@ def bench_batch_workload(env, name, steps, warmup, detail):
         pipe.submit_graphs(c["adjs"], c["w_list"], c["h_member"], c["h_total"], predict="mwis", remove_zero_weight=True)
 
     def timed_pipe(step_fn):
-        for i in range(max(4, warmup // 2)):
+        for i in range(max(4, warmup // 2, 3 * len(pipe.ctxs))):   # every context: buffers sized, tile-plan hint in place
             step_fn(i)
         pipe.wait()
         barrier()
@@ -577,7 +577,7 @@ def bench_batch_workload(env, name, steps, warmup, detail):
             for t in ts:
                 t.join()
             pipe.wait()
-        go(0, max(4, warmup // 2))
+        go(0, max(4, warmup // 2, 3 * n_thr))
         barrier()
         t0 = time.perf_counter()
         go(0, steps)
@@ -607,9 +607,9 @@ def bench_batch_workload(env, name, steps, warmup, detail):
         "e2e": {"value": world * n_graphs * steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / steps,
                 "h2d_gbs_per_rank": h2d / (e2e_ms / steps) / 1e6,
-                "api": "engine.HostPipeline.submit (dg_solve_host_upper, 2 contexts in turn): pinned host arrays - row offsets and "
+                "api": "engine.HostPipeline.submit (dg_solve_host_upper, %d contexts in turn): pinned host arrays - row offsets and "
                        "16-bit graph-local column ids of the entries above the diagonal, weights - in, membership + totals out, "
-                       "every step; wall clock over the K steps",
+                       "every step; wall clock over the K steps" % args.pipe_depth,
                 "gpu_launches": int(pipe_launches),
                 "from_reference_inputs": {
                     "value": world * n_graphs * steps / (ref_ms / 1e3), "unit": UNIT, "ms_per_step": ref_ms / steps,
@@ -1001,6 +1001,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--main-only", action="store_true", help="skip the `configs` block (other workloads)")
+    ap.add_argument("--pipe-depth", type=int, default=4, help="contexts the end-to-end pipeline takes its steps on in turn")
     ap.add_argument("--synth-graphs", type=int, default=16384, help="graphs in the config-4 batch of `configs`")
     ap.add_argument("--part-nodes", type=int, default=0,
                     help="vertices of the row-partitioned graph (N >= 2); 0 = 6 M per GPU (48 M at N = 8: BASELINE config 5 is 50 M)")

@@ -1064,6 +1064,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             }
             if (P.do_lgs) {
                 // -- local greedy search (heuristics.py:77-116); neighbour sets as bit rows in registers -----------
+                TC_TRACE(20, 0);
                 uint32_t nbm[12];
 #pragma unroll
                 for (int w = 0; w < 12; ++w) nbm[w] = 0u;
@@ -1083,7 +1084,9 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 for (int w = 0; w < 12; ++w) nbr[w] = nbm[w];
                 const int w0 = G.fb * 4, nw = G.nb * 4;
                 if (lane == 0) remain[warp] = keepw[warp];
+                TC_TRACE(20, 1);
                 bar_sync(dom_bar, dom_cnt);
+                TC_TRACE(20, 2);
                 // nbm := the neighbours that beat this vertex (larger utility, or equal and smaller id - heuristics.py:
                 // 96-111), found once; a round is then a handful of word operations: the vertex joins iff none of them
                 // is still there.  NaN utilities beat and are beaten by nobody's rule: they block, as np.max does.
@@ -1117,6 +1120,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                     }
                 }
                 // nbr := all kept neighbours (for the removal of a joined vertex's neighbourhood)
+                TC_TRACE(20, 3);
                 int rounds = 0, steps = 0;
                 for (;;) {
                     if (DIT && rounds >= 1) break;   // one greedy round per re-scoring
@@ -1153,6 +1157,10 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                     ++rounds;
                     bar_sync(dom_bar, dom_cnt);
                 }
+                TC_TRACE(20, 4);
+#ifdef DG_TC_TRACE
+                if (lane == 0 && P.trace && t == P.trace_tile) P.trace[((size_t)warp * 24 + 20) * 8 + 7] = rounds;   // (a count)
+#endif
                 if (DIT) {
                     keep = valid && ((remain[warp] >> lane) & 1u);   // the residual graph of the next iteration
                     bar_sync(dom_bar, dom_cnt);                      // (every thread of the graph has read `remain`)
@@ -1169,6 +1177,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                         if (lane == 0) P.total[G.g] = acc;
                     }
                 }
+                TC_TRACE(20, 5);
             }
         }
         if (timing) {
@@ -1678,12 +1687,12 @@ int tc_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const double *
             fprintf(stderr, "\n");
             long long t0 = 0;
             for (int w = 0; w < 16; ++w) if (tr[(size_t)w * 24 * 8] && (!t0 || tr[(size_t)w * 24 * 8] < t0)) t0 = tr[(size_t)w * 24 * 8];
-            for (int h = 0; h < std::min(p.n_hidden, 24); ++h)
+            for (int h = 0; h < 24; ++h)
                 for (int w = 0; w < 16; ++w) {
                     const long long *e = &tr[((size_t)w * 24 + h) * 8];
                     if (!e[0]) continue;
                     fprintf(stderr, "[tc trace] h %2d warp %2d:", h, w);
-                    for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", e[k] ? e[k] - t0 : -1);
+                    for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", (h == 20 && k == 7) ? e[k] : e[k] ? e[k] - t0 : -1);
                     fprintf(stderr, "\n");
                 }
         }

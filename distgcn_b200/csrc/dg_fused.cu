@@ -977,8 +977,10 @@ size_t fused_smem_bytes(int cp, int cap_n, int cap_nnz, bool has_hidden, size_t 
 template <int CP, bool DIT, bool MMA>
 int launch_t(dg_context *ctx, const FusedParams &p, size_t smem, int n_tiles) {
     auto kern = fused_solve_kernel<CP, DIT, MMA>;
-    // attribute and occupancy are queried once per (device, instantiation, shared-memory size): they cost microseconds
-    // of host time that the streaming path would pay on every call
+    // attribute and occupancy are queried once per (thread, device, instantiation, shared-memory size): they cost
+    // microseconds of host time that the streaming path would pay on every call.  The attribute is always the device's
+    // opt-in maximum: a per-call value would let one host thread lower it under another thread's launch (contexts of
+    // several producer threads share the function).
     static thread_local int c_dev = -1;
     static thread_local size_t c_smem = 0;
     static thread_local int c_per_sm = 0;
@@ -986,7 +988,14 @@ int launch_t(dg_context *ctx, const FusedParams &p, size_t smem, int n_tiles) {
     if (c_dev == ctx->device && c_smem == smem) {
         per_sm = c_per_sm;
     } else {
-        DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DG_REQUIRE(smem <= (size_t)ctx->max_smem_optin, DG_ERR_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory (limit %d)",
+                   smem, ctx->max_smem_optin);
+        cudaFuncAttributes fa;
+        DG_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
+        const int dyn_max = ctx->max_smem_optin - (int)fa.sharedSizeBytes;   // (static shared memory counts against the limit)
+        DG_REQUIRE((long long)smem <= (long long)dyn_max, DG_ERR_UNSUPPORTED,
+                   "fused kernel needs %zu bytes of dynamic shared memory (limit %d)", smem, dyn_max);
+        DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
         DG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
         c_dev = ctx->device, c_smem = smem, c_per_sm = per_sm;
     }

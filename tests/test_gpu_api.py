@@ -399,3 +399,50 @@ def test_native_ingest_upper_option(monkeypatch):
         with pytest.raises(_lib.DistGCNError):
             agent.solve_mwis_batch([skew], np.ones(3))
         monkeypatch.delenv("DG_INGEST_UPPER")
+
+
+def test_producer_threads_on_the_cuda_core_kernel():
+    """Four producer threads, one per context, submit batches of different shapes through the CUDA-core graph-resident
+    kernel at the same time (its shared-memory size depends on the batch: a per-call function attribute set by one thread
+    used to undercut another thread's launch)."""
+    import threading
+    from distgcn_b200 import engine as E
+    pb, w = util.small_graphs()
+    layers = util.load_layers("is4sat_l1")
+    acts = E.gcn_dqn_acts(len(layers))
+    ctx = E.Context(0)
+    model = E.Model(ctx, layers, acts)
+    shapes = [(0, 50), (0, 7), (10, 40), (45, 50)]
+    subs, refs = [], []
+    for lo, hi in shapes:
+        sub = pb.slice(lo, hi)
+        ws = w[int(pb.graph_ptr[lo]):int(pb.graph_ptr[hi])].copy()
+        subs.append(([sp.csr_matrix(sub.graph_adj(g)) for g in range(sub.n_graphs)], ws, sub))
+        refs.append(E.solve_host(ctx, model, sub, ws)[0])
+    pipe = E.HostPipeline(0, layers, acts, depth=4)
+    errors = []
+    outs = {}
+
+    def producer(k):
+        try:
+            for i in range(12):
+                j = (i + k) % len(shapes)
+                adjs, ws, sub = subs[j]
+                m = E.pinned_empty(sub.n_nodes, np.uint8)
+                pipe.submit_graphs(adjs, ws, m, None, slot=k)
+                pipe.wait(k)
+                outs[(k, i)] = (j, np.asarray(m).copy())
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=producer, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    pipe.close()
+    assert not errors, errors
+    assert len(outs) == 48
+    for (k, i), (j, m) in outs.items():
+        assert np.array_equal(m, refs[j]), (k, i, j)
+    model.close()
+    ctx.close()

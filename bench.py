@@ -417,14 +417,15 @@ def bench_batch_workload(env, name, steps, warmup, detail):
     layers, desc, sets = device_copies(env, name, args.seed, R)
     # two contexts (streams) of the same GPU take the resident batches in turn, as engine.HostPipeline does for host
     # batches: the tail of one launch (SMs whose tiles are done) overlaps the head of the next
-    ctxs = [E.Context(env.local_rank), E.Context(env.local_rank)]
+    NC = max(2, int(args.resident_contexts))
+    ctxs = [E.Context(env.local_rank) for _ in range(NC)]
     ctx = ctxs[0]
     lib = ctx._lib
     models = [E.Model(c, layers, E.gcn_dqn_acts(len(layers))) for c in ctxs]
     copies = []
     input_bytes = 0
     for r, (pb, w) in enumerate(sets):
-        dev_batch = E.DeviceBatch(ctxs[r % 2], pb)
+        dev_batch = E.DeviceBatch(ctxs[r % NC], pb)
         d_w = torch.from_numpy(w).to(env.dev)
         d_member = torch.empty(pb.n_nodes, dtype=torch.uint8, device=env.dev)
         d_total = torch.empty(pb.n_graphs, dtype=torch.float64, device=env.dev)
@@ -455,17 +456,19 @@ def bench_batch_workload(env, name, steps, warmup, detail):
 
     def device_step(i):
         c = copies[i % R]
-        k = (i % R) % 2
+        k = (i % R) % NC
         E.solve_device(ctxs[k], models[k], c["dev"], c["d_w"], c["d_member"], predict="mwis", remove_zero_weight=True,
                        total=c["d_total"])
 
     def timed_block(k_steps, first):
         ev = DeviceTimer(ctx)
         ev.start()                                                    # start event on the first context's stream ...
-        E.check(lib.dg_context_wait(ctxs[1].handle, ctxs[0].handle))  # ... which the second context's work follows
+        for c in ctxs[1:]:
+            E.check(lib.dg_context_wait(c.handle, ctxs[0].handle))    # ... which the other contexts' work follows
         for i in range(k_steps):
             device_step(first + i)
-        E.check(lib.dg_context_wait(ctxs[0].handle, ctxs[1].handle))  # the stop event follows both streams' last kernels
+        for c in ctxs[1:]:
+            E.check(lib.dg_context_wait(ctxs[0].handle, c.handle))    # the stop event follows every stream's last kernel
         return ev.stop()  # synchronises
 
     # ---- value: inputs resident in HBM, CUDA events on the library's streams ----------------------------
@@ -492,7 +495,7 @@ def bench_batch_workload(env, name, steps, warmup, detail):
     # roofline pass (not part of `value`): the same steps on ONE context, launches back to back without overlap, CUDA
     # events around every dominant-kernel launch (dg_profile_*)
     tot_ms, n_launch, alg_bytes = C.c_double(), C.c_uint64(), C.c_double()
-    own = [r for r in range(R) if r % 2 == 0]
+    own = [r for r in range(R) if r % NC == 0]   # the input sets resident on the first context
     n_prof = max(3, min(steps, 50))
     lib.dg_profile_enable(ctx.handle, 1)
     ev = DeviceTimer(ctx)
@@ -925,7 +928,8 @@ def run_ours(args):
             "config": bench_config(main_rec["workload"], main_rec["graphs_per_step_per_gpu"]),
             "run_info": {"nodes_per_step": main_rec["nodes_per_step"], "nnz_per_step": main_rec["nnz_per_step"],
                          "parallelism": "graph-batch sharding, no collectives",
-                         "streams": "two contexts of the library on the GPU take the steps in turn (value and e2e alike)",
+                         "streams": "%d contexts of the library on the GPU take the resident steps in turn, %d the end-to-end ones"
+                                    % (max(2, args.resident_contexts), args.pipe_depth),
                          "l2_policy": main_rec["l2_policy"], "paths_agree": main_rec["paths_agree"],
                          "wall_ms_per_step": main_rec["wall_ms_per_step"], "blocks": main_rec.get("blocks")},
             "e2e": main_rec["e2e"],
@@ -1001,6 +1005,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--main-only", action="store_true", help="skip the `configs` block (other workloads)")
+    ap.add_argument("--resident-contexts", type=int, default=2,
+                    help="contexts (streams) the resident batches are taken on in turn: one launch's tail overlaps the next one's head")
     ap.add_argument("--pipe-depth", type=int, default=4, help="contexts the end-to-end pipeline takes its steps on in turn")
     ap.add_argument("--synth-graphs", type=int, default=16384, help="graphs in the config-4 batch of `configs`")
     ap.add_argument("--part-nodes", type=int, default=0,

@@ -105,6 +105,7 @@ SIGNATURES = {
     "dg_wireless_seq_weights": (C.c_int, [_p, _i32, _i32]),
     "dg_wireless_seq_serve": (C.c_int, [_p, _i32, _i32]),
     "dg_wireless_end_slot": (C.c_int, [_p, _i32]),
+    "dg_wireless_run": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_double, C.c_int32, C.c_int32]),
     "dg_wireless_read_history": (C.c_int, [_p, _p]),
 }
 

@@ -84,6 +84,35 @@ __global__ void wl_end_kernel(int n, const double *__restrict__ cap, double *__r
     hist[l] = v;
 }
 
+// Joint form, one kernel per slot boundary: close slot t (capacity of the scheduled vertex, departures, history row) and
+// open slot t + 1 (arrivals, the joint graph's weights) for one link - the same arithmetic, in the same order, as
+// wl_joint_serve_kernel + wl_end_kernel + wl_begin_kernel + wl_joint_weights_kernel.
+__global__ void wl_joint_turn_kernel(int n_links, int n_ch, const uint8_t *__restrict__ member, const int32_t *__restrict__ rates_close,
+                                     double *__restrict__ hist_close, const double *__restrict__ arr_open,
+                                     const int32_t *__restrict__ rates_open, const int32_t *__restrict__ v0,
+                                     const int32_t *__restrict__ nf, double *__restrict__ q, double *__restrict__ qest,
+                                     double *__restrict__ cap, double *__restrict__ w) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_links) return;
+    const int base = v0[l], stride = nf[l];
+    double v = q[l];
+    if (rates_close) {
+        double c = 0.0;
+        for (int k = 0; k < n_ch; ++k)
+            if (member[base + k * stride]) c = (double)rates_close[(size_t)l * n_ch + k];
+        v = v - fmin(v, c);
+        hist_close[l] = v;
+        cap[l] = c;
+    }
+    if (arr_open) {
+        v = v + arr_open[l];
+        qest[l] = v;
+        cap[l] = 0.0;
+        for (int k = 0; k < n_ch; ++k) w[base + k * stride] = v * (double)rates_open[(size_t)l * n_ch + k];
+    }
+    q[l] = v;
+}
+
 inline int blocks(int n) { return (n + 255) / 256; }
 
 template <typename T>
@@ -228,6 +257,71 @@ int dg_wireless_end_slot(dg_wireless *s, int32_t t) {
     wl_end_kernel<<<blocks(s->n_links), 256, 0, st>>>(s->n_links, s->cap, s->q, s->history + (size_t)t * s->n_links);
     s->ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());
+    return DG_OK;
+}
+
+// The slot loop itself (wireless_dqn_test_mc.py:225-366), slots t_first .. t_first + n_slots - 1, enqueued from here instead
+// of from Python: begin, weights, the slot's scheduler on the resident buffers, capacities, departures - per slot (joint
+// graph) or per slot and channel (the sequential variants).  Nothing is synchronised; dg_wireless_read_history ends the sweep.
+int dg_wireless_run(dg_wireless *s, const dg_model *model, dg_batch *const *batches, int32_t n_batches, int32_t scheduler,
+                    int32_t sequential, int predict, int remove_zero_weight, double epsilon, int32_t t_first, int32_t n_slots) {
+    clear_error();
+    DG_REQUIRE(s && batches && n_batches >= 1, DG_ERR_INVALID, "null argument");
+    DG_REQUIRE(scheduler >= DG_WL_LGS && scheduler <= DG_WL_SOLVE_DIT, DG_ERR_INVALID, "unknown scheduler %d", scheduler);
+    DG_REQUIRE(scheduler < DG_WL_SOLVE || model != nullptr, DG_ERR_INVALID, "this scheduler needs a model");
+    DG_REQUIRE(n_batches == (sequential ? s->n_ch : 1), DG_ERR_INVALID,
+               "%d batches: the joint form takes one, the sequential form one per channel (%d)", n_batches, s->n_ch);
+    DG_REQUIRE(n_slots >= 0 && t_first >= 1 && (n_slots == 0 || t_first + n_slots - 1 < s->T), DG_ERR_INVALID,
+               "slots %d .. %d outside 1 .. %d", t_first, t_first + n_slots - 1, s->T - 1);
+    dg_context *ctx = s->ctx;
+    auto schedule = [&](dg_batch *b) -> int {
+        switch (scheduler) {
+        case DG_WL_LGS:
+            if (sequential) DG_TRY(dg_batch_set_keep_from_weights(b, s->w, DG_MEM_DEVICE));   // the non-zero sub-graph (:299-301)
+            return dg_lgs(ctx, b, s->w, -1, s->member, nullptr, nullptr, nullptr, nullptr, nullptr, DG_MEM_DEVICE);
+        case DG_WL_DIST_GREEDY:
+            return dg_dist_greedy(ctx, b, s->w, epsilon, s->member, nullptr, DG_MEM_DEVICE);
+        case DG_WL_SOLVE:
+            return dg_solve(ctx, model, b, s->w, predict, remove_zero_weight, s->member, nullptr, nullptr, nullptr, nullptr,
+                            DG_MEM_DEVICE);
+        default:
+            return dg_solve_dit(ctx, model, b, s->w, predict, s->member, nullptr, nullptr, DG_MEM_DEVICE);
+        }
+    };
+    if (!sequential && n_slots > 0 && s->n_links > 0) {   // joint form: the scheduler + ONE bookkeeping kernel per slot
+        DG_REQUIRE(s->link_v0 != nullptr, DG_ERR_INVALID, "no joint-graph vertex map was given");
+        const size_t row = (size_t)s->n_links;
+        auto turn = [&](int32_t t_close, int32_t t_open) -> int {
+            wl_joint_turn_kernel<<<blocks(s->n_links), 256, 0, ctx->stream>>>(
+                s->n_links, s->n_ch, s->member, t_close ? s->rates + (size_t)t_close * row * s->n_ch : nullptr,
+                t_close ? s->history + (size_t)t_close * row : nullptr, t_open ? s->arrivals + (size_t)t_open * row : nullptr,
+                t_open ? s->rates + (size_t)t_open * row * s->n_ch : nullptr, s->link_v0, s->link_nf, s->q, s->qest, s->cap, s->w);
+            ctx->launches++;
+            DG_CUDA_CHECK(cudaGetLastError());
+            return DG_OK;
+        };
+        DG_TRY(turn(0, t_first));
+        for (int32_t t = t_first; t < t_first + n_slots; ++t) {
+            DG_TRY(schedule(batches[0]));
+            DG_TRY(turn(t, t + 1 < t_first + n_slots ? t + 1 : 0));
+        }
+        return DG_OK;
+    }
+    for (int32_t t = t_first; t < t_first + n_slots; ++t) {
+        DG_TRY(dg_wireless_begin_slot(s, t));
+        if (!sequential) {
+            DG_TRY(dg_wireless_joint_weights(s, t));
+            DG_TRY(schedule(batches[0]));
+            DG_TRY(dg_wireless_joint_serve(s, t));
+        } else {
+            for (int32_t ic = 0; ic < s->n_ch; ++ic) {
+                DG_TRY(dg_wireless_seq_weights(s, t, ic));
+                DG_TRY(schedule(batches[ic]));
+                DG_TRY(dg_wireless_seq_serve(s, t, ic));
+            }
+        }
+        DG_TRY(dg_wireless_end_slot(s, t));
+    }
     return DG_OK;
 }
 

@@ -330,20 +330,16 @@ class BatchedScheduler:
         lib = self.ctx._lib
         h, w, member = self._device_state()
         t0 = self.t
-        for s in range(n):
-            t = self.t + 1
-            engine.check(lib.dg_wireless_begin_slot(h, t))
-            if not self.seq:
-                engine.check(lib.dg_wireless_joint_weights(h, t))
-                self._solve_device(0, w, member)
-                engine.check(lib.dg_wireless_joint_serve(h, t))
-            else:
-                for ic in range(self.n_ch):
-                    engine.check(lib.dg_wireless_seq_weights(h, t, ic))
-                    self._solve_device(ic, w, member)
-                    engine.check(lib.dg_wireless_seq_serve(h, t, ic))
-            engine.check(lib.dg_wireless_end_slot(h, t))
-            self.t = t
+        if n > 0:   # the whole sweep is one native call (dg_wireless_run): five enqueues per slot without Python in between
+            import ctypes as C
+            sched = (3 if self.algo == "DGCN-LGS-it" else 1 if self.algo == "Greedy-Th" else 2 if self.algo.startswith("DGCN")
+                     else 0)
+            handles = (C.c_void_p * len(self.batches))(*[b.handle for b in self.batches])
+            engine.check(lib.dg_wireless_run(h, None if self.model is None else self.model.handle, handles, len(self.batches),
+                                             sched, 1 if self.seq else 0, engine.predict_code(self.predict),
+                                             1 if self._remove_zero else 0, C.c_double(GREEDY_TH_EPSILON), self.t + 1, n))
+            self.solver_calls += n * (self.n_ch if self.seq else 1)
+            self.t += n
         self._t_device = self.t
         hist = np.empty((self.T, self.n_links), dtype=np.float64)
         engine.check(lib.dg_wireless_read_history(h, hist.ctypes.data))

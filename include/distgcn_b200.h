@@ -302,6 +302,18 @@ DG_API int dg_wireless_joint_serve(dg_wireless *s, int32_t t);
 DG_API int dg_wireless_seq_weights(dg_wireless *s, int32_t t, int32_t channel);
 DG_API int dg_wireless_seq_serve(dg_wireless *s, int32_t t, int32_t channel);
 DG_API int dg_wireless_end_slot(dg_wireless *s, int32_t t);
+/* The slot loop itself for slots t_first .. t_first + n_slots - 1 (wireless_dqn_test_mc.py:225-366), enqueued natively: one call
+ * per sweep instead of five per slot.  `scheduler`: DG_WL_LGS = heuristics.local_greedy_search ("Greedy" / "LGS-Seq"),
+ * DG_WL_DIST_GREEDY = dist_greedy_search(epsilon) ("Greedy-Th"), DG_WL_SOLVE = DQNAgent.solve_mwis ("DGCN-LGS" /
+ * "DGCN-LGS-Seq"), DG_WL_SOLVE_DIT = MWISSolver.solve_mwis_dit ("DGCN-LGS-it").  `sequential` != 0: per channel, one batch
+ * per channel (vertex = link); else one batch of joint graphs. */
+#define DG_WL_LGS 0
+#define DG_WL_DIST_GREEDY 1
+#define DG_WL_SOLVE 2
+#define DG_WL_SOLVE_DIT 3
+DG_API int dg_wireless_run(dg_wireless *s, const dg_model *model, dg_batch *const *batches, int32_t n_batches, int32_t scheduler,
+                           int32_t sequential, int predict, int remove_zero_weight, double epsilon, int32_t t_first,
+                           int32_t n_slots);
 /* synchronise and copy the queue history [n_slots][n_links] (row t = queues after slot t; row 0 zeros) to the host */
 DG_API int dg_wireless_read_history(dg_wireless *s, double *history);
 

@@ -113,6 +113,35 @@ __global__ void wl_joint_turn_kernel(int n_links, int n_ch, const uint8_t *__res
     q[l] = v;
 }
 
+// Sequential form, one kernel between two scheduler calls: serve channel ic_close (capacity, queue estimate), optionally end
+// the slot (departures, history row) and begin the next one (arrivals), then the weights of channel ic_open - per link, in
+// the order of wl_seq_serve_kernel, wl_end_kernel, wl_begin_kernel, wl_seq_weights_kernel.
+__global__ void wl_seq_turn_kernel(int n_links, int n_ch, int ic_close, int ic_open, const uint8_t *__restrict__ member,
+                                   const int32_t *__restrict__ rates_close, double *__restrict__ hist_end,
+                                   const double *__restrict__ arr_begin, const int32_t *__restrict__ rates_open,
+                                   double *__restrict__ q, double *__restrict__ qest, double *__restrict__ cap,
+                                   double *__restrict__ w) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_links) return;
+    double qe = qest[l], c = cap[l], v = q[l];
+    if (ic_close >= 0 && member[l]) {
+        const double r = (double)rates_close[(size_t)l * n_ch + ic_close];
+        c = r;
+        qe -= fmin(qe, r);
+    }
+    if (hist_end) {
+        v = v - fmin(v, c);
+        hist_end[l] = v;
+    }
+    if (arr_begin) {
+        v = v + arr_begin[l];
+        qe = v;
+        c = 0.0;
+    }
+    q[l] = v, qest[l] = qe, cap[l] = c;
+    if (ic_open >= 0) w[l] = qe * (double)rates_open[(size_t)l * n_ch + ic_open];
+}
+
 inline int blocks(int n) { return (n + 255) / 256; }
 
 template <typename T>
@@ -304,6 +333,32 @@ int dg_wireless_run(dg_wireless *s, const dg_model *model, dg_batch *const *batc
         for (int32_t t = t_first; t < t_first + n_slots; ++t) {
             DG_TRY(schedule(batches[0]));
             DG_TRY(turn(t, t + 1 < t_first + n_slots ? t + 1 : 0));
+        }
+        return DG_OK;
+    }
+    if (sequential && n_slots > 0 && s->n_links > 0) {   // sequential form: ONE bookkeeping kernel between two scheduler calls
+        const size_t row = (size_t)s->n_links;
+        auto rates_of = [&](int32_t t) { return s->rates + (size_t)t * row * s->n_ch; };
+        auto turn = [&](int ic_close, int32_t t_close, bool end, int32_t t_begin, int ic_open, int32_t t_open) -> int {
+            wl_seq_turn_kernel<<<blocks(s->n_links), 256, 0, ctx->stream>>>(
+                s->n_links, s->n_ch, ic_close, ic_open, s->member, ic_close >= 0 ? rates_of(t_close) : nullptr,
+                end ? s->history + (size_t)t_close * row : nullptr, t_begin ? s->arrivals + (size_t)t_begin * row : nullptr,
+                ic_open >= 0 ? rates_of(t_open) : nullptr, s->q, s->qest, s->cap, s->w);
+            ctx->launches++;
+            DG_CUDA_CHECK(cudaGetLastError());
+            return DG_OK;
+        };
+        DG_TRY(turn(-1, 0, false, t_first, 0, t_first));
+        for (int32_t t = t_first; t < t_first + n_slots; ++t) {
+            for (int32_t ic = 0; ic < s->n_ch; ++ic) {
+                DG_TRY(schedule(batches[ic]));
+                if (ic + 1 < s->n_ch) {
+                    DG_TRY(turn(ic, t, false, 0, ic + 1, t));
+                } else {
+                    const bool more = t + 1 < t_first + n_slots;
+                    DG_TRY(turn(ic, t, true, more ? t + 1 : 0, more ? 0 : -1, t + 1));
+                }
+            }
         }
         return DG_OK;
     }

@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
     uint32_t *cnt_p = reinterpret_cast<uint32_t *>(bar_full + 22);     // [4] per block: warps whose H terms are in place
     uint32_t *cnt_a = cnt_p + 4;                                        // [4] per graph: warps whose Y digits are in place
     uint32_t *cnt_w = cnt_p + 8;                                        // [2] per ring buffer: blocks done with its layer
+    uint32_t *base_da = cnt_p + 10;                                     // [4] per block: parity of bar_da's phases before this tile
     uint64_t *bar_dp = bar_full + 6;    // [4] per block: projection MMAs complete
     uint64_t *bar_da = bar_full + 10;   // [4] per block: aggregation MMAs complete
     uint64_t *bar_ra = bar_full + 14;   // [4] per graph: the aggregation's B operand (Y digits) is complete (one arrival per warp)
@@ -471,6 +472,13 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
     tc_fence_after();
     const uint32_t tmem = tmem_sm;
     uint32_t wseq = 0;  // hidden-layer weight fills of the tiles this CTA has finished (every thread keeps its own copy)
+    // The per-block barriers bar_dp / bar_da are armed ONCE (prologue) and their phases run on across tiles: a thread always
+    // belongs to the same block (tid >> 7), so it carries the parity of the phases its block's barriers have completed in
+    // earlier tiles.  (Re-arming them per tile - mbarrier.inval + mbarrier.init, which ptxas lowers to an invalidate and a
+    // plain 64-bit store when the address is not uniform - was seen to leave block 0's barriers in their OLD state: invisible
+    // while a tile completes an even number of phases, i.e. with the shipped 20-layer model, a dead-lock with an odd number
+    // of hidden layers; profiles/micro/tc_odd_depth_probe.py.)
+    uint32_t ea_base = 0, ep_base = 0;
 
     const bool timing = P.dbg != nullptr && tid == 0;
     long long tm[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -517,12 +525,6 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 mbar_init(&bar_mx[gi], 4 * m.nb);
                 mbar_init(&bar_ra[gi], 4 * m.nb);
             }
-            for (int b = 0; b < fb; ++b) {
-                mbar_inval(&bar_dp[b]);
-                mbar_inval(&bar_da[b]);
-                mbar_init(&bar_dp[b], 1);
-                mbar_init(&bar_da[b], 1);
-            }
             tinfo->ng = ng;
             tinfo->nblocks = fb;
             tinfo->pool_used = off;
@@ -550,6 +552,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
         double wt_v = 0.0;
         if (tid < kTcVertexThreads) {
             const int b = tid >> 7;
+            if ((tid & 127) == 0) base_da[b] = ea_base;   // read by the other blocks of the graph (agg_drained), two barriers on
             if (b < nblocks) gi = tinfo->blkg[b];
             if (gi >= 0) {
                 G = meta[gi];
@@ -854,11 +857,11 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
             // such wait is needed: a block writes new Y digits only after its own next projection has completed, and the
             // tensor pipe runs the MMAs in issue order, so every aggregation issued before that projection is done.)
             auto agg_drained = [&]() {
-                if (b != lastb) mbar_wait(&bar_da[lastb], (ea - 1u) & 1u, 4);
+                if (b != lastb) mbar_wait(&bar_da[lastb], (base_da[lastb] + ea - 1u) & 1u, 4);
             };
 
             // -- first layer (rank 1): s = (L x0)_i, H1 = act(x0 colsum(W_0) + s colsum(W_1) + b) -----------------
-            mbar_wait(&bar_da[b], ea & 1u, 6);
+            mbar_wait(&bar_da[b], (ea + ea_base) & 1u, 6);
             ++ea;
             tc_fence_after();
             if (live) {
@@ -902,7 +905,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 const float *bias = reinterpret_cast<const float *>(wb + 12288);
                 const float *rinv = bias + 32;
                 long long tq = timing ? clock64() : 0;
-                mbar_wait(&bar_dp[b], ep & 1u, 7);
+                mbar_wait(&bar_dp[b], (ep + ep_base) & 1u, 7);
                 ++ep;
                 tc_fence_after();
                 TC_TRACE(h, 2);
@@ -975,7 +978,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                     tm[4] += now - tq;
                     tq = now;
                 }
-                mbar_wait(&bar_da[b], ea & 1u, 9);
+                mbar_wait(&bar_da[b], (ea + ea_base) & 1u, 9);
                 ++ea;
                 tc_fence_after();
                 TC_TRACE(h, 6);
@@ -1038,7 +1041,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
                 fence_async_smem();
                 tc_fence_before();
                 hand_off_agg(true);
-                mbar_wait(&bar_da[b], ea & 1u, 10);
+                mbar_wait(&bar_da[b], (ea + ea_base) & 1u, 10);
                 ++ea;
                 tc_fence_after();
                 uint32_t d4[4];
@@ -1191,6 +1194,10 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) tc_solve_kernel(cons
         __syncthreads();  // the next iteration reuses tensor memory, the Y regions and the weight ring
         tc_fence_after();
         }  // dit_iter
+        if (gi >= 0) {   // the phases this tile has added to the block's barriers
+            ea_base = (ea_base + ea) & 1u;
+            ep_base = (ep_base + ep) & 1u;
+        }
         if (DIT && gi >= 0) {   // per-graph outputs of the iterative solve
             const TcMeta G2 = meta[gi];
             const int b2 = tid >> 7;

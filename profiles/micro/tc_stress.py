@@ -17,7 +17,7 @@ def main():
     import torch
     import bench
     from distgcn_b200 import engine as E
-    pb0, w0, layers, desc = bench.load_workload(workload, 0)
+    pb0, w0, layers, desc = bench.load_host_workload(workload, 0)
     rng = np.random.default_rng(1)
     ctx = E.Context(0)
     model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))

@@ -1055,3 +1055,44 @@ def test_error_reporting(gpu_ctx):
     with pytest.raises(_lib.DistGCNError) as ei:
         E.DeviceBatch(gpu_ctx, bad)
     assert ei.value.code == _lib.ERR_INVALID
+
+
+@pytest.mark.gpu
+def test_tensor_core_kernel_odd_depth_many_tiles(gpu_ctx, monkeypatch):
+    """tc_solve_kernel with an ODD number of hidden layers on more tiles than SMs: every CTA takes several tiles and its
+    per-block barriers complete an odd number of phases per tile (the shipped 20-layer model: an even number).  The
+    barriers used to be re-armed per tile, which block 0's did not always take: a dead-lock in exactly this case.  Scores
+    against the CUDA-core kernel, memberships against the reference rule on the kernel's own utilities."""
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    from distgcn_b200.ckpt import LayerWeights
+    monkeypatch.delenv("DG_DISABLE_FUSED", raising=False)
+    monkeypatch.delenv("DG_DISABLE_TC", raising=False)
+    rng = np.random.default_rng(3)
+    adjs = []
+    for k in range(500):
+        n = int(rng.integers(100, 301))
+        up = np.triu(rng.random((n, n)) < 6.0 / n, k=1)
+        adjs.append(sp.csr_matrix((up | up.T).astype(np.float64)))
+    pb = pack_graphs(adjs)
+    w = rng.random(pb.n_nodes)
+    w[rng.random(pb.n_nodes) < 0.05] = 0.0
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    for dims in ((1, 32, 32, 32, 32, 1), (1, 32, 32, 1), (1, 32, 32, 32, 1)):   # 3, 1 and 2 hidden layers
+        layers = [LayerWeights(weights=[(rng.standard_normal((ci, co)) / np.sqrt(ci + co)).astype(np.float32) for _ in range(2)])
+                  for ci, co in zip(dims[:-1], dims[1:])]
+        acts = [1] * (len(dims) - 2) + [0]
+        model = E.Model(gpu_ctx, layers, acts)
+        for rep in range(2):   # the second launch starts from whatever the first one left in shared memory
+            r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True, want_steps=True)
+            assert gpu_ctx.last_kernel == "tc_solve_kernel", dims
+            o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, r.util, init_remain=(w > 0).astype(np.uint8))
+            assert np.array_equal(o.member, r.member) and np.array_equal(o.steps, r.steps), dims
+        monkeypatch.setenv("DG_DISABLE_TC", "1")
+        r2 = E.solve(gpu_ctx, model, batch, w, want_score=True)
+        monkeypatch.delenv("DG_DISABLE_TC")
+        assert gpu_ctx.last_kernel != "tc_solve_kernel"
+        assert _rel_err(r.score[:, 0], r2.score[:, 0].astype(np.float64)) <= SCORE_RTOL, dims
+        model.close()
+    batch.close()

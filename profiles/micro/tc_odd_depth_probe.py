@@ -34,3 +34,18 @@ for dims in ((1, 32, 32, 32, 32, 1), (1, 32, 32, 1), (1, 32, 32, 32, 32, 32, 32,
     print("hidden layers %d: %s vs %s, memberships equal %s, max score difference / scale %.2e" % (
         len(dims) - 3, k1, k2, bool(np.array_equal(r.member, r2.member)), float(np.abs(r.score - r2.score).max() / scale)))
     model.close()
+# the iterative solve (solve_mwis_dit) with an odd number of hidden layers: completes, and agrees with the CUDA-core path up to
+# near-tie flips
+for dims in ((1, 32, 32, 32, 32, 1),):
+    layers = [LayerWeights(weights=[(rng.standard_normal((ci, co)) / np.sqrt(ci + co)).astype(np.float32) for _ in range(2)])
+              for ci, co in zip(dims[:-1], dims[1:])]
+    acts = [1] * (len(dims) - 2) + [0]
+    model = E.Model(ctx, layers, acts)
+    os.environ.pop("DG_DISABLE_TC", None); E.reload_env()
+    r = E.solve_dit(ctx, model, batch, w)
+    k1 = ctx.last_kernel
+    os.environ["DG_DISABLE_TC"] = "1"; E.reload_env()
+    r2 = E.solve_dit(ctx, model, batch, w)
+    print("iterative, hidden layers %d: %s vs %s, vertices differing %d of %d, members %d / %d" % (
+        len(dims) - 3, k1, ctx.last_kernel, int((r.member != r2.member).sum()), pb.n_nodes, int(r.member.sum()), int(r2.member.sum())))
+    model.close()

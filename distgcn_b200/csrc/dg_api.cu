@@ -725,6 +725,110 @@ symmetrize_upper_kernel(const int32_t *__restrict__ graph_ptr, const int32_t *__
     }
 }
 
+
+// The same for graphs whose lists fit in shared memory (every graph of the reference's sets): the upper lists are staged
+// with coalesced loads, counted, scanned, expanded and sorted entirely in shared memory as 16-bit local ids, and the full
+// rows leave with coalesced stores.  (The global-memory version above walks its rows thread by thread and insertion-sorts
+// in global memory: 45 us for the 500-graph ER set against 52 us for the solve itself.)
+__host__ __device__ inline size_t sym_smem_bytes(int n, int nnz_u) {
+    // rp_u [n + 1] + cnt [n] + low [n] ints, then col_u [nnz_u] and full [2 nnz_u] 16-bit ids (each padded to 4 bytes)
+    return sizeof(int) * (3 * (size_t)n + 2) + sizeof(uint16_t) * (3 * (size_t)nnz_u + 4);
+}
+__global__ void __launch_bounds__(256)
+symmetrize_upper_smem_kernel(const int32_t *__restrict__ graph_ptr, const int32_t *__restrict__ row_ptr_u,
+                             const uint16_t *__restrict__ col_u, int32_t *__restrict__ row_ptr, int32_t *__restrict__ col_idx,
+                             int n_graphs) {
+    extern __shared__ int sym_sm[];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int v0 = graph_ptr[g], n = graph_ptr[g + 1] - v0;
+    const int eu0 = row_ptr_u[v0], nu = row_ptr_u[v0 + n] - eu0;
+    int *rp = sym_sm;                 // [n + 1] upper row offsets, local
+    int *cnt = rp + n + 1;            // [n] degree, then exclusive offsets
+    int *low = cnt + n;               // [n] entries below the diagonal (cursor while filling)
+    uint16_t *cu = reinterpret_cast<uint16_t *>(low + n + 1);   // [nu] upper lists
+    uint16_t *full = cu + ((nu + 1) & ~1);                       // [2 nu] full rows, local ids
+    __shared__ int part[256];
+    const int base = 2 * eu0;
+    for (int i = tid; i <= n; i += 256) rp[i] = row_ptr_u[v0 + i] - eu0;
+    for (int e = tid; e < nu; e += 256) cu[e] = col_u[eu0 + e];
+    for (int i = tid; i < n; i += 256) cnt[i] = 0, low[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int b0 = rp[i], b1 = rp[i + 1];
+        atomicAdd(&cnt[i], b1 - b0);
+        for (int e = b0; e < b1; ++e) {
+            const int j = cu[e];
+            atomicAdd(&cnt[j], 1);
+            atomicAdd(&low[j], 1);
+        }
+    }
+    __syncthreads();
+    const int chunk = (n + 255) / 256;
+    const int c0 = min(tid * chunk, n), c1 = min(c0 + chunk, n);
+    int sum = 0;
+    for (int i = c0; i < c1; ++i) sum += cnt[i];
+    part[tid] = sum;
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the 256 partial sums: 8 per lane, then a warp scan
+        int loc[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            loc[k] = tot;
+            tot += part[tid * 8 + k];
+        }
+        int inc = tot;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, inc, off);
+            if (tid >= off) inc += up;
+        }
+        const int excl = inc - tot;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part[tid * 8 + k] = excl + loc[k];
+    }
+    __syncthreads();
+    int run = part[tid];
+    for (int i = c0; i < c1; ++i) {
+        const int v = cnt[i];
+        cnt[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int b0 = rp[i], b1 = rp[i + 1];
+        uint16_t *dst = full + cnt[i] + low[i];
+        for (int e = b0; e < b1; ++e) dst[e - b0] = cu[e];
+    }
+    __syncthreads();   // `low` becomes the fill cursor counting down
+    for (int i = tid; i < n; i += 256) {
+        const int b0 = rp[i], b1 = rp[i + 1];
+        for (int e = b0; e < b1; ++e) {
+            const int j = cu[e];
+            const int pos = atomicSub(&low[j], 1) - 1;
+            full[cnt[j] + pos] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {   // every row's lower part in ascending order (short lists: insertion sort)
+        const int deg = ((i + 1 < n) ? cnt[i + 1] : 2 * nu) - cnt[i];
+        const int nl = deg - (rp[i + 1] - rp[i]);
+        uint16_t *a = full + cnt[i];
+        for (int x = 1; x < nl; ++x) {
+            const uint16_t key = a[x];
+            int y = x - 1;
+            while (y >= 0 && a[y] > key) {
+                a[y + 1] = a[y];
+                --y;
+            }
+            a[y + 1] = key;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) row_ptr[v0 + i] = base + cnt[i];
+    if (g == n_graphs - 1 && tid == 0) row_ptr[v0 + n] = base + 2 * nu;
+    for (int k = tid; k < 2 * nu; k += 256) col_idx[base + k] = v0 + (int)full[k];
+}
+
 // batch-global int32 column ids (and, for the upper format, the full symmetric CSR) of a batch that arrived in a compact
 // host format (no-op otherwise)
 static int batch_ensure_cols(dg_batch *b) {
@@ -732,6 +836,20 @@ static int batch_ensure_cols(dg_batch *b) {
     dg_context *ctx = b->ctx;
     if (b->upper_pending) {
         if (b->n_graphs > 0 && b->n_nodes > 0) {
+            // (max_graph_nnz still counts upper entries here)
+            const size_t smem_fast = sym_smem_bytes(std::max(b->max_graph_nodes, 1), std::max(b->max_graph_nnz, 0));
+            if (smem_fast <= 64 * 1024) {   // several CTAs per SM: the reference's graphs need 10-30 KB
+                static bool fast_attr_set = false;
+                if (!fast_attr_set) {
+                    DG_CUDA_CHECK(cudaFuncSetAttribute(symmetrize_upper_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       64 * 1024));
+                    fast_attr_set = true;
+                }
+                symmetrize_upper_smem_kernel<<<b->n_graphs, 256, smem_fast, ctx->stream>>>(b->graph_ptr, b->row_ptr_u, b->col16,
+                                                                                          b->row_ptr, b->col_idx, b->n_graphs);
+                ctx->launches++;
+                DG_CUDA_CHECK(cudaGetLastError());
+            } else {
             const size_t smem = sizeof(int) * 2 * (size_t)std::max(b->max_graph_nodes, 1);
             static bool attr_set = false;
             if (!attr_set) {
@@ -743,6 +861,7 @@ static int batch_ensure_cols(dg_batch *b) {
                                                                             b->col_idx, b->n_graphs);
             ctx->launches++;
             DG_CUDA_CHECK(cudaGetLastError());
+            }
         }
         b->upper_pending = false;
         b->cols_pending = false;

@@ -234,6 +234,7 @@ struct dg_batch {
     bool tiles_valid = false;
     int tiles_hint_n = 0, tiles_hint_graphs = 0, tiles_hint_min_n = 0, tiles_hint_cp = 0;  // the previous plan's shape
     bool tiles_hint_hidden = false;
+    unsigned tiles_hint_calls = 0;
     // tile table of the tensor-core kernel (dg_tc.cu): up to 4 graph ids per tile
     int *tc_tiles_dev = nullptr;
     size_t tc_tiles_cap = 0;

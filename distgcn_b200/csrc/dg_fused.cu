@@ -28,6 +28,8 @@
 #include <algorithm>
 #include <functional>
 
+#include <chrono>
+
 #include "dg_common.cuh"
 
 namespace dg {
@@ -981,23 +983,28 @@ int launch_t(dg_context *ctx, const FusedParams &p, size_t smem, int n_tiles) {
     // microseconds of host time that the streaming path would pay on every call.  The attribute is always the device's
     // opt-in maximum: a per-call value would let one host thread lower it under another thread's launch (contexts of
     // several producer threads share the function).
-    static thread_local int c_dev = -1;
-    static thread_local size_t c_smem = 0;
-    static thread_local int c_per_sm = 0;
-    int per_sm = 0;
-    if (c_dev == ctx->device && c_smem == smem) {
-        per_sm = c_per_sm;
-    } else {
-        DG_REQUIRE(smem <= (size_t)ctx->max_smem_optin, DG_ERR_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory (limit %d)",
-                   smem, ctx->max_smem_optin);
+    struct Cache {
+        int dev = -1, dyn_max = 0, n = 0;
+        size_t smem[16];
+        int per_sm[16];
+    };
+    static thread_local Cache c;
+    if (c.dev != ctx->device) {
         cudaFuncAttributes fa;
         DG_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
         const int dyn_max = ctx->max_smem_optin - (int)fa.sharedSizeBytes;   // (static shared memory counts against the limit)
-        DG_REQUIRE((long long)smem <= (long long)dyn_max, DG_ERR_UNSUPPORTED,
-                   "fused kernel needs %zu bytes of dynamic shared memory (limit %d)", smem, dyn_max);
         DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+        c.dev = ctx->device, c.dyn_max = dyn_max, c.n = 0;
+    }
+    DG_REQUIRE((long long)smem <= (long long)c.dyn_max, DG_ERR_UNSUPPORTED,
+               "fused kernel needs %zu bytes of dynamic shared memory (limit %d)", smem, c.dyn_max);
+    int per_sm = 0;
+    for (int k = 0; k < c.n; ++k)
+        if (c.smem[k] == smem) per_sm = c.per_sm[k];
+    if (per_sm == 0) {   // (a stream of batches alternates between a few tile capacities: one entry per size)
         DG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-        c_dev = ctx->device, c_smem = smem, c_per_sm = per_sm;
+        const int slot = c.n < 16 ? c.n++ : 15;
+        c.smem[slot] = smem, c.per_sm[slot] = per_sm;
     }
     DG_REQUIRE(per_sm > 0, DG_ERR_UNSUPPORTED, "fused kernel does not fit on an SM with %zu bytes of shared memory",
                smem);
@@ -1011,6 +1018,7 @@ int launch_t(dg_context *ctx, const FusedParams &p, size_t smem, int n_tiles) {
 
 struct Tile {
     int v0, n, e0, nnz, g0, ng;
+    long long cost;   // tile_cost(), filled in when the tile is closed
 };
 
 // Cost model of a tile for scheduling decisions, in SM cycles for an 18-hidden-layer model, fitted to
@@ -1027,19 +1035,22 @@ void pack_tiles(const dg_batch *b, int cap_n, int cap_nnz, bool subset, std::vec
     out->clear();
     const auto &gp = b->h_graph_ptr;
     const auto &ge = b->h_graph_e;
-    Tile cur{0, 0, 0, 0, 0, 0};
+    Tile cur{0, 0, 0, 0, 0, 0, 0};
+    auto close = [&]() {
+        cur.cost = tile_cost(cur);
+        out->push_back(cur);
+        cur = Tile{0, 0, 0, 0, 0, 0, 0};
+    };
     for (int g = 0; g < b->n_graphs; ++g) {
         if (subset && !b->tc_skip[(size_t)g]) {
-            if (cur.ng > 0) out->push_back(cur);
-            cur = Tile{0, 0, 0, 0, 0, 0};
+            if (cur.ng > 0) close();
             continue;
         }
         const int gn = gp[g + 1] - gp[g], gz = ge[g + 1] - ge[g];
         // cap_nnz bounds the PADDED neighbour lists (each row rounded up to a multiple of 4)
         if (cur.ng > 0 && (cur.n + gn > cap_n || cur.nnz + gz + 3 * (cur.n + gn) > cap_nnz ||
                            cur.ng >= kFusedMaxTileGraphs)) {
-            out->push_back(cur);
-            cur = Tile{0, 0, 0, 0, 0, 0};
+            close();
         }
         if (cur.ng == 0) {
             cur.v0 = gp[g];
@@ -1050,8 +1061,8 @@ void pack_tiles(const dg_batch *b, int cap_n, int cap_nnz, bool subset, std::vec
         cur.nnz += gz;
         cur.ng += 1;
     }
-    if (cur.ng > 0) out->push_back(cur);
-    std::stable_sort(out->begin(), out->end(), [](const Tile &a, const Tile &c) { return tile_cost(a) > tile_cost(c); });
+    if (cur.ng > 0) close();
+    std::stable_sort(out->begin(), out->end(), [](const Tile &a, const Tile &c) { return a.cost > c.cost; });
 }
 
 // makespan of heaviest-first list scheduling of the tiles on `workers` CTAs (what the kernel's
@@ -1061,7 +1072,7 @@ long long simulate_makespan(const std::vector<Tile> &tiles, int workers) {
     std::make_heap(load.begin(), load.end(), std::greater<long long>());
     for (const Tile &t : tiles) {
         std::pop_heap(load.begin(), load.end(), std::greater<long long>());
-        load.back() += tile_cost(t);
+        load.back() += t.cost;
         std::push_heap(load.begin(), load.end(), std::greater<long long>());
     }
     return *std::max_element(load.begin(), load.end());
@@ -1095,27 +1106,35 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
     // A context that solves a stream of similar batches (dg_solve_host*) re-plans on every call: when the previous plan
     // was made for a batch of the same shape (graph count, largest graph), only its capacity and the two neighbouring
     // ones are simulated again.
-    const bool hinted = !subset && b->tiles_hint_n > 0 && b->tiles_hint_graphs == b->n_graphs &&
-                        b->tiles_hint_min_n == min_n && b->tiles_hint_cp == cp && b->tiles_hint_hidden == has_hidden;
-    for (int cap_n = min_n; cap_n <= 1024; cap_n += 32) {
-        if (forced_rows > 0 && cap_n != std::max(min_n, (forced_rows + 31) / 32 * 32)) continue;
-        if (forced_rows <= 0 && hinted && (cap_n < b->tiles_hint_n - 32 || cap_n > b->tiles_hint_n + 32)) continue;
-        // give the neighbour lists whatever shared memory is left (bounded by 48 padded entries per row)
-        const size_t fixed = fused_smem_bytes(cp, cap_n, 0, has_hidden, wblob);
-        if (fixed + sizeof(uint16_t) * (size_t)min_nnz > budget) break;
-        long long cap_nnz = (long long)((budget - fixed) / sizeof(uint16_t));
-        cap_nnz = std::min<long long>(cap_nnz, std::max<long long>(min_nnz, 48LL * cap_n));
-        cap_nnz = cap_nnz / 64 * 64;
-        if (cap_nnz < min_nnz) break;
-        pack_tiles(b, cap_n, (int)cap_nnz, subset, &tiles);
-        const long long span = simulate_makespan(tiles, ctx->sm_count);
-        if (best_span < 0 || span < best_span) {
-            best_span = span;
-            best_n = cap_n;
-            best_nnz = (int)cap_nnz;
-            best_tiles.swap(tiles);
+    // (Only the hinted capacity itself: a plan costs ~20 us per candidate for 500 graphs in random order, most of it the
+    // sort and the simulated schedule.  Every 64th call searches all capacities again, so a hint taken from an unlucky
+    // first batch does not stick.)
+    bool hinted = !subset && b->tiles_hint_n > 0 && b->tiles_hint_graphs == b->n_graphs &&
+                  b->tiles_hint_min_n == min_n && b->tiles_hint_cp == cp && b->tiles_hint_hidden == has_hidden;
+    if (hinted && (++b->tiles_hint_calls & 63) == 0) hinted = false;
+    auto search = [&](bool use_hint) {
+        for (int cap_n = min_n; cap_n <= 1024; cap_n += 32) {
+            if (forced_rows > 0 && cap_n != std::max(min_n, (forced_rows + 31) / 32 * 32)) continue;
+            if (forced_rows <= 0 && use_hint && cap_n != b->tiles_hint_n) continue;
+            // give the neighbour lists whatever shared memory is left (bounded by 48 padded entries per row)
+            const size_t fixed = fused_smem_bytes(cp, cap_n, 0, has_hidden, wblob);
+            if (fixed + sizeof(uint16_t) * (size_t)min_nnz > budget) break;
+            long long cap_nnz = (long long)((budget - fixed) / sizeof(uint16_t));
+            cap_nnz = std::min<long long>(cap_nnz, std::max<long long>(min_nnz, 48LL * cap_n));
+            cap_nnz = cap_nnz / 64 * 64;
+            if (cap_nnz < min_nnz) break;
+            pack_tiles(b, cap_n, (int)cap_nnz, subset, &tiles);
+            const long long span = simulate_makespan(tiles, ctx->sm_count);
+            if (best_span < 0 || span < best_span) {
+                best_span = span;
+                best_n = cap_n;
+                best_nnz = (int)cap_nnz;
+                best_tiles.swap(tiles);
+            }
         }
-    }
+    };
+    search(hinted);
+    if (best_span < 0 && hinted) search(false);   // the hinted capacity does not take this batch's largest graph
     if (best_span < 0) return DG_OK;
     if (!subset) {
         b->tiles_hint_n = best_n, b->tiles_hint_graphs = b->n_graphs, b->tiles_hint_min_n = min_n;
@@ -1150,8 +1169,8 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
     b->tiles_subset = subset;
     b->tiles_valid = true;
     if (ctx->env.fused_timing)
-        fprintf(stderr, "[fused tiles] %d tiles, cap_n %d, cap_nnz %d, simulated makespan %lld\n", b->n_tiles, best_n,
-                best_nnz, best_span);
+        fprintf(stderr, "[fused tiles] %d tiles, cap_n %d, cap_nnz %d, simulated makespan %lld (hinted %d: min_n %d, max nodes %d, "
+                "max nnz %d)\n", b->n_tiles, best_n, best_nnz, best_span, (int)hinted, min_n, b->max_graph_nodes, b->max_graph_nnz);
     *ok = b->n_tiles > 0;
     return DG_OK;
 }
@@ -1195,7 +1214,11 @@ int fused_try_solve(dg_context *ctx, const dg_model *m, dg_batch *b, const doubl
     const size_t wblob = use_mma ? sizeof(float) * (size_t)(2 * 2 * 32 * 40 + 32)
                                  : sizeof(float) * (size_t)(2 * m->fused_cp * m->fused_cp + m->fused_cp);
     bool ok = false;
+    const auto t_plan0 = std::chrono::steady_clock::now();
     DG_TRY(build_tiles(ctx, b, m->fused_cp, has_hidden, wblob, subset, &ok));
+    if (ctx->env.ingest_timing)
+        fprintf(stderr, "[fused] tile plan %.0f us\n",
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_plan0).count());
     if (!ok) return DG_OK;
     FusedParams p{};
     p.tiles = b->tiles_dev;

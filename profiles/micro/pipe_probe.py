@@ -7,17 +7,20 @@ from distgcn_b200 import engine as E
 from distgcn_b200.batch import PackedBatch
 wl = sys.argv[1] if len(sys.argv) > 1 else "er500"
 pb, w, layers, desc = bench.load_host_workload(wl, 0)
-rp_u, c16 = pb.upper_compact()
 def pin(a):
     h = E.pinned_empty(a.shape, a.dtype); h[:] = a; return h
 sets = []
-for r in range(8):
-    sets.append(dict(pb=PackedBatch(pin(pb.graph_ptr), pin(pb.row_ptr), pb.col_idx), up=(pin(rp_u), pin(c16)), w=pin(w),
-                     m=E.pinned_empty(pb.n_nodes, np.uint8), t=E.pinned_empty(pb.n_graphs, np.float64)))
+NSETS = int(os.environ.get("PIPE_SETS", "8"))
+rng = np.random.default_rng(1)
+for r in range(NSETS):
+    pbr, wr = (pb, w) if (r == 0 or not os.environ.get("PIPE_SHUFFLE")) else bench.shuffled_copy(pb, w, rng)[:2]
+    rp_u, c16 = pbr.upper_compact()
+    sets.append(dict(pb=PackedBatch(pin(pbr.graph_ptr), pin(pbr.row_ptr), pbr.col_idx), up=(pin(rp_u), pin(c16)), w=pin(wr),
+                     m=E.pinned_empty(pbr.n_nodes, np.uint8), t=E.pinned_empty(pbr.n_graphs, np.float64)))
 for depth in (1, 2, 4):
     pipe = E.HostPipeline(0, layers, E.gcn_dqn_acts(len(layers)), depth=depth)
     def step(i, acc):
-        c = sets[i % 8]
+        c = sets[i % NSETS]
         slot = pipe._next
         t0 = time.perf_counter()
         pipe.wait(slot)

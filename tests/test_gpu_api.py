@@ -362,6 +362,19 @@ def test_upper_host_format_matches_the_packed_one(short, nl, monkeypatch):
     assert np.array_equal(m3, m3f)
     monkeypatch.delenv("DG_DISABLE_FUSED")
     monkeypatch.delenv("DG_DISABLE_TC")
+    # a graph whose lists do not fit the shared-memory expansion (the global-memory one takes it), next to small ones
+    nb = 6000
+    src = rng.integers(0, nb, 30000)
+    dst = rng.integers(0, nb, 30000)
+    ok = src != dst
+    big = sp.csr_matrix((np.ones(int(ok.sum())), (src[ok], dst[ok])), shape=(nb, nb))
+    big = ((big + big.T) > 0).astype(np.float64).tocsr()
+    pbb = pack_graphs([adjs[0], big, adjs[1]])
+    wb = rng.random(pbb.n_nodes)
+    wb[rng.random(pbb.n_nodes) < 0.1] = 0.0
+    mb_full, _ = E.solve_host(ctx, model, pbb, wb)
+    mb_up, _ = E.solve_host(ctx, model, pbb, wb, upper=pbb.upper_compact())
+    assert np.array_equal(mb_full, mb_up)
     pipe = E.HostPipeline(0, layers, E.gcn_dqn_acts(len(layers)), depth=2)
     outs = [(E.pinned_empty(pb.n_nodes, np.uint8), E.pinned_empty(pb.n_graphs, np.float64)) for _ in range(4)]
     for k in range(4):

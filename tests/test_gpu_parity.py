@@ -1096,3 +1096,63 @@ def test_tensor_core_kernel_odd_depth_many_tiles(gpu_ctx, monkeypatch):
         assert _rel_err(r.score[:, 0], r2.score[:, 0].astype(np.float64)) <= SCORE_RTOL, dims
         model.close()
     batch.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_models_and_batches_across_paths(gpu_ctx, seed, monkeypatch):
+    """Differential test over what the shipped checkpoints do not vary: random 32-wide models of 1-6 hidden layers (bias,
+    mixed activations), random batches of 150-450 graphs of 1-330 vertices (densities 0.01-0.2, zero weights, ties) - more
+    tiles than SMs for the larger ones - through the tensor-core, CUDA-core and per-layer paths, host formats included.
+    Scores agree across paths; every path's memberships obey the reference rule on its own utilities."""
+    E = _engine()
+    from oracle import lgs as L
+    from distgcn_b200.batch import pack_graphs
+    from distgcn_b200.ckpt import LayerWeights
+    for name in ("DG_DISABLE_FUSED", "DG_DISABLE_TC"):
+        monkeypatch.delenv(name, raising=False)
+    rng = np.random.default_rng(1000 + seed)
+    n_graphs = int(rng.integers(150, 451))
+    adjs = []
+    for k in range(n_graphs):
+        n = int(rng.integers(1, 331))
+        p = float(rng.choice([0.01, 0.03, 0.08, 0.2]))
+        up = np.triu(rng.random((n, n)) < p, k=1)
+        adjs.append(sp.csr_matrix((up | up.T).astype(np.float64)))
+    pb = pack_graphs(adjs)
+    w = rng.random(pb.n_nodes)
+    w[rng.random(pb.n_nodes) < 0.08] = 0.0
+    w[rng.random(pb.n_nodes) < 0.1] = 0.25
+    n_hidden = int(rng.integers(1, 7))
+    dims = (1,) + (32,) * (n_hidden + 1) + (1,)
+    layers = []
+    for ci, co in zip(dims[:-1], dims[1:]):
+        lw = LayerWeights(weights=[(rng.standard_normal((ci, co)) / np.sqrt(ci + co)).astype(np.float32) for _ in range(2)])
+        if seed % 2 == 0:
+            lw.bias = (0.1 * rng.standard_normal(co)).astype(np.float32)
+        layers.append(lw)
+    acts = [int(a) for a in rng.integers(0, 3, len(dims) - 2)] + [0]
+    model = E.Model(gpu_ctx, layers, acts)
+    batch = E.DeviceBatch(gpu_ctx, pb)
+    keep0 = (w > 0).astype(np.uint8)
+    results = {}
+    for path, env in (("tensor_core", {}), ("fused", {"DG_DISABLE_TC": "1"}), ("layers", {"DG_DISABLE_TC": "1", "DG_DISABLE_FUSED": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = E.solve(gpu_ctx, model, batch, w, want_score=True, want_util=True, want_steps=True)
+        results[path] = (r, gpu_ctx.last_kernel)
+        o = L.run_batch(pb.graph_ptr, pb.row_ptr, pb.col_idx, r.util, init_remain=keep0)
+        assert np.array_equal(o.member, r.member) and np.array_equal(o.steps, r.steps), (path, seed)
+        for k in env:
+            monkeypatch.delenv(k)
+    assert results["tensor_core"][1] == "tc_solve_kernel" and results["fused"][1] == "fused_solve_kernel"
+    ref = results["layers"][0].score[:, 0].astype(np.float64)
+    for path in ("tensor_core", "fused"):
+        assert _rel_err(results[path][0].score[:, 0], ref) <= 2 * SCORE_RTOL, (path, seed, n_hidden)
+    # host formats: packed int32, 16-bit local ids, upper triangle - the same memberships as the resident batch
+    m_res = results["tensor_core"][0].member
+    for kw in ({}, {"col_local16": pb.local_columns()}, {"upper": pb.upper_compact()}):
+        m_h, _ = E.solve_host(gpu_ctx, model, pb, w, **kw)
+        assert np.array_equal(m_h, m_res), (list(kw), seed)
+    batch.close()
+    model.close()

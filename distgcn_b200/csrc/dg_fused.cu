@@ -1124,7 +1124,8 @@ int build_tiles(dg_context *ctx, dg_batch *b, int cp, bool has_hidden, size_t wb
             cap_nnz = cap_nnz / 64 * 64;
             if (cap_nnz < min_nnz) break;
             pack_tiles(b, cap_n, (int)cap_nnz, subset, &tiles);
-            const long long span = simulate_makespan(tiles, ctx->sm_count);
+            // (a single hinted candidate is taken as it is: nothing to compare its simulated schedule with)
+            const long long span = (use_hint && forced_rows <= 0) ? 0 : simulate_makespan(tiles, ctx->sm_count);
             if (best_span < 0 || span < best_span) {
                 best_span = span;
                 best_n = cap_n;

@@ -839,24 +839,16 @@ static int batch_ensure_cols(dg_batch *b) {
             // (max_graph_nnz still counts upper entries here)
             const size_t smem_fast = sym_smem_bytes(std::max(b->max_graph_nodes, 1), std::max(b->max_graph_nnz, 0));
             if (smem_fast <= 64 * 1024) {   // several CTAs per SM: the reference's graphs need 10-30 KB
-                static bool fast_attr_set = false;
-                if (!fast_attr_set) {
-                    DG_CUDA_CHECK(cudaFuncSetAttribute(symmetrize_upper_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       64 * 1024));
-                    fast_attr_set = true;
-                }
+                static std::atomic<unsigned long long> fast_attr_done{0};
+                DG_CUDA_CHECK(smem_attr_once(symmetrize_upper_smem_kernel, ctx->device, 64 * 1024, &fast_attr_done));
                 symmetrize_upper_smem_kernel<<<b->n_graphs, 256, smem_fast, ctx->stream>>>(b->graph_ptr, b->row_ptr_u, b->col16,
                                                                                           b->row_ptr, b->col_idx, b->n_graphs);
                 ctx->launches++;
                 DG_CUDA_CHECK(cudaGetLastError());
             } else {
             const size_t smem = sizeof(int) * 2 * (size_t)std::max(b->max_graph_nodes, 1);
-            static bool attr_set = false;
-            if (!attr_set) {
-                DG_CUDA_CHECK(cudaFuncSetAttribute(symmetrize_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)(sizeof(int) * 2 * kSymMaxNodes)));
-                attr_set = true;
-            }
+            static std::atomic<unsigned long long> attr_done{0};
+            DG_CUDA_CHECK(smem_attr_once(symmetrize_upper_kernel, ctx->device, (int)(sizeof(int) * 2 * kSymMaxNodes), &attr_done));
             symmetrize_upper_kernel<<<b->n_graphs, 256, smem, ctx->stream>>>(b->graph_ptr, b->row_ptr_u, b->col16, b->row_ptr,
                                                                             b->col_idx, b->n_graphs);
             ctx->launches++;

@@ -5,12 +5,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
 #include "../../include/distgcn_b200.h"
 
 namespace dg {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per DEVICE and call site (the attribute belongs to the function on a
+// device: a process that drives two GPUs must set it on both).  `done` is a static bit mask owned by the call site.
+template <typename Kernel>
+inline cudaError_t smem_attr_once(Kernel kern, int device, int bytes, std::atomic<unsigned long long> *done) {
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done->load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done->fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 void set_error(const char *fmt, ...);
 void clear_error();

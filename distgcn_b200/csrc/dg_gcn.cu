@@ -462,9 +462,10 @@ template <int CPI, int CPO, bool IMPLICIT_IN, bool TAIL>
 int launch_layer_t(dg_context *ctx, const LayerArgs &args) {
     auto kern = gc_layer_kernel<CPI, CPO, IMPLICIT_IN, TAIL>;
     constexpr size_t smem = layer_smem_bytes<CPI, CPO>();
+    static std::atomic<unsigned long long> attr_done{0};   // (the attribute: once per device)
+    DG_CUDA_CHECK(smem_attr_once(kern, ctx->device, (int)smem, &attr_done));
     static int blocks_per_sm = 0;  // per instantiation; every context uses the same device kind
     if (blocks_per_sm == 0) {
-        DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
         DG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
         DG_REQUIRE(nb > 0, DG_ERR_CUDA, "gc_layer_kernel<%d,%d> does not fit on an SM", CPI, CPO);

@@ -659,11 +659,8 @@ int dist_greedy_device(dg_context *ctx, const dg_batch *b, const double *wts, do
     DG_REQUIRE(smem <= (size_t)ctx->max_smem_optin, DG_ERR_UNSUPPORTED,
                "dist_greedy_search runs one CTA per graph: a graph of %d vertices needs %zu bytes of shared memory (limit %d, "
                "about %d vertices)", b->max_graph_nodes, smem, ctx->max_smem_optin, ctx->max_smem_optin * 2 - 64);
-    static size_t smem_set = 0;   // the attribute only ever grows (per device kind)
-    if (smem > 48 * 1024 && smem > smem_set) {
-        DG_CUDA_CHECK(cudaFuncSetAttribute(dgs_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_smem_optin));
-        smem_set = (size_t)ctx->max_smem_optin;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (smem > 48 * 1024) DG_CUDA_CHECK(smem_attr_once(dgs_cta_kernel, ctx->device, ctx->max_smem_optin, &attr_done));
     dgs_cta_kernel<<<G, kLgsCtaThreads, smem, ctx->stream>>>(b->graph_ptr, b->row_ptr, b->col_idx, wts, b->keep, alpha,
                                                              kLgsRoundCap, words_cap, member, steps, ctx->d_status);
     ctx->launches++;

@@ -374,11 +374,8 @@ template <bool IMPLICIT_IN, bool TAIL, bool SPMM_ONLY = false>
 int gs_launch(dg_context *ctx, dg_batch *b, const LayerArgs &a) {
     auto kern = gs_layer_kernel<IMPLICIT_IN, TAIL, SPMM_ONLY>;
     constexpr size_t smem = gs_smem_bytes();
-    static bool attr_set = false;
-    if (!attr_set) {
-        DG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    DG_CUDA_CHECK(smem_attr_once(kern, ctx->device, (int)smem, &attr_done));
     GsArgs P;
     P.tiles = reinterpret_cast<const int4 *>(b->gs_tiles_dev);
     P.cta_first = b->gs_tiles_dev + (size_t)b->gs_n_tiles * 4;

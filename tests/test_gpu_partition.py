@@ -1,6 +1,8 @@
 """Row-partitioned single-graph path, checked against the CPU oracle: scores within 1e-5 of
 the float64 evaluation, membership exactly what oracle.lgs gives on the same utilities.  world_size 1 on one GPU;
 test_partitioned_multi_rank spawns the 2-rank run (tests/run_partition_2gpu.py) when the box has two GPUs."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -100,3 +102,43 @@ def test_partitioned_multi_rank(world):
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "PARTITION_2GPU_OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process():
+    """One process driving two GPUs: every kernel's opt-in shared-memory attribute belongs to the function ON A DEVICE, so
+    the second device must get its own (they used to be set once per process).  The same batches through the tensor-core,
+    CUDA-core (upper-triangle host format: the expansion kernel too) and per-layer paths and the threshold greedy on
+    device 0, then on device 1: identical results."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from distgcn_b200 import engine as E
+    pb, w = util.small_graphs()
+    pb = pb.slice(0, 24)
+    w = w[: pb.n_nodes].copy()
+    w[::6] = 0.0
+    upper = pb.upper_compact()
+    out = {}
+    for dev in (0, 1):
+        ctx = E.Context(dev)
+        res = []
+        for short in ("is4sat_l20_c32", "is4sat_l1", "is4sat_l3_c16"):
+            layers = util.load_layers(short)
+            model = E.Model(ctx, layers, E.gcn_dqn_acts(len(layers)))
+            res.append(E.solve_host(ctx, model, pb, w, upper=upper)[0])
+            os.environ["DG_DISABLE_TC"] = "1"
+            os.environ["DG_DISABLE_FUSED"] = "1"
+            E.reload_env()
+            res.append(E.solve_host(ctx, model, pb, w)[0])
+            del os.environ["DG_DISABLE_TC"], os.environ["DG_DISABLE_FUSED"]
+            E.reload_env()
+            model.close()
+        batch = E.DeviceBatch(ctx, pb)
+        res.append(E.dist_greedy(ctx, batch, w, 0.1).member)
+        res.append(E.lgs(ctx, batch, w).member)
+        batch.close()
+        ctx.close()
+        out[dev] = res
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)

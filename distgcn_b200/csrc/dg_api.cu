@@ -120,6 +120,8 @@ int copy_out(dg_context *ctx, T *host, const T *dev, size_t count) {
 static void set_kernel_status_error(int code) {
     if (code == DG_ERR_NOT_CONVERGED)
         set_error("greedy search hit the round cap (NaN utilities or self-loops?)");
+    else if (code == DG_ERR_INVALID)
+        set_error("malformed graph: a column id points outside its graph");
     else if (code == DG_ERR_CUDA)
         set_error("a device-side wait gave up: the peer barrier of a row-partitioned solve timed out (a rank missing "
                   "or its arena not mapped?)");

@@ -75,6 +75,7 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
     }
 
     int rounds = 0;
+    bool bad_col = false;
     long long bst_acc = 0;
     unsigned long long p2p_acc = 0;
     int joined_mine = 0;
@@ -96,6 +97,10 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
                 int cnt = 0;
                 for (int e = beg; e < end; ++e) {
                     const int u = col_idx[e] - v0;
+                    if ((unsigned)u >= (unsigned)n) {   // a column id outside its graph: malformed CSR, reported, never followed
+                        bad_col = true;
+                        continue;
+                    }
                     if ((remain[u >> 5] >> (u & 31)) & 1u) {
                         ++cnt;
                         if (dominates(util[v0 + u], u, wv, v)) {
@@ -124,7 +129,7 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
         n_remain = 0;
         for (int base = 0; base < span; base += kLgsCtaThreads) {
             const int v = base + threadIdx.x;
-            bool still = false;
+            bool still = false, excluded_v = false;
             if (v < span) {
                 const bool active = (remain[v >> 5] >> lane) & 1u;
                 const bool join = (joined[v >> 5] >> lane) & 1u;
@@ -133,25 +138,28 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
                     bool excluded = false;
                     for (int e = beg; e < end; ++e) {
                         const int u = col_idx[e] - v0;
+                        if ((unsigned)u >= (unsigned)n) {
+                            bad_col = true;
+                            continue;
+                        }
                         if ((joined[u >> 5] >> (u & 31)) & 1u) {
                             excluded = true;
                             break;
                         }
                     }
-                    if (excluded) {
-                        if (nb_is) nb_is[v0 + v] = 1;
-                    } else {
-                        still = true;
-                    }
+                    excluded_v = excluded;
+                    still = !excluded;
                 }
             }
             const uint32_t rw = __ballot_sync(0xffffffffu, still);
+            if (excluded_v && nb_is) nb_is[v0 + v] = 1;   // (after the warp has reconverged)
             __syncwarp();  // every lane has read this word (WAR within the warp)
             if (lane == 0 && v < span) remain[v >> 5] = rw;
             n_remain += __syncthreads_count(still);
         }
         ++rounds;
     }
+    if (bad_col) atomicExch(status, DG_ERR_INVALID);
     if (STATS) {
         atomicAdd(&p2p_sm, p2p_acc);
         atomicAdd(&member_sm, joined_mine);
@@ -402,7 +410,7 @@ lgs_remove_global(int n, int n_graphs, const int *__restrict__ graph_ptr, const 
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int n_words = (n + 31) / 32;
-    bool still = false;
+    bool still = false, excluded_v = false;
     if ((v >> 5) < n_words) {
         const bool active = (remain[v >> 5] >> lane) & 1u;
         const bool join = (joined[v >> 5] >> lane) & 1u;
@@ -416,14 +424,12 @@ lgs_remove_global(int n, int n_graphs, const int *__restrict__ graph_ptr, const 
                     break;
                 }
             }
-            if (excluded) {
-                if (nb_is) nb_is[v] = 1;
-            } else {
-                still = true;
-            }
+            excluded_v = excluded;
+            still = !excluded;
         }
     }
     const uint32_t rw = __ballot_sync(0xffffffffu, still);
+    if (excluded_v && nb_is) nb_is[v] = 1;   // (after the warp has reconverged)
     if (lane == 0 && (v >> 5) < n_words) remain[v >> 5] = rw;
     if (n_graphs == 1) {
         const int c = __syncthreads_count(still);

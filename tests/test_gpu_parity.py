@@ -1055,6 +1055,22 @@ def test_error_reporting(gpu_ctx):
     with pytest.raises(_lib.DistGCNError) as ei:
         E.DeviceBatch(gpu_ctx, bad)
     assert ei.value.code == _lib.ERR_INVALID
+    # a column id that points into ANOTHER graph of the batch: the local greedy search reports it instead of following it
+    cross = PackedBatch(np.array([0, 3, 6], np.int32), np.array([0, 1, 2, 2, 3, 4, 4], np.int32), np.array([1, 0, 4, 5], np.int32))
+    cross.col_idx[2] = 1          # vertex 3 (second graph) names vertex 1 (first graph)
+    try:
+        batch = E.DeviceBatch(gpu_ctx, cross)
+    except _lib.DistGCNError as e:    # (refused at creation: fine as well)
+        assert e.code == _lib.ERR_INVALID
+    else:
+        with pytest.raises(_lib.DistGCNError) as ei:
+            E.lgs(gpu_ctx, batch, np.arange(6, dtype=np.float64) + 1.0)
+        assert ei.value.code == _lib.ERR_INVALID
+        batch.close()
+        small, ws = util.small_graphs()   # the context is still usable
+        b2 = E.DeviceBatch(gpu_ctx, small)
+        E.lgs(gpu_ctx, b2, ws)
+        b2.close()
 
 
 @pytest.mark.gpu

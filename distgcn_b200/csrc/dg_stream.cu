@@ -131,9 +131,11 @@ __global__ void __launch_bounds__(kGsThreads, kGsBufs == 1 ? 2 : 1) gs_layer_ker
                 cp_async16(hs + (item >> 3) * kGsStride + 4 * (item & 7), src + (size_t)item * 4);
         }
         const int ea = e0 & ~3;            // 16-byte aligned start of the column window around [e0, e0 + nnz)
-        const int chunks = (nnz + (e0 - ea) + 3) >> 2;
+        const int total = nnz + (e0 - ea);
+        const int chunks = total >> 2;     // whole 16-byte chunks; the last ids one by one (never past the end of col_idx)
         const int *csrc = a.col_idx + ea;
         for (int c = tid; c < chunks; c += kGsThreads) cp_async16(cols + 4 * c, csrc + 4 * c);
+        for (int k = 4 * chunks + tid; k < total; k += kGsThreads) cp_async4(cols + k, csrc + k);
         for (int r = tid; r <= n; r += kGsThreads) cp_async4(rp + r, a.row_ptr + v0 + r);
         for (int r = tid; r < n; r += kGsThreads) cp_async4(dinv_s + r, a.dinv + v0 + r);
         cp_async_commit();

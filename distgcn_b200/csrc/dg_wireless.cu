@@ -206,6 +206,8 @@ int dg_wireless_create(dg_context *ctx, int32_t n_links, int32_t n_ch, int32_t n
             }
         }
         DG_CUDA_CHECK(cudaMemsetAsync(s->q, 0, sizeof(double) * std::max<size_t>(nl, 1), ctx->stream));
+        DG_CUDA_CHECK(cudaMemsetAsync(s->qest, 0, sizeof(double) * std::max<size_t>(nl, 1), ctx->stream));
+        DG_CUDA_CHECK(cudaMemsetAsync(s->cap, 0, sizeof(double) * std::max<size_t>(nl, 1), ctx->stream));
         DG_CUDA_CHECK(cudaMemsetAsync(s->history, 0, sizeof(double) * std::max<size_t>(nl * n_slots, 1), ctx->stream));
         DG_CUDA_CHECK(cudaMemsetAsync(s->w, 0, sizeof(double) * nw, ctx->stream));
         DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the caller may release its arrays

@@ -96,11 +96,11 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
                 bool blocked = false;
                 int cnt = 0;
                 for (int e = beg; e < end; ++e) {
-                    const int u = col_idx[e] - v0;
-                    if ((unsigned)u >= (unsigned)n) {   // a column id outside its graph: malformed CSR, reported, never followed
-                        bad_col = true;
-                        continue;
-                    }
+                    int u = col_idx[e] - v0;
+                    // a column id outside its graph (malformed CSR) is reported and read as the vertex itself, never followed
+                    const bool bad = (unsigned)u >= (unsigned)n;
+                    bad_col |= bad;
+                    u = bad ? v : u;
                     if ((remain[u >> 5] >> (u & 31)) & 1u) {
                         ++cnt;
                         if (dominates(util[v0 + u], u, wv, v)) {
@@ -137,11 +137,10 @@ lgs_cta_kernel(const int *__restrict__ graph_ptr, const int *__restrict__ row_pt
                     const int beg = row_ptr[v0 + v], end = row_ptr[v0 + v + 1];
                     bool excluded = false;
                     for (int e = beg; e < end; ++e) {
-                        const int u = col_idx[e] - v0;
-                        if ((unsigned)u >= (unsigned)n) {
-                            bad_col = true;
-                            continue;
-                        }
+                        int u = col_idx[e] - v0;
+                        const bool bad = (unsigned)u >= (unsigned)n;
+                        bad_col |= bad;
+                        u = bad ? v : u;
                         if ((joined[u >> 5] >> (u & 31)) & 1u) {
                             excluded = true;
                             break;

@@ -256,7 +256,7 @@ struct dg_batch {
     // tile table of the graph-staged streaming layer kernel (dg_stream.cu): row ranges aligned to graph boundaries
     int *gs_tiles_dev = nullptr;
     size_t gs_tiles_cap = 0;
-    int gs_n_tiles = 0, gs_grid = 0;
+    int gs_n_tiles = 0, gs_grid = 0, gs_grid_spmm = 0;
     bool gs_valid = false;
     bool tc_plan_ready = false;      // tc_tiles_host already holds the plan of the current batch (made ahead, on a pool thread)
     bool meta_ready = false;         // host metadata (h_graph_ptr, h_graph_e, maxima) already describe the batch being filled

@@ -68,13 +68,19 @@ constexpr size_t gs_smem_bytes() {
                             + (size_t)kGsWarps * kGsUnit * kGsStride  // per-warp (L H) scratch
                             + 2 * kGsC * kGsC + kGsC);                // [W_0 ; W_1], bias
 }
+// The stand-alone SpMM needs neither the scratch nor the weights, and keeps its column ids as 16-bit tile-local ids: 67 KB per
+// CTA instead of 114 KB, i.e. THREE CTAs (24 warps) per SM instead of two - the kernel is latency-bound (barrier / shared-memory
+// / global scoreboard stalls), so the extra warps are what it lacks.
+constexpr int kGsSpmmCtas = 3;
+constexpr int kGsSpmmBufWords = kGsMaxRows * kGsStride + kGsMaxRows + (kGsMaxNnz + 8) / 2 + (kGsMaxRows + 8);
+constexpr size_t gs_spmm_smem_bytes() { return sizeof(float) * (size_t)kGsSpmmBufWords; }
 
 // SPMM_ONLY: Y = L.Z alone (the reference's sparse_tensor_dense_matmul(support[1], pre_sup), gcn/layers.py:206) - no
 // projection; the staged rows are pre-scaled by dinv once (G_j = dinv_j Z_j, two roundings per term like the unfused
 // multiply-then-add of the reference's CPU kernel), so the gather is a plain sum of shared-memory rows, and the row's
 // own value comes from global memory again (an L2 hit: the tile has just been read).
 template <bool IMPLICIT_IN, bool TAIL, bool SPMM_ONLY = false>
-__global__ void __launch_bounds__(kGsThreads, kGsBufs == 1 ? 2 : 1) gs_layer_kernel(const GsArgs P) {
+__global__ void __launch_bounds__(kGsThreads, SPMM_ONLY ? kGsSpmmCtas : (kGsBufs == 1 ? 2 : 1)) gs_layer_kernel(const GsArgs P) {
     extern __shared__ __align__(16) unsigned char gs_smem[];
     float *buf0 = reinterpret_cast<float *>(gs_smem);                     // two staged tiles
     float *us_all = buf0 + kGsBufs * kGsBufWords;                         // [warps][16][36]
@@ -108,10 +114,10 @@ __global__ void __launch_bounds__(kGsThreads, kGsBufs == 1 ? 2 : 1) gs_layer_ker
     const int t_begin = P.cta_first[blockIdx.x], t_end = P.cta_first[blockIdx.x + 1];
     // stage tile t into buffer `which` (asynchronous copies; one commit group per tile)
     auto stage = [&](int t, int which) {
-        float *hs = buf0 + which * kGsBufWords;
+        float *hs = buf0 + which * (SPMM_ONLY ? kGsSpmmBufWords : kGsBufWords);
         float *dinv_s = hs + kGsMaxRows * kGsStride;
         int *cols = reinterpret_cast<int *>(dinv_s + kGsMaxRows);
-        int *rp = cols + kGsMaxNnz + 8;
+        int *rp = cols + (SPMM_ONLY ? (kGsMaxNnz + 8) / 2 : kGsMaxNnz + 8);
         const int4 tile = __ldg(P.tiles + t);
         const int v0 = tile.x, n = tile.y, e0 = tile.z, nnz = tile.w;
         if (IMPLICIT_IN) {
@@ -134,8 +140,19 @@ __global__ void __launch_bounds__(kGsThreads, kGsBufs == 1 ? 2 : 1) gs_layer_ker
         const int total = nnz + (e0 - ea);
         const int chunks = total >> 2;     // whole 16-byte chunks; the last ids one by one (never past the end of col_idx)
         const int *csrc = a.col_idx + ea;
-        for (int c = tid; c < chunks; c += kGsThreads) cp_async16(cols + 4 * c, csrc + 4 * c);
-        for (int k = 4 * chunks + tid; k < total; k += kGsThreads) cp_async4(cols + k, csrc + k);
+        if (SPMM_ONLY) {   // 16-bit tile-local ids (a tile has at most 304 rows): loaded, narrowed, stored
+            uint16_t *c16 = reinterpret_cast<uint16_t *>(cols);
+            for (int c = tid; c < chunks; c += kGsThreads) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(csrc) + c);
+                // (ids of the previous tile's last rows in front of e0 fall below v0: never read, any value will do)
+                *reinterpret_cast<uint2 *>(c16 + 4 * c) = make_uint2(((unsigned)(v.x - v0) & 0xffffu) | ((unsigned)(v.y - v0) << 16),
+                                                                      ((unsigned)(v.z - v0) & 0xffffu) | ((unsigned)(v.w - v0) << 16));
+            }
+            for (int k = 4 * chunks + tid; k < total; k += kGsThreads) c16[k] = (uint16_t)(__ldg(csrc + k) - v0);
+        } else {
+            for (int c = tid; c < chunks; c += kGsThreads) cp_async16(cols + 4 * c, csrc + 4 * c);
+            for (int k = 4 * chunks + tid; k < total; k += kGsThreads) cp_async4(cols + k, csrc + k);
+        }
         for (int r = tid; r <= n; r += kGsThreads) cp_async4(rp + r, a.row_ptr + v0 + r);
         for (int r = tid; r < n; r += kGsThreads) cp_async4(dinv_s + r, a.dinv + v0 + r);
         cp_async_commit();
@@ -151,10 +168,11 @@ __global__ void __launch_bounds__(kGsThreads, kGsBufs == 1 ? 2 : 1) gs_layer_ker
             cp_async_wait_group<0>();
         }
         __syncthreads();
-        float *hs = buf0 + which * kGsBufWords;
+        float *hs = buf0 + which * (SPMM_ONLY ? kGsSpmmBufWords : kGsBufWords);
         float *dinv_s = hs + kGsMaxRows * kGsStride;
         int *cols = reinterpret_cast<int *>(dinv_s + kGsMaxRows);
-        int *rp = cols + kGsMaxNnz + 8;
+        const uint16_t *cols16 = reinterpret_cast<const uint16_t *>(cols);
+        int *rp = cols + (SPMM_ONLY ? (kGsMaxNnz + 8) / 2 : kGsMaxNnz + 8);
         const int4 tile = __ldg(P.tiles + t);
         const int v0 = tile.x, n = tile.y, e0 = tile.z;
         const int ea = e0 & ~3;
@@ -191,14 +209,14 @@ __global__ void __launch_bounds__(kGsThreads, kGsBufs == 1 ? 2 : 1) gs_layer_ker
                 int jl = 0;
                 float d = 0.f;
                 if (beg + q < end) {
-                    jl = cols[beg + q] - v0;      // neighbour's row inside the tile
+                    jl = SPMM_ONLY ? (int)cols16[beg + q] : cols[beg + q] - v0;      // neighbour's row inside the tile
                     if (!SPMM_ONLY) d = dinv_s[jl];
                 }
                 for (int e = beg; __any_sync(0xffffffffu, e < end); e += 8) {
                     int jl_next = 0;
                     float d_next = 0.f;
                     if (e + 8 + q < end) {
-                        jl_next = cols[e + 8 + q] - v0;
+                        jl_next = SPMM_ONLY ? (int)cols16[e + 8 + q] : cols[e + 8 + q] - v0;
                         if (!SPMM_ONLY) d_next = dinv_s[jl_next];
                     }
 #pragma unroll
@@ -336,21 +354,28 @@ int gs_build_plan(dg_context *ctx, dg_batch *b, bool *ok) {
     flush();
     const int n_tiles = (int)cost.size();
     if (n_tiles == 0) return DG_OK;
-    const int grid = std::min(n_tiles, ctx->sm_count * (kGsBufs == 1 ? 2 : 1));
-    // contiguous runs of tiles with balanced cost: CTA c starts at the first tile whose cost prefix reaches c / grid
-    std::vector<int> first((size_t)grid + 1, n_tiles);
     std::vector<long long> prefix((size_t)n_tiles + 1, 0);
     for (int t = 0; t < n_tiles; ++t) prefix[(size_t)t + 1] = prefix[(size_t)t] + cost[(size_t)t];
     const long long total = prefix.back();
-    first[0] = 0;
-    for (int c = 1; c < grid; ++c) {
-        const long long target = total * c / grid;
-        int t = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
-        // the boundary goes to the nearer side of the target
-        if (t > 0 && t <= n_tiles && target - prefix[(size_t)t - 1] < prefix[(size_t)std::min(t, n_tiles)] - target) --t;
-        first[(size_t)c] = std::min(std::max(t, first[(size_t)c - 1]), n_tiles);
-    }
-    first[(size_t)grid] = n_tiles;
+    // contiguous runs of tiles with balanced cost: CTA c starts at the first tile whose cost prefix reaches c / grid
+    auto runs = [&](int grid, std::vector<int> *first) {
+        first->assign((size_t)grid + 1, n_tiles);
+        (*first)[0] = 0;
+        for (int c = 1; c < grid; ++c) {
+            const long long target = total * c / grid;
+            int t = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+            // the boundary goes to the nearer side of the target
+            if (t > 0 && t <= n_tiles && target - prefix[(size_t)t - 1] < prefix[(size_t)std::min(t, n_tiles)] - target) --t;
+            (*first)[(size_t)c] = std::min(std::max(t, (*first)[(size_t)c - 1]), n_tiles);
+        }
+        (*first)[(size_t)grid] = n_tiles;
+    };
+    const int grid = std::min(n_tiles, ctx->sm_count * (kGsBufs == 1 ? 2 : 1));
+    const int grid_spmm = std::min(n_tiles, ctx->sm_count * kGsSpmmCtas);   // the stand-alone SpMM runs three CTAs per SM
+    std::vector<int> first, first_spmm;
+    runs(grid, &first);
+    runs(grid_spmm, &first_spmm);
+    first.insert(first.end(), first_spmm.begin(), first_spmm.end());
     const size_t words = flat.size() + first.size();
     if (b->gs_tiles_cap < words || !b->gs_tiles_dev) {
         if (b->gs_tiles_dev) {
@@ -368,6 +393,7 @@ int gs_build_plan(dg_context *ctx, dg_batch *b, bool *ok) {
     DG_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the pageable sources die with this call
     b->gs_n_tiles = n_tiles;
     b->gs_grid = grid;
+    b->gs_grid_spmm = grid_spmm;
     *ok = true;
     return DG_OK;
 }
@@ -375,12 +401,13 @@ int gs_build_plan(dg_context *ctx, dg_batch *b, bool *ok) {
 template <bool IMPLICIT_IN, bool TAIL, bool SPMM_ONLY = false>
 int gs_launch(dg_context *ctx, dg_batch *b, const LayerArgs &a) {
     auto kern = gs_layer_kernel<IMPLICIT_IN, TAIL, SPMM_ONLY>;
-    constexpr size_t smem = gs_smem_bytes();
+    constexpr size_t smem = SPMM_ONLY ? gs_spmm_smem_bytes() : gs_smem_bytes();
     static std::atomic<unsigned long long> attr_done{0};
     DG_CUDA_CHECK(smem_attr_once(kern, ctx->device, (int)smem, &attr_done));
     GsArgs P;
     P.tiles = reinterpret_cast<const int4 *>(b->gs_tiles_dev);
-    P.cta_first = b->gs_tiles_dev + (size_t)b->gs_n_tiles * 4;
+    // two run tables follow the tiles: for the layers' grid, then for the stand-alone SpMM's
+    P.cta_first = b->gs_tiles_dev + (size_t)b->gs_n_tiles * 4 + (SPMM_ONLY ? (size_t)b->gs_grid + 1 : 0);
     P.a = a;
     const double n = (double)a.n, nnz = (double)a.nnz;
     // B_layer / B_spmm of SURVEY.md 8d
@@ -388,7 +415,7 @@ int gs_launch(dg_context *ctx, dg_batch *b, const LayerArgs &a) {
                          4.0 * n * (TAIL ? 2 : kGsC) + (SPMM_ONLY ? 0.0 : 4.0 * (2 * kGsC * kGsC + kGsC));
     ctx->last_kernel = SPMM_ONLY ? "gs_spmm_kernel" : "gs_layer_kernel";
     prof_begin(ctx);
-    kern<<<b->gs_grid, kGsThreads, smem, ctx->stream>>>(P);
+    kern<<<SPMM_ONLY ? b->gs_grid_spmm : b->gs_grid, kGsThreads, smem, ctx->stream>>>(P);
     prof_end(ctx, bytes);
     ctx->launches++;
     DG_CUDA_CHECK(cudaGetLastError());

@@ -1,5 +1,5 @@
-"""Slots/s of the batched multi-channel scheduler (BASELINE configs[2]) on cuda:0, with the per-instance CPU
-restatement (oracle/wireless_oracle.py) timed on a few instances beside it.  Measurement aid, not a test."""
+"""Slots/s of the batched multi-channel scheduler (BASELINE configs[2]) on cuda:0.  The per-instance CPU restatement's
+timing lives in tests/probe_wireless_cpu.py (only tests/, smoke() and bench.py may run the oracle).  Measurement aid, not a test."""
 import json
 import os
 import sys
@@ -37,16 +37,6 @@ def main():
                                          "graphs_per_s": n * sim.graphs_per_slot / dt, "mean_queue": float(qs.mean())}
             sim.close()
         model.close()
-    # CPU restatement, one instance at a time like the reference script
-    from oracle import wireless_oracle as WO
-    layers = util.load_layers("is4sat_l1")
-    for algo in ("Greedy", "DGCN-LGS"):
-        t0 = time.perf_counter()
-        k = 0
-        for inst in insts[:6]:
-            WO.run_instance(inst.adj_list, inst.adj_gK, inst.arrivals, inst.rates, algo, layers, n_slots=40)
-            k += 40
-        out["cpu_port/%s" % algo] = {"instance_slots_per_s": k / (time.perf_counter() - t0)}
     print(json.dumps(out, indent=1))
 
 

@@ -1,6 +1,6 @@
 """Runs tests/test_gpu_parity.py::test_random_models_and_batches_across_paths for many seeds (a one-off soak, not a test)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from distgcn_b200 import engine as E
 from tests import test_gpu_parity as T
